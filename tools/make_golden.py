@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference in this container.
+
+    python tools/make_golden.py            # needs /root/reference and transformers; CPU only
+
+The reference modules (``gen_utils``, ``control_gen_utils``, ``clip.clip``, ``utils``) are imported
+from /root/reference exactly as they are.  What is supplied around them:
+
+* a 1-line ``colorlog`` shim and stub ``sentiments_classifer`` / ``POS_classifier`` modules
+  (NLTK / colorlog are not installed and there is no network);
+* HF ``BertForMaskedLM(BertConfig())`` / ``CLIPModel(CLIPConfig())`` loaded with the synthetic
+  state dicts from ``conzic_b200.synth`` (no pretrained weights exist offline);
+* the synthetic string tokenizers of ``conzic_b200.synth``.
+
+Recording is done by wrapping callables at run time (the model's forward, ``generate_caption_step``
+and ``compute_image_text_similarity_via_raw_text``); no reference file is edited or copied.
+Each fixture holds one record per Gibbs step plus the call's return value, and the crc32 of the
+weights it was made with.  The GPU box never runs this script; it only reads the fixtures.
+"""
+import logging
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from conzic_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+LOGIT_COLS = torch.arange(0, synth.BERT_VOCAB, 61)  # 501 strided vocabulary columns kept per row
+
+
+def import_reference(sentiment_table):
+    sys.path.insert(0, REF)
+    sys.modules["colorlog"] = types.SimpleNamespace(
+        ColoredFormatter=lambda *a, **k: logging.Formatter("%(message)s"))
+    tok = synth.SynthBertTokenizer()
+
+    def table_scorer(batch_texts, temperature, device, sentiment_ctl=None, batch_size_image=1):
+        # same maths as sentiments_classifer.py:35-48 with a per-word table for SentiWordNet
+        s = torch.zeros(len(batch_texts))
+        for i, t in enumerate(batch_texts):
+            v = sum(float(sentiment_table[tok.vocab[w]]) for w in t.split())
+            s[i] = -v if sentiment_ctl == "negative" else v
+        sb = s.view(batch_size_image, -1).to(device)
+        return torch.softmax(sb / temperature, dim=1).to(device), sb, [], []
+
+    sys.modules["sentiments_classifer"] = types.SimpleNamespace(batch_texts_POS_Sentiments_analysis=table_scorer)
+    sys.modules["POS_classifier"] = types.SimpleNamespace(batch_texts_POS_analysis=None)
+    import utils, gen_utils, control_gen_utils  # noqa: E401  (unmodified reference modules)
+    from clip.clip import CLIP
+    return utils, gen_utils, control_gen_utils, CLIP
+
+
+def build_models(bert_sd, clip_sd, CLIP, multi):
+    from transformers import BertConfig, BertForMaskedLM, CLIPConfig, CLIPModel
+    bert = BertForMaskedLM(BertConfig()).eval()
+    missing = bert.load_state_dict(bert_sd, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    clipm = CLIPModel(CLIPConfig()).eval()
+    missing = clipm.load_state_dict(clip_sd, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    clip = CLIP.__new__(CLIP)
+    torch.nn.Module.__init__(clip)
+    clip.model, clip.processor = clipm, synth.SynthProcessor()
+    clip.tokenizer, clip.cuda_has_been_checked = synth.SynthCLIPTokenizer(multi), False
+    return bert, clip
+
+
+class Recorder:
+    def __init__(self, bert, clip, mod, embed_stride=1):
+        self.steps, self.cur, self.embed_stride = [], None, embed_stride
+        self.bert, self.clip, self.mod = bert, clip, mod
+        orig_fwd, orig_step = bert.forward, mod.generate_caption_step
+        orig_sim = clip.compute_image_text_similarity_via_raw_text
+        rec = self
+
+        def fwd(inp, *a, **k):
+            rec.cur = {"inp": inp.clone()}
+            out = orig_fwd(inp, *a, **k)
+            rec.cur["_logits"] = out.logits
+            return out
+
+        def step(out, gen_idx, mask, temperature=None, top_k=100):
+            probs, ids = orig_step(out, gen_idx=gen_idx, mask=mask, temperature=temperature, top_k=top_k)
+            row = rec.cur.pop("_logits")[:, gen_idx]
+            cols = torch.cat([LOGIT_COLS.expand(row.shape[0], -1), ids], dim=1)
+            rec.cur.update(pos=int(gen_idx), token_mask_dot=float(mask[0, synth.DOT_ID]),
+                           logit_cols=cols.to(torch.int32), logit_vals=row.gather(1, cols).clone(),
+                           logit_max=row.max(dim=1).values.clone(),
+                           logit_lse=torch.logsumexp(row.double() / temperature, dim=1).float(),
+                           probs=probs.clone(), idxs=ids.clone())
+            return probs, ids
+
+        def sim(image_embeds, text_list):
+            ids = clip.tokenizer(text_list, padding=True, return_tensors="pt", max_length=77,
+                                 truncation=True)["input_ids"]
+            text_embeds = clip.compute_text_representation(text_list)
+            score, ref = clip.compute_image_text_similarity_via_embeddings(image_embeds, text_embeds)
+            keep = torch.arange(0, len(text_list), rec.embed_stride)
+            rec.cur.update(clip_ids=ids.to(torch.int32), text_embeds=text_embeds[keep].clone(), embed_rows=keep,
+                           clip_score=score.clone(), clip_ref=ref.clone(), n_texts=len(text_list),
+                           image_embeds=image_embeds.clone())
+            rec.steps.append(rec.cur)
+            return score, ref
+
+        bert.forward = fwd
+        mod.generate_caption_step = step
+        clip.compute_image_text_similarity_via_raw_text = sim
+        self._restore = lambda: (setattr(mod, "generate_caption_step", orig_step))
+
+    def close(self):
+        self._restore()
+
+
+CASES = [
+    # name, kwargs
+    dict(name="seq_b2_n4_k8", order="sequential", B=2, n=4, K=8, iters=2),
+    dict(name="shuffle_b3_n5_k16_multi", order="shuffle", B=3, n=5, K=16, iters=2, multi=True),
+    dict(name="random_b2_n3_k8", order="random", B=2, n=3, K=8, iters=2),
+    dict(name="senti_seq_b2_n4_k8", order="sequential", B=2, n=4, K=8, iters=2, gamma=5.0, style="positive"),
+    dict(name="senti_shuffle_neg_b2_n4_k8", order="shuffle", B=2, n=4, K=8, iters=2, gamma=5.0, style="negative"),
+    dict(name="peaked_seq_b2_n4_k32", order="sequential", B=2, n=4, K=32, iters=2, peaked=True),
+    dict(name="seq_b1_n10_k200", order="sequential", B=1, n=10, K=200, iters=1),
+]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    table = synth.make_sentiment_table()
+    utils, gen_utils, control_gen_utils, CLIP = import_reference(table)
+    logger = logging.getLogger("golden")
+    logger.addHandler(logging.NullHandler())
+    clip_sd = synth.make_clip_state_dict(0)
+    sds = {False: synth.make_bert_state_dict(0), True: synth.make_bert_state_dict(0, peaked=True)}
+    only = set(sys.argv[1:])
+    for case in CASES:
+        if only and case["name"] not in only:
+            continue
+        peaked, multi = case.get("peaked", False), case.get("multi", False)
+        bert_sd = sds[peaked]
+        bert, clip = build_models(bert_sd, clip_sd, CLIP, multi)
+        B, n, K = case["B"], case["n"], case["K"]
+        pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+        token_mask = synth.make_token_mask()
+        gamma = case.get("gamma")
+        mod = control_gen_utils if gamma is not None else gen_utils
+        rec = Recorder(bert, clip, mod, embed_stride=13 if K >= 100 else 1)
+        utils.set_seed(42)
+        names = [f"img{i}.jpg" for i in range(B)]
+        kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1,
+                  max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
+        with torch.no_grad():
+            if gamma is None:
+                texts, scores = gen_utils.generate_caption(names, bert, clip, synth.SynthBertTokenizer(), pix,
+                                                           token_mask, logger, **kw)
+            else:
+                texts, scores = control_gen_utils.control_generate_caption(
+                    names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask, logger, gamma=gamma,
+                    ctl_type="sentiment", style_type=case["style"], **kw)
+        rec.close()
+        fixture = dict(case=case, steps=rec.steps, texts=texts, scores=scores,
+                       bert_crc=synth.state_dict_checksum(bert_sd), clip_crc=synth.state_dict_checksum(clip_sd),
+                       torch=torch.__version__)
+        path = os.path.join(OUT, case["name"] + ".pt")
+        torch.save(fixture, path)
+        print(f"{case['name']}: {len(rec.steps)} steps, {os.path.getsize(path)/1024:.0f} KiB; final={texts[-2]}")
+
+
+if __name__ == "__main__":
+    main()
