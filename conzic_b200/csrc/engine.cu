@@ -1,0 +1,596 @@
+// libconzic.so: context (weights in operand format + TMA descriptors), the two towers as sequences of
+// kernel launches on one stream, and the extern "C" boundary declared in include/conzic.h.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/conzic.h"
+#include "kernels.h"
+
+namespace conzic {
+
+static thread_local std::string g_err;
+uint64_t g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+namespace {
+
+__global__ void find_eos_kernel(const int32_t* ids, int N, int T, int eos, int32_t* eos_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int r = 0;  // HF:models/clip/modeling_clip.py:564-584: argmax of (ids == eos), 0 when absent
+  for (int t = 0; t < T; ++t)
+    if (ids[static_cast<size_t>(i) * T + t] == eos) { r = t; break; }
+  eos_idx[i] = r;
+}
+__global__ void add_one_kernel(int32_t* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += 1;
+}
+
+struct Layer {
+  LinearW qkv, o, f1, f2;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  Bump(void* p, size_t c) : base(static_cast<char*>(p)), cap(c) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+}  // namespace
+}  // namespace conzic
+
+using namespace conzic;
+
+struct conzic_ctx {
+  conzic_config cfg;
+  int split = 0;
+  GemmOpts gopt;
+  std::vector<void*> owned;
+  // BERT
+  float *b_word = nullptr, *b_pos = nullptr, *b_type = nullptr, *b_eln_g = nullptr, *b_eln_b = nullptr;
+  float *b_hln_g = nullptr, *b_hln_b = nullptr;
+  LinearW b_transform, b_decoder;
+  std::vector<Layer> bert;
+  // CLIP text
+  float *c_tok = nullptr, *c_pos = nullptr, *c_fln_g = nullptr, *c_fln_b = nullptr;
+  LinearW c_proj;
+  std::vector<Layer> clip;
+  // bert id -> clip ids
+  int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
+  int max_tok_per_word = 1;
+  int chunk_rows = 16384;
+  uint64_t launches0 = 0;
+
+  ~conzic_ctx() {
+    for (void* p : owned) cudaFree(p);
+  }
+  template <typename T>
+  T* dalloc(size_t n) {
+    void* p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, n * sizeof(T)), "cudaMalloc(weights)")) return nullptr;
+    owned.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+  float* copy_f32(const void* src, size_t n, cudaStream_t st) {
+    float* d = dalloc<float>(n);
+    if (d) cuda_ok(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy weights");
+    return d;
+  }
+  int ldw(int K) const { return split ? 2 * K : K; }
+  // Build a LinearW from `parts` row blocks of fp32 [n_i, K] (e.g. q, k, v stacked into one [3H, K]).
+  bool make_linear(LinearW* L, const void* const* w_parts, const void* const* b_parts, const int* n_parts, int parts,
+                   int K, cudaStream_t st) {
+    int N = 0;
+    for (int i = 0; i < parts; ++i) N += n_parts[i];
+    L->N = N;
+    L->K = K;
+    const int ld = ldw(K);
+    L->w = dalloc<bf16>(static_cast<size_t>(N) * ld);
+    if (!L->w) return false;
+    float* bias = nullptr;
+    if (b_parts) {
+      bias = dalloc<float>(N);
+      if (!bias) return false;
+    }
+    int r0 = 0;
+    for (int i = 0; i < parts; ++i) {
+      launch_f32_to_act(static_cast<const float*>(w_parts[i]), n_parts[i], K, K, L->w + static_cast<size_t>(r0) * ld, ld,
+                        split, st);
+      if (b_parts)
+        cuda_ok(cudaMemcpyAsync(bias + r0, b_parts[i], n_parts[i] * sizeof(float), cudaMemcpyDeviceToDevice, st),
+                "copy bias");
+      r0 += n_parts[i];
+    }
+    L->bias = bias;
+    if (cfg.gemm_impl == CONZIC_GEMM_TCGEN05) {
+      if (!make_tmap_bf16_2d(&L->tmap128, L->w, N, ld, ld, 128)) return false;
+      if (!make_tmap_bf16_2d(&L->tmap256, L->w, N, ld, ld, 256)) return false;
+    }
+    return true;
+  }
+};
+
+namespace {
+
+struct Plan {
+  // BERT
+  float *bx, *by;
+  bf16 *bh, *battn, *bffn;
+  void* bqkv;
+  float *bt, *logits;
+  bf16* bt_act;
+  int ldl;
+  // top-k / assembly
+  float *probs, *repeats, *senti;
+  int64_t *ids, *ids_masked;
+  int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx, *pool_rows;
+  // CLIP chunk
+  float* cx;
+  bf16 *ch, *cattn, *cffn, *cpool;
+  void* cqkv;
+  float* text;
+  size_t bytes;
+};
+
+int chunk_cap_rows(const conzic_ctx* c, int K) {
+  const int per_img = c->cfg.clip_maxpos * (K + 1);
+  return c->chunk_rows > per_img ? c->chunk_rows : per_img;
+}
+
+Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
+  const conzic_config& g = c->cfg;
+  const int s = c->split;
+  Bump b(ws, 0);
+  Plan p;
+  const size_t Mb = static_cast<size_t>(B) * (L > 0 ? L : 1);
+  const int Hb = g.bert_hidden, Fb = g.bert_ffn, Hc = g.clip_hidden, Fc = g.clip_ffn;
+  p.bx = b.take<float>(Mb * Hb);
+  p.by = b.take<float>(Mb * Hb);
+  p.bh = b.take<bf16>(Mb * Hb * (1 + s));
+  p.battn = b.take<bf16>(Mb * Hb * (1 + s));
+  p.bffn = b.take<bf16>(Mb * Fb * (1 + s));
+  p.bqkv = b.take<char>(Mb * 3 * Hb * (s ? 4 : 2));
+  p.bt = b.take<float>(static_cast<size_t>(B) * Hb);
+  p.bt_act = b.take<bf16>(static_cast<size_t>(B) * Hb * (1 + s));
+  p.ldl = (g.bert_vocab + 3) & ~3;
+  p.logits = b.take<float>(static_cast<size_t>(B) * p.ldl);
+  const size_t BK = static_cast<size_t>(B) * K;
+  p.probs = b.take<float>(BK);
+  p.repeats = b.take<float>(BK);
+  p.senti = b.take<float>(BK);
+  p.ids = b.take<int64_t>(BK);
+  p.ids_masked = b.take<int64_t>(BK);
+  p.ids_prefix = b.take<int32_t>(static_cast<size_t>(B) * g.clip_maxpos);
+  p.ids_suffix = b.take<int32_t>(BK * g.clip_maxpos);
+  p.p0 = b.take<int32_t>(B);
+  p.eos_idx = b.take<int32_t>(BK);
+  p.pool_rows = b.take<int32_t>(BK);
+  const size_t Mc = chunk_cap_rows(c, K);
+  p.cx = b.take<float>(Mc * Hc);
+  p.ch = b.take<bf16>(Mc * Hc * (1 + s));
+  p.cattn = b.take<bf16>(Mc * Hc * (1 + s));
+  p.cffn = b.take<bf16>(Mc * Fc * (1 + s));
+  p.cqkv = b.take<char>(Mc * 3 * Hc * (s ? 4 : 2));
+  p.cpool = b.take<bf16>(BK * Hc * (1 + s));
+  p.text = b.take<float>(BK * g.clip_proj);
+  p.bytes = align_up(b.off, 256);
+  return p;
+}
+
+bool check_ws(const conzic_ctx* c, size_t ws_bytes, int B, int L, int K) {
+  Plan p = make_plan(c, nullptr, B, L, K);
+  if (ws_bytes < p.bytes) {
+    set_error("workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(ws_bytes));
+    return false;
+  }
+  return true;
+}
+
+Epi epi_act_out(const LinearW& W, bf16* out, int ld, int outK, int act) {
+  Epi e;
+  e.bias = W.bias; e.out_act = out; e.ldo_act = ld; e.out_K = outK; e.act = act;
+  return e;
+}
+Epi epi_f32_out(const LinearW& W, float* out, int ld, const float* resid, int ldr, int act) {
+  Epi e;
+  e.bias = W.bias; e.out_f32 = out; e.ldo_f32 = ld; e.resid = resid; e.ldr = ldr; e.act = act;
+  return e;
+}
+
+// ---- BERT: logits of row `pos` for every image ------------------------------------------------------
+bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, float* logits, int ldl, Plan& p,
+                     cudaStream_t st) {
+  const conzic_config& g = c->cfg;
+  const int H = g.bert_hidden, F = g.bert_ffn, s = c->split;
+  const int M = B * L;
+  const int ldh = H * (1 + s), ldf = F * (1 + s);
+  if (L > g.bert_maxpos) { set_error("bert: sequence longer than position table"); return false; }
+  launch_bert_embed_ln(inp, M, L, c->b_word, c->b_pos, c->b_type, c->b_eln_g, c->b_eln_b, g.bert_ln_eps, H, p.bx, p.bh,
+                       ldh, s, st);
+  for (size_t l = 0; l < c->bert.size(); ++l) {
+    const Layer& ly = c->bert[l];
+    Act h{p.bh, ldh, H};
+    Epi e;
+    if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.bqkv), 3 * H, nullptr, 0, ACT_NONE);
+    else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.bqkv), 3 * H, 0, ACT_NONE);
+    GemmOpts o = c->gopt;
+    if (s) { /* fp32 qkv output in parity mode */ }
+    if (!launch_linear(h, M, ly.qkv, e, o, st, nullptr)) return false;
+    if (!s) {
+      // bf16 qkv is not a split Act even though the GEMM flag is global: qkv never feeds a GEMM
+    }
+    AttnArgs at;
+    at.qkv = p.bqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = nullptr;
+    at.B = B; at.P = 0; at.K = 1; at.S = L; at.H = H; at.heads = g.bert_heads; at.causal = 0;
+    at.scale = 0.125f; at.out_act = p.battn; at.ld_act = ldh; at.split = s;
+    if (!launch_attention(at, st)) return false;
+    Act a{p.battn, ldh, H};
+    if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.by, H, p.bx, H, ACT_NONE), o, st, nullptr)) return false;
+    LNArgs ln{p.by, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
+    launch_layernorm(ln, st);
+    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), o, st, nullptr)) return false;
+    Act f{p.bffn, ldf, F};
+    if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.by, H, p.bx, H, ACT_NONE), o, st, nullptr)) return false;
+    LNArgs ln2{p.by, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
+    launch_layernorm(ln2, st);
+  }
+  // MLM head on row `pos` only: a strided view of the hidden states (row stride L*ldh) needs no gather.
+  Act hrow{p.bh + static_cast<size_t>(pos) * ldh, L * ldh, H};
+  GemmOpts o = c->gopt;
+  if (!launch_linear(hrow, B, c->b_transform, epi_f32_out(c->b_transform, p.bt, H, nullptr, 0, ACT_ERF_GELU), o, st,
+                     nullptr))
+    return false;
+  LNArgs lnh{p.bt, nullptr, B, H, c->b_hln_g, c->b_hln_b, g.bert_ln_eps, nullptr, p.bt_act, ldh, s};
+  launch_layernorm(lnh, st);
+  Act t{p.bt_act, ldh, H};
+  return launch_linear(t, B, c->b_decoder, epi_f32_out(c->b_decoder, logits, ldl, nullptr, 0, ACT_NONE), o, st, nullptr);
+}
+
+// ---- CLIP text tower over packed prefix/suffix rows, in L2-sized chunks of images -------------------
+bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0,
+                 const int32_t* eos_idx, int B, int P, int K, int S, float* text, Plan& p, cudaStream_t st) {
+  const conzic_config& g = c->cfg;
+  const int H = g.clip_hidden, F = g.clip_ffn, s = c->split;
+  const int ldh = H * (1 + s), ldf = F * (1 + s);
+  const int per_img = P + K * S;
+  int Bc = c->chunk_rows / per_img;
+  if (Bc < 1) Bc = 1;
+  if (Bc > B) Bc = B;
+  if (static_cast<size_t>(Bc) * per_img > static_cast<size_t>(chunk_cap_rows(c, K))) {
+    set_error("clip_encode: chunk exceeds workspace plan");
+    return false;
+  }
+  const float scale = 0.125f;  // head_dim^-0.5, HF:models/clip/modeling_clip.py:283
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
+    const int M = nb * per_img;
+    const int32_t* idp = P > 0 ? ids_prefix + static_cast<size_t>(b0) * P : nullptr;
+    const int32_t* ids = ids_suffix + static_cast<size_t>(b0) * K * S;
+    const int32_t* p0c = p0 ? p0 + b0 : nullptr;
+    launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, st);
+    for (size_t l = 0; l < c->clip.size(); ++l) {
+      const Layer& ly = c->clip[l];
+      LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+      launch_layernorm(ln1, st);
+      Act h{p.ch, ldh, H};
+      Epi e;
+      if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
+      else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.cqkv), 3 * H, 0, ACT_NONE);
+      if (!launch_linear(h, M, ly.qkv, e, c->gopt, st, nullptr)) return false;
+      AttnArgs at;
+      at.qkv = p.cqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = p0c;
+      at.B = nb; at.P = P; at.K = K; at.S = S; at.H = H; at.heads = g.clip_heads; at.causal = 1;
+      at.scale = scale; at.out_act = p.cattn; at.ld_act = ldh; at.split = s;
+      if (!launch_attention(at, st)) return false;
+      Act a{p.cattn, ldh, H};
+      if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr)) return false;
+      LNArgs ln2{p.cx, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+      launch_layernorm(ln2, st);
+      if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
+        return false;
+      Act f{p.cffn, ldf, F};
+      if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr))
+        return false;
+    }
+    // pooled = final LN of the hidden state at the first EOS; text_projection without bias
+    launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
+    LNArgs lnf{p.cx, p.pool_rows, nb * K, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
+    launch_layernorm(lnf, st);
+    Act pooled{p.cpool, ldh, H};
+    Epi e;
+    e.out_f32 = text + static_cast<size_t>(b0) * K * g.clip_proj;
+    e.ldo_f32 = g.clip_proj;
+    if (!launch_linear(pooled, nb * K, c->c_proj, e, c->gopt, st, nullptr)) return false;
+  }
+  return cuda_ok(cudaGetLastError(), "clip_encode");
+}
+
+bool have_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    set_error("no CUDA device: libconzic has no CPU fallback");
+    return false;
+  }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("libconzic is built for sm_100a (B200) only; device compute capability major is " + std::to_string(major));
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int conzic_abi_version(void) { return CONZIC_ABI_VERSION; }
+const char* conzic_last_error(void) { return g_err.c_str(); }
+
+int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_bert, const void* const* cw, int n_clip,
+                      void* stream, conzic_ctx** out) {
+  if (!cfg || !bw || !cw || !out) { set_error("ctx_create: null argument"); return -1; }
+  if (!have_device()) return -2;
+  if (n_bert != CONZIC_BERT_GLOBALS + CONZIC_PER_LAYER * cfg->bert_layers ||
+      n_clip != CONZIC_CLIP_GLOBALS + CONZIC_PER_LAYER * cfg->clip_layers) {
+    set_error("ctx_create: weight table length does not match the layer counts");
+    return -1;
+  }
+  if (cfg->bert_hidden != cfg->bert_heads * 64 || cfg->clip_hidden != cfg->clip_heads * 64) {
+    set_error("ctx_create: head_dim must be 64");
+    return -1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  conzic_ctx* c = new conzic_ctx();
+  c->cfg = *cfg;
+  c->split = cfg->precision == CONZIC_PREC_BF16X3 ? 1 : 0;
+  c->gopt.split = c->split;
+  c->gopt.impl = cfg->gemm_impl;
+  c->gopt.bn = 128;
+  c->gopt.stages = 3;
+  if (const char* e = getenv("CONZIC_GEMM_BN")) c->gopt.bn = atoi(e);
+  if (const char* e = getenv("CONZIC_GEMM_STAGES")) c->gopt.stages = atoi(e);
+  c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 16384;
+  if (const char* e = getenv("CONZIC_CLIP_CHUNK_ROWS")) c->chunk_rows = atoi(e);
+  bool ok = true;
+  if (cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ok = tma_init() && gemm_configure();
+  ok = ok && topk_configure();
+  const int Hb = cfg->bert_hidden, Fb = cfg->bert_ffn, Vb = cfg->bert_vocab;
+  const int Hc = cfg->clip_hidden, Fc = cfg->clip_ffn;
+  if (ok) {
+    c->b_word = c->copy_f32(bw[0], static_cast<size_t>(Vb) * Hb, st);
+    c->b_pos = c->copy_f32(bw[1], static_cast<size_t>(cfg->bert_maxpos) * Hb, st);
+    c->b_type = c->copy_f32(bw[2], static_cast<size_t>(2) * Hb, st);
+    c->b_eln_g = c->copy_f32(bw[3], Hb, st);
+    c->b_eln_b = c->copy_f32(bw[4], Hb, st);
+    c->b_hln_g = c->copy_f32(bw[8], Hb, st);
+    c->b_hln_b = c->copy_f32(bw[9], Hb, st);
+    ok = c->b_word && c->b_pos && c->b_type && c->b_eln_g && c->b_eln_b && c->b_hln_g && c->b_hln_b;
+  }
+  if (ok) {
+    const void* w1[1] = {bw[6]}; const void* b1[1] = {bw[7]}; int n1[1] = {Hb};
+    ok = c->make_linear(&c->b_transform, w1, b1, n1, 1, Hb, st);
+    const void* w2[1] = {bw[0]}; const void* b2[1] = {bw[5]}; int n2[1] = {Vb};
+    ok = ok && c->make_linear(&c->b_decoder, w2, b2, n2, 1, Hb, st);  // decoder tied to word embeddings
+  }
+  for (int l = 0; ok && l < cfg->bert_layers; ++l) {
+    const void* const* t = bw + CONZIC_BERT_GLOBALS + CONZIC_PER_LAYER * l;
+    Layer ly;
+    const void* wq[3] = {t[0], t[2], t[4]}; const void* bq[3] = {t[1], t[3], t[5]}; int nq[3] = {Hb, Hb, Hb};
+    ok = c->make_linear(&ly.qkv, wq, bq, nq, 3, Hb, st);
+    const void* wo[1] = {t[6]}; const void* bo[1] = {t[7]}; int no[1] = {Hb};
+    ok = ok && c->make_linear(&ly.o, wo, bo, no, 1, Hb, st);
+    ly.ln1_g = c->copy_f32(t[8], Hb, st); ly.ln1_b = c->copy_f32(t[9], Hb, st);
+    const void* wf[1] = {t[10]}; const void* bf[1] = {t[11]}; int nf[1] = {Fb};
+    ok = ok && c->make_linear(&ly.f1, wf, bf, nf, 1, Hb, st);
+    const void* wg[1] = {t[12]}; const void* bg[1] = {t[13]}; int ng[1] = {Hb};
+    ok = ok && c->make_linear(&ly.f2, wg, bg, ng, 1, Fb, st);
+    ly.ln2_g = c->copy_f32(t[14], Hb, st); ly.ln2_b = c->copy_f32(t[15], Hb, st);
+    ok = ok && ly.ln1_g && ly.ln1_b && ly.ln2_g && ly.ln2_b;
+    c->bert.push_back(ly);
+  }
+  if (ok) {
+    c->c_tok = c->copy_f32(cw[0], static_cast<size_t>(cfg->clip_vocab) * Hc, st);
+    c->c_pos = c->copy_f32(cw[1], static_cast<size_t>(cfg->clip_maxpos) * Hc, st);
+    c->c_fln_g = c->copy_f32(cw[2], Hc, st);
+    c->c_fln_b = c->copy_f32(cw[3], Hc, st);
+    const void* wp[1] = {cw[4]}; int np[1] = {cfg->clip_proj};
+    ok = c->c_tok && c->c_pos && c->c_fln_g && c->c_fln_b && c->make_linear(&c->c_proj, wp, nullptr, np, 1, Hc, st);
+  }
+  for (int l = 0; ok && l < cfg->clip_layers; ++l) {
+    const void* const* t = cw + CONZIC_CLIP_GLOBALS + CONZIC_PER_LAYER * l;
+    Layer ly;
+    ly.ln1_g = c->copy_f32(t[0], Hc, st); ly.ln1_b = c->copy_f32(t[1], Hc, st);
+    const void* wq[3] = {t[2], t[4], t[6]}; const void* bq[3] = {t[3], t[5], t[7]}; int nq[3] = {Hc, Hc, Hc};
+    ok = c->make_linear(&ly.qkv, wq, bq, nq, 3, Hc, st);
+    const void* wo[1] = {t[8]}; const void* bo[1] = {t[9]}; int no[1] = {Hc};
+    ok = ok && c->make_linear(&ly.o, wo, bo, no, 1, Hc, st);
+    ly.ln2_g = c->copy_f32(t[10], Hc, st); ly.ln2_b = c->copy_f32(t[11], Hc, st);
+    const void* wf[1] = {t[12]}; const void* bf[1] = {t[13]}; int nf[1] = {Fc};
+    ok = ok && c->make_linear(&ly.f1, wf, bf, nf, 1, Hc, st);
+    const void* wg[1] = {t[14]}; const void* bg[1] = {t[15]}; int ng[1] = {Hc};
+    ok = ok && c->make_linear(&ly.f2, wg, bg, ng, 1, Fc, st);
+    ok = ok && ly.ln1_g && ly.ln1_b && ly.ln2_g && ly.ln2_b;
+    c->clip.push_back(ly);
+  }
+  ok = ok && cuda_ok(cudaStreamSynchronize(st), "ctx_create sync");
+  if (!ok) { delete c; return -3; }
+  c->launches0 = g_launches;
+  *out = c;
+  return 0;
+}
+
+void conzic_ctx_destroy(conzic_ctx* ctx) { delete ctx; }
+
+int conzic_set_bert2clip(conzic_ctx* c, const int32_t* off, const int32_t* tok, int n_tok, int max_tok_per_word,
+                         void* stream) {
+  if (!c || !off || (!tok && n_tok > 0)) { set_error("set_bert2clip: null argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  c->b2c_off = c->dalloc<int32_t>(c->cfg.bert_vocab + 1);
+  c->b2c_tok = c->dalloc<int32_t>(n_tok > 0 ? n_tok : 1);
+  if (!c->b2c_off || !c->b2c_tok) return -3;
+  bool ok = cuda_ok(cudaMemcpyAsync(c->b2c_off, off, (c->cfg.bert_vocab + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st), "copy b2c off");
+  if (n_tok > 0)
+    ok = ok && cuda_ok(cudaMemcpyAsync(c->b2c_tok, tok, n_tok * sizeof(int32_t), cudaMemcpyDeviceToDevice, st), "copy b2c tok");
+  c->max_tok_per_word = max_tok_per_word > 0 ? max_tok_per_word : 1;
+  return ok ? 0 : -3;
+}
+
+size_t conzic_workspace_bytes(const conzic_ctx* c, int B, int L, int K) {
+  if (!c) return 0;
+  return make_plan(c, nullptr, B, L, K).bytes;
+}
+
+uint64_t conzic_launch_count(const conzic_ctx* c) { return c ? g_launches - c->launches0 : 0; }
+
+int conzic_bert_mlm_row(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, float* logits, int ldl, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (!c || !inp || !logits || !ws) { set_error("bert_mlm_row: null argument"); return -1; }
+  if (pos < 0 || pos >= L || ldl < c->cfg.bert_vocab || (ldl & 3)) { set_error("bert_mlm_row: bad pos / ldl"); return -1; }
+  if (!check_ws(c, ws_bytes, B, L, 1)) return -1;
+  Plan p = make_plan(c, ws, B, L, 1);
+  return bert_row_logits(c, inp, B, L, pos, logits, ldl, p, static_cast<cudaStream_t>(stream)) ? 0 : -4;
+}
+
+int conzic_topk_mask(conzic_ctx* c, const float* logits, int ldl, int B, const float* token_mask, float temperature,
+                     int K, float* probs, int64_t* ids, void* stream) {
+  if (!c || !logits || !token_mask || !probs || !ids) { set_error("topk_mask: null argument"); return -1; }
+  return launch_topk(logits, ldl, B, c->cfg.bert_vocab, token_mask, temperature, K, probs, ids,
+                     static_cast<cudaStream_t>(stream)) ? 0 : -4;
+}
+
+static void fill_assemble(const conzic_ctx* c, AssembleArgs& a) {
+  const conzic_config& g = c->cfg;
+  a.off = c->b2c_off; a.tok = c->b2c_tok; a.V = g.bert_vocab;
+  a.special[0] = g.pad_id; a.special[1] = g.unk_id; a.special[2] = g.cls_id; a.special[3] = g.sep_id;
+  a.special[4] = g.mask_id;
+  a.bos = g.clip_bos; a.eos = g.clip_eos; a.maxlen = g.clip_maxpos;
+}
+
+int conzic_build_clip_ids(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, const int64_t* ids,
+                          const float* token_mask, int K, int32_t* clip_ids, int T, int32_t* clip_len,
+                          int64_t* ids_masked, void* stream) {
+  if (!c || !inp || !ids || !token_mask || !clip_ids || !clip_len || !ids_masked) { set_error("build_clip_ids: null argument"); return -1; }
+  if (!c->b2c_off) { set_error("build_clip_ids: conzic_set_bert2clip has not been called"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AssembleArgs a{};
+  fill_assemble(c, a);
+  a.inp = inp; a.ids = ids; a.token_mask = token_mask; a.senti_table = nullptr;
+  a.B = B; a.L = L; a.K = K; a.pos = pos;
+  a.ids_prefix = nullptr; a.ids_suffix = clip_ids; a.p0 = nullptr; a.eos_idx = clip_len; a.P = 0; a.S = T;
+  a.ids_masked = ids_masked; a.repeats = nullptr; a.senti = nullptr;
+  launch_assemble(a, st);
+  add_one_kernel<<<(B * K + 255) / 256, 256, 0, st>>>(clip_len, B * K);
+  ++g_launches;
+  return cuda_ok(cudaGetLastError(), "build_clip_ids") ? 0 : -4;
+}
+
+int conzic_clip_text_encode(conzic_ctx* c, const int32_t* clip_ids, int N, int T, float* text, void* ws,
+                            size_t ws_bytes, void* stream) {
+  if (!c || !clip_ids || !text || !ws) { set_error("clip_text_encode: null argument"); return -1; }
+  if (T < 1 || T > c->cfg.clip_maxpos) { set_error("clip_text_encode: T must be in [1, 77]"); return -1; }
+  if (!check_ws(c, ws_bytes, N, 0, 1)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan p = make_plan(c, ws, N, 0, 1);
+  find_eos_kernel<<<(N + 255) / 256, 256, 0, st>>>(clip_ids, N, T, c->cfg.clip_eos, p.eos_idx);
+  ++g_launches;
+  if (!clip_encode(c, nullptr, clip_ids, nullptr, p.eos_idx, N, 0, 1, T, p.text, p, st)) return -4;
+  return cuda_ok(cudaMemcpyAsync(text, p.text, static_cast<size_t>(N) * c->cfg.clip_proj * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st), "copy text embeds") ? 0 : -4;
+}
+
+int conzic_image_text_similarity(conzic_ctx* c, const float* text, const float* image, int B, int K, float scale,
+                                 float* clip_score, float* clip_ref, void* stream) {
+  if (!c || !text || !image) { set_error("image_text_similarity: null argument"); return -1; }
+  if (K > 1024) { set_error("image_text_similarity: K > 1024"); return -1; }
+  SelectArgs a{};
+  a.text = text; a.image = image; a.B = B; a.K = K; a.D = c->cfg.clip_proj; a.scale = scale;
+  a.tr_clip_score = clip_score; a.tr_clip_ref = clip_ref;
+  launch_score_select(a, static_cast<cudaStream_t>(stream));
+  return cuda_ok(cudaGetLastError(), "image_text_similarity") ? 0 : -4;
+}
+
+int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t ws_bytes, void* stream) {
+  if (!c || !s || !ws || !s->inp || !s->token_mask || !s->image_embeds) { set_error("gibbs_step: null argument"); return -1; }
+  if (!c->b2c_off) { set_error("gibbs_step: conzic_set_bert2clip has not been called"); return -1; }
+  const int B = s->B, L = s->L, K = s->K, pos = s->pos;
+  if (B < 1 || K < 1 || K > 1024 || pos < 1 || pos >= L - 1) { set_error("gibbs_step: bad B / K / pos"); return -1; }
+  if (!check_ws(c, ws_bytes, B, L, K)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan p = make_plan(c, ws, B, L, K);
+  const conzic_config& g = c->cfg;
+  launch_step_prologue(s->inp, B, L, pos, g.mask_id, s->token_mask, g.dot_id, s->dot_allowed, st);
+  float* logits = s->tr_logits ? s->tr_logits : p.logits;
+  if (!bert_row_logits(c, s->inp, B, L, pos, logits, p.ldl, p, st)) return -4;
+  float* probs = s->tr_probs ? s->tr_probs : p.probs;
+  int64_t* ids = s->tr_ids ? s->tr_ids : p.ids;
+  if (!launch_topk(logits, p.ldl, B, g.bert_vocab, s->token_mask, s->temperature, K, probs, ids, st)) return -4;
+  const int W = c->max_tok_per_word;
+  const int cap = g.clip_maxpos - 1;
+  int P = 1 + W * s->visited_before; if (P > cap) P = cap;
+  int S = W * (1 + s->visited_after) + 1; if (S > cap) S = cap;
+  const bool ctl = s->senti_table != nullptr;
+  AssembleArgs a{};
+  fill_assemble(c, a);
+  a.inp = s->inp; a.ids = ids; a.token_mask = s->token_mask; a.senti_table = s->senti_table;
+  a.B = B; a.L = L; a.K = K; a.pos = pos;
+  a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
+  a.ids_masked = p.ids_masked; a.repeats = ctl ? p.repeats : nullptr; a.senti = ctl ? p.senti : nullptr;
+  launch_assemble(a, st);
+  if (!clip_encode(c, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.text, p, st)) return -4;
+  SelectArgs q{};
+  q.text = p.text; q.image = s->image_embeds; q.B = B; q.K = K; q.D = g.clip_proj; q.scale = s->logit_scale_exp;
+  q.probs = probs; q.ids_masked = p.ids_masked; q.senti = ctl ? p.senti : nullptr; q.repeats = ctl ? p.repeats : nullptr;
+  q.alpha = s->alpha; q.beta = s->beta; q.gamma = s->gamma;
+  q.inp = s->inp; q.L = L; q.pos = pos;
+  q.out_clip_ref = s->out_clip_ref; q.out_senti = s->out_senti;
+  q.tr_clip_score = s->tr_clip_score; q.tr_clip_ref = s->tr_clip_ref; q.tr_final = s->tr_final; q.tr_best = s->tr_best;
+  launch_score_select(q, st);
+  return cuda_ok(cudaGetLastError(), "gibbs_step") ? 0 : -4;
+}
+
+int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const float* bias, const float* resid, int M,
+                        int N, int K, int act, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!c || !A || !Wf || !out || !ws) { set_error("debug_linear: null argument"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int s = c->split, ld = K * (1 + s);
+  const size_t need = (static_cast<size_t>(M) + N) * ld * sizeof(bf16) + 1024;
+  if (ws_bytes < need) { set_error("debug_linear: workspace too small, need " + std::to_string(need)); return -1; }
+  Bump b(ws, ws_bytes);
+  bf16* a_act = b.take<bf16>(static_cast<size_t>(M) * ld);
+  bf16* w_act = b.take<bf16>(static_cast<size_t>(N) * ld);
+  launch_f32_to_act(A, M, K, K, a_act, ld, s, st);
+  launch_f32_to_act(Wf, N, K, K, w_act, ld, s, st);
+  LinearW W;
+  W.w = w_act; W.bias = bias; W.N = N; W.K = K;
+  if (c->cfg.gemm_impl == CONZIC_GEMM_TCGEN05) {
+    if (!make_tmap_bf16_2d(&W.tmap128, w_act, N, ld, ld, 128)) return -4;
+    if (!make_tmap_bf16_2d(&W.tmap256, w_act, N, ld, ld, 256)) return -4;
+  }
+  Epi e;
+  e.bias = bias; e.resid = resid; e.ldr = N; e.out_f32 = out; e.ldo_f32 = N; e.act = act;
+  Act a{a_act, ld, K};
+  return launch_linear(a, M, W, e, c->gopt, st, nullptr) ? 0 : -4;
+}
+
+}  // extern "C"

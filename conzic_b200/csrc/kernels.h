@@ -1,0 +1,152 @@
+// Internal interfaces between the translation units of libconzic.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace conzic {
+
+typedef __nv_bfloat16 bf16;
+
+extern uint64_t g_launches;  // kernels launched by this library (all contexts)
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t e, const char* what);
+
+// A GEMM-input activation matrix.  bf16 mode: [rows, K].  bf16x3 mode: [rows, 2K], the bf16 "hi" plane in
+// columns [0,K) and the residual "lo" plane (x - float(hi)) in [K,2K).
+struct Act {
+  bf16* p;
+  int ld;  // elements per row: K or 2K
+  int K;
+};
+
+// A linear layer's weight in operand format ([N,K] or [N,2K] like Act) plus its TMA descriptors.
+struct LinearW {
+  bf16* w = nullptr;
+  const float* bias = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap tmap128;  // box 128 rows x 64 cols, 128B swizzle
+  CUtensorMap tmap256;  // box 256 rows x 64 cols
+};
+
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_ERF_GELU = 2 };
+
+// Epilogue: v = acc + bias[n] ; v = act(v) ; v += resid[m,n] ; then written as fp32 and/or as an Act.
+struct Epi {
+  const float* bias = nullptr;
+  const float* resid = nullptr;
+  int ldr = 0;
+  float* out_f32 = nullptr;
+  int ldo_f32 = 0;
+  bf16* out_act = nullptr;
+  int ldo_act = 0;
+  int out_K = 0;  // column offset of the lo plane when writing a split Act
+  int act = ACT_NONE;
+};
+
+struct GemmOpts {
+  int split = 0;    // 1 = bf16x3
+  int impl = 0;     // 0 tcgen05, 1 SIMT debug
+  int bn = 128;     // N tile: 128 or 256
+  int stages = 3;   // smem pipeline depth
+};
+
+bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
+bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows);
+bool gemm_configure();  // opt-in to large dynamic shared memory for every instantiation
+bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st,
+                   uint64_t* launches);
+
+// ---- transformer pieces (transformer_ops.cu) ---------------------------------------------------------
+void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, int ldd, int split, cudaStream_t st);
+
+struct LNArgs {
+  const float* x;      // [*, H] fp32
+  const int32_t* rows; // optional gather: output row r reads input row rows[r]; null = identity
+  int n_rows, H;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out_f32;      // optional [n_rows, H]
+  bf16* out_act;       // optional Act [n_rows, ld]
+  int ld_act, split;
+};
+void launch_layernorm(const LNArgs& a, cudaStream_t st);
+
+void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,
+                          const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
+                          int split, cudaStream_t st);
+void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
+                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st);
+
+// Attention over packed token rows.  Row layout: B*P "prefix" rows (image b, position t) followed by
+// B*K*S "suffix" rows (image b, candidate k, offset s).  A suffix row attends to its image's first p0[b]
+// prefix rows and to suffix rows 0..s of its own candidate (causal) -- or to all S rows when !causal.
+// qkv is either bf16 [rows, 3H] (split=0) or fp32 [rows, 3H] (split=1).
+struct AttnArgs {
+  const void* qkv;
+  int ld_qkv;      // elements per row
+  int qkv_f32;     // 1 = fp32 qkv
+  const int32_t* p0;  // [B] or null (=> P rows all valid for prefix rows; suffix sees min(P, .))
+  int B, P, K, S, H, heads;
+  int causal;
+  float scale;
+  bf16* out_act;
+  int ld_act, split;
+};
+bool launch_attention(const AttnArgs& a, cudaStream_t st);
+
+// ---- selection pieces (select_ops.cu) -----------------------------------------------------------------
+bool topk_configure();
+bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, float temperature, int K, float* probs,
+                 int64_t* ids, cudaStream_t st);
+
+struct AssembleArgs {
+  const int64_t* inp;       // [B,L], [MASK] at pos
+  const int64_t* ids;       // [B,K] top-k ids
+  const float* token_mask;  // [V]
+  const int32_t* off;       // CSR bert id -> clip tokens
+  const int32_t* tok;
+  const float* senti_table; // [V] or null
+  int B, L, K, pos, V;
+  int special[5];
+  int bos, eos, maxlen;     // maxlen = 77
+  // outputs
+  int32_t* ids_prefix;  // [B,P] or null when P == 0 (dense mode: everything goes to the suffix)
+  int32_t* ids_suffix;  // [B,K,S]
+  int32_t* p0;          // [B]
+  int32_t* eos_idx;     // [B*K] suffix-relative index of the first EOS
+  int P, S;
+  int64_t* ids_masked;  // [B,K]
+  float* repeats;       // [B,K] or null
+  float* senti;         // [B,K] or null
+};
+void launch_assemble(const AssembleArgs& a, cudaStream_t st);
+
+void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
+                          int dot_allowed, cudaStream_t st);
+void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t st);
+void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st);
+
+struct SelectArgs {
+  const float* text;   // [B*K, D]
+  const float* image;  // [B, D]
+  int B, K, D;
+  float scale;
+  const float* probs;        // [B,K] or null (similarity only)
+  const int64_t* ids_masked; // [B,K]
+  const float* senti;        // [B,K] raw control scores or null
+  const float* repeats;      // [B,K] or null
+  float alpha, beta, gamma;
+  int64_t* inp; int L, pos;  // winner written to inp[b,pos] when inp != null
+  float* out_clip_ref;       // [B]
+  float* out_senti;          // [B] or null
+  float* tr_clip_score; float* tr_clip_ref; float* tr_final; int64_t* tr_best;
+};
+void launch_score_select(const SelectArgs& a, cudaStream_t st);
+
+}  // namespace conzic

@@ -1,0 +1,270 @@
+"""Python host side of libconzic.so: owns the device tensors, passes raw pointers through the C ABI.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only; every compute call
+below lands in a hand-written sm_100a kernel.  Nothing here falls back to torch ops or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import synth as _dims
+
+SD = Dict[str, torch.Tensor]
+
+
+def _bert_table(sd: SD, layers: int):
+    e, p = "bert.embeddings.", "cls.predictions."
+    names = [e + "word_embeddings.weight", e + "position_embeddings.weight", e + "token_type_embeddings.weight",
+             e + "LayerNorm.weight", e + "LayerNorm.bias", p + "bias", p + "transform.dense.weight",
+             p + "transform.dense.bias", p + "transform.LayerNorm.weight", p + "transform.LayerNorm.bias"]
+    for i in range(layers):
+        q = f"bert.encoder.layer.{i}."
+        names += [q + "attention.self.query.weight", q + "attention.self.query.bias",
+                  q + "attention.self.key.weight", q + "attention.self.key.bias",
+                  q + "attention.self.value.weight", q + "attention.self.value.bias",
+                  q + "attention.output.dense.weight", q + "attention.output.dense.bias",
+                  q + "attention.output.LayerNorm.weight", q + "attention.output.LayerNorm.bias",
+                  q + "intermediate.dense.weight", q + "intermediate.dense.bias",
+                  q + "output.dense.weight", q + "output.dense.bias",
+                  q + "output.LayerNorm.weight", q + "output.LayerNorm.bias"]
+    return names
+
+
+def _clip_table(sd: SD, layers: int):
+    names = ["text_model.embeddings.token_embedding.weight", "text_model.embeddings.position_embedding.weight",
+             "text_model.final_layer_norm.weight", "text_model.final_layer_norm.bias", "text_projection.weight"]
+    for i in range(layers):
+        q = f"text_model.encoder.layers.{i}."
+        names += [q + "layer_norm1.weight", q + "layer_norm1.bias",
+                  q + "self_attn.q_proj.weight", q + "self_attn.q_proj.bias",
+                  q + "self_attn.k_proj.weight", q + "self_attn.k_proj.bias",
+                  q + "self_attn.v_proj.weight", q + "self_attn.v_proj.bias",
+                  q + "self_attn.out_proj.weight", q + "self_attn.out_proj.bias",
+                  q + "layer_norm2.weight", q + "layer_norm2.bias",
+                  q + "mlp.fc1.weight", q + "mlp.fc1.bias", q + "mlp.fc2.weight", q + "mlp.fc2.bias"]
+    return names
+
+
+def _count_layers(sd: SD, fmt: str) -> int:
+    n = 0
+    while fmt.format(n) in sd:
+        n += 1
+    return n
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One context per (BERT weights, CLIP text weights, device).  Mirrors what `model(inp).logits`,
+    `generate_caption_step` and `CLIP.compute_text_representation / ..._similarity_via_embeddings` compute in the
+    reference (gen_utils.py:64-81, clip/clip.py:64-98)."""
+
+    def __init__(self, bert_sd: SD, clip_sd: SD, device="cuda:0", precision: str = "bf16",
+                 gemm_impl: str = "tcgen05", special_ids: Sequence[int] = _dims.SPECIAL_IDS,
+                 dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
+                 clip_chunk_rows: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.precision = precision
+        nb = _count_layers(bert_sd, "bert.encoder.layer.{}.attention.self.query.weight")
+        nc = _count_layers(clip_sd, "text_model.encoder.layers.{}.layer_norm1.weight")
+        word = bert_sd["bert.embeddings.word_embeddings.weight"]
+        tok = clip_sd["text_model.embeddings.token_embedding.weight"]
+        cfg = _lib.Config()
+        cfg.bert_layers, cfg.bert_hidden, cfg.bert_vocab = nb, word.shape[1], word.shape[0]
+        cfg.bert_heads = word.shape[1] // 64
+        cfg.bert_ffn = bert_sd["bert.encoder.layer.0.intermediate.dense.weight"].shape[0]
+        cfg.bert_maxpos = bert_sd["bert.embeddings.position_embeddings.weight"].shape[0]
+        cfg.bert_ln_eps = _dims.BERT_LN_EPS
+        cfg.clip_layers, cfg.clip_hidden, cfg.clip_vocab = nc, tok.shape[1], tok.shape[0]
+        cfg.clip_heads = tok.shape[1] // 64
+        cfg.clip_ffn = clip_sd["text_model.encoder.layers.0.mlp.fc1.weight"].shape[0]
+        cfg.clip_maxpos = clip_sd["text_model.embeddings.position_embedding.weight"].shape[0]
+        cfg.clip_proj = clip_sd["text_projection.weight"].shape[0]
+        cfg.clip_ln_eps = _dims.CLIP_LN_EPS
+        cfg.pad_id, cfg.unk_id, cfg.cls_id, cfg.sep_id, cfg.mask_id = [int(x) for x in special_ids]
+        cfg.dot_id, cfg.clip_bos, cfg.clip_eos = int(dot_id), int(clip_bos), int(clip_eos)
+        cfg.precision = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}[precision]
+        cfg.gemm_impl = {"tcgen05": _lib.GEMM_TCGEN05, "simt_debug": _lib.GEMM_SIMT_DEBUG}[gemm_impl]
+        cfg.clip_chunk_rows = int(clip_chunk_rows)
+        self.cfg = cfg
+        self.V, self.D = cfg.bert_vocab, cfg.clip_proj
+        self.ldl = (self.V + 3) & ~3
+        self.mask_id = cfg.mask_id
+
+        def table(names, sd):
+            ts = [sd[n].detach().to(self.device, torch.float32).contiguous() for n in names]
+            arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+            return ts, arr
+
+        bt, barr = table(_bert_table(bert_sd, nb), bert_sd)
+        ct, carr = table(_clip_table(clip_sd, nc), clip_sd)
+        ctx = C.c_void_p()
+        rc = self.lib.conzic_ctx_create(C.byref(cfg), barr, len(bt), carr, len(ct), self._stream(), C.byref(ctx))
+        _lib.check(rc, "conzic_ctx_create")
+        del bt, ct  # the context holds its own copies; create synchronised the stream
+        self.ctx = ctx
+        ls = clip_sd.get("logit_scale")
+        self.logit_scale_exp = float(torch.as_tensor(ls).float().exp()) if ls is not None else 100.0
+        self._ws = None
+        self.has_table = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.conzic_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace(self, B: int, L: int, K: int) -> torch.Tensor:
+        need = int(self.lib.conzic_workspace_bytes(self.ctx, B, L, K))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launch_count(self) -> int:
+        return int(self.lib.conzic_launch_count(self.ctx))
+
+    def set_bert2clip(self, off: torch.Tensor, tok: torch.Tensor):
+        """CSR table BERT id -> CLIP BPE ids (int32).  See conzic_b200.tokens for how it is built."""
+        off = off.to(self.device, torch.int32).contiguous()
+        tok = tok.to(self.device, torch.int32).contiguous()
+        assert off.numel() == self.V + 1
+        w = int((off[1:] - off[:-1]).max().item()) if off.numel() > 1 else 1
+        rc = self.lib.conzic_set_bert2clip(self.ctx, _ptr(off), _ptr(tok), int(tok.numel()), max(w, 1), self._stream())
+        _lib.check(rc, "conzic_set_bert2clip")
+        torch.cuda.current_stream(self.device).synchronize()
+        self.max_tok_per_word = max(w, 1)
+        self.has_table = True
+
+    # ------------------------------------------------------------------ pieces
+    def bert_mlm_row(self, inp: torch.Tensor, pos: int) -> torch.Tensor:
+        """logits[:, pos] of BertForMaskedLM (gen_utils.py:69,42): f32[B,V]."""
+        B, L = inp.shape
+        inp = inp.to(self.device, torch.int64).contiguous()
+        out = torch.empty((B, self.ldl), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, L, 1)
+        rc = self.lib.conzic_bert_mlm_row(self.ctx, _ptr(inp), B, L, int(pos), _ptr(out), self.ldl, _ptr(ws),
+                                          ws.numel(), self._stream())
+        _lib.check(rc, "conzic_bert_mlm_row")
+        return out[:, : self.V]
+
+    def topk_mask(self, logits: torch.Tensor, token_mask: torch.Tensor, temperature: float, K: int):
+        """generate_caption_step (gen_utils.py:33-49) on one row of logits per image."""
+        B = logits.shape[0]
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1
+        probs = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        ids = torch.empty((B, K), dtype=torch.int64, device=self.device)
+        tm = token_mask.reshape(-1)
+        rc = self.lib.conzic_topk_mask(self.ctx, _ptr(logits), int(logits.stride(0)), B, _ptr(tm), float(temperature),
+                                       int(K), _ptr(probs), _ptr(ids), self._stream())
+        _lib.check(rc, "conzic_topk_mask")
+        return probs, ids
+
+    def build_clip_ids(self, inp: torch.Tensor, pos: int, ids: torch.Tensor, token_mask: torch.Tensor, T: int):
+        B, L = inp.shape
+        K = ids.shape[1]
+        clip_ids = torch.empty((B * K, T), dtype=torch.int32, device=self.device)
+        clip_len = torch.empty((B * K,), dtype=torch.int32, device=self.device)
+        ids_masked = torch.empty((B, K), dtype=torch.int64, device=self.device)
+        rc = self.lib.conzic_build_clip_ids(self.ctx, _ptr(inp), B, L, int(pos), _ptr(ids), _ptr(token_mask.reshape(-1)),
+                                            K, _ptr(clip_ids), int(T), _ptr(clip_len), _ptr(ids_masked), self._stream())
+        _lib.check(rc, "conzic_build_clip_ids")
+        return clip_ids, clip_len, ids_masked
+
+    def clip_text_encode(self, clip_ids: torch.Tensor) -> torch.Tensor:
+        """CLIP.compute_text_representation after tokenisation (clip/clip.py:78-83): f32[N,512]."""
+        clip_ids = clip_ids.to(self.device, torch.int32).contiguous()
+        N, T = clip_ids.shape
+        out = torch.empty((N, self.D), dtype=torch.float32, device=self.device)
+        ws = self.workspace(N, 0, 1)
+        rc = self.lib.conzic_clip_text_encode(self.ctx, _ptr(clip_ids), N, T, _ptr(out), _ptr(ws), ws.numel(),
+                                              self._stream())
+        _lib.check(rc, "conzic_clip_text_encode")
+        return out
+
+    def image_text_similarity(self, image_embeds: torch.Tensor, text_embeds: torch.Tensor):
+        """compute_image_text_similarity_via_embeddings (clip/clip.py:86-98)."""
+        B = image_embeds.shape[0]
+        K = text_embeds.numel() // (B * self.D)
+        score = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        ref = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        rc = self.lib.conzic_image_text_similarity(self.ctx, _ptr(text_embeds.contiguous()),
+                                                   _ptr(image_embeds.contiguous()), B, K, self.logit_scale_exp,
+                                                   _ptr(score), _ptr(ref), self._stream())
+        _lib.check(rc, "conzic_image_text_similarity")
+        return score, ref
+
+    def debug_linear(self, A, W, bias=None, resid=None, act: int = 0):
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        need = (M + N) * K * 4 + 4096
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self.lib.conzic_debug_linear(self.ctx, _ptr(A.contiguous()), _ptr(W.contiguous()), _ptr(bias),
+                                          _ptr(resid), M, N, K, int(act), _ptr(out), _ptr(ws), ws.numel(),
+                                          self._stream())
+        _lib.check(rc, "conzic_debug_linear")
+        return out
+
+    # ------------------------------------------------------------------ the fused step
+    def gibbs_step(self, inp: torch.Tensor, token_mask: torch.Tensor, image_embeds: torch.Tensor, pos: int,
+                   dot_allowed: bool, K: int, temperature: float, alpha: float, beta: float,
+                   visited_before: int, visited_after: int, gamma: Optional[float] = None,
+                   senti_table: Optional[torch.Tensor] = None, out_clip_ref: Optional[torch.Tensor] = None,
+                   out_senti: Optional[torch.Tensor] = None, trace: bool = False):
+        """One position update, in place on `inp` (int64[B,L]) and `token_mask` (f32[1,V]); gen_utils.py:66-81,
+        control_gen_utils.py:45-67.  Returns (clip_ref[B], senti[B] or None, trace dict or None) -- device tensors,
+        nothing is synchronised."""
+        assert self.has_table, "call Engine.set_bert2clip first"
+        B, L = inp.shape
+        assert inp.dtype == torch.int64 and inp.is_contiguous() and inp.device == self.device
+        assert token_mask.dtype == torch.float32 and token_mask.is_contiguous() and token_mask.numel() == self.V
+        ctl = gamma is not None
+        if out_clip_ref is None:
+            out_clip_ref = torch.empty((B,), dtype=torch.float32, device=self.device)
+        if ctl and out_senti is None:
+            out_senti = torch.empty((B,), dtype=torch.float32, device=self.device)
+        a = _lib.StepArgs()
+        a.inp, a.token_mask, a.image_embeds = inp.data_ptr(), token_mask.data_ptr(), image_embeds.data_ptr()
+        a.senti_table = senti_table.data_ptr() if ctl else None
+        a.B, a.L, a.K, a.pos = B, L, int(K), int(pos)
+        a.dot_allowed = 1 if dot_allowed else 0
+        a.visited_before, a.visited_after = int(visited_before), int(visited_after)
+        a.temperature, a.alpha, a.beta = float(temperature), float(alpha), float(beta)
+        a.gamma = float(gamma) if ctl else 0.0
+        a.logit_scale_exp = self.logit_scale_exp
+        a.out_clip_ref = out_clip_ref.data_ptr()
+        a.out_senti = out_senti.data_ptr() if ctl else None
+        tr = None
+        if trace:
+            f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
+            tr = dict(probs=f(B, K), idxs=torch.empty((B, K), dtype=torch.int64, device=self.device),
+                      clip_score=f(B, K), clip_ref=f(B, K), final=f(B, K),
+                      best=torch.empty((B,), dtype=torch.int64, device=self.device), logits=f(B, self.ldl))
+            a.tr_probs, a.tr_ids = tr["probs"].data_ptr(), tr["idxs"].data_ptr()
+            a.tr_clip_score, a.tr_clip_ref = tr["clip_score"].data_ptr(), tr["clip_ref"].data_ptr()
+            a.tr_final, a.tr_best, a.tr_logits = tr["final"].data_ptr(), tr["best"].data_ptr(), tr["logits"].data_ptr()
+        ws = self.workspace(B, L, K)
+        rc = self.lib.conzic_gibbs_step(self.ctx, C.byref(a), _ptr(ws), ws.numel(), self._stream())
+        _lib.check(rc, "conzic_gibbs_step")
+        return out_clip_ref, (out_senti if ctl else None), tr

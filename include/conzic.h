@@ -1,0 +1,169 @@
+/*
+ * conzic.h -- C ABI of libconzic.so: the B200 (sm_100a) Gibbs-BERT caption-polishing step.
+ *
+ * The reference (joeyz0z/ConZIC) is pure Python and has no FFI; the functions below are what a
+ * binding for its hot path would attach to.  Each entry point cites the reference lines it replaces
+ * (paths relative to the reference repo; "HF:" = the transformers package the reference calls into).
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a DEVICE pointer owned by the caller (PyTorch tensors in practice);
+ *     "host" pointers are ordinary host memory; nothing here allocates or frees caller memory;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the
+ *     device, no call copies device->host;
+ *   - scratch memory is one caller-owned device buffer `ws` of at least conzic_workspace_bytes();
+ *   - return value: 0 = ok, negative = error; conzic_last_error() gives the message (thread local);
+ *   - integer ids are int64 where the reference holds torch.long tensors, int32 for CLIP ids.
+ *   - there is NO CPU fallback: on a machine without an sm_100a device every compute call fails.
+ */
+#ifndef CONZIC_H_
+#define CONZIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CONZIC_ABI_VERSION 1
+
+typedef struct conzic_ctx conzic_ctx;
+
+/* arithmetic mode of the GEMM operands (accumulation, LayerNorm, softmax, scores are always fp32) */
+enum {
+  CONZIC_PREC_BF16 = 0,      /* bf16 operands, one tcgen05.mma per k-step (throughput mode)            */
+  CONZIC_PREC_BF16X3 = 1     /* each fp32 operand split hi+lo bf16, 3 MMAs per k-step (parity mode)   */
+};
+
+/* GEMM implementation: 0 is the product path; 1 is a slow SIMT kernel kept for cross-checking in tests */
+enum { CONZIC_GEMM_TCGEN05 = 0, CONZIC_GEMM_SIMT_DEBUG = 1 };
+
+typedef struct conzic_config {
+  /* BERT masked LM (HF:models/bert/configuration_bert.py defaults = bert-base-uncased) */
+  int32_t bert_layers, bert_hidden, bert_heads, bert_ffn, bert_vocab, bert_maxpos;
+  float bert_ln_eps;
+  /* CLIP text tower (HF:models/clip/configuration_clip.py defaults = ViT-B/32 text) */
+  int32_t clip_layers, clip_hidden, clip_heads, clip_ffn, clip_vocab, clip_maxpos, clip_proj;
+  float clip_ln_eps;
+  /* ids that tokenizer.batch_decode(skip_special_tokens=True) drops (gen_utils.py:75) */
+  int32_t pad_id, unk_id, cls_id, sep_id, mask_id;
+  int32_t dot_id;              /* tokenizer.vocab['.'] (utils.py:53-59) */
+  int32_t clip_bos, clip_eos;  /* 49406 / 49407; pad id == eos id (clip/clip.py:71-72) */
+  int32_t precision;           /* CONZIC_PREC_* */
+  int32_t gemm_impl;           /* CONZIC_GEMM_* */
+  int32_t clip_chunk_rows;     /* CLIP token rows processed per pass (sized to stay L2 resident); 0 = default */
+} conzic_config;
+
+/* ---- weight tables: arrays of fp32 DEVICE pointers in this order (HF state-dict tensors) -------------
+ * BERT (n = 10 + 16*layers):
+ *   0 word_embeddings[V,H] 1 position_embeddings[P,H] 2 token_type_embeddings[2,H] 3 emb LN gamma 4 emb LN beta
+ *   5 cls.predictions.bias[V] 6 cls.predictions.transform.dense.weight[H,H] 7 .bias 8 transform LN gamma 9 beta
+ *   per layer l at 10+16*l: q.w q.b k.w k.b v.w v.b attn.out.w attn.out.b attnLN.g attnLN.b
+ *                           intermediate.w[F,H] intermediate.b output.w[H,F] output.b outLN.g outLN.b
+ * CLIP text (n = 5 + 16*layers):
+ *   0 token_embedding[V,H] 1 position_embedding[77,H] 2 final_layer_norm gamma 3 beta 4 text_projection.weight[P,H]
+ *   per layer l at 5+16*l: ln1.g ln1.b q.w q.b k.w k.b v.w v.b out.w out.b ln2.g ln2.b fc1.w[F,H] fc1.b fc2.w[H,F] fc2.b
+ * The context makes its own bf16 copies; the caller may free the fp32 tensors after create returns and
+ * the stream has drained.
+ */
+#define CONZIC_BERT_GLOBALS 10
+#define CONZIC_CLIP_GLOBALS 5
+#define CONZIC_PER_LAYER 16
+
+/* Replaces model/clip construction + .to(device) (run.py:134-141, clip/clip.py:7-18) for this path. */
+int conzic_ctx_create(const conzic_config* cfg, const void* const* bert_weights_dev, int n_bert,
+                      const void* const* clip_weights_dev, int n_clip, void* stream, conzic_ctx** out);
+void conzic_ctx_destroy(conzic_ctx* ctx);
+const char* conzic_last_error(void);
+int conzic_abi_version(void);
+
+/* BERT id -> CLIP BPE ids, CSR (off[V+1], tok[off[V]]), int32 DEVICE arrays copied into the context.
+ * Device-side replacement of tokenizer.batch_decode + CLIPTokenizer for vocabularies without '##'
+ * merges (gen_utils.py:75, clip/clip.py:71-72).  Special ids must have empty rows. */
+int conzic_set_bert2clip(conzic_ctx* ctx, const int32_t* off_dev, const int32_t* tok_dev, int n_tok,
+                         int max_tok_per_word, void* stream);
+
+/* Scratch bytes needed by any call below with at most B images, L BERT tokens, K candidates. */
+size_t conzic_workspace_bytes(const conzic_ctx* ctx, int B, int L, int K);
+
+/* model(inp).logits[:, pos] (gen_utils.py:69 + :42; HF:models/bert/modeling_bert.py:944-987) --
+ * the MLM head is evaluated on row `pos` only.  inp int64[B,L] dev (already holding [MASK] where the
+ * caller wants it); logits f32[B,ldl] dev, ldl >= V and ldl % 4 == 0. */
+int conzic_bert_mlm_row(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L, int pos, float* logits_dev,
+                        int ldl, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* generate_caption_step (gen_utils.py:33-49): softmax(logits/temperature) * token_mask, top-K.
+ * Ties (equal probabilities, e.g. underflowed zeros) are ordered by ascending vocabulary index.
+ * probs f32[B,K], ids int64[B,K], sorted by descending probability.  K <= 1024. */
+int conzic_topk_mask(conzic_ctx* ctx, const float* logits_dev, int ldl, int B, const float* token_mask_dev,
+                     float temperature, int K, float* probs_dev, int64_t* ids_dev, void* stream);
+
+/* Candidate captions as CLIP ids (gen_utils.py:71-75 + clip/clip.py:71-77), dense form:
+ * clip_ids int32[B*K,T] (BOS .. EOS, right padded with EOS, truncated to 77), clip_len int32[B*K]
+ * (tokens up to and including the first EOS), ids_masked int64[B,K] = ids * token_mask[ids]. */
+int conzic_build_clip_ids(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L, int pos, const int64_t* ids_dev,
+                          const float* token_mask_dev, int K, int32_t* clip_ids_dev, int T, int32_t* clip_len_dev,
+                          int64_t* ids_masked_dev, void* stream);
+
+/* CLIP.compute_text_representation after tokenisation (clip/clip.py:78-83;
+ * HF:models/clip/modeling_clip.py:531-589): clip_ids int32[N,T] right padded with EOS ->
+ * text_embeds f32[N,proj]. */
+int conzic_clip_text_encode(conzic_ctx* ctx, const int32_t* clip_ids_dev, int N, int T, float* text_embeds_dev,
+                            void* ws_dev, size_t ws_bytes, void* stream);
+
+/* compute_image_text_similarity_via_embeddings (clip/clip.py:86-98): text f32[B*K,D], image f32[B,D]
+ * -> clip_score f32[B,K] (softmax over K of scale*cos) and clip_ref f32[B,K] (cos). */
+int conzic_image_text_similarity(conzic_ctx* ctx, const float* text_embeds_dev, const float* image_embeds_dev,
+                                 int B, int K, float logit_scale_exp, float* clip_score_dev, float* clip_ref_dev,
+                                 void* stream);
+
+/* One whole Gibbs step (gen_utils.py:66-81, control_gen_utils.py:45-67) with no host round trip:
+ *   token_mask[dot_id] = dot_allowed; inp[:,pos] = [MASK]; BERT row logits; top-K; candidates -> CLIP ids
+ *   (shared caption prefix encoded once per image, candidate suffixes per candidate); CLIP text tower;
+ *   cosine / softmax; alpha*p + beta*c (+ gamma*softmax_K(senti) + 0.1*(1-exp(repeats))); argmax;
+ *   inp[:,pos] = winner.
+ * In/out: inp int64[B,L] dev, token_mask f32[V] dev (mutated like utils.py:53-59).
+ * In: image_embeds f32[B,proj] dev; senti_table f32[V] dev or NULL (NULL = caption mode; the table is
+ *     the per-word control score, sign already applied for "negative"); visited_after = upper bound on the
+ *     number of caption positions > pos that hold a word (host bookkeeping, sizes the suffix tile);
+ *     visited_before likewise for positions < pos (prompt words included).
+ * Out: out_clip_ref f32[B] (cosine of the winner, gen_utils.py:80), out_senti f32[B] or NULL.
+ * Optional trace (any may be NULL): tr_probs f32[B,K], tr_ids int64[B,K], tr_clip_score f32[B,K],
+ *     tr_clip_ref f32[B,K], tr_final f32[B,K], tr_best int64[B]. */
+typedef struct conzic_step_args {
+  int64_t* inp;
+  float* token_mask;
+  const float* image_embeds;
+  const float* senti_table;
+  int32_t B, L, K, pos;
+  int32_t dot_allowed;
+  int32_t visited_before, visited_after;
+  float temperature, alpha, beta, gamma, logit_scale_exp;
+  float* out_clip_ref;
+  float* out_senti;
+  float* tr_probs;
+  int64_t* tr_ids;
+  float* tr_clip_score;
+  float* tr_clip_ref;
+  float* tr_final;
+  int64_t* tr_best;
+  float* tr_logits;   /* f32[B, ldl = roundup(V,4)] or NULL */
+} conzic_step_args;
+
+int conzic_gibbs_step(conzic_ctx* ctx, const conzic_step_args* args, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Counters: kernels launched by this library since the context was created (bench.py "gpu_launches"). */
+uint64_t conzic_launch_count(const conzic_ctx* ctx);
+
+/* Plain GEMM entry used by tests and the roofline microbench:
+ *   out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ resid), A/W fp32 dev, converted internally to the
+ *   context's operand format; exercises exactly the kernel the towers use.  act: 0 none, 1 quick_gelu,
+ *   2 erf-gelu.  out fp32[M,N]. */
+int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev, const float* bias_dev,
+                        const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONZIC_H_ */

@@ -1,0 +1,119 @@
+"""Shared helpers for the -m gpu parity tests and tools/gpu_diag.py: build engines on synthetic weights,
+replay golden fixtures through the C ABI, measure error magnitudes against the CPU oracle."""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from conzic_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+_SD = {}
+_ENG = {}
+
+
+def weights(kind, peaked=False):
+    key = (kind, peaked)
+    if key not in _SD:
+        _SD[key] = synth.make_bert_state_dict(0, peaked=peaked) if kind == "bert" else synth.make_clip_state_dict(0)
+    return _SD[key]
+
+
+def engine(precision="bf16x3", impl="tcgen05", peaked=False, multi=False):
+    """Engines are cached per configuration (weights upload takes a few seconds)."""
+    from conzic_b200.engine import Engine
+    key = (precision, impl, peaked, multi)
+    if key not in _ENG:
+        e = Engine(weights("bert", peaked), weights("clip"), device="cuda:0", precision=precision, gemm_impl=impl)
+        off, tok = synth.build_bert2clip_table(multi)
+        e.set_bert2clip(off, tok)
+        _ENG[key] = e
+    return _ENG[key]
+
+
+def drop_engines():
+    for e in _ENG.values():
+        e.close()
+    _ENG.clear()
+    torch.cuda.empty_cache()
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+
+
+def visible_counts(inp_row_batch: torch.Tensor, pos: int):
+    """Upper bounds the host loop would pass: words before / after `pos` (special ids hold no word)."""
+    special = torch.tensor(synth.SPECIAL_IDS)
+    vis = ~torch.isin(inp_row_batch, special)
+    before = int(vis[:, :pos].sum(dim=1).max())
+    after = int(vis[:, pos + 1:].sum(dim=1).max())
+    return before, after
+
+
+def replay_fixture(eng, g, max_steps=None):
+    """Teacher-forced replay of every recorded step of a golden fixture through conzic_gibbs_step.
+    Returns a dict of worst-case error magnitudes and mismatch counts."""
+    case = g["case"]
+    n, K = case["n"], case["K"]
+    gamma = case.get("gamma")
+    table = synth.make_sentiment_table()
+    if case.get("style") == "negative":
+        table = -table
+    dev = eng.device
+    table_d = table.to(dev) if gamma is not None else None
+    m = dict(steps=0, logit_err=0.0, prob_relerr=0.0, topk_id_mismatch=0, clip_ref_err=0.0, clip_score_err=0.0,
+             final_err=0.0, winner_mismatch=0, winner_checked=0, min_margin_at_mismatch=None, dot_mismatch=0)
+    steps = g["steps"][:max_steps] if max_steps else g["steps"]
+    for si, s in enumerate(steps):
+        inp = s["inp"].clone().to(dev)
+        pos = s["pos"]
+        ii = pos - 4
+        token_mask = synth.make_token_mask(dev)
+        before, after = visible_counts(s["inp"], pos)
+        img = s["image_embeds"].to(dev).contiguous()
+        clip_ref, senti, tr = eng.gibbs_step(inp, token_mask, img, pos, ii == n - 1, K, 0.1, 0.02, 2.0, before, after,
+                                             gamma=gamma, senti_table=table_d, trace=True)
+        torch.cuda.synchronize()
+        tr = {k: v.cpu() for k, v in tr.items()}
+        m["steps"] += 1
+        if float(token_mask[0, synth.DOT_ID]) != s["token_mask_dot"]:
+            m["dot_mismatch"] += 1
+        cols = s["logit_cols"].long()
+        m["logit_err"] = max(m["logit_err"], float((tr["logits"][:, : eng.V].gather(1, cols) - s["logit_vals"]).abs().max()))
+        nz = s["probs"] > 0
+        distinct = torch.ones_like(nz)
+        # a rank is comparable only if its probability differs from both neighbours by more than fp noise
+        p = s["probs"]
+        rel = (p[:, :-1] - p[:, 1:]) / p[:, :-1].clamp_min(1e-30)
+        close = rel < 1e-3
+        distinct[:, :-1] &= ~close
+        distinct[:, 1:] &= ~close
+        cmp = nz & distinct
+        m["topk_id_mismatch"] += int((tr["idxs"][cmp] != s["idxs"][cmp]).sum())
+        same = tr["idxs"] == s["idxs"]
+        if bool((same & nz).any()):
+            pr = ((tr["probs"] - s["probs"]).abs() / s["probs"].clamp_min(1e-30))[same & nz]
+            m["prob_relerr"] = max(m["prob_relerr"], float(pr.max()))
+        if bool(same.all()):
+            m["clip_ref_err"] = max(m["clip_ref_err"], float((tr["clip_ref"] - s["clip_ref"]).abs().max()))
+            m["clip_score_err"] = max(m["clip_score_err"], float((tr["clip_score"] - s["clip_score"]).abs().max()))
+            # the reference's winner is visible in the next recorded step's inp
+            if si + 1 < len(g["steps"]) and g["steps"][si + 1]["pos"] != pos:
+                nxt = g["steps"][si + 1]["inp"][:, pos]
+                got = inp[:, pos].cpu()
+                m["winner_checked"] += int(nxt.numel())
+                bad = got != nxt
+                if bool(bad.any()):
+                    m["winner_mismatch"] += int(bad.sum())
+                    top2 = tr["final"].topk(2, dim=1).values
+                    marg = float((top2[:, 0] - top2[:, 1])[bad].min())
+                    m["min_margin_at_mismatch"] = marg if m["min_margin_at_mismatch"] is None else min(
+                        m["min_margin_at_mismatch"], marg)
+    return m
