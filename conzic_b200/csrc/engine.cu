@@ -21,6 +21,44 @@ bool cuda_ok(cudaError_t e, const char* what) {
 }
 
 namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int c, double work, cudaStream_t s) : cat(c), st(s), on(g_prof_on) {
+  if (!on) return;
+  ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.cat = c;
+  r.work = work;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (on) cudaEventRecord(g_prof.back().b, st);
+}
+void prof_enable(bool on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on;
+}
+bool prof_read(int cat, double* ms, double* work, int* n) {
+  double t = 0, w = 0;
+  int c = 0;
+  for (auto& r : g_prof) {
+    if (r.cat != cat) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return false;
+    float e = 0;
+    if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) return false;
+    t += e; w += r.work; ++c;
+  }
+  *ms = t; *work = w; *n = c;
+  return true;
+}
+
+namespace {
 
 __global__ void find_eos_kernel(const int32_t* ids, int N, int T, int eos, int32_t* eos_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -459,6 +497,17 @@ int conzic_set_bert2clip(conzic_ctx* c, const int32_t* off, const int32_t* tok, 
 size_t conzic_workspace_bytes(const conzic_ctx* c, int B, int L, int K) {
   if (!c) return 0;
   return make_plan(c, nullptr, B, L, K).bytes;
+}
+
+int conzic_profile(conzic_ctx* c, int enable) {
+  (void)c;
+  prof_enable(enable != 0);
+  return 0;
+}
+int conzic_profile_read(conzic_ctx* c, int category, double* ms, double* work, int* launches) {
+  (void)c;
+  if (category < 0 || category >= CAT_COUNT || !ms || !work || !launches) { set_error("profile_read: bad argument"); return -1; }
+  return prof_read(category, ms, work, launches) ? 0 : -4;
 }
 
 uint64_t conzic_launch_count(const conzic_ctx* c) { return c ? g_launches - c->launches0 : 0; }

@@ -324,6 +324,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   p.M = M; p.N = W.N; p.K = W.K; p.split = o.split; p.e = epi;
   (void)launches;
   ++g_launches;
+  ProfScope prof_(CAT_GEMM, 2.0 * M * static_cast<double>(W.N) * W.K * (o.split ? 3 : 1), st);
   if ((epi.out_f32 && (epi.ldo_f32 & 3)) || (epi.resid && (epi.ldr & 3)) || (epi.out_act && (epi.ldo_act & 7)) ||
       (A.ld & 7)) {
     set_error("linear: leading dimensions must keep rows 16-byte aligned");

@@ -15,6 +15,17 @@ extern uint64_t g_launches;  // kernels launched by this library (all contexts)
 void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 
+// Optional per-category device timing (CUDA events around each launch on the launching stream); off by default.
+enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_LN = 2, CAT_EMBED = 3, CAT_TOPK = 4, CAT_ASSEMBLE = 5, CAT_SELECT = 6,
+       CAT_MISC = 7, CAT_COUNT = 8 };
+struct ProfScope {
+  int cat; cudaStream_t st; bool on;
+  ProfScope(int cat, double work, cudaStream_t st);
+  ~ProfScope();
+};
+void prof_enable(bool on);
+bool prof_read(int cat, double* ms, double* work, int* n);
+
 // A GEMM-input activation matrix.  bf16 mode: [rows, K].  bf16x3 mode: [rows, 2K], the bf16 "hi" plane in
 // columns [0,K) and the residual "lo" plane (x - float(hi)) in [K,2K).
 struct Act {

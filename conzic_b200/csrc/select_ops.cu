@@ -405,6 +405,7 @@ bool topk_configure() {
 bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, float temperature, int K, float* probs,
                  int64_t* ids, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_TOPK, static_cast<double>(B) * V, st);
   if (K < 1 || K > 1024 || K > V) {
     set_error("topk: K must be in [1, min(1024, V)]");
     return false;
@@ -420,26 +421,34 @@ bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, 
   return cuda_ok(cudaGetLastError(), "topk launch");
 }
 
-void launch_assemble(const AssembleArgs& a, cudaStream_t st) { assemble_kernel<<<a.B, 256, 0, st>>>(a); }
+void launch_assemble(const AssembleArgs& a, cudaStream_t st) {
+  ++g_launches;
+  ProfScope prof_(CAT_ASSEMBLE, 0, st);
+  assemble_kernel<<<a.B, 256, 0, st>>>(a);
+}
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_MISC, 0, st);
   step_prologue_kernel<<<(B + 255) / 256, 256, 0, st>>>(inp, B, L, pos, mask_id, token_mask, dot_id, dot_allowed);
 }
 
 void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_MISC, 0, st);
   gather_rows_index_kernel<<<(B + 255) / 256, 256, 0, st>>>(rows, B, L, pos);
 }
 
 void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_MISC, 0, st);
   pool_index_kernel<<<(B * K + 255) / 256, 256, 0, st>>>(rows, eos_idx, B, P, K, S);
 }
 
 void launch_score_select(const SelectArgs& a, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_SELECT, 0, st);
   const size_t smem = static_cast<size_t>(a.D + 3 * a.K + 40) * sizeof(float);
   score_select_kernel<<<a.B, SEL_THREADS, smem, st>>>(a);
 }

@@ -174,7 +174,7 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkp = nk_cap | 1;  // odd stride for the transposed K
-  const int per_warp = HD * nkp + HD * nk_cap + HD + nkp;
+  const int per_warp = (HD * nkp + HD * nk_cap + HD + nkp + 3) & ~3;  // keep every warp's slice 16B aligned
   float* Kt = sm + static_cast<size_t>(wib) * per_warp;  // [64][nkp]
   float* Vs = Kt + HD * nkp;                               // [nk][64]
   float* qs = Vs + HD * nk_cap;                            // [64]
@@ -292,6 +292,7 @@ int row_grid(int rows, int warps_per_block) {
 
 void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, int ldd, int split, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_MISC, 0, st);
   const size_t total = static_cast<size_t>(rows) * (K / 4);
   int grid = static_cast<int>((total + 255) / 256);
   const int cap = num_sms() * 16;
@@ -302,6 +303,7 @@ void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, in
 
 void launch_layernorm(const LNArgs& a, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_LN, static_cast<double>(a.n_rows) * a.H, st);
   if (a.n_rows <= 0) return;
   const int grid = row_grid(a.n_rows, 8);
   switch (a.H / 128) {
@@ -316,6 +318,7 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_EMBED, static_cast<double>(rows) * H, st);
   const int grid = row_grid(rows, 8);
   switch (H / 128) {
     case 4: bert_embed_ln_kernel<4><<<grid, 256, 0, st>>>(inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
@@ -328,6 +331,7 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
                        int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_EMBED, 0, st);
   const int rows = B * P + B * K * S;
   if (rows <= 0) return;
   clip_embed_kernel<<<row_grid(rows, 8), 256, 0, st>>>(ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
@@ -336,6 +340,7 @@ void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, con
 
 bool launch_attention(const AttnArgs& a, cudaStream_t st) {
   ++g_launches;
+  ProfScope prof_(CAT_ATTN, 0, st);
   if (a.H != a.heads * HD) {
     set_error("attention: head_dim must be 64");
     return false;
@@ -346,7 +351,7 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     return false;
   }
   const int nkp = nk_cap | 1;
-  const size_t per_warp = static_cast<size_t>(HD * nkp + HD * nk_cap + HD + nkp) * sizeof(float);
+  const size_t per_warp = static_cast<size_t>((HD * nkp + HD * nk_cap + HD + nkp + 3) & ~3) * sizeof(float);
   int warps = static_cast<int>((200 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;

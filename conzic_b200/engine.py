@@ -144,6 +144,22 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.conzic_launch_count(self.ctx))
 
+    PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed", "topk", "assemble", "select", "misc")
+
+    def profile(self, enable: bool):
+        """CUDA-event timing of every launch by category (conzic_profile); off by default."""
+        _lib.check(self.lib.conzic_profile(self.ctx, 1 if enable else 0), "conzic_profile")
+
+    def profile_read(self):
+        """{category: (milliseconds, work, launches)}; waits for the recorded events."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_CATEGORIES):
+            ms, work, n = C.c_double(), C.c_double(), C.c_int()
+            _lib.check(self.lib.conzic_profile_read(self.ctx, i, C.byref(ms), C.byref(work), C.byref(n)),
+                       "conzic_profile_read")
+            out[name] = (ms.value, work.value, n.value)
+        return out
+
     def set_bert2clip(self, off: torch.Tensor, tok: torch.Tensor):
         """CSR table BERT id -> CLIP BPE ids (int32).  See conzic_b200.tokens for how it is built."""
         off = off.to(self.device, torch.int32).contiguous()

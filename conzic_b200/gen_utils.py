@@ -1,0 +1,205 @@
+"""Drop-in for the reference's `gen_utils` generation API (gen_utils.py:33-49, 51-146, 197-242, 289-333):
+same function names, arguments, defaults, return structure, log lines and RNG consumption.  The per-position
+work -- BERT row logits, masked top-k, candidate CLIP encoding, cosine/softmax, score fuse, argmax and the
+write-back -- is ONE call into libconzic.so (`conzic_gibbs_step`); the host only walks the visiting order and,
+once per sweep, reads ids and scores back to build the strings the reference returns and logs."""
+from __future__ import annotations
+
+import random
+import time
+
+import numpy as np
+import torch
+
+from . import runtime
+from .utils import get_init_text
+
+__all__ = ["generate_caption_step", "sequential_generation", "shuffle_generation", "random_generation",
+           "span_generation", "parallel_generation", "generate_caption"]
+
+
+def generate_caption_step(out, gen_idx, mask, temperature=None, top_k=100):
+    """softmax(out[:, gen_idx] / temperature) * mask -> top_k (probs, ids); gen_utils.py:33-49.
+    Equal probabilities are ordered by ascending vocabulary id (torch leaves that order unspecified)."""
+    eng = runtime.any_engine()
+    row = out[:, gen_idx].to(eng.device, torch.float32).contiguous()
+    m = mask.to(eng.device, torch.float32).contiguous()
+    return eng.topk_mask(row, m, 1.0 if temperature is None else temperature, top_k)
+
+
+class _Chain:
+    """State of one generate call: ids on the device, which positions hold a word (sizes the CLIP tiles),
+    and per-step result slots that are read back once per flush."""
+
+    def __init__(self, model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, ctl):
+        self.eng = runtime.engine_for(model, clip, tokenizer)
+        eng = self.eng
+        self.tokenizer, self.max_len, self.B = tokenizer, max_len, batch_size
+        self.seed_len = len(prompt.split()) + 1
+        batch = get_init_text(tokenizer, prompt, max_len, batch_size)
+        self.image_embeds = clip.compute_image_representation_from_image_instance(image_instance)
+        self.image_embeds = self.image_embeds.to(eng.device, torch.float32).contiguous()
+        self.inp = torch.tensor(batch).to(eng.device)
+        special = {eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id}
+        self.holds_word = [t not in special for t in batch[0]]
+        self.user_mask = token_mask
+        if token_mask.device == eng.device and token_mask.dtype == torch.float32 and token_mask.is_contiguous():
+            self.mask = token_mask
+        else:
+            self.mask = token_mask.to(eng.device, torch.float32).contiguous()
+        n = max_len
+        self.clip_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device)
+        self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
+        self.inp_slots = None
+
+    def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None):
+        pos = self.seed_len + ii
+        before = sum(self.holds_word[:pos])
+        after = sum(self.holds_word[pos + 1:])
+        self.eng.gibbs_step(self.inp, self.mask, self.image_embeds, pos, ii == self.max_len - 1, top_k,
+                            1.0 if temperature is None else temperature, alpha, beta, before, after, gamma=gamma,
+                            senti_table=senti_table, out_clip_ref=self.clip_slots[slot],
+                            out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
+        self.holds_word[pos] = True
+
+    def finish(self):
+        if self.mask is not self.user_mask:  # keep the reference's in-place side effect on the caller's mask
+            self.user_mask.copy_(self.mask.to(self.user_mask.device, self.user_mask.dtype).view_as(self.user_mask))
+
+
+def _sweeps(name, img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger, max_len, top_k,
+            temperature, alpha, beta, max_iters, batch_size, verbose, order, gamma=None, senti_table=None):
+    """Sequential / shuffled sweeps (gen_utils.py:51-146, control_gen_utils.py:30-134)."""
+    ch = _Chain(model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, gamma is not None)
+    best_score, best_caption = [0] * batch_size, ["None"] * batch_size
+    texts, scores = [], []
+    cur_text, cur_score = None, None
+    for it in range(max_iters):
+        for slot, ii in enumerate(order):
+            ch.step(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table)
+        last = len(order) - 1
+        ids = ch.inp.cpu()  # one device->host read per sweep
+        cur_score = ch.clip_slots[last].cpu().numpy().tolist()
+        cur_senti = ch.senti_slots[last].cpu().numpy().tolist() if gamma is not None else None
+        if verbose:
+            shown = tokenizer.batch_decode(ids)
+            cur_text = tokenizer.batch_decode(ids, skip_special_tokens=True)
+            for jj in range(batch_size):
+                if best_score[jj] < cur_score[jj]:
+                    best_score[jj], best_caption[jj] = cur_score[jj], cur_text[jj]
+                if gamma is None:
+                    logger.info(f"iter {it + 1}, The {jj+1}-th image: {img_name[jj]},"
+                                f"clip score {cur_score[jj]:.3f}: " + shown[jj])
+                else:
+                    logger.info(f"iter {it + 1}, The {jj+1}-th image: {img_name[jj]}, clip score {cur_score[jj]:.3f}"
+                                f", ctl score {cur_senti[jj]:.3f}: " + shown[jj])
+        texts.append(cur_text)
+        scores.append(cur_score)
+    texts.append(best_caption)
+    scores.append(best_score)
+    ch.finish()
+    return texts, scores
+
+
+def sequential_generation(img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger,
+                          max_len=15, top_k=100, temperature=None, alpha=0.7, beta=1,
+                          max_iters=20, batch_size=1, verbose=True):
+    """One position at a time, left to right (gen_utils.py:51-96)."""
+    return _sweeps("sequential", img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger, max_len,
+                   top_k, temperature, alpha, beta, max_iters, batch_size, verbose, list(range(max_len)))
+
+
+def shuffle_generation(img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger,
+                       max_len=15, top_k=0, temperature=None, alpha=0.7, beta=1,
+                       max_iters=20, batch_size=1, verbose=True):
+    """One permutation per call from Python's global RNG, reused by every sweep (gen_utils.py:98-146)."""
+    order = list(range(max_len))
+    random.shuffle(order)
+    logger.info(f"Order_list:{order}")
+    return _sweeps("shuffle", img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger, max_len,
+                   top_k, temperature, alpha, beta, max_iters, batch_size, verbose, order)
+
+
+def random_generation(img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger,
+                      max_len=15, top_k=0, temperature=None, alpha=0.7, beta=2, max_iters=300, print_every=10,
+                      batch_size=1, verbose=True):
+    """A uniformly random position per step from numpy's global RNG; best caption tracked after every step
+    (gen_utils.py:197-242).  Steps are issued back to back; ids and scores of each step are kept on the
+    device and read once per `print_every` steps."""
+    ch = _Chain(model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, False)
+    eng = ch.eng
+    group = max(1, int(print_every))
+    ch.clip_slots = torch.zeros((group, batch_size), dtype=torch.float32, device=eng.device)
+    inp_slots = torch.zeros((group,) + tuple(ch.inp.shape), dtype=torch.int64, device=eng.device)
+    best_score, best_caption = [0] * batch_size, ["None"] * batch_size
+    texts, scores = [], []
+    done = 0
+    while done < max_iters:
+        n = min(group, max_iters - done)
+        for slot in range(n):
+            kk = np.random.randint(0, max_len)
+            ch.step(slot, kk, top_k, temperature, alpha, beta)
+            inp_slots[slot].copy_(ch.inp)
+        ids_all = inp_slots[:n].cpu()
+        sc_all = ch.clip_slots[:n].cpu().numpy().tolist()
+        for slot in range(n):
+            cur_text = tokenizer.batch_decode(ids_all[slot], skip_special_tokens=True)
+            cur_score = sc_all[slot]
+            for jj in range(batch_size):
+                if best_score[jj] < cur_score[jj]:
+                    best_score[jj], best_caption[jj] = cur_score[jj], cur_text[jj]
+            step_no = done + slot + 1
+            if verbose and step_no % print_every == 0:
+                shown = tokenizer.batch_decode(ids_all[slot])
+                for jj in range(batch_size):
+                    logger.info(f"iter {step_no}, The {jj+1}-th image: {img_name[jj]},"
+                                f"clip score {cur_score[jj]:.3f}: " + shown[jj])
+                texts.append(cur_text)
+                scores.append(cur_score)
+        done += n
+    texts.append(best_caption)
+    scores.append(best_score)
+    ch.finish()
+    return texts, scores
+
+
+def span_generation(*args, **kwargs):
+    raise NotImplementedError("--order span is not part of the accelerated path yet (SURVEY.md section 8f, rank 3)")
+
+
+def parallel_generation(*args, **kwargs):
+    raise NotImplementedError("'parallel' is unreachable from the reference CLI and is not provided")
+
+
+def generate_caption(img_name, model, clip, tokenizer, image_instance, token_mask, logger,
+                     prompt="", batch_size=1, max_len=15,
+                     top_k=100, temperature=1.0, max_iter=500, alpha=0.7, beta=1,
+                     generate_order="sequential"):
+    """Entry point used by demo.py / run.py (gen_utils.py:289-333): returns (generate_texts, clip_scores), one
+    list per sweep plus the best-by-CLIP-score list last; [-2] is the final sweep."""
+    start_time = time.time()
+    common = dict(batch_size=batch_size, max_len=max_len, top_k=top_k, alpha=alpha, beta=beta,
+                  temperature=temperature)
+    if generate_order == "sequential":
+        generate_texts, clip_scores = sequential_generation(img_name, model, clip, tokenizer, image_instance,
+                                                            token_mask, prompt, logger, max_iters=max_iter, **common)
+    elif generate_order == "shuffle":
+        generate_texts, clip_scores = shuffle_generation(img_name, model, clip, tokenizer, image_instance, token_mask,
+                                                         prompt, logger, max_iters=max_iter, **common)
+    elif generate_order == "random":
+        generate_texts, clip_scores = random_generation(img_name, model, clip, tokenizer, image_instance, token_mask,
+                                                        prompt, logger, max_iters=max_iter * max_len,
+                                                        print_every=max_len, verbose=True, **common)
+    elif generate_order == "span":
+        return span_generation()
+    elif generate_order == "parallel":
+        return parallel_generation()
+    else:
+        raise ValueError(f"unknown generate_order {generate_order!r}")
+    logger.info("Finished in %.3fs" % (time.time() - start_time))
+    final_caption, best_caption = generate_texts[-2], generate_texts[-1]
+    for i in range(batch_size):
+        logger.info(f"The {i+1}-th image: {img_name[i]}")
+        logger.info(f"final caption: {final_caption[i]}")
+        logger.info(f"best caption: {best_caption[i]}")
+    return generate_texts, clip_scores
