@@ -75,11 +75,11 @@ def gather_ids_scores(ids: torch.Tensor, scores: torch.Tensor, world: int):
         return ids, scores
     ids = ids.contiguous()
     scores = scores.contiguous()
-    out_i = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-    out_s = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    out_i = torch.empty((world * ids.shape[0],) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
+    out_s = torch.empty((world * scores.shape[0],) + tuple(scores.shape[1:]), dtype=scores.dtype, device=scores.device)
     dist.all_gather_into_tensor(out_i, ids)
     dist.all_gather_into_tensor(out_s, scores)
-    return out_i.flatten(0, 1), out_s.flatten(0, 1)
+    return out_i, out_s
 
 
 def gather_objects(obj, world: int):

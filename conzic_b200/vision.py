@@ -15,7 +15,11 @@ def image_embeds(sd: Dict[str, torch.Tensor], pixel_values: torch.Tensor, heads:
     e = "vision_model.embeddings."
     B = pixel_values.shape[0]
     patch = sd[e + "patch_embedding.weight"]
-    x = F.conv2d(pixel_values, patch, stride=patch.shape[-1]).flatten(2).transpose(1, 2)
+    ps = patch.shape[-1]
+    g = pixel_values.shape[-1] // ps
+    # patch embedding as an fp32 matmul over unfolded patches (cuDNN convolutions default to TF32)
+    cols = pixel_values.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * ps * ps)
+    x = cols @ patch.reshape(patch.shape[0], -1).t()
     x = torch.cat([sd[e + "class_embedding"].expand(B, 1, -1), x], dim=1) + sd[e + "position_embedding.weight"]
     H = x.shape[-1]
     ln = lambda t, n: F.layer_norm(t, (H,), sd[n + ".weight"], sd[n + ".bias"], eps)
@@ -27,8 +31,8 @@ def image_embeds(sd: Dict[str, torch.Tensor], pixel_values: torch.Tensor, heads:
         h = ln(x, p + "layer_norm1")
         N, T, _ = h.shape
         sh = lambda t: t.view(N, T, heads, H // heads).transpose(1, 2)
-        a = F.scaled_dot_product_attention(sh(lin(h, "self_attn.q_proj")), sh(lin(h, "self_attn.k_proj")),
-                                           sh(lin(h, "self_attn.v_proj")))
+        q, k, v = sh(lin(h, "self_attn.q_proj")), sh(lin(h, "self_attn.k_proj")), sh(lin(h, "self_attn.v_proj"))
+        a = torch.softmax((q @ k.transpose(-1, -2)) * (H // heads) ** -0.5, dim=-1) @ v
         x = x + lin(a.transpose(1, 2).reshape(N, T, H), "self_attn.out_proj")
         h = lin(ln(x, p + "layer_norm2"), "mlp.fc1")
         x = x + lin(h * torch.sigmoid(1.702 * h), "mlp.fc2")

@@ -1,0 +1,102 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/conzic.h declares, refuses to
+compute without a GPU (no fallback), and the host-side helpers behave like the reference's."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from conzic_b200 import _lib, synth, tokens, utils
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "conzic.h")).read()
+    declared = sorted(set(re.findall(r"\b(conzic_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"libconzic.so does not export {name}"
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.conzic_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    cfg = _lib.Config()
+    arr = (C.c_void_p * 10)()
+    ctx = C.c_void_p()
+    rc = lib.conzic_ctx_create(C.byref(cfg), arr, 10, arr, 5, None, C.byref(ctx))
+    assert rc != 0 and "no CPU fallback" in _lib.last_error()
+    from conzic_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine({}, {}, device="cuda:0")
+
+
+def test_config_struct_matches_header_field_count():
+    hdr = open(os.path.join(ROOT, "include", "conzic.h")).read()
+    body = hdr.split("typedef struct conzic_config {")[1].split("} conzic_config;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    n = sum(len(d.split(",")) for d in re.findall(r"(?:int32_t|float)\s+([^;]+);", body))
+    assert n == len(_lib.Config._fields_)
+    body = hdr.split("typedef struct conzic_step_args {")[1].split("} conzic_step_args;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    n = sum(len(d.split(",")) for d in re.findall(r"(?:const\s+)?(?:int32_t|int64_t|float)\s*\*?\s*([^;]+);", body))
+    assert n == len(_lib.StepArgs._fields_)
+
+
+def test_init_text_and_dot_rule():
+    tok = synth.SynthBertTokenizer()
+    batch = utils.get_init_text(tok, synth.SYNTH_PROMPT, 4, batch_size=3)
+    assert batch == [[101, 3746, 1997, 1037, 103, 103, 103, 103, 102]] * 3
+    m = synth.make_token_mask()
+    for i in range(4):
+        out = utils.update_token_mask(tok, m, 4, i)
+        assert out is m and float(m[0, synth.DOT_ID]) == (1.0 if i == 3 else 0.0)
+
+
+def test_set_seed_reproduces_reference_visiting_orders():
+    utils.set_seed(42)
+    a = list(range(10)); random.shuffle(a)
+    r = [np.random.randint(0, 10) for _ in range(5)]
+    random.seed(42); np.random.seed(42)
+    b = list(range(10)); random.shuffle(b)
+    assert a == b and r == [np.random.randint(0, 10) for _ in range(5)]
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_generic_table_builder_matches_synthetic_table(multi):
+    """tokens.build_bert2clip walks the vocabulary through decode + CLIP tokenise; on the synthetic vocabularies it
+    must reproduce the closed-form table."""
+    V = 3000
+    off, tok, needs_host = tokens.build_bert2clip(synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(multi), V,
+                                                  synth.SPECIAL_IDS)
+    off2, tok2 = synth.build_bert2clip_table(multi, vocab=V)
+    assert torch.equal(off, off2) and torch.equal(tok, tok2) and needs_host == []
+    for s in synth.SPECIAL_IDS:
+        assert int(off[s + 1] - off[s]) == 0
+
+
+def test_reference_api_surface():
+    """Same public names and keyword defaults as gen_utils.py:289-292 / control_gen_utils.py:197-200."""
+    import inspect
+    from conzic_b200 import control_gen_utils, gen_utils
+    sig = inspect.signature(gen_utils.generate_caption)
+    assert list(sig.parameters)[:7] == ["img_name", "model", "clip", "tokenizer", "image_instance", "token_mask", "logger"]
+    d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    assert d == dict(prompt="", batch_size=1, max_len=15, top_k=100, temperature=1.0, max_iter=500, alpha=0.7, beta=1,
+                     generate_order="sequential")
+    sig = inspect.signature(control_gen_utils.control_generate_caption)
+    d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    assert d["gamma"] == 5 and d["ctl_type"] == "sentiment" and d["style_type"] == "positive" and d["max_len"] == 25
+    sig = inspect.signature(gen_utils.sequential_generation)
+    d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    assert d == dict(max_len=15, top_k=100, temperature=None, alpha=0.7, beta=1, max_iters=20, batch_size=1, verbose=True)
+    for name in ("shuffle_generation", "random_generation", "generate_caption_step"):
+        assert hasattr(gen_utils, name)
+    for name in ("sentiment_sequential_generation", "sentiment_shuffle_generation", "generate_caption_step"):
+        assert hasattr(control_gen_utils, name)

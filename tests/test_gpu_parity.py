@@ -1,0 +1,281 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of libconzic.so;
+the CPU oracle and the golden fixtures recorded from the unmodified reference are the checkers.
+
+Tolerances (stated here, measured margins in profiles/r01_parity.md):
+  * bf16x3 mode (3-pass split operands, the parity mode): BERT row logits within 1e-3 of the reference,
+    CLIP cosine within 2e-5, softmax_K score within 2e-4; top-k ids identical wherever the reference's
+    probabilities are non-zero and distinct; chosen token ids identical.
+  * bf16 mode (throughput mode): logits within 0.08, cosine within 4e-3; chosen ids must agree whenever
+    the reference's own top-2 margin exceeds what a 4e-3 cosine error can move.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_common as gc
+from conzic_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32",
+            "random_b2_n3_k8", "senti_seq_b2_n4_k8", "seq_b1_n10_k200"]
+
+
+def _ref_linear(A, W, bias, resid, act, bf16_round):
+    if bf16_round:
+        A, W = A.bfloat16().float(), W.bfloat16().float()
+    y = A.double() @ W.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act == 1:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    if resid is not None:
+        y = y + resid.double()
+    return y.float()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("shape", [(128, 128, 64, 0), (200, 512, 512, 1), (1000, 1536, 512, 0), (333, 2048, 512, 1),
+                                   (4096, 512, 2048, 0), (64, 30524, 768, 0), (18, 768, 768, 2), (1, 512, 512, 0)])
+def test_tcgen05_linear_matches_fp64(prec, shape):
+    """The GEMM both towers are made of, against an fp64 torch matmul of the same operands."""
+    M, N, K, act = shape
+    eng = gc.engine(prec, "tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    out = eng.debug_linear(A, W, bias, resid, act)
+    ref = _ref_linear(A, W, bias, resid, act, prec == "bf16")
+    tol = (3e-4 if prec == "bf16" else 3e-4) * float(ref.abs().max())
+    assert float((out - ref).abs().max()) < tol
+
+
+def test_tcgen05_matches_simt_debug_kernel():
+    a = gc.engine("bf16", "tcgen05")
+    b = gc.engine("bf16", "simt_debug")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(300, 512, device="cuda", generator=g)
+    W = torch.randn(640, 512, device="cuda", generator=g) * 0.05
+    torch.testing.assert_close(a.debug_linear(A, W), b.debug_linear(A, W), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-3), ("bf16", 0.08)])
+def test_bert_row_logits_vs_oracle(prec, tol):
+    from oracle import conzic_oracle as orc
+    sd = gc.weights("bert")
+    inp = torch.tensor([[101, 3746, 1997, 1037, 103, 103, 103, 103, 102],
+                        [101, 3746, 1997, 1037, 5000, 103, 7000, 2500, 102],
+                        [101, 3746, 1997, 1037, 0, 103, 1012, 2500, 102]])
+    with torch.no_grad():
+        ref = orc.bert_mlm_head(sd, orc.bert_encoder(sd, inp)[:, 5])
+    out = gc.engine(prec).bert_mlm_row(inp.cuda(), 5).cpu()
+    assert float((out - ref).abs().max()) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 0.05)])
+def test_clip_text_encode_vs_oracle(prec, tol):
+    """Ragged lengths, EOS padding, T up to the 77-token cap."""
+    from oracle import conzic_oracle as orc
+    sd = gc.weights("clip")
+    torch.manual_seed(1)
+    for N, T in ((37, 11), (5, 77), (130, 6)):
+        ids = torch.randint(300, 40000, (N, T))
+        ids[:, 0] = synth.CLIP_BOS
+        lens = torch.randint(2, T + 1, (N,))
+        for i in range(N):
+            ids[i, lens[i] - 1:] = synth.CLIP_EOS
+        with torch.no_grad():
+            ref = orc.clip_text_embeds(sd, ids)
+        out = gc.engine(prec).clip_text_encode(ids.int().cuda()).cpu()
+        assert float((out - ref).abs().max()) < tol
+
+
+def test_similarity_vs_oracle():
+    from oracle import conzic_oracle as orc
+    eng = gc.engine("bf16x3")
+    torch.manual_seed(2)
+    img, txt = torch.randn(3, 512), torch.randn(3 * 12, 512)
+    rs, rr = orc.image_text_similarity(img, txt, torch.tensor(synth.LOGIT_SCALE))
+    gs, gr = eng.image_text_similarity(img.cuda(), txt.cuda())
+    torch.testing.assert_close(gs.cpu(), rs, rtol=0, atol=2e-6)
+    torch.testing.assert_close(gr.cpu(), rr, rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("K", [1, 8, 200, 512, 1000])
+def test_topk_mask_exact_ids_and_tie_contract(K):
+    """ids bit-exact where probabilities are non-zero; zero-probability ties come out in ascending id order
+    starting from the lowest ids (the contract that replaces torch.topk's unspecified tie order)."""
+    eng = gc.engine("bf16x3")
+    V = synth.BERT_VOCAB
+    torch.manual_seed(0)
+    for case in ("smooth", "peaked", "sparse"):
+        if case == "sparse":  # a few live tokens, everything else underflows to exactly 0 on any device
+            logits = torch.where(torch.rand(3, V) < 0.002, torch.randn(3, V) * 0.3, torch.full((3, V), -30.0))
+        else:
+            logits = torch.randn(3, V) * (0.56 if case == "smooth" else 3.5)
+        mask = synth.make_token_mask()
+        probs = torch.softmax(logits / 0.1, dim=-1) * mask
+        rp, ri = probs.topk(K, dim=-1)
+        gp, gi = eng.topk_mask(logits.cuda(), mask.cuda(), 0.1, K)
+        gp, gi = gp.cpu(), gi.cpu()
+        nz = rp > 0
+        assert torch.equal(gi[nz], ri[nz])
+        torch.testing.assert_close(gp[nz], rp[nz], rtol=2e-5, atol=0)
+        assert bool((gp[:, 1:] <= gp[:, :-1]).all())
+        for r in range(3):
+            z = gi[r][~nz[r]]
+            if z.numel():
+                zero_ids = torch.nonzero(probs[r] == 0).flatten()
+                assert torch.equal(z, zero_ids[: z.numel()])
+
+
+def test_build_clip_ids_matches_string_round_trip():
+    """Device CSR assembly == tokenizer.batch_decode + CLIP tokenizer of the oracle (multi-token words,
+    masked candidates that vanish, specials dropped)."""
+    eng = gc.engine("bf16x3", multi=True)
+    tok, ctok = synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(True)
+    inp = torch.tensor([[101, 3746, 1997, 1037, 2003, 103, 103, 7003, 102],
+                        [101, 3746, 1997, 1037, 0, 103, 1012, 2500, 102]])
+    ids = torch.tensor([[2010, 5, 7010, 1012], [3000, 2999, 100, 4003]])
+    mask = synth.make_token_mask()
+    mask[0, 1012] = 1
+    pos = 5
+    idm = (ids * mask[0][ids]).long()
+    cand = inp.unsqueeze(1).repeat(1, 4, 1)
+    cand[:, :, pos] = idm
+    texts = tok.batch_decode(cand.view(-1, inp.shape[1]), skip_special_tokens=True)
+    ref = ctok(texts)["input_ids"]
+    T = ref.shape[1] + 2
+    got, glen, gidm = eng.build_clip_ids(inp.cuda(), pos, ids.cuda(), mask.cuda(), T)
+    got, glen = got.cpu(), glen.cpu()
+    assert torch.equal(gidm.cpu(), idm)
+    assert torch.equal(got[:, : ref.shape[1]].long(), ref)
+    assert bool((got[:, ref.shape[1]:] == synth.CLIP_EOS).all())
+    ref_len = (ref == synth.CLIP_EOS).int().argmax(1) + 1
+    assert torch.equal(glen.long(), ref_len)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_gibbs_step_teacher_forced_bf16x3(name):
+    """Every recorded step of the unmodified reference, fed its own `inp`: one conzic_gibbs_step must give the
+    same logits / top-k ids / cosine / softmax / winner."""
+    g = gc.load_golden(name)
+    case = g["case"]
+    eng = gc.engine("bf16x3", "tcgen05", case.get("peaked", False), case.get("multi", False))
+    m = gc.replay_fixture(eng, g)
+    assert m["dot_mismatch"] == 0
+    assert m["logit_err"] < 1e-3
+    assert m["topk_id_mismatch"] == 0
+    assert m["clip_ref_err"] < 2e-5
+    assert m["clip_score_err"] < 2e-4
+    assert m["winner_mismatch"] == 0
+    assert m["winner_checked"] > 0
+
+
+@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8"])
+def test_gibbs_step_teacher_forced_bf16(name):
+    g = gc.load_golden(name)
+    eng = gc.engine("bf16", "tcgen05")
+    m = gc.replay_fixture(eng, g)
+    assert m["logit_err"] < 0.08
+    assert m["clip_ref_err"] < 4e-3
+    # a flipped winner is only acceptable on a near tie of the fused score
+    assert m["winner_mismatch"] == 0 or m["min_margin_at_mismatch"] < 2.0 * 100 * 4e-3
+
+
+def _models(case):
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    bert = BertMLM(gc.weights("bert", case.get("peaked", False)))
+    clip = CLIP(state_dict=gc.weights("clip"), tokenizer=synth.SynthCLIPTokenizer(case.get("multi", False)),
+                processor=synth.SynthProcessor())
+    return bert, clip.to("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "random_b2_n3_k8", "senti_seq_b2_n4_k8",
+                                  "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32"])
+def test_free_running_call_matches_reference(name, monkeypatch):
+    """generate_caption / control_generate_caption through the drop-in API under set_seed(42): same captions per
+    sweep, same best list, same CLIP scores as the unmodified reference returned (bf16x3 mode)."""
+    import logging
+    from conzic_b200 import control_gen_utils, gen_utils, runtime
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    runtime.clear()
+    g = gc.load_golden(name)
+    case = g["case"]
+    bert, clip = _models(case)
+    B, n, K = case["B"], case["n"], case["K"]
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    token_mask = synth.make_token_mask("cuda")
+    logger = logging.getLogger("test")
+    names = [f"img{i}.jpg" for i in range(B)]
+    kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=case["iters"],
+              alpha=0.02, beta=2.0, generate_order=case["order"])
+    set_seed(42)
+    if case.get("gamma") is None:
+        texts, scores = gen_utils.generate_caption(names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask,
+                                                   logger, **kw)
+    else:
+        texts, scores = control_gen_utils.control_generate_caption(
+            names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask, logger, gamma=case["gamma"],
+            ctl_type="sentiment", style_type=case["style"], sentiment_table=synth.make_sentiment_table(), **kw)
+    runtime.clear()
+    assert texts == g["texts"]
+    for a, b in zip(scores, g["scores"]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_prefix_sharing_equals_dense_encode():
+    """Size-independent property: encoding candidates as shared prefix + per-candidate suffix gives the same
+    cosine as encoding every full caption densely (causal tower => prefix states do not depend on the suffix)."""
+    eng = gc.engine("bf16x3")
+    B, n, K = 4, 6, 32
+    L = n + 5
+    torch.manual_seed(5)
+    inp = torch.tensor([[101, 3746, 1997, 1037] + [2000 + 11 * j for j in range(n)] + [102]] * B).cuda()
+    inp[1, 6] = 0
+    tm = synth.make_token_mask("cuda")
+    img = torch.randn(B, 512, device="cuda")
+    pos = 7
+    inp0 = inp.clone()
+    _, _, tr = eng.gibbs_step(inp, tm, img, pos, False, K, 0.1, 0.02, 2.0, 3 + 3, n - 4, trace=True)
+    masked = inp0.clone()
+    masked[:, pos] = synth.MASK_ID
+    cids, clen, idm = eng.build_clip_ids(masked, pos, tr["idxs"], tm, 20)
+    emb = eng.clip_text_encode(cids)
+    score, ref = eng.image_text_similarity(img, emb)
+    torch.testing.assert_close(ref, tr["clip_ref"], rtol=0, atol=3e-6)
+    torch.testing.assert_close(score, tr["clip_score"], rtol=0, atol=3e-5)
+
+
+def test_full_size_step_properties():
+    """BASELINE config 2 sizes (B=64, K=200, len=10): winners are legal (unmasked) ids, scores are cosines,
+    the step is deterministic, and the bf16 path picks the same winner as bf16x3 on all but near ties."""
+    B, n, K = 64, 10, 200
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=torch.Generator().manual_seed(9)), dim=-1).cuda()
+    base = torch.tensor([[101, 3746, 1997, 1037] + [2000 + 7 * j for j in range(n)] + [102]] * B).cuda()
+    outs = {}
+    for prec in ("bf16x3", "bf16"):
+        eng = gc.engine(prec)
+        runs = []
+        for _ in range(2):
+            inp = base.clone()
+            tm = synth.make_token_mask("cuda")
+            cr, _, tr = eng.gibbs_step(inp, tm, img, 9, False, K, 0.1, 0.02, 2.0, 8, 4, trace=True)
+            runs.append((inp.cpu(), cr.cpu(), tr["final"].cpu()))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+        w = runs[0][0][:, 9]
+        assert bool((w >= 1996).all()) and bool((runs[0][1].abs() <= 1.0).all())
+        outs[prec] = runs[0]
+    same = outs["bf16"][0][:, 9] == outs["bf16x3"][0][:, 9]
+    top2 = outs["bf16x3"][2].topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    assert bool(same[margin > 0.8].all()), "bf16 flipped a winner whose fp32 margin was large"
+    gc.drop_engines()
