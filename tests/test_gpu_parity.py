@@ -121,11 +121,20 @@ def test_topk_mask_exact_ids_and_tie_contract(K):
             logits = torch.randn(3, V) * (0.56 if case == "smooth" else 3.5)
         mask = synth.make_token_mask()
         probs = torch.softmax(logits / 0.1, dim=-1) * mask
-        rp, ri = probs.topk(K, dim=-1)
+        rp1, ri1 = probs.topk(K + 1, dim=-1)
+        rp, ri = rp1[:, :K], ri1[:, :K]
         gp, gi = eng.topk_mask(logits.cuda(), mask.cuda(), 0.1, K)
         gp, gi = gp.cpu(), gi.cpu()
         nz = rp > 0
-        assert torch.equal(gi[nz], ri[nz])
+        # a rank is comparable id-for-id only if its probability is separated from both neighbours (rank K+1
+        # included) by more than the few-ulp difference between the device's and the host's expf
+        rel = (rp1[:, :-1] - rp1[:, 1:]) / rp1[:, :-1].clamp_min(1e-37)
+        sep = rel > 1e-5
+        distinct = sep.clone()
+        distinct[:, 1:] &= sep[:, :-1]
+        cmp = nz & distinct
+        assert int(cmp.sum()) > 0.9 * int(nz.sum())
+        assert torch.equal(gi[cmp], ri[cmp])
         torch.testing.assert_close(gp[nz], rp[nz], rtol=2e-5, atol=0)
         assert bool((gp[:, 1:] <= gp[:, :-1]).all())
         for r in range(3):
