@@ -68,6 +68,11 @@ __global__ void find_eos_kernel(const int32_t* ids, int N, int T, int eos, int32
     if (ids[static_cast<size_t>(i) * T + t] == eos) { r = t; break; }
   eos_idx[i] = r;
 }
+__global__ void bf16_to_f32_kernel(const bf16* src, float* dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
 __global__ void add_one_kernel(int32_t* v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] += 1;
@@ -271,11 +276,8 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
     if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.bqkv), 3 * H, nullptr, 0, ACT_NONE);
     else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.bqkv), 3 * H, 0, ACT_NONE);
     GemmOpts o = c->gopt;
-    if (s) { /* fp32 qkv output in parity mode */ }
+    o.persist = 0;  // BERT has few token rows (B*L): the (n, m)-gridded kernel spreads them over more SMs
     if (!launch_linear(h, M, ly.qkv, e, o, st, nullptr)) return false;
-    if (!s) {
-      // bf16 qkv is not a split Act even though the GEMM flag is global: qkv never feeds a GEMM
-    }
     AttnArgs at;
     at.qkv = p.bqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = nullptr;
     at.B = B; at.P = 0; at.K = 1; at.S = L; at.H = H; at.heads = g.bert_heads; at.causal = 0;
@@ -294,6 +296,7 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
   // MLM head on row `pos` only: a strided view of the hidden states (row stride L*ldh) needs no gather.
   Act hrow{p.bh + static_cast<size_t>(pos) * ldh, L * ldh, H};
   GemmOpts o = c->gopt;
+  o.persist = 0;
   if (!launch_linear(hrow, B, c->b_transform, epi_f32_out(c->b_transform, p.bt, H, nullptr, 0, ACT_ERF_GELU), o, st,
                      nullptr))
     return false;
@@ -408,6 +411,11 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->gopt.stages = 3;
   if (const char* e = getenv("CONZIC_GEMM_BN")) c->gopt.bn = atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_STAGES")) c->gopt.stages = atoi(e);
+  // CLIP linears: persistent A-resident kernel (bf16 mode); CONZIC_GEMM_CG=2 pairs CTAs (tcgen05 cta_group::2)
+  c->gopt.persist = c->split ? 0 : 1;
+  c->gopt.cg = 2;
+  if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
+  if (const char* e = getenv("CONZIC_GEMM_CG")) c->gopt.cg = atoi(e);
   c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 16384;
   if (const char* e = getenv("CONZIC_CLIP_CHUNK_ROWS")) c->chunk_rows = atoi(e);
   bool ok = true;
@@ -622,8 +630,11 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
                         int N, int K, int act, float* out, void* ws, size_t ws_bytes, void* stream) {
   if (!c || !A || !Wf || !out || !ws) { set_error("debug_linear: null argument"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf16_out = (act & 16) != 0;  // exercise the bf16 activation output path (bf16 mode only)
+  act &= 15;
+  if (bf16_out && (c->split || resid)) { set_error("debug_linear: bf16 output needs bf16 mode and no residual"); return -1; }
   const int s = c->split, ld = K * (1 + s);
-  const size_t need = (static_cast<size_t>(M) + N) * ld * sizeof(bf16) + 1024;
+  const size_t need = (static_cast<size_t>(M) + N) * ld * sizeof(bf16) + (bf16_out ? static_cast<size_t>(M) * N * 2 : 0) + 2048;
   if (ws_bytes < need) { set_error("debug_linear: workspace too small, need " + std::to_string(need)); return -1; }
   Bump b(ws, ws_bytes);
   bf16* a_act = b.take<bf16>(static_cast<size_t>(M) * ld);
@@ -637,9 +648,21 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
     if (!make_tmap_bf16_2d(&W.tmap256, w_act, N, ld, ld, 256)) return -4;
   }
   Epi e;
-  e.bias = bias; e.resid = resid; e.ldr = N; e.out_f32 = out; e.ldo_f32 = N; e.act = act;
+  e.bias = bias; e.resid = resid; e.ldr = N; e.act = act;
+  bf16* o16 = nullptr;
+  if (bf16_out) {
+    o16 = b.take<bf16>(static_cast<size_t>(M) * N);
+    e.out_act = o16; e.ldo_act = N; e.out_K = 0;
+  } else {
+    e.out_f32 = out; e.ldo_f32 = N;
+  }
   Act a{a_act, ld, K};
-  return launch_linear(a, M, W, e, c->gopt, st, nullptr) ? 0 : -4;
+  if (!launch_linear(a, M, W, e, c->gopt, st, nullptr)) return -4;
+  if (bf16_out) {
+    bf16_to_f32_kernel<<<1184, 256, 0, st>>>(o16, out, static_cast<size_t>(M) * N);
+    ++g_launches;
+  }
+  return cuda_ok(cudaGetLastError(), "debug_linear") ? 0 : -4;
 }
 
 }  // extern "C"

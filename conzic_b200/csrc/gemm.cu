@@ -229,6 +229,325 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant for the big CLIP linears (M = tens of thousands of token rows, N and K small).
+//   * one CTA (CG == 1) or one CTA pair sharing every B tile through tcgen05 cta_group::2 (CG == 2) per SM;
+//   * work unit = (128-row m tile per CTA, 256-column n tile); each CTA group walks a contiguous range of
+//     the unit list, so the A tile of an m tile is fetched once and stays in shared memory for all its n
+//     tiles (ARES, K <= 512) while only W streams through the TMA ring;
+//   * the accumulator is double buffered in TMEM (2 x 256 columns): the 8 epilogue warps drain tile i while
+//     the tensor core works on tile i+1.
+// Per CTA and k block the L2 -> SM traffic is 32 KB / CG (B only) for 2*128*256*64 FLOP.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PBN = 256;
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_MAX_KB = 8;  // A-resident mode: K <= 512
+
+struct PGemmParams {
+  int M, N, K;
+  int m_tiles;  // per-CTA-group tiles of CG*128 rows
+  int n_tiles;
+  Epi e;
+};
+
+template <int CG, bool ARES>
+struct PSmem {
+  static constexpr int A_SLOT = BM * BK * 2;               // 16 KB
+  static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
+  static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
+  static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
+  static constexpr int STAGES = ARES ? (CG == 1 ? 2 : 4) : (CG == 1 ? 4 : 6);
+  static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 128 B transpose buffers
+  static constexpr int STG_BYTES = P_EPI_WARPS * 4096;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int N_BARS = 2 * STAGES + P_MAX_KB + 4;
+  static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+// Epilogue of the persistent kernel.  tcgen05.ld hands every thread one accumulator ROW; storing that way makes
+// each warp store touch 32 different cache lines.  So every warp transposes its 32-row chunk through a private
+// 4 KB shared-memory buffer (rows of 128 B, 16-byte pieces XOR-swizzled by row so both phases are conflict
+// free) and then reads / writes global memory with 8 lanes per row: every access is a full 128-byte line.
+__device__ __forceinline__ uint32_t stg_off(int r, int piece) { return r * 128 + ((piece ^ (r & 7)) << 4); }
+
+// fp32 path: 32 columns [n0, n0+32) of rows [row0, row0+32); v = this lane's row (row0 + lane).
+// The residual (which the engine aliases with the output: x += ...) is fetched into registers by
+// prefetch_resid BEFORE the accumulator is read, so its latency hides behind tcgen05.ld and the math and the
+// eight loads are not serialised behind the eight stores.
+__device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, int row0, int n0, float4 (&rr)[8]) {
+  const Epi& e = p.e;
+  const int pc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int grow = row0 + (lane >> 3) + 4 * i;
+    rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.resid && grow < p.M)
+      rr[i] = *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(grow) * e.ldr + n0 + pc * 4);
+  }
+}
+
+__device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
+                                                   float (&v)[32], const float4 (&rr)[8]) {
+  const Epi& e = p.e;
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, false);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + stg_off(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int pc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i;
+    const int grow = row0 + r;
+    float4 x = *reinterpret_cast<const float4*>(stg + stg_off(r, pc));
+    if (grow < p.M) {
+      const int col = n0 + pc * 4;
+      x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
+      if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col) = x;
+      if (e.out_act) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(e.out_act + static_cast<size_t>(grow) * e.ldo_act + col) = u;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// bf16-only path (no residual, no fp32 output): 64 columns [n0, n0+64) per chunk.
+__device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
+                                                    float (&v)[64]) {
+  const Epi& e = p.e;
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], e.act, false);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = u;
+  }
+  __syncwarp();
+  const int pc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i;
+    const int grow = row0 + r;
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + stg_off(r, pc));
+    if (grow < p.M) *reinterpret_cast<uint4*>(e.out_act + static_cast<size_t>(grow) * e.ldo_act + n0 + pc * 8) = x;
+  }
+  __syncwarp();
+}
+
+template <int CG, bool ARES>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const PGemmParams p) {
+  using SL = PSmem<CG, ARES>;
+  constexpr int STAGES = SL::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sStage = smem + SL::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* empty_a = empty_bar + STAGES;
+  uint64_t* tfull_bar = empty_a + P_MAX_KB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const long long n_groups = gridDim.x / CG;
+  const long long group = blockIdx.x / CG;
+  const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  const long long u0 = group * U / n_groups, u1 = (group + 1) * U / n_groups;
+  const int nkb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int k = 0; k < P_MAX_KB; ++k) mbar_init(&empty_a[k], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], CG * P_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg<CG>(tmem_slot, 512);
+    tmem_relinquish_cg<CG>();
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane; in a pair both CTAs load their own rows of A and their half of B) =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; int cur_m = -1; uint32_t m_started = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
+        const bool newm = (m != cur_m);
+        cur_m = m;
+        const bool load_a = !ARES || newm;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (ARES && newm) mbar_wait(&empty_a[kb], (m_started & 1) ^ 1);
+          const uint32_t bytes = SL::B_STAGE + (load_a ? SL::A_SLOT : 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
+          const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
+          uint8_t* st = sStage + s * SL::STAGE;
+          if (load_a)
+            tma_load_2d_cg<CG>(ARES ? sA + kb * SL::A_SLOT : st, &tmA, bar, kb * BK,
+                               (m * CG + static_cast<int>(cta_rank)) * BM);
+          tma_load_2d_cg<CG>(ARES ? st : st + SL::A_SLOT, &tmB, bar, kb * BK,
+                             n * PBN + static_cast<int>(cta_rank) * (PBN / CG));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (newm) ++m_started;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane of the leader CTA) =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, PBN);
+      int s = 0; uint32_t ph = 0; uint32_t acc = 0, acc_ph = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int n = static_cast<int>(u % p.n_tiles);
+        const bool last_of_m = (n == p.n_tiles - 1) || (u == u1 - 1);
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * PBN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          uint8_t* st = sStage + s * SL::STAGE;
+          const uint32_t a0 = smem_u32(ARES ? sA + kb * SL::A_SLOT : st);
+          const uint32_t b0 = smem_u32(ARES ? st : st + SL::A_SLOT);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
+            const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
+            umma_bf16_cg<CG>(d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_cg<CG>(&empty_bar[s]);
+          if (ARES && last_of_m) umma_commit_cg<CG>(&empty_a[kb]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_cg<CG>(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: 8 warps, warp%4 = TMEM lane quarter, (warp-2)/4 = column half of the 256-wide tile =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint32_t acc = 0, acc_ph = 0;
+    const uint32_t tempty_addr0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
+    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 4096;
+    const bool bf16_only = p.e.out_act && !p.e.out_f32 && !p.e.resid;
+    for (long long u = u0; u < u1; ++u) {
+      const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
+      const int nbase = n * PBN + half * (PBN / 2);
+      auto release = [&]() {
+        // everything this warp needs from the accumulator is in registers: hand the buffer back to the MMA
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_addr0 + acc * 8);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      };
+      if (bf16_only && nbase + PBN / 2 <= p.N) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[64];
+          tmem_ld32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          tmem_ld32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+          tmem_ld_wait();
+          if (c == 1) release();
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 64, v);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int n0 = nbase + c * 32;
+          float4 rr[8];
+          if (n0 + 32 <= p.N) prefetch_resid(p, lane, row0, n0, rr);
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == 3) release();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (n0 + 32 <= p.N) {
+            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr);
+          } else if (row0 + lane < p.M && n0 < p.N) {
+            GemmParams gp;
+            gp.M = p.M; gp.N = p.N; gp.K = p.K; gp.split = 0; gp.e = p.e;
+            epilogue_chunk(gp, row0 + lane, n0, v);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
 // Slow reference kernel on CUDA cores with the same operand format and epilogue (tests / bring-up only).
 __global__ void gemm_simt_debug_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw,
                                        const GemmParams p) {
@@ -308,7 +627,40 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return true;
 }
 
+template <int CG, bool ARES>
+bool configure_persist() {
+  return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PSmem<CG, ARES>::DYN_BYTES),
+                 "cudaFuncSetAttribute(gemm_persist)");
+}
+
+template <int CG, bool ARES>
+bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int sms, cudaStream_t st) {
+  const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  long long groups = sms / CG;
+  if (groups > U) groups = U;
+  if (groups < 1) groups = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = PSmem<CG, ARES>::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, p), "gemm_persist launch");
+}
+
+int g_sm_count = 0;
+
 bool gemm_configure() {
+  if (!(configure_persist<1, true>() && configure_persist<1, false>() && configure_persist<2, true>() &&
+        configure_persist<2, false>()))
+    return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
          configure_one<256, 2>() && configure_one<256, 4>();
 }
@@ -339,6 +691,23 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   if (!make_tmap_bf16_2d(&ta, A.p, static_cast<uint64_t>(M), static_cast<uint64_t>(W.K) * (o.split ? 2 : 1),
                          static_cast<uint64_t>(A.ld), BM))
     return false;
+  if (o.persist && !o.split) {
+    if (g_sm_count == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    const int cg = o.cg == 2 ? 2 : 1;
+    PGemmParams pp;
+    pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi;
+    pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
+    pp.n_tiles = (W.N + PBN - 1) / PBN;
+    const bool ares = W.K <= P_MAX_KB * BK;
+    const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;
+    if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
+    return ares ? launch_persist<1, true>(ta, tb, pp, g_sm_count, st) : launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
+  }
   const int key = o.bn * 10 + o.stages;
   switch (key) {
     case 1282: launch_one<128, 2>(ta, W.tmap128, p, st); break;

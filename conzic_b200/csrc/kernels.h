@@ -63,6 +63,8 @@ struct GemmOpts {
   int impl = 0;     // 0 tcgen05, 1 SIMT debug
   int bn = 128;     // N tile: 128 or 256
   int stages = 3;   // smem pipeline depth
+  int persist = 0;  // 1 = persistent A-resident kernel with double-buffered TMEM accumulators (bf16 mode only)
+  int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)

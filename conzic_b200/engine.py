@@ -234,7 +234,7 @@ class Engine:
         M, K = A.shape
         N = W.shape[0]
         out = torch.empty((M, N), dtype=torch.float32, device=self.device)
-        need = (M + N) * K * 4 + 4096
+        need = (M + N) * K * 4 + M * N * 2 + 8192
         ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         rc = self.lib.conzic_debug_linear(self.ctx, _ptr(A.contiguous()), _ptr(W.contiguous()), _ptr(bias),
                                           _ptr(resid), M, N, K, int(act), _ptr(out), _ptr(ws), ws.numel(),

@@ -165,7 +165,8 @@ int conzic_profile_read(conzic_ctx* ctx, int category, double* ms, double* work,
 /* Plain GEMM entry used by tests and the roofline microbench:
  *   out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ resid), A/W fp32 dev, converted internally to the
  *   context's operand format; exercises exactly the kernel the towers use.  act: 0 none, 1 quick_gelu,
- *   2 erf-gelu.  out fp32[M,N]. */
+ *   2 erf-gelu; act | 16 routes the result through the kernel's bf16 activation output (bf16 mode, no
+ *   residual) before it is widened into out.  out fp32[M,N]. */
 int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev, const float* bias_dev,
                         const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);

@@ -210,6 +210,54 @@ def stage_perf_gemm():
                                    tflops_incl_convert=2.0 * M * N * K / ms / 1e9))
 
 
+def stage_persist(cg):
+    """Persistent GEMM (CONZIC_GEMM_PERSIST=1, CONZIC_GEMM_CG=cg): correctness against fp64, then GEMM-only time
+    from the library's per-launch CUDA events (operand conversion excluded)."""
+    import torch
+    import gpu_common as gc
+    os.environ["CONZIC_GEMM_PERSIST"] = "1" if cg else "0"
+    os.environ["CONZIC_GEMM_CG"] = str(cg or 1)
+    eng = gc.engine("bf16", "tcgen05")
+    for (M, N, K, act) in ((128, 256, 64, 0), (256, 256, 128, 0), (200, 512, 512, 1), (1000, 1536, 512, 0),
+                           (333, 2048, 512, 1), (4096, 512, 2048, 0), (20000, 512, 512, 0), (37, 768, 768, 2),
+                           (5000, 30524, 768, 0)):
+        g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+        bias = torch.randn(N, device="cuda", generator=g)
+        resid = torch.randn(M, N, device="cuda", generator=g) if N % 4 == 0 else None
+        out = eng.debug_linear(A, W, bias, resid, act)
+        torch.cuda.synchronize()
+        ref = ref_linear(A, W, bias, resid, act, True)
+        err = float((out - ref).abs().max())
+        emit("persist", dict(cg=cg, M=M, N=N, K=K, act=act, max_err=err, ref_max=float(ref.abs().max()),
+                             ok=bool(err < 3e-4 * float(ref.abs().max()))))
+        if N % 8:
+            continue
+        out = eng.debug_linear(A, W, bias, None, act | 16)  # bf16 activation output path
+        torch.cuda.synchronize()
+        ref = ref_linear(A, W, bias, None, act, True).bfloat16().float()
+        err = float((out - ref).abs().max())
+        emit("persist_bf16out", dict(cg=cg, M=M, N=N, K=K, act=act, max_err=err, ref_max=float(ref.abs().max()),
+                                     ok=bool(err < 1.6e-2 * float(ref.abs().max()))))
+    for (M, N, K) in ((18944, 1536, 512), (18944, 512, 512), (18944, 2048, 512), (18944, 512, 2048),
+                      (75776, 1536, 512), (75776, 512, 512), (75776, 2048, 512), (75776, 512, 2048)):
+        A = torch.randn(M, K, device="cuda")
+        W = torch.randn(N, K, device="cuda") * 0.05
+        bias = torch.randn(N, device="cuda")
+        resid = torch.randn(M, N, device="cuda")
+        for mode, (rs, act) in (("f32", (None, 0)), ("f32+resid", (resid, 0)), ("bf16+gelu", (None, 17)), ("bf16", (None, 16))):
+            for _ in range(3):
+                eng.debug_linear(A, W, bias, rs, act)
+            eng.profile(True)
+            for _ in range(10):
+                eng.debug_linear(A, W, bias, rs, act)
+            ms, work, n = eng.profile_read()["gemm"]
+            eng.profile(False)
+            emit("persist_perf", dict(cg=cg, mode=mode, M=M, N=N, K=K, ms=round(ms / n, 4),
+                                      tflops=round(work / (ms / 1e3) / 1e12, 1)))
+
+
 def stage_perf_step():
     import torch
     import gpu_common as gc
@@ -249,7 +297,8 @@ def main():
     a = ap.parse_args()
     if a.stage:
         fn = {"gemm": stage_gemm, "gemm_simt": lambda: stage_gemm("simt_debug"), "bert": stage_bert, "topk": stage_topk,
-              "clip": stage_clip, "step": stage_step, "perf_gemm": stage_perf_gemm, "perf_step": stage_perf_step}[a.stage]
+              "clip": stage_clip, "step": stage_step, "perf_gemm": stage_perf_gemm, "perf_step": stage_perf_step, "persist0": lambda: stage_persist(0),
+              "persist1": lambda: stage_persist(1), "persist2": lambda: stage_persist(2)}[a.stage]
         fn()
         return
     for st in a.stages.split(","):
