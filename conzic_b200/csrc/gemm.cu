@@ -38,7 +38,11 @@ __device__ __forceinline__ float apply_act(float v, int act, bool precise) {
   if (act == ACT_QUICK_GELU) {
     // x * sigmoid(1.702 x)   (HF:activations.py:122-123)
     if (precise) return v / (1.0f + expf(-1.702f * v));
-    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+    // sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU op per element instead of two (the fc1 epilogue is
+    // MUFU-bound otherwise); tanh.approx is good to ~2^-11, the result is rounded to bf16 (2^-9) anyway
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * v));
+    return v * fmaf(0.5f, t, 0.5f);
   }
   if (act == ACT_ERF_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
   return v;
@@ -104,9 +108,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       }
     }
   } else {
-    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {  // unrolled with a predicate: a dynamic index would push v[] into local memory
       const int n = n0 + j;
-      if (n >= p.N) break;
+      if (n >= p.N) continue;
       float x = v[j];
       if (e.bias) x += __ldg(e.bias + n);
       x = apply_act(x, e.act, precise);
@@ -257,10 +262,11 @@ struct PSmem {
   static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
   static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
   static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
-  static constexpr int STAGES = ARES ? (CG == 1 ? 2 : 4) : (CG == 1 ? 4 : 6);
+  static constexpr int STAGES = ARES ? (CG == 1 ? 2 : 3) : (CG == 1 ? 3 : 5);
   static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 128 B transpose buffers
   static constexpr int STG_BYTES = P_EPI_WARPS * 4096;
-  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int BIAS_OFF = STG_OFF + STG_BYTES;      // per-epilogue-warp bias slice: 128 floats
+  static constexpr int BAR_OFF = BIAS_OFF + P_EPI_WARPS * 512;
   static constexpr int N_BARS = 2 * STAGES + P_MAX_KB + 4;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -289,12 +295,12 @@ __device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, i
 }
 
 __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
-                                                   float (&v)[32], const float4 (&rr)[8]) {
+                                                   float (&v)[32], const float4 (&rr)[8], const float* sbias) {
   const Epi& e = p.e;
-  if (e.bias) {
+  if (e.bias) {  // sbias: this chunk's 32 bias values in shared memory (all lanes read the same address)
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+      float4 b = *reinterpret_cast<const float4*>(sbias + j);
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
@@ -327,23 +333,24 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
   __syncwarp();
 }
 
-// bf16-only path (no residual, no fp32 output): 64 columns [n0, n0+64) per chunk.
-__device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
-                                                    float (&v)[64]) {
+// bf16-only path (no residual, no fp32 output): a chunk is 64 columns [n0, n0+64) = one 128-byte row of the
+// transpose buffer, filled in two 32-column halves so only 32 accumulator values are live at a time.
+__device__ __forceinline__ void epilogue_bf16_half(const PGemmParams& p, uint8_t* stg, int lane, int n0, int half,
+                                                   float (&v)[32], const float* sbias) {
   const Epi& e = p.e;
   if (e.bias) {
 #pragma unroll
-    for (int j = 0; j < 64; j += 4) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = *reinterpret_cast<const float4*>(sbias + j);
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], e.act, false);
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, false);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
     __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
     __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
@@ -351,8 +358,11 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
     u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = u;
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, half * 4 + j)) = u;
   }
+}
+__device__ __forceinline__ void epilogue_bf16_store(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0) {
+  const Epi& e = p.e;
   __syncwarp();
   const int pc = lane & 7;
 #pragma unroll
@@ -430,6 +440,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (ARES && newm) mbar_wait(&empty_a[kb], (m_started & 1) ^ 1);
           const uint32_t bytes = SL::B_STAGE + (load_a ? SL::A_SLOT : 0);
+          if (p.e.resid) {
+            // pull this unit's residual tile (128 rows x 1 KB) into L2 well before the epilogue reads it
+            const int rows_per_kb = (BM + nkb - 1) / nkb;
+            const int r_lo = (m * CG + static_cast<int>(cta_rank)) * BM + kb * rows_per_kb;
+            const int r_hi = min(min(r_lo + rows_per_kb, (m * CG + static_cast<int>(cta_rank) + 1) * BM), p.M);
+            const int c0 = n * PBN;
+            const int nbytes = min(PBN, p.N - c0) * 4;
+            if ((nbytes & 15) == 0 && nbytes > 0)
+              for (int r = r_lo; r < r_hi; ++r)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr + c0),
+                             "r"(nbytes) : "memory");
+          }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
           const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
           uint8_t* st = sStage + s * SL::STAGE;
@@ -484,9 +506,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc = 0, acc_ph = 0;
     const uint32_t tempty_addr0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 4096;
+    float* sbias = reinterpret_cast<float*>(smem + SL::BIAS_OFF + (warp - 2) * 512);
     const bool bf16_only = p.e.out_act && !p.e.out_f32 && !p.e.resid;
     for (long long u = u0; u < u1; ++u) {
       const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
+      {
+        // this warp's 128 bias values -> shared memory, while the tensor core is still busy with the tile
+        const int nb = n * PBN + half * (PBN / 2) + lane * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.e.bias && nb + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + nb));
+        __syncwarp();
+        *reinterpret_cast<float4*>(sbias + lane * 4) = bv;
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
@@ -503,16 +535,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       if (bf16_only && nbase + PBN / 2 <= p.N) {
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[64];
-          tmem_ld32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-          tmem_ld32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (c == 1) release();
-          float v[64];
+          if (c == 3) release();
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 64, v);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_bf16_half(p, stg, lane, nbase + (c >> 1) * 64, c & 1, v, sbias + c * 32);
+          if (c & 1) epilogue_bf16_store(p, stg, lane, row0, nbase + (c >> 1) * 64);
         }
       } else {
 #pragma unroll 1
@@ -528,7 +560,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (n0 + 32 <= p.N) {
-            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr);
+            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, sbias + c * 32);
           } else if (row0 + lane < p.M && n0 < p.N) {
             GemmParams gp;
             gp.M = p.M; gp.N = p.N; gp.K = p.K; gp.split = 0; gp.e = p.e;

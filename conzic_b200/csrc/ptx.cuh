@@ -45,16 +45,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (a CUDA error the host sees) instead of a hung GPU.
+// (No printf here: its argument buffer would give every kernel that waits a local-memory stack frame.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("conzic: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
-      __trap();
-    }
+    if (((++spins) & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

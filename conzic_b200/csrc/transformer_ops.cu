@@ -1,5 +1,7 @@
 // Non-GEMM pieces of the two towers: operand conversion, embeddings, LayerNorm, short-sequence attention.
 // All are HBM/L2-bandwidth kernels: one warp per token row, float4 / bf16x2 vector accesses, fp32 math.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace conzic {
@@ -271,6 +273,252 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bf16 attention for many very short sequences on the warp-level tensor-core path (mma.sync m16n8k16; the
+// sequences are far too short -- <= 16 queries x <= 32 keys typically -- to fill a 128-row tcgen05 tile).
+// One warp owns (image b, head h, a group of up to 8 candidates).  It stages the K / V rows of the image's
+// shared prefix once in its private shared-memory slice, then for every candidate appends the candidate's own
+// rows, forms S = Q K^T with ldmatrix-fed MMAs, does the masked softmax on the accumulator fragments in fp32,
+// and multiplies by V with the probabilities split into bf16 hi + lo parts (two MMAs) so P keeps fp32
+// accuracy.  All global accesses are whole 128-byte head rows (8 lanes x 16 B); the smem tiles are XOR
+// swizzled so both the 16-byte row writes and the ldmatrix reads are conflict free.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ATT_CAND_PER_TASK = 8;
+
+__device__ __forceinline__ uint32_t sw_off(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// hi = bf16(x), lo = bf16(x - hi) for a pair of probabilities
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = pack_bf16(a - __bfloat162float(h.x), b - __bfloat162float(h.y));
+}
+
+// Copies `n_rows` head rows (64 bf16 = 8 pieces of 16 B) into a swizzled smem tile starting at tile row `dst0`.
+// Source row i is global row (i < split ? base0 + i : base1 + i - split).
+__device__ __forceinline__ void att_load_rows(const bf16* __restrict__ src, int ld, int col0, int base0, int split,
+                                              int base1, int n_rows, uint8_t* tile, int dst0, int lane) {
+  for (int idx = lane; idx < n_rows * 8; idx += 32) {
+    const int i = idx >> 3, pc = idx & 7;
+    const int grow = i < split ? base0 + i : base1 + (i - split);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(grow) * ld + col0 + pc * 8);
+    *reinterpret_cast<uint4*>(tile + sw_off(dst0 + i, pc)) = v;
+  }
+}
+
+template <int NT, bool PFON>  // NT key tiles of 8: up to NT*8 keys per sequence; PFON: register prefetch of own rows
+__global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t att_smem[];
+  constexpr int KV_BYTES = NT * 8 * 128;
+  constexpr int WARP_BYTES = 2 * KV_BYTES + 16 * 128;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sK = att_smem + wib * WARP_BYTES;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;  // 16 query rows; reused to stage the 16 output rows
+  const uint32_t sK_a = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t sV_a = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  const uint32_t sQ_a = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+
+  const bf16* qkv = reinterpret_cast<const bf16*>(a.qkv);
+  const int H = a.H, ld = a.ld_qkv;
+  const int groups = (a.K + ATT_CAND_PER_TASK - 1) / ATT_CAND_PER_TASK;
+  const int n_pre_tasks = a.P > 0 ? a.B * a.heads : 0;
+  const long long n_tasks = n_pre_tasks + static_cast<long long>(a.B) * a.heads * groups;
+  const long long task = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wib;
+  if (task >= n_tasks) return;
+
+  int b, head, k0, k1, pl, nq;
+  bool is_prefix;
+  if (task < n_pre_tasks) {
+    is_prefix = true;
+    b = static_cast<int>(task / a.heads); head = static_cast<int>(task % a.heads);
+    k0 = 0; k1 = 1; pl = 0; nq = a.P;
+  } else {
+    is_prefix = false;
+    // consecutive warps = consecutive heads of the same (image, candidate group): together they read whole
+    // q / k / v rows (heads x 128 B contiguous), which keeps DRAM pages and L2 lines fully used
+    const long long t = task - n_pre_tasks;
+    head = static_cast<int>(t % a.heads);
+    const long long bg = t / a.heads;
+    const int g = static_cast<int>(bg % groups);
+    b = static_cast<int>(bg / groups);
+    k0 = g * ATT_CAND_PER_TASK; k1 = min(a.K, k0 + ATT_CAND_PER_TASK);
+    pl = a.P > 0 ? (a.p0 ? min(a.p0[b], a.P) : a.P) : 0;
+    nq = a.S;
+  }
+  const int nk = pl + nq;
+  const int col_q = head * 64, col_k = H + head * 64, col_v = 2 * H + head * 64;
+  const int pre_base = b * a.P;
+  const int n_pre_rows = a.B * a.P;
+
+  // rows past the last key must be finite: P = 0 there, and 0 * garbage could be NaN
+  for (int idx = lane; idx < (NT * 8 - nk) * 8; idx += 32)
+    *reinterpret_cast<uint4*>(sV + sw_off(nk + (idx >> 3), idx & 7)) = make_uint4(0, 0, 0, 0);
+  if (!is_prefix && pl > 0) {
+    att_load_rows(qkv, ld, col_k, pre_base, pl, 0, pl, sK, 0, lane);
+    att_load_rows(qkv, ld, col_v, pre_base, pl, 0, pl, sV, 0, lane);
+  }
+  const int g = lane >> 2, qd = lane & 3;
+  const int lm_r = lane & 7, lm_m = lane >> 3;  // ldmatrix: row within the 8x8 matrix, matrix index
+
+  // Own rows (q, k, v of one candidate: 24 * nq pieces of 16 B) are fetched one candidate ahead into
+  // registers so the global-load latency of candidate k+1 hides behind the math of candidate k.
+  constexpr int PF = PFON ? 9 : 1;
+  const bool single = nq <= 16;
+  const bool pf_ok = PFON && !is_prefix && nq * 24 <= 32 * PF;
+  uint4 pf[PF];
+  auto pf_load = [&](int kk) {
+    const int base = n_pre_rows + (b * a.K + kk) * a.S;
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int e = i * 32 + lane;
+      if (e < nq * 24) {
+        const int which = e / (nq * 8), rem = e - which * (nq * 8);
+        pf[i] = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(base + (rem >> 3)) * ld + which * H +
+                                                head * 64 + (rem & 7) * 8);
+      }
+    }
+  };
+  auto pf_store = [&]() {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int e = i * 32 + lane;
+      if (e < nq * 24) {
+        const int which = e / (nq * 8), rem = e - which * (nq * 8);
+        const int r = rem >> 3, pc = rem & 7;
+        uint8_t* dst = which == 0 ? sQ + sw_off(r, pc) : (which == 1 ? sK : sV) + sw_off(pl + r, pc);
+        *reinterpret_cast<uint4*>(dst) = pf[i];
+      }
+    }
+  };
+  if (pf_ok) pf_load(k0);
+
+  for (int k = k0; k < k1; ++k) {
+    const int own_base = is_prefix ? pre_base : n_pre_rows + (b * a.K + k) * a.S;
+    __syncwarp();
+    if (pf_ok) {
+      pf_store();
+      if (k + 1 < k1) pf_load(k + 1);
+    } else {
+      att_load_rows(qkv, ld, col_k, own_base, nq, 0, nq, sK, pl, lane);
+      att_load_rows(qkv, ld, col_v, own_base, nq, 0, nq, sV, pl, lane);
+      if (single) att_load_rows(qkv, ld, col_q, own_base, nq, 0, nq, sQ, 0, lane);
+    }
+    for (int mt = 0; mt * 16 < nq; ++mt) {
+      const int q_rows = min(16, nq - mt * 16);
+      if (!single) {
+        __syncwarp();
+        att_load_rows(qkv, ld, col_q, own_base + mt * 16, q_rows, 0, q_rows, sQ, 0, lane);
+      }
+      __syncwarp();
+      uint32_t qa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        ldmatrix_x4(sQ_a + sw_off(lm_r + 8 * (lm_m & 1), 2 * ks + (lm_m >> 1)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      // ---- S = Q K^T
+      float sc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+        if (nt * 8 < nk) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(sK_a + sw_off(nt * 8 + lm_r, 4 * hf + lm_m), b0, b1, b2, b3);
+            mma_bf16_16816(sc[nt], qa[2 * hf][0], qa[2 * hf][1], qa[2 * hf][2], qa[2 * hf][3], b0, b1);
+            mma_bf16_16816(sc[nt], qa[2 * hf + 1][0], qa[2 * hf + 1][1], qa[2 * hf + 1][2], qa[2 * hf + 1][3], b2, b3);
+          }
+        }
+      }
+      // ---- masked softmax over keys, rows g and g+8 of this query tile
+      const int t0 = mt * 16 + g, t1 = t0 + 8;
+      const int lim0 = a.causal ? min(nk, pl + t0 + 1) : nk;
+      const int lim1 = a.causal ? min(nk, pl + t1 + 1) : nk;
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int j = nt * 8 + qd * 2;
+        sc[nt][0] = (j < lim0) ? sc[nt][0] * a.scale : -INFINITY;
+        sc[nt][1] = (j + 1 < lim0) ? sc[nt][1] * a.scale : -INFINITY;
+        sc[nt][2] = (j < lim1) ? sc[nt][2] * a.scale : -INFINITY;
+        sc[nt][3] = (j + 1 < lim1) ? sc[nt][3] * a.scale : -INFINITY;
+        m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+        m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      if (m0 == -INFINITY) m0 = 0.f;  // rows past the sequence end (never stored)
+      if (m1 == -INFINITY) m1 = 0.f;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sc[nt][0] = expf(sc[nt][0] - m0); sc[nt][1] = expf(sc[nt][1] - m0);
+        sc[nt][2] = expf(sc[nt][2] - m1); sc[nt][3] = expf(sc[nt][3] - m1);
+        s0 += sc[nt][0] + sc[nt][1];
+        s1 += sc[nt][2] + sc[nt][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = s0 > 0.f ? 1.0f / s0 : 0.f, i1 = s1 > 0.f ? 1.0f / s1 : 0.f;
+      // ---- O = P V
+      float o[8][4];
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NT / 2; ++ks) {
+        if (ks * 16 < nk) {
+          uint32_t ph[4], plo[4];
+          split_pair(sc[2 * ks][0] * i0, sc[2 * ks][1] * i0, ph[0], plo[0]);
+          split_pair(sc[2 * ks][2] * i1, sc[2 * ks][3] * i1, ph[1], plo[1]);
+          split_pair(sc[2 * ks + 1][0] * i0, sc[2 * ks + 1][1] * i0, ph[2], plo[2]);
+          split_pair(sc[2 * ks + 1][2] * i1, sc[2 * ks + 1][3] * i1, ph[3], plo[3]);
+#pragma unroll
+          for (int d2 = 0; d2 < 4; ++d2) {
+            uint32_t v0, v1, v2, v3;
+            ldmatrix_x4_trans(sV_a + sw_off(ks * 16 + (lm_m & 1) * 8 + lm_r, d2 * 2 + (lm_m >> 1)), v0, v1, v2, v3);
+            mma_bf16_16816(o[2 * d2], ph[0], ph[1], ph[2], ph[3], v0, v1);
+            mma_bf16_16816(o[2 * d2], plo[0], plo[1], plo[2], plo[3], v0, v1);
+            mma_bf16_16816(o[2 * d2 + 1], ph[0], ph[1], ph[2], ph[3], v2, v3);
+            mma_bf16_16816(o[2 * d2 + 1], plo[0], plo[1], plo[2], plo[3], v2, v3);
+          }
+        }
+      }
+      // ---- stage the 16 x 64 output tile in the Q buffer, then store whole rows
+      __syncwarp();
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        *reinterpret_cast<uint32_t*>(sQ + sw_off(g, dt) + qd * 4) = pack_bf16(o[dt][0], o[dt][1]);
+        *reinterpret_cast<uint32_t*>(sQ + sw_off(g + 8, dt) + qd * 4) = pack_bf16(o[dt][2], o[dt][3]);
+      }
+      __syncwarp();
+      for (int idx = lane; idx < q_rows * 8; idx += 32) {
+        const int r = idx >> 3, pc = idx & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(sQ + sw_off(r, pc));
+        *reinterpret_cast<uint4*>(a.out_act + static_cast<size_t>(own_base + mt * 16 + r) * a.ld_act + head * 64 + pc * 8) = v;
+      }
+    }
+  }
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -346,6 +594,43 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     return false;
   }
   const int nk_cap = a.P + a.S;
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("CONZIC_ATTN_MMA");
+    use_mma = e ? atoi(e) : 1;
+  }
+  if (!a.qkv_f32 && !a.split && use_mma && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
+    const int groups = (a.K + ATT_CAND_PER_TASK - 1) / ATT_CAND_PER_TASK;
+    const long long tasks = (a.P > 0 ? static_cast<long long>(a.B) * a.heads : 0) +
+                            static_cast<long long>(a.B) * a.heads * groups;
+    const int warps = 8;
+    const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
+    if (tasks <= 0) return true;
+    static int use_pf = -1;
+    if (use_pf < 0) {
+      const char* e = getenv("CONZIC_ATTN_PF");
+      use_pf = e ? atoi(e) : 0;
+    }
+    const int nt = nk_cap <= 32 ? 4 : (nk_cap <= 64 ? 8 : 12);
+    const size_t smem = static_cast<size_t>(warps) * (2 * nt * 1024 + 2048);
+    auto launch = [&](auto kern) -> bool {
+      static size_t configured = 0;  // one static per instantiation of this lambda's call operator
+      if (smem > 48 * 1024 && smem > configured) {
+        if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                     "cudaFuncSetAttribute(attention_mma)"))
+          return false;
+        configured = smem;
+      }
+      kern<<<grid, warps * 32, smem, st>>>(a);
+      return true;
+    };
+    bool ok;
+    if (nt == 4) ok = use_pf ? launch(attention_mma_kernel<4, true>) : launch(attention_mma_kernel<4, false>);
+    else if (nt == 8) ok = use_pf ? launch(attention_mma_kernel<8, true>) : launch(attention_mma_kernel<8, false>);
+    else ok = use_pf ? launch(attention_mma_kernel<12, true>) : launch(attention_mma_kernel<12, false>);
+    if (!ok) return false;
+    return cuda_ok(cudaGetLastError(), "attention_mma launch");
+  }
   if (nk_cap > 32 * MAX_SLOTS) {
     set_error("attention: more than 96 keys per sequence is not supported (sentence_len too large)");
     return false;
