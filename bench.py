@@ -53,6 +53,17 @@ def peaks():
     return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
 
 
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture has been summarised."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes_per_launch": d.get("dram_bytes_per_launch"), "kernel": d.get("kernel"), "shape": d.get("shape"),
+            "algorithmic_bytes_per_launch": d.get("algorithmic_bytes_per_launch"), "source": d.get("source")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -277,9 +288,10 @@ def run_ours(args, rank, local_rank, world):
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
-                "roofline": {"kernel": "gemm_tcgen05_kernel (CLIP/BERT linear layers)", "bound": "tensor",
+                "roofline": {"kernel": "gemm_persist_kernel<2,*> (CLIP linears; CTA pairs, tcgen05 cta_group::2) + "
+                                       "gemm_tcgen05_kernel (BERT linears)", "bound": "tensor",
                              "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
-                             "peak_source": f"{pk['src']} sustained bf16", "traffic": None,
+                             "peak_source": f"{pk['src']} sustained bf16", "traffic": ncu_traffic(),
                              "launches_profiled": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
                              "flops_per_launch": g_flops / max(g_n, 1),
                              "share_of_step": g_ms / total_ms if total_ms else None},

@@ -120,7 +120,7 @@ struct conzic_ctx {
   // bert id -> clip ids
   int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
   int max_tok_per_word = 1;
-  int chunk_rows = 16384;
+  int chunk_rows = 75776;
   uint64_t launches0 = 0;
 
   ~conzic_ctx() {
@@ -416,7 +416,8 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->gopt.cg = 2;
   if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_CG")) c->gopt.cg = atoi(e);
-  c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 16384;
+  // default: 4 x (148 SMs x 128 rows) token rows per pass -- whole waves of the persistent GEMM's 128-row tiles
+  c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 75776;
   if (const char* e = getenv("CONZIC_CLIP_CHUNK_ROWS")) c->chunk_rows = atoi(e);
   bool ok = true;
   if (cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ok = tma_init() && gemm_configure();

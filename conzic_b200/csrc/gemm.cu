@@ -7,6 +7,8 @@
 //   warps 2-5: epilogue      -- tcgen05.ld (thread = output row), bias / activation / residual, global store
 // Several CTAs are resident per SM so one CTA's epilogue overlaps another's main loop.
 // bf16x3 mode runs three passes over K (hi*hi, lo*hi, hi*lo) into the same accumulator.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -262,7 +264,8 @@ struct PSmem {
   static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
   static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
   static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
-  static constexpr int STAGES = ARES ? (CG == 1 ? 2 : 3) : (CG == 1 ? 3 : 5);
+  static constexpr int STAGES = ARES ? 3 : (CG == 1 ? 3 : 5);
+  static_assert(!ARES || CG == 2, "A-resident mode needs the CTA pair");
   static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 128 B transpose buffers
   static constexpr int STG_BYTES = P_EPI_WARPS * 4096;
   static constexpr int BIAS_OFF = STG_OFF + STG_BYTES;      // per-epilogue-warp bias slice: 128 floats
@@ -529,8 +532,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(tempty_addr0 + acc * 8);
-          else mbar_arrive(&tempty_bar[acc]);
+          if (CG == 2) mbar_arrive_cluster_relaxed(tempty_addr0 + acc * 8);
+          else mbar_arrive_relaxed(&tempty_bar[acc]);
         }
       };
       if (bf16_only && nbase + PBN / 2 <= p.N) {
@@ -690,8 +693,7 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
 int g_sm_count = 0;
 
 bool gemm_configure() {
-  if (!(configure_persist<1, true>() && configure_persist<1, false>() && configure_persist<2, true>() &&
-        configure_persist<2, false>()))
+  if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>()))
     return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
          configure_one<256, 2>() && configure_one<256, 4>();
@@ -735,10 +737,15 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi;
     pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
     pp.n_tiles = (W.N + PBN - 1) / PBN;
-    const bool ares = W.K <= P_MAX_KB * BK;
+    static int allow_ares = -1;
+    if (allow_ares < 0) {
+      const char* e = getenv("CONZIC_GEMM_ARES");
+      allow_ares = e ? atoi(e) : 1;
+    }
+    const bool ares = allow_ares && cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
     const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;
     if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
-    return ares ? launch_persist<1, true>(ta, tb, pp, g_sm_count, st) : launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
+    return launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
   }
   const int key = o.bn * 10 + o.stages;
   switch (key) {

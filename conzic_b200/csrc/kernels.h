@@ -110,6 +110,8 @@ struct AttnArgs {
   float scale;
   bf16* out_act;
   int ld_act, split;
+  int cpt = 1;            // filled by launch_attention: candidates packed into one 16-row query tile
+  int cand_per_task = 8;  // filled by launch_attention: candidates per warp task
 };
 bool launch_attention(const AttnArgs& a, cudaStream_t st);
 

@@ -129,6 +129,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed arrives: for hand-offs that carry no ordinary memory (e.g. "this TMEM accumulator has been read",
+// already ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The default .release form makes
+// the warp drain all of its outstanding global stores first (MEMBAR + ERRBAR), which stalls an epilogue.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -283,7 +283,6 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
 // accuracy.  All global accesses are whole 128-byte head rows (8 lanes x 16 B); the smem tiles are XOR
 // swizzled so both the 16-byte row writes and the ldmatrix reads are conflict free.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ATT_CAND_PER_TASK = 8;
 
 __device__ __forceinline__ uint32_t sw_off(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
@@ -325,7 +324,7 @@ __device__ __forceinline__ void att_load_rows(const bf16* __restrict__ src, int 
   }
 }
 
-template <int NT, bool PFON>  // NT key tiles of 8: up to NT*8 keys per sequence; PFON: register prefetch of own rows
+template <int NT>  // NT key tiles of 8: up to NT*8 keys per tile
 __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   constexpr int KV_BYTES = NT * 8 * 128;
@@ -340,18 +339,21 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
 
   const bf16* qkv = reinterpret_cast<const bf16*>(a.qkv);
   const int H = a.H, ld = a.ld_qkv;
-  const int groups = (a.K + ATT_CAND_PER_TASK - 1) / ATT_CAND_PER_TASK;
+  const int groups = (a.K + a.cand_per_task - 1) / a.cand_per_task;
   const int n_pre_tasks = a.P > 0 ? a.B * a.heads : 0;
   const long long n_tasks = n_pre_tasks + static_cast<long long>(a.B) * a.heads * groups;
   const long long task = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wib;
   if (task >= n_tasks) return;
 
-  int b, head, k0, k1, pl, nq;
+  // A task: (image b, head, a range [k0, k1) of candidates).  `cpt` candidates share one 16-row query tile
+  // when their sequences are short (cpt * nq <= 16): the tile then holds the image prefix keys followed by
+  // the own keys of all cpt candidates, and the mask lets a query see the prefix and its own candidate only.
+  int b, head, k0, k1, pl, nq, cpt;
   bool is_prefix;
   if (task < n_pre_tasks) {
     is_prefix = true;
     b = static_cast<int>(task / a.heads); head = static_cast<int>(task % a.heads);
-    k0 = 0; k1 = 1; pl = 0; nq = a.P;
+    k0 = 0; k1 = 1; pl = 0; nq = a.P; cpt = 1;
   } else {
     is_prefix = false;
     // consecutive warps = consecutive heads of the same (image, candidate group): together they read whole
@@ -359,20 +361,19 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
     const long long t = task - n_pre_tasks;
     head = static_cast<int>(t % a.heads);
     const long long bg = t / a.heads;
-    const int g = static_cast<int>(bg % groups);
+    const int grp = static_cast<int>(bg % groups);
     b = static_cast<int>(bg / groups);
-    k0 = g * ATT_CAND_PER_TASK; k1 = min(a.K, k0 + ATT_CAND_PER_TASK);
+    k0 = grp * a.cand_per_task; k1 = min(a.K, k0 + a.cand_per_task);
     pl = a.P > 0 ? (a.p0 ? min(a.p0[b], a.P) : a.P) : 0;
-    nq = a.S;
+    nq = a.S; cpt = a.cpt;
   }
-  const int nk = pl + nq;
   const int col_q = head * 64, col_k = H + head * 64, col_v = 2 * H + head * 64;
   const int pre_base = b * a.P;
   const int n_pre_rows = a.B * a.P;
 
-  // rows past the last key must be finite: P = 0 there, and 0 * garbage could be NaN
-  for (int idx = lane; idx < (NT * 8 - nk) * 8; idx += 32)
-    *reinterpret_cast<uint4*>(sV + sw_off(nk + (idx >> 3), idx & 7)) = make_uint4(0, 0, 0, 0);
+  // V rows that hold no key must be finite: P = 0 there, and 0 * garbage could be NaN
+  for (int idx = lane; idx < (NT * 8 - pl) * 8; idx += 32)
+    *reinterpret_cast<uint4*>(sV + sw_off(pl + (idx >> 3), idx & 7)) = make_uint4(0, 0, 0, 0);
   if (!is_prefix && pl > 0) {
     att_load_rows(qkv, ld, col_k, pre_base, pl, 0, pl, sK, 0, lane);
     att_load_rows(qkv, ld, col_v, pre_base, pl, 0, pl, sV, 0, lane);
@@ -380,51 +381,18 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   const int g = lane >> 2, qd = lane & 3;
   const int lm_r = lane & 7, lm_m = lane >> 3;  // ldmatrix: row within the 8x8 matrix, matrix index
 
-  // Own rows (q, k, v of one candidate: 24 * nq pieces of 16 B) are fetched one candidate ahead into
-  // registers so the global-load latency of candidate k+1 hides behind the math of candidate k.
-  constexpr int PF = PFON ? 9 : 1;
-  const bool single = nq <= 16;
-  const bool pf_ok = PFON && !is_prefix && nq * 24 <= 32 * PF;
-  uint4 pf[PF];
-  auto pf_load = [&](int kk) {
-    const int base = n_pre_rows + (b * a.K + kk) * a.S;
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const int e = i * 32 + lane;
-      if (e < nq * 24) {
-        const int which = e / (nq * 8), rem = e - which * (nq * 8);
-        pf[i] = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(base + (rem >> 3)) * ld + which * H +
-                                                head * 64 + (rem & 7) * 8);
-      }
-    }
-  };
-  auto pf_store = [&]() {
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const int e = i * 32 + lane;
-      if (e < nq * 24) {
-        const int which = e / (nq * 8), rem = e - which * (nq * 8);
-        const int r = rem >> 3, pc = rem & 7;
-        uint8_t* dst = which == 0 ? sQ + sw_off(r, pc) : (which == 1 ? sK : sV) + sw_off(pl + r, pc);
-        *reinterpret_cast<uint4*>(dst) = pf[i];
-      }
-    }
-  };
-  if (pf_ok) pf_load(k0);
-
-  for (int k = k0; k < k1; ++k) {
+  for (int k = k0; k < k1; k += cpt) {
+    const int nc = min(cpt, k1 - k);
+    const int n_own = nc * nq;          // query rows = own key rows of this iteration (contiguous in memory)
+    const int nk = pl + n_own;
     const int own_base = is_prefix ? pre_base : n_pre_rows + (b * a.K + k) * a.S;
+    const bool single = n_own <= 16;
     __syncwarp();
-    if (pf_ok) {
-      pf_store();
-      if (k + 1 < k1) pf_load(k + 1);
-    } else {
-      att_load_rows(qkv, ld, col_k, own_base, nq, 0, nq, sK, pl, lane);
-      att_load_rows(qkv, ld, col_v, own_base, nq, 0, nq, sV, pl, lane);
-      if (single) att_load_rows(qkv, ld, col_q, own_base, nq, 0, nq, sQ, 0, lane);
-    }
-    for (int mt = 0; mt * 16 < nq; ++mt) {
-      const int q_rows = min(16, nq - mt * 16);
+    att_load_rows(qkv, ld, col_k, own_base, n_own, 0, n_own, sK, pl, lane);
+    att_load_rows(qkv, ld, col_v, own_base, n_own, 0, n_own, sV, pl, lane);
+    if (single) att_load_rows(qkv, ld, col_q, own_base, n_own, 0, n_own, sQ, 0, lane);
+    for (int mt = 0; mt * 16 < n_own; ++mt) {
+      const int q_rows = min(16, n_own - mt * 16);
       if (!single) {
         __syncwarp();
         att_load_rows(qkv, ld, col_q, own_base + mt * 16, q_rows, 0, q_rows, sQ, 0, lane);
@@ -449,24 +417,34 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
           }
         }
       }
-      // ---- masked softmax over keys, rows g and g+8 of this query tile
-      const int t0 = mt * 16 + g, t1 = t0 + 8;
-      const int lim0 = a.causal ? min(nk, pl + t0 + 1) : nk;
-      const int lim1 = a.causal ? min(nk, pl + t1 + 1) : nk;
+      // ---- masked softmax over keys, rows g and g+8 of this query tile.  Query row r belongs to candidate
+      // c = r / nq at position t = r % nq and sees keys [0, pl) and [pl + c*nq, pl + c*nq + t] (causal) or
+      // every key (bidirectional, one sequence per tile).
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      int lo0 = 0, hi0 = nk - 1, lo1 = 0, hi1 = nk - 1;
+      if (a.causal) {
+        const int c0 = r0 / nq, c1 = r1 / nq;
+        lo0 = pl + c0 * nq; hi0 = min(nk - 1, lo0 + (r0 - c0 * nq));
+        lo1 = pl + c1 * nq; hi1 = min(nk - 1, lo1 + (r1 - c1 * nq));
+      }
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int j = nt * 8 + qd * 2;
-        sc[nt][0] = (j < lim0) ? sc[nt][0] * a.scale : -INFINITY;
-        sc[nt][1] = (j + 1 < lim0) ? sc[nt][1] * a.scale : -INFINITY;
-        sc[nt][2] = (j < lim1) ? sc[nt][2] * a.scale : -INFINITY;
-        sc[nt][3] = (j + 1 < lim1) ? sc[nt][3] * a.scale : -INFINITY;
+        const bool v00 = a.causal ? (j < pl || (j >= lo0 && j <= hi0)) : (j < nk);
+        const bool v01 = a.causal ? (j + 1 < pl || (j + 1 >= lo0 && j + 1 <= hi0)) : (j + 1 < nk);
+        const bool v10 = a.causal ? (j < pl || (j >= lo1 && j <= hi1)) : (j < nk);
+        const bool v11 = a.causal ? (j + 1 < pl || (j + 1 >= lo1 && j + 1 <= hi1)) : (j + 1 < nk);
+        sc[nt][0] = v00 ? sc[nt][0] * a.scale : -INFINITY;
+        sc[nt][1] = v01 ? sc[nt][1] * a.scale : -INFINITY;
+        sc[nt][2] = v10 ? sc[nt][2] * a.scale : -INFINITY;
+        sc[nt][3] = v11 ? sc[nt][3] * a.scale : -INFINITY;
         m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
         m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
       }
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      if (m0 == -INFINITY) m0 = 0.f;  // rows past the sequence end (never stored)
+      if (m0 == -INFINITY) m0 = 0.f;  // rows past the last query (never stored)
       if (m1 == -INFINITY) m1 = 0.f;
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -600,35 +578,30 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     use_mma = e ? atoi(e) : 1;
   }
   if (!a.qkv_f32 && !a.split && use_mma && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
-    const int groups = (a.K + ATT_CAND_PER_TASK - 1) / ATT_CAND_PER_TASK;
+    AttnArgs aa = a;
+    aa.cpt = (a.causal && a.S <= 8 && a.P + (16 / a.S) * a.S <= 96) ? 16 / a.S : 1;
+    aa.cand_per_task = aa.cpt >= 4 ? 2 * aa.cpt : (aa.cpt > 1 ? ((8 + aa.cpt - 1) / aa.cpt) * aa.cpt : 8);
+    const int keys_cap = a.P + (aa.cpt > 1 ? aa.cpt * a.S : a.S);
+    const int groups = (a.K + aa.cand_per_task - 1) / aa.cand_per_task;
     const long long tasks = (a.P > 0 ? static_cast<long long>(a.B) * a.heads : 0) +
                             static_cast<long long>(a.B) * a.heads * groups;
+    if (tasks <= 0) return true;
     const int warps = 8;
     const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
-    if (tasks <= 0) return true;
-    static int use_pf = -1;
-    if (use_pf < 0) {
-      const char* e = getenv("CONZIC_ATTN_PF");
-      use_pf = e ? atoi(e) : 0;
-    }
-    const int nt = nk_cap <= 32 ? 4 : (nk_cap <= 64 ? 8 : 12);
+    const int nt = keys_cap <= 32 ? 4 : (keys_cap <= 64 ? 8 : 12);
     const size_t smem = static_cast<size_t>(warps) * (2 * nt * 1024 + 2048);
-    auto launch = [&](auto kern) -> bool {
-      static size_t configured = 0;  // one static per instantiation of this lambda's call operator
-      if (smem > 48 * 1024 && smem > configured) {
-        if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
-                     "cudaFuncSetAttribute(attention_mma)"))
-          return false;
-        configured = smem;
-      }
-      kern<<<grid, warps * 32, smem, st>>>(a);
-      return true;
-    };
-    bool ok;
-    if (nt == 4) ok = use_pf ? launch(attention_mma_kernel<4, true>) : launch(attention_mma_kernel<4, false>);
-    else if (nt == 8) ok = use_pf ? launch(attention_mma_kernel<8, true>) : launch(attention_mma_kernel<8, false>);
-    else ok = use_pf ? launch(attention_mma_kernel<12, true>) : launch(attention_mma_kernel<12, false>);
-    if (!ok) return false;
+    static size_t configured[3] = {0, 0, 0};
+    const int which_nt = nt == 4 ? 0 : (nt == 8 ? 1 : 2);
+    if (smem > 48 * 1024 && smem > configured[which_nt]) {
+      cudaError_t e = nt == 4 ? cudaFuncSetAttribute(attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                    : nt == 8 ? cudaFuncSetAttribute(attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                              : cudaFuncSetAttribute(attention_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (!cuda_ok(e, "cudaFuncSetAttribute(attention_mma)")) return false;
+      configured[which_nt] = smem;
+    }
+    if (nt == 4) attention_mma_kernel<4><<<grid, warps * 32, smem, st>>>(aa);
+    else if (nt == 8) attention_mma_kernel<8><<<grid, warps * 32, smem, st>>>(aa);
+    else attention_mma_kernel<12><<<grid, warps * 32, smem, st>>>(aa);
     return cuda_ok(cudaGetLastError(), "attention_mma launch");
   }
   if (nk_cap > 32 * MAX_SLOTS) {
