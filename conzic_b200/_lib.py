@@ -20,7 +20,7 @@ EXPORTS = [
     "conzic_abi_version", "conzic_last_error", "conzic_ctx_create", "conzic_ctx_destroy", "conzic_set_bert2clip",
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
-    "conzic_debug_linear", "conzic_profile", "conzic_profile_read",
+    "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_debug_mlp",
 ]
 
 
@@ -80,6 +80,8 @@ def _declare(lib):
     lib.conzic_launch_count.argtypes = [vp]
     lib.conzic_debug_linear.restype = C.c_int
     lib.conzic_debug_linear.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
+    lib.conzic_debug_mlp.restype = C.c_int
+    lib.conzic_debug_mlp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
     lib.conzic_profile.restype = C.c_int
     lib.conzic_profile.argtypes = [vp, i32]
     lib.conzic_profile_read.restype = C.c_int

@@ -121,6 +121,7 @@ struct conzic_ctx {
   int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
   int max_tok_per_word = 1;
   int chunk_rows = 75776;
+  int mlp_fused = 0;  // fc1 + fc2 of a CLIP block in one persistent launch (bf16 mode, CTA pairs)
   uint64_t launches0 = 0;
 
   ~conzic_ctx() {
@@ -188,7 +189,7 @@ struct Plan {
   int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx, *pool_rows;
   // CLIP chunk
   float* cx;
-  bf16 *ch, *cattn, *cffn, *cpool;
+  bf16 *ch, *cattn, *cffn, *cpool, *cscratch;
   void* cqkv;
   float* text;
   size_t bytes;
@@ -234,6 +235,7 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   p.cffn = b.take<bf16>(Mc * Fc * (1 + s));
   p.cqkv = b.take<char>(Mc * 3 * Hc * (s ? 4 : 2));
   p.cpool = b.take<bf16>(BK * Hc * (1 + s));
+  p.cscratch = b.take<bf16>(c->mlp_fused ? static_cast<size_t>(mlp_scratch_rows()) * Fc : 1);
   p.text = b.take<float>(BK * g.clip_proj);
   p.bytes = align_up(b.off, 256);
   return p;
@@ -346,11 +348,15 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
       if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr)) return false;
       LNArgs ln2{p.cx, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
       launch_layernorm(ln2, st);
-      if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
-        return false;
-      Act f{p.cffn, ldf, F};
-      if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr))
-        return false;
+      if (c->mlp_fused) {
+        if (!launch_mlp_fused(h, M, ly.f1, ly.f2, p.cscratch, ACT_QUICK_GELU, p.cx, H, p.cx, H, nullptr, 0, st)) return false;
+      } else {
+        if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
+          return false;
+        Act f{p.cffn, ldf, F};
+        if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr))
+          return false;
+      }
     }
     // pooled = final LN of the hidden state at the first EOS; text_projection without bias
     launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
@@ -416,6 +422,11 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->gopt.cg = 2;
   if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_CG")) c->gopt.cg = atoi(e);
+  // fc1+fc2 in one launch (mlp_persist_kernel): measured equal to the two-launch path on B200 (the 78 MB of
+  // per-CTA scratch tiles do not survive in L2 between fc1 and fc2), so it is opt-in: CONZIC_MLP_FUSED=1
+  c->mlp_fused = 0;
+  if (const char* e = getenv("CONZIC_MLP_FUSED"))
+    c->mlp_fused = (atoi(e) && c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
   // default: 4 x (148 SMs x 128 rows) token rows per pass -- whole waves of the persistent GEMM's 128-row tiles
   c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 75776;
   if (const char* e = getenv("CONZIC_CLIP_CHUNK_ROWS")) c->chunk_rows = atoi(e);
@@ -664,6 +675,31 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
     ++g_launches;
   }
   return cuda_ok(cudaGetLastError(), "debug_linear") ? 0 : -4;
+}
+
+int conzic_debug_mlp(conzic_ctx* c, const float* X, const float* W1f, const float* b1, const float* W2f, const float* b2,
+                     int M, int H, int F, int act, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!c || !X || !W1f || !W2f || !out || !ws) { set_error("debug_mlp: null argument"); return -1; }
+  if (c->split || c->cfg.gemm_impl != CONZIC_GEMM_TCGEN05) { set_error("debug_mlp: bf16 tcgen05 mode only"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need = (static_cast<size_t>(M) * H + 2 * static_cast<size_t>(H) * F +
+                       static_cast<size_t>(mlp_scratch_rows()) * F) * sizeof(bf16) + 4096;
+  if (ws_bytes < need) { set_error("debug_mlp: workspace too small, need " + std::to_string(need)); return -1; }
+  Bump b(ws, ws_bytes);
+  bf16* x_act = b.take<bf16>(static_cast<size_t>(M) * H);
+  bf16* w1 = b.take<bf16>(static_cast<size_t>(F) * H);
+  bf16* w2 = b.take<bf16>(static_cast<size_t>(H) * F);
+  bf16* scratch = b.take<bf16>(static_cast<size_t>(mlp_scratch_rows()) * F);
+  launch_f32_to_act(X, M, H, H, x_act, H, 0, st);
+  launch_f32_to_act(W1f, F, H, H, w1, H, 0, st);
+  launch_f32_to_act(W2f, H, F, F, w2, F, 0, st);
+  LinearW L1, L2;
+  L1.w = w1; L1.bias = b1; L1.N = F; L1.K = H;
+  L2.w = w2; L2.bias = b2; L2.N = H; L2.K = F;
+  if (!make_tmap_bf16_2d(&L1.tmap128, w1, F, H, H, 128) || !make_tmap_bf16_2d(&L2.tmap128, w2, H, F, F, 128)) return -4;
+  Act a{x_act, H, H};
+  // out = X + fc2(act(fc1(bf16(X))))
+  return launch_mlp_fused(a, M, L1, L2, scratch, act, X, H, out, H, nullptr, 0, st) ? 0 : -4;
 }
 
 }  // extern "C"

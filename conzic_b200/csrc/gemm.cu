@@ -256,6 +256,8 @@ struct PGemmParams {
   int m_tiles;  // per-CTA-group tiles of CG*128 rows
   int n_tiles;
   Epi e;
+  uint64_t st_policy = 0;  // non-zero: L2 eviction-priority hint for the output stores / residual loads
+  uint64_t ld_policy = 0;
 };
 
 template <int CG, bool ARES>
@@ -264,67 +266,74 @@ struct PSmem {
   static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
   static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
   static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
-  static constexpr int STAGES = ARES ? 3 : (CG == 1 ? 3 : 5);
+  static constexpr int STAGES = ARES ? 5 : (CG == 1 ? 4 : 6);
   static_assert(!ARES || CG == 2, "A-resident mode needs the CTA pair");
-  static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 128 B transpose buffers
-  static constexpr int STG_BYTES = P_EPI_WARPS * 4096;
-  static constexpr int BIAS_OFF = STG_OFF + STG_BYTES;      // per-epilogue-warp bias slice: 128 floats
-  static constexpr int BAR_OFF = BIAS_OFF + P_EPI_WARPS * 512;
+  static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 64 B transpose buffers
+  static constexpr int STG_BYTES = P_EPI_WARPS * 2048;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int N_BARS = 2 * STAGES + P_MAX_KB + 4;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static constexpr int DYN_BYTES = TOTAL;  // the dynamic smem window is 1024-byte aligned (checked in the kernel)
+  static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
 };
 
 // Epilogue of the persistent kernel.  tcgen05.ld hands every thread one accumulator ROW; storing that way makes
 // each warp store touch 32 different cache lines.  So every warp transposes its 32-row chunk through a private
-// 4 KB shared-memory buffer (rows of 128 B, 16-byte pieces XOR-swizzled by row so both phases are conflict
-// free) and then reads / writes global memory with 8 lanes per row: every access is a full 128-byte line.
-__device__ __forceinline__ uint32_t stg_off(int r, int piece) { return r * 128 + ((piece ^ (r & 7)) << 4); }
+// 2 KB shared-memory buffer (32 rows of 64 B, 16-byte pieces XOR-swizzled so both phases are conflict free) and
+// then reads / writes global memory with 4 lanes per row: every access covers whole 32-byte sectors, 64
+// contiguous bytes per row.  Bias lives in registers (lane l holds the 4 values of columns 4l..4l+3 of the
+// warp's 128 columns) and reaches the lane that needs it by shuffle, so no shared memory is spent on it.
+__device__ __forceinline__ uint32_t stg_off(int r, int piece) { return r * 64 + ((piece ^ ((r >> 1) & 3)) << 4); }
 
-// fp32 path: 32 columns [n0, n0+32) of rows [row0, row0+32); v = this lane's row (row0 + lane).
-// The residual (which the engine aliases with the output: x += ...) is fetched into registers by
-// prefetch_resid BEFORE the accumulator is read, so its latency hides behind tcgen05.ld and the math and the
-// eight loads are not serialised behind the eight stores.
-__device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, int row0, int n0, float4 (&rr)[8]) {
+// The residual (which the engine aliases with the output: x += ...) is fetched into registers BEFORE the
+// accumulator is read, so its latency hides behind tcgen05.ld and the loads are not serialised behind stores.
+__device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, int row0, int n0, float4 (&rr)[4]) {
   const Epi& e = p.e;
-  const int pc = lane & 7;
+  const int pc = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int grow = row0 + (lane >> 3) + 4 * i;
+  for (int i = 0; i < 4; ++i) {
+    const int grow = row0 + (lane >> 2) + 8 * i;
     rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e.resid && grow < p.M)
-      rr[i] = *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(grow) * e.ldr + n0 + pc * 4);
+    if (e.resid && grow < p.M) {
+      const float* src = e.resid + static_cast<size_t>(grow) * e.ldr + n0 + pc * 4;
+      rr[i] = p.ld_policy ? ld_global_v4f_hint(src, p.ld_policy) : *reinterpret_cast<const float4*>(src);
+    }
   }
 }
 
+// fp32 path: 16 columns [n0, n0+16) of rows [row0, row0+32); v = this lane's row (row0 + lane);
+// bias4 = this lane's slice of the warp's bias, chunk = index of the 16-column chunk inside the warp's 128.
 __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
-                                                   float (&v)[32], const float4 (&rr)[8], const float* sbias) {
+                                                   float (&v)[16], const float4 (&rr)[4], const float4& bias4,
+                                                   int chunk) {
   const Epi& e = p.e;
-  if (e.bias) {  // sbias: this chunk's 32 bias values in shared memory (all lanes read the same address)
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 b = *reinterpret_cast<const float4*>(sbias + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
-  }
-  if (e.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, false);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 4; ++j)
     *reinterpret_cast<float4*>(stg + stg_off(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
-  const int pc = lane & 7;
+  const int pc = lane & 3;
+  const int src = chunk * 4 + pc;
+  float4 bb;
+  bb.x = __shfl_sync(0xffffffffu, bias4.x, src); bb.y = __shfl_sync(0xffffffffu, bias4.y, src);
+  bb.z = __shfl_sync(0xffffffffu, bias4.z, src); bb.w = __shfl_sync(0xffffffffu, bias4.w, src);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = (lane >> 3) + 4 * i;
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
     const int grow = row0 + r;
     float4 x = *reinterpret_cast<const float4*>(stg + stg_off(r, pc));
+    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+    if (e.act != ACT_NONE) {
+      x.x = apply_act(x.x, e.act, false); x.y = apply_act(x.y, e.act, false);
+      x.z = apply_act(x.z, e.act, false); x.w = apply_act(x.w, e.act, false);
+    }
     if (grow < p.M) {
       const int col = n0 + pc * 4;
       x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
-      if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col) = x;
+      if (e.out_f32) {
+        float* dst = e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col;
+        if (p.st_policy) st_global_v4f_hint(dst, x, p.st_policy);
+        else *reinterpret_cast<float4*>(dst) = x;
+      }
       if (e.out_act) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
         uint2 u;
@@ -336,17 +345,17 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
   __syncwarp();
 }
 
-// bf16-only path (no residual, no fp32 output): a chunk is 64 columns [n0, n0+64) = one 128-byte row of the
-// transpose buffer, filled in two 32-column halves so only 32 accumulator values are live at a time.
-__device__ __forceinline__ void epilogue_bf16_half(const PGemmParams& p, uint8_t* stg, int lane, int n0, int half,
-                                                   float (&v)[32], const float* sbias) {
+// bf16-only path (no residual, no fp32 output): 32 columns [n0, n0+32) per chunk = 64-byte rows of bf16.
+__device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
+                                                    float (&v)[32], const float4& bias4, int chunk) {
   const Epi& e = p.e;
-  if (e.bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 b = *reinterpret_cast<const float4*>(sbias + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
+  for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
+    const int src = chunk * 8 + jj;
+    v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
+    v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+    v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+    v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
@@ -361,19 +370,20 @@ __device__ __forceinline__ void epilogue_bf16_half(const PGemmParams& p, uint8_t
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
     u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(stg + stg_off(lane, half * 4 + j)) = u;
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = u;
   }
-}
-__device__ __forceinline__ void epilogue_bf16_store(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0) {
-  const Epi& e = p.e;
   __syncwarp();
-  const int pc = lane & 7;
+  const int pc = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = (lane >> 3) + 4 * i;
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
     const int grow = row0 + r;
     const uint4 x = *reinterpret_cast<const uint4*>(stg + stg_off(r, pc));
-    if (grow < p.M) *reinterpret_cast<uint4*>(e.out_act + static_cast<size_t>(grow) * e.ldo_act + n0 + pc * 8) = x;
+    if (grow < p.M) {
+      bf16* dst = e.out_act + static_cast<size_t>(grow) * e.ldo_act + n0 + pc * 8;
+      if (p.st_policy) st_global_v4_hint(dst, x, p.st_policy);
+      else *reinterpret_cast<uint4*>(dst) = x;
+    }
   }
   __syncwarp();
 }
@@ -384,8 +394,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const PGemmParams p) {
   using SL = PSmem<CG, ARES>;
   constexpr int STAGES = SL::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t psmem[];
+  uint8_t* smem = psmem;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* sA = smem;
   uint8_t* sStage = smem + SL::A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
@@ -508,25 +519,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 2) >> 2;
     uint32_t acc = 0, acc_ph = 0;
     const uint32_t tempty_addr0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
-    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 4096;
-    float* sbias = reinterpret_cast<float*>(smem + SL::BIAS_OFF + (warp - 2) * 512);
+    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
     const bool bf16_only = p.e.out_act && !p.e.out_f32 && !p.e.resid;
     for (long long u = u0; u < u1; ++u) {
       const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
-      {
-        // this warp's 128 bias values -> shared memory, while the tensor core is still busy with the tile
-        const int nb = n * PBN + half * (PBN / 2) + lane * 4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.e.bias && nb + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + nb));
-        __syncwarp();
-        *reinterpret_cast<float4*>(sbias + lane * 4) = bv;
-        __syncwarp();
-      }
+      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      const int nbase = n * PBN + half * (PBN / 2);
+      // this lane's 4 bias values of the warp's 128 columns (loaded while the tensor core is still busy)
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.e.bias && nbase + lane * 4 + 4 <= p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
-      const int nbase = n * PBN + half * (PBN / 2);
       auto release = [&]() {
         // everything this warp needs from the accumulator is in registers: hand the buffer back to the MMA
         tc_fence_before();
@@ -546,25 +550,36 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_bf16_half(p, stg, lane, nbase + (c >> 1) * 64, c & 1, v, sbias + c * 32);
-          if (c & 1) epilogue_bf16_store(p, stg, lane, row0, nbase + (c >> 1) * 64);
+          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
+        }
+      } else if (nbase + PBN / 2 <= p.N) {
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int n0 = nbase + c * 16;
+          float4 rr[4];
+          prefetch_resid(p, lane, row0, n0, rr);
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
+          tmem_ld_wait();
+          if (c == 7) release();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c);
         }
       } else {
+        // ragged last n tile (N not a multiple of 128): plain row-per-thread epilogue
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int n0 = nbase + c * 32;
-          float4 rr[8];
-          if (n0 + 32 <= p.N) prefetch_resid(p, lane, row0, n0, rr);
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
           if (c == 3) release();
-          float v[32];
+          const int n0 = nbase + c * 32;
+          if (row0 + lane < p.M && n0 < p.N) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (n0 + 32 <= p.N) {
-            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, sbias + c * 32);
-          } else if (row0 + lane < p.M && n0 < p.N) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             GemmParams gp;
             gp.M = p.M; gp.N = p.N; gp.K = p.K; gp.split = 0; gp.e = p.e;
             epilogue_chunk(gp, row0 + lane, n0, v);
@@ -577,6 +592,239 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused MLP of one transformer block: x += fc2(act(fc1(h))) in ONE persistent launch.
+// Each CTA pair takes 256-row tiles; per tile it runs the F/256 fc1 units (h x W1^T, bias, activation) whose
+// bf16 results go to a per-CTA scratch tile [128, F] that is re-used for every tile (it stays in L2: the
+// [M, F] intermediate, 8 KB of HBM traffic per token row, never exists), then the H/256 fc2 units read that
+// scratch tile back through TMA as their A operand (bias, + residual, fp32 out).  fc2's k blocks 4j..4j+3 only
+// need fc1 unit j, so the producer waits on per-unit "ready" barriers and the tensor core never idles between
+// the two GEMMs.  Same pipeline as gemm_persist_kernel<2, false>: 6-stage TMA ring of (A 16 KB | B 16 KB),
+// tcgen05 cta_group::2 256x256x16 MMAs, two 256-column TMEM accumulators, 8 epilogue warps.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MLP_MAX_N1 = 16;
+
+struct MlpParams {
+  int M, m_tiles, H, F;
+  const float* bias1;
+  const float* bias2;
+  bf16* scratch;       // [gridDim.x * 128, F]
+  const float* resid;  // x, fp32 [M, ldr]
+  int ldr;
+  float* out_f32;      // new x (may alias resid)
+  int ldo_f32;
+  bf16* out_act;       // optional bf16 copy of the new x
+  int ldo_act;
+  int act;
+};
+
+struct MlpSmem {
+  static constexpr int STAGE = 2 * BM * BK * 2;  // A 16 KB + B 16 KB
+  static constexpr int STAGES = 6;
+  static constexpr int STG_OFF = STAGES * STAGE;
+  static constexpr int BAR_OFF = STG_OFF + P_EPI_WARPS * 2048;
+  static constexpr int N_BARS = 2 * STAGES + 4 + MLP_MAX_N1;
+  static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
+                   const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW2,
+                   const MlpParams p) {
+  using SL = MlpSmem;
+  constexpr int CG = 2;
+  constexpr int STAGES = SL::STAGES;
+  extern __shared__ __align__(1024) uint8_t psmem[];
+  uint8_t* smem = psmem;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sStage = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* fready_bar = tempty_bar + 2;  // [n1]: fc1 unit j of the current tile is in the scratch tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fready_bar + MLP_MAX_N1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_groups = gridDim.x / CG;
+  const int group = blockIdx.x / CG;
+  const int n1 = p.F / PBN, n2 = p.H / PBN;      // fc1 / fc2 units per tile
+  const int nkb1 = p.H / BK, nkb2 = p.F / BK;    // k blocks of fc1 / fc2
+  const int kb_per_unit1 = PBN / BK;             // fc2 k blocks produced by one fc1 unit (4)
+  const int srow0 = blockIdx.x * BM;             // this CTA's rows of the scratch tensor
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmF); tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], CG * P_EPI_WARPS); }
+    for (int j = 0; j < MLP_MAX_N1; ++j) mbar_init(&fready_bar[j], P_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg<CG>(tmem_slot, 512);
+    tmem_relinquish_cg<CG>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; uint32_t tile_it = 0;
+      for (int m = group; m < p.m_tiles; m += n_groups, ++tile_it) {
+        const int arow = (m * CG + static_cast<int>(cta_rank)) * BM;
+        for (int u = 0; u < n1 + n2; ++u) {
+          const bool is1 = u < n1;
+          const int n = is1 ? u : u - n1;
+          const int nkb = is1 ? nkb1 : nkb2;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (!is1 && (kb % kb_per_unit1) == 0) {
+              // scratch columns [64 kb, 64 kb + 256) were written by the epilogue of fc1 unit kb / 4 (generic
+              // proxy); make them visible to the TMA (async proxy) read below
+              mbar_wait(&fready_bar[kb / kb_per_unit1], tile_it & 1);
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+            if (!is1 && p.resid) {
+              const int rows_per_kb = (BM + nkb - 1) / nkb;
+              const int r_lo = arow + kb * rows_per_kb;
+              const int r_hi = min(min(r_lo + rows_per_kb, arow + BM), p.M);
+              for (int r = r_lo; r < r_hi; ++r)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.resid + static_cast<size_t>(r) * p.ldr + n * PBN),
+                             "r"(PBN * 4) : "memory");
+            }
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * SL::STAGE);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            uint8_t* st = sStage + s * SL::STAGE;
+            // L2 priorities: the scratch tile and the weights are the re-used data; h streams through once
+            if (is1) {
+              tma_load_2d_pair_hint(st, &tmH, bar, kb * BK, arow, L2_EVICT_FIRST);
+              tma_load_2d_pair_hint(st + SL::STAGE / 2, &tmW1, bar, kb * BK, n * PBN + static_cast<int>(cta_rank) * BM, L2_EVICT_LAST);
+            } else {
+              tma_load_2d_pair_hint(st, &tmF, bar, kb * BK, srow0, L2_EVICT_LAST);
+              tma_load_2d_pair_hint(st + SL::STAGE / 2, &tmW2, bar, kb * BK, n * PBN + static_cast<int>(cta_rank) * BM, L2_EVICT_LAST);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, PBN);
+      int s = 0; uint32_t ph = 0; uint32_t acc = 0, acc_ph = 0;
+      for (int m = group; m < p.m_tiles; m += n_groups) {
+        for (int u = 0; u < n1 + n2; ++u) {
+          const int nkb = u < n1 ? nkb1 : nkb2;
+          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * PBN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sStage + s * SL::STAGE);
+            const uint32_t b0 = a0 + SL::STAGE / 2;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
+              const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
+              umma_bf16_cg<CG>(d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_cg<CG>(&empty_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit_cg<CG>(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint32_t acc = 0, acc_ph = 0;
+    const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
+    // fc1 epilogue: bf16 into this CTA's scratch tile; fc2 epilogue: fp32 (+ residual) into x
+    PGemmParams p1{}, p2{};
+    p1.M = 0x7fffffff; p1.N = p.F; p1.K = p.H;
+    p1.e.out_act = p.scratch; p1.e.ldo_act = p.F; p1.e.act = p.act;
+    p2.M = p.M; p2.N = p.H; p2.K = p.F;
+    p2.e.resid = p.resid; p2.e.ldr = p.ldr; p2.e.out_f32 = p.out_f32; p2.e.ldo_f32 = p.ldo_f32;
+    p2.e.out_act = p.out_act; p2.e.ldo_act = p.ldo_act; p2.e.act = ACT_NONE;
+    p1.st_policy = L2_EVICT_LAST;                                   // scratch tile: keep in L2 until fc2 has read it
+    p2.st_policy = L2_EVICT_FIRST; p2.ld_policy = L2_EVICT_FIRST;   // the residual stream passes through once
+    for (int m = group; m < p.m_tiles; m += n_groups) {
+      for (int u = 0; u < n1 + n2; ++u) {
+        const bool is1 = u < n1;
+        const int n = is1 ? u : u - n1;
+        const int nbase = n * PBN + half * (PBN / 2);
+        const float* bias = is1 ? p.bias1 : p.bias2;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bias4 = __ldg(reinterpret_cast<const float4*>(bias + nbase + lane * 4));
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + acc * 8);
+        };
+        if (is1) {
+          const int row0 = srow0 + q * 32;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if (c == 3) release();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_bf16_chunk(p1, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          }
+          // publish this warp's part of fc1 unit u to the TMA reads of the fc2 units
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&fready_bar[u]);
+        } else {
+          const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            const int n0 = nbase + c * 16;
+            float4 rr[4];
+            prefetch_resid(p2, lane, row0, n0, rr);
+            uint32_t r[16];
+            tmem_ld16(taddr + c * 16, r);
+            tmem_ld_wait();
+            if (c == 7) release();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_f32_chunk(p2, stg, lane, row0, n0, v, rr, bias4, c);
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_cg<CG>(tmem_base, 512);
@@ -691,8 +939,60 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
 }
 
 int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+int mlp_scratch_rows() { return (sm_count() / 2) * 2 * BM; }
+
+bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W2, bf16* scratch, int act,
+                      const float* resid, int ldr, float* out_f32, int ldo_f32, bf16* out_act, int ldo_act,
+                      cudaStream_t st) {
+  if (M <= 0) return true;
+  const int H = W1.K, F = W1.N;
+  if (W2.K != F || W2.N != H || Hin.K != H || (H % PBN) || (F % PBN) || F / PBN > MLP_MAX_N1) {
+    set_error("mlp_fused: unsupported shape");
+    return false;
+  }
+  ++g_launches;
+  ProfScope prof_(CAT_GEMM, 4.0 * M * static_cast<double>(H) * F, st);
+  const int grid = (sm_count() / 2) * 2;
+  CUtensorMap th, tf;
+  if (!make_tmap_bf16_2d(&th, Hin.p, static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(Hin.ld), BM))
+    return false;
+  if (!make_tmap_bf16_2d(&tf, scratch, static_cast<uint64_t>(grid) * BM, static_cast<uint64_t>(F), static_cast<uint64_t>(F), BM))
+    return false;
+  MlpParams p;
+  p.M = M; p.m_tiles = (M + 2 * BM - 1) / (2 * BM); p.H = H; p.F = F;
+  p.bias1 = W1.bias; p.bias2 = W2.bias; p.scratch = scratch;
+  p.resid = resid; p.ldr = ldr; p.out_f32 = out_f32; p.ldo_f32 = ldo_f32; p.out_act = out_act; p.ldo_act = ldo_act;
+  p.act = act;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = MlpSmem::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, mlp_persist_kernel, th, W1.tmap128, tf, W2.tmap128, p), "mlp_persist launch");
+}
+
+static bool configure_mlp() {
+  return cuda_ok(cudaFuncSetAttribute(mlp_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::DYN_BYTES),
+                 "cudaFuncSetAttribute(mlp_persist)");
+}
 
 bool gemm_configure() {
+  if (!configure_mlp()) return false;
   if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>()))
     return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&

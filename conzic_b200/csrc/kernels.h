@@ -74,6 +74,13 @@ bool gemm_configure();  // opt-in to large dynamic shared memory for every insta
 bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st,
                    uint64_t* launches);
 
+// Fused MLP (bf16 mode): x_out = resid + fc2(act(fc1(Hin))) in one persistent launch; `scratch` is a bf16
+// buffer of mlp_scratch_rows() x W1.N elements that holds the per-CTA fc1 tiles (L2 resident, re-used per tile).
+int mlp_scratch_rows();
+bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W2, bf16* scratch, int act,
+                      const float* resid, int ldr, float* out_f32, int ldo_f32, bf16* out_act, int ldo_act,
+                      cudaStream_t st);
+
 // ---- transformer pieces (transformer_ops.cu) ---------------------------------------------------------
 void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, int ldd, int split, cudaStream_t st);
 

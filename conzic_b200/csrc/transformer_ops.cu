@@ -324,6 +324,26 @@ __device__ __forceinline__ void att_load_rows(const bf16* __restrict__ src, int 
   }
 }
 
+// Batched variant for up to 16 rows: all loads are issued before the first shared-memory store, so the warp
+// pays ONE global-memory latency per call (the plain loop above serialises load -> store per 4 rows).
+// Rows are consecutive global rows starting at `base`.
+__device__ __forceinline__ void att_fetch16(const bf16* __restrict__ src, int ld, int col0, int base, int n_rows,
+                                            int lane, uint4 (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane;
+    const int row = min(idx >> 3, n_rows - 1);  // clamp instead of predicate: keeps r[] in registers, loads stay in bounds
+    r[i] = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(base + row) * ld + col0 + (idx & 7) * 8);
+  }
+}
+__device__ __forceinline__ void att_put16(uint8_t* tile, int dst0, int n_rows, int lane, const uint4 (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane;
+    if ((idx >> 3) < n_rows) *reinterpret_cast<uint4*>(tile + sw_off(dst0 + (idx >> 3), idx & 7)) = r[i];
+  }
+}
+
 template <int NT>  // NT key tiles of 8: up to NT*8 keys per tile
 __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
@@ -375,11 +395,18 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   for (int idx = lane; idx < (NT * 8 - pl) * 8; idx += 32)
     *reinterpret_cast<uint4*>(sV + sw_off(pl + (idx >> 3), idx & 7)) = make_uint4(0, 0, 0, 0);
   if (!is_prefix && pl > 0) {
-    att_load_rows(qkv, ld, col_k, pre_base, pl, 0, pl, sK, 0, lane);
-    att_load_rows(qkv, ld, col_v, pre_base, pl, 0, pl, sV, 0, lane);
+    for (int r0 = 0; r0 < pl; r0 += 16) {
+      uint4 rk[4], rv[4];
+      const int nr = min(16, pl - r0);
+      att_fetch16(qkv, ld, col_k, pre_base + r0, nr, lane, rk);
+      att_fetch16(qkv, ld, col_v, pre_base + r0, nr, lane, rv);
+      att_put16(sK, r0, nr, lane, rk);
+      att_put16(sV, r0, nr, lane, rv);
+    }
   }
   const int g = lane >> 2, qd = lane & 3;
   const int lm_r = lane & 7, lm_m = lane >> 3;  // ldmatrix: row within the 8x8 matrix, matrix index
+  const float sl2 = a.scale * 1.4426950408889634f;
 
   for (int k = k0; k < k1; k += cpt) {
     const int nc = min(cpt, k1 - k);
@@ -388,14 +415,31 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
     const int own_base = is_prefix ? pre_base : n_pre_rows + (b * a.K + k) * a.S;
     const bool single = n_own <= 16;
     __syncwarp();
-    att_load_rows(qkv, ld, col_k, own_base, n_own, 0, n_own, sK, pl, lane);
-    att_load_rows(qkv, ld, col_v, own_base, n_own, 0, n_own, sV, pl, lane);
-    if (single) att_load_rows(qkv, ld, col_q, own_base, n_own, 0, n_own, sQ, 0, lane);
+    if (single) {
+      uint4 rk[4], rv[4], rq[4];
+      att_fetch16(qkv, ld, col_k, own_base, n_own, lane, rk);
+      att_fetch16(qkv, ld, col_v, own_base, n_own, lane, rv);
+      att_fetch16(qkv, ld, col_q, own_base, n_own, lane, rq);
+      att_put16(sK, pl, n_own, lane, rk);
+      att_put16(sV, pl, n_own, lane, rv);
+      att_put16(sQ, 0, n_own, lane, rq);
+    } else {
+      for (int r0 = 0; r0 < n_own; r0 += 16) {
+        uint4 rk[4], rv[4];
+        const int nr = min(16, n_own - r0);
+        att_fetch16(qkv, ld, col_k, own_base + r0, nr, lane, rk);
+        att_fetch16(qkv, ld, col_v, own_base + r0, nr, lane, rv);
+        att_put16(sK, pl + r0, nr, lane, rk);
+        att_put16(sV, pl + r0, nr, lane, rv);
+      }
+    }
     for (int mt = 0; mt * 16 < n_own; ++mt) {
       const int q_rows = min(16, n_own - mt * 16);
       if (!single) {
         __syncwarp();
-        att_load_rows(qkv, ld, col_q, own_base + mt * 16, q_rows, 0, q_rows, sQ, 0, lane);
+        uint4 rq[4];
+        att_fetch16(qkv, ld, col_q, own_base + mt * 16, q_rows, lane, rq);
+        att_put16(sQ, 0, q_rows, lane, rq);
       }
       __syncwarp();
       uint32_t qa[4][4];
@@ -435,10 +479,10 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
         const bool v01 = a.causal ? (j + 1 < pl || (j + 1 >= lo0 && j + 1 <= hi0)) : (j + 1 < nk);
         const bool v10 = a.causal ? (j < pl || (j >= lo1 && j <= hi1)) : (j < nk);
         const bool v11 = a.causal ? (j + 1 < pl || (j + 1 >= lo1 && j + 1 <= hi1)) : (j + 1 < nk);
-        sc[nt][0] = v00 ? sc[nt][0] * a.scale : -INFINITY;
-        sc[nt][1] = v01 ? sc[nt][1] * a.scale : -INFINITY;
-        sc[nt][2] = v10 ? sc[nt][2] * a.scale : -INFINITY;
-        sc[nt][3] = v11 ? sc[nt][3] * a.scale : -INFINITY;
+        sc[nt][0] = v00 ? sc[nt][0] * sl2 : -INFINITY;   // scores in log2 units: exp(x) = exp2(x * log2 e)
+        sc[nt][1] = v01 ? sc[nt][1] * sl2 : -INFINITY;
+        sc[nt][2] = v10 ? sc[nt][2] * sl2 : -INFINITY;
+        sc[nt][3] = v11 ? sc[nt][3] * sl2 : -INFINITY;
         m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
         m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
       }
@@ -449,8 +493,8 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        sc[nt][0] = expf(sc[nt][0] - m0); sc[nt][1] = expf(sc[nt][1] - m0);
-        sc[nt][2] = expf(sc[nt][2] - m1); sc[nt][3] = expf(sc[nt][3] - m1);
+        sc[nt][0] = exp2f(sc[nt][0] - m0); sc[nt][1] = exp2f(sc[nt][1] - m0);
+        sc[nt][2] = exp2f(sc[nt][2] - m1); sc[nt][3] = exp2f(sc[nt][3] - m1);
         s0 += sc[nt][0] + sc[nt][1];
         s1 += sc[nt][2] + sc[nt][3];
       }

@@ -242,6 +242,19 @@ class Engine:
         _lib.check(rc, "conzic_debug_linear")
         return out
 
+    def debug_mlp(self, X, W1, b1, W2, b2, act: int = 1):
+        """X + fc2(act(fc1(X))) through the fused persistent MLP kernel (bf16 mode)."""
+        M, H = X.shape
+        F = W1.shape[0]
+        out = torch.empty((M, H), dtype=torch.float32, device=self.device)
+        need = (M * H + 2 * H * F + 160 * 128 * F) * 2 + 8192
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self.lib.conzic_debug_mlp(self.ctx, _ptr(X.contiguous()), _ptr(W1.contiguous()), _ptr(b1),
+                                       _ptr(W2.contiguous()), _ptr(b2), M, H, F, int(act), _ptr(out), _ptr(ws),
+                                       ws.numel(), self._stream())
+        _lib.check(rc, "conzic_debug_mlp")
+        return out
+
     # ------------------------------------------------------------------ the fused step
     def gibbs_step(self, inp: torch.Tensor, token_mask: torch.Tensor, image_embeds: torch.Tensor, pos: int,
                    dot_allowed: bool, K: int, temperature: float, alpha: float, beta: float,

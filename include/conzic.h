@@ -171,6 +171,13 @@ int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev,
                         const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
 
+/* Fused MLP entry used by tests: out[M,H] = X + fc2(act(fc1(X))) with X f32[M,H] (the residual; its bf16
+ * rounding is the GEMM operand), W1 f32[F,H], b1[F], W2 f32[H,F], b2[H] -- one launch of the persistent
+ * fc1+fc2 kernel the CLIP tower uses (HF:models/clip/modeling_clip.py:347-351,380-384).  bf16 mode only. */
+int conzic_debug_mlp(conzic_ctx* ctx, const float* X_dev, const float* W1_dev, const float* b1_dev,
+                     const float* W2_dev, const float* b2_dev, int M, int H, int F, int act, float* out_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,50 @@ def test_tcgen05_matches_simt_debug_kernel():
     torch.testing.assert_close(a.debug_linear(A, W), b.debug_linear(A, W), rtol=0, atol=2e-4)
 
 
+@pytest.mark.parametrize("mode", ["f32", "f32+resid", "bf16", "bf16+gelu"])
+@pytest.mark.parametrize("shape", [(700, 1536, 512), (20000, 512, 512), (333, 2048, 512), (4096, 512, 2048),
+                                   (75776, 512, 512)])
+def test_persistent_pair_gemm_all_epilogues(mode, shape):
+    """gemm_persist_kernel (CTA pairs, cta_group::2): every epilogue path against fp64 on bf16-rounded operands;
+    M tails, A-resident (K=512) and streamed (K=2048) operands, whole-wave M."""
+    M, N, K = shape
+    eng = gc.engine("bf16", "tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if mode == "f32+resid" else None
+    act = {"f32": 0, "f32+resid": 0, "bf16": 16, "bf16+gelu": 17}[mode]
+    out = eng.debug_linear(A, W, bias, resid, act)
+    ref = _ref_linear(A, W, bias, resid, act & 15, True)
+    if act & 16:  # bf16 output: one bf16 ulp (2^-8 relative) of slack; quick-gelu uses tanh.approx (~2^-11)
+        assert float(((out - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 2 ** -7
+    else:
+        assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M", [256, 1000, 37888 + 77])
+def test_fused_mlp_matches_fp64(M):
+    """mlp_persist_kernel: x + fc2(quick_gelu(fc1(x))) with the bf16 intermediate kept in the per-CTA scratch
+    tile, against fp64 with the same bf16 rounding points (operands and intermediate)."""
+    eng = gc.engine("bf16", "tcgen05")
+    H, F = 512, 2048
+    g = torch.Generator(device="cuda").manual_seed(M)
+    X = torch.randn(M, H, device="cuda", generator=g)
+    W1 = torch.randn(F, H, device="cuda", generator=g) * 0.04
+    W2 = torch.randn(H, F, device="cuda", generator=g) * 0.02
+    b1 = torch.randn(F, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(H, device="cuda", generator=g) * 0.1
+    out = eng.debug_mlp(X, W1, b1, W2, b2, act=1)
+    xb, w1, w2 = X.bfloat16().double(), W1.bfloat16().double(), W2.bfloat16().double()
+    h = xb @ w1.t() + b1.double()
+    h = (h * torch.sigmoid(1.702 * h)).float().bfloat16().double()
+    ref = (X.double() + h @ w2.t() + b2.double()).float()
+    # the intermediate is rounded to bf16 from slightly different fp32 values: allow a few flipped roundings
+    assert float((out - ref).abs().max()) < 2e-2
+    assert float((out - ref).abs().mean()) < 1e-3
+
+
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-3), ("bf16", 0.08)])
 def test_bert_row_logits_vs_oracle(prec, tol):
     from oracle import conzic_oracle as orc
