@@ -188,7 +188,7 @@ struct Plan {
   int64_t *ids, *ids_masked;
   int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx, *pool_rows;
   // CLIP chunk
-  float* cx;
+  float *cx, *cxe;
   bf16 *ch, *cattn, *cffn, *cpool, *cscratch;
   void* cqkv;
   float* text;
@@ -237,6 +237,7 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   p.cpool = b.take<bf16>(BK * Hc * (1 + s));
   p.cscratch = b.take<bf16>(c->mlp_fused ? static_cast<size_t>(mlp_scratch_rows()) * Fc : 1);
   p.text = b.take<float>(BK * g.clip_proj);
+  p.cxe = b.take<float>(BK * Hc);
   p.bytes = align_up(b.off, 256);
   return p;
 }
@@ -330,8 +331,11 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     const int32_t* ids = ids_suffix + static_cast<size_t>(b0) * K * S;
     const int32_t* p0c = p0 ? p0 + b0 : nullptr;
     launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, st);
+    const int NE = nb * K;  // candidate captions of this chunk = rows that are pooled (one EOS row each)
+    float* xe = p.cxe + static_cast<size_t>(b0) * K * H;
     for (size_t l = 0; l < c->clip.size(); ++l) {
       const Layer& ly = c->clip[l];
+      const bool last = (l + 1 == c->clip.size());
       LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
       launch_layernorm(ln1, st);
       Act h{p.ch, ldh, H};
@@ -344,29 +348,45 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
       at.B = nb; at.P = P; at.K = K; at.S = S; at.H = H; at.heads = g.clip_heads; at.causal = 1;
       at.scale = scale; at.out_act = p.cattn; at.ld_act = ldh; at.split = s;
       if (!launch_attention(at, st)) return false;
-      Act a{p.cattn, ldh, H};
-      if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr)) return false;
-      LNArgs ln2{p.cx, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+      // The tower's output is read at ONE row per caption (its first EOS) and a row of the last block depends on
+      // other rows only through this block's attention: after it, only the EOS rows go on (exact, not an
+      // approximation).  Rows are compacted: attention out -> ch, residual -> xe; LN2 output re-uses cattn.
+      int Mr = M;
+      float* x = p.cx;
+      bf16 *a_in = p.cattn, *h2 = p.ch;
+      if (last) {
+        launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
+        launch_gather_rows(p.cattn, static_cast<size_t>(ldh) * sizeof(bf16), p.pool_rows, NE, p.ch, st);
+        launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
+        Mr = NE; x = xe; a_in = p.ch; h2 = p.cattn;
+      }
+      Act a{a_in, ldh, H};
+      if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), c->gopt, st, nullptr)) return false;
+      LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
       launch_layernorm(ln2, st);
+      Act hh{h2, ldh, H};
       if (c->mlp_fused) {
-        if (!launch_mlp_fused(h, M, ly.f1, ly.f2, p.cscratch, ACT_QUICK_GELU, p.cx, H, p.cx, H, nullptr, 0, st)) return false;
+        if (!launch_mlp_fused(hh, Mr, ly.f1, ly.f2, p.cscratch, ACT_QUICK_GELU, x, H, x, H, nullptr, 0, st)) return false;
       } else {
-        if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
+        if (!launch_linear(hh, Mr, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
           return false;
         Act f{p.cffn, ldf, F};
-        if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.cx, H, p.cx, H, ACT_NONE), c->gopt, st, nullptr))
+        if (!launch_linear(f, Mr, ly.f2, epi_f32_out(ly.f2, x, H, x, H, ACT_NONE), c->gopt, st, nullptr))
           return false;
       }
     }
-    // pooled = final LN of the hidden state at the first EOS; text_projection without bias
-    launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
-    LNArgs lnf{p.cx, p.pool_rows, nb * K, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
+    if (c->clip.empty()) {  // degenerate 0-layer tower: pool straight from the embeddings
+      launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
+      launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
+    }
+    // pooled = final LN of the hidden state at the first EOS (already compacted); text_projection without bias
+    LNArgs lnf{xe, nullptr, NE, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
     launch_layernorm(lnf, st);
     Act pooled{p.cpool, ldh, H};
     Epi e;
     e.out_f32 = text + static_cast<size_t>(b0) * K * g.clip_proj;
     e.ldo_f32 = g.clip_proj;
-    if (!launch_linear(pooled, nb * K, c->c_proj, e, c->gopt, st, nullptr)) return false;
+    if (!launch_linear(pooled, NE, c->c_proj, e, c->gopt, st, nullptr)) return false;
   }
   return cuda_ok(cudaGetLastError(), "clip_encode");
 }

@@ -97,6 +97,8 @@ struct LNArgs {
 };
 void launch_layernorm(const LNArgs& a, cudaStream_t st);
 
+void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, int n, void* dst, cudaStream_t st);
+
 void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st);

@@ -541,6 +541,17 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   }
 }
 
+// dst row r = src row rows[r]; rows of `row_bytes` bytes (a multiple of 16).  One warp per row.
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, size_t row_bytes, const int32_t* __restrict__ rows,
+                                   int n, uint8_t* __restrict__ dst) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < n; r += gridDim.x * warps) {
+    const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(rows[r]) * row_bytes);
+    uint4* d = reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * row_bytes);
+    for (int i = lane; i < static_cast<int>(row_bytes >> 4); i += 32) d[i] = s[i];
+  }
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -569,6 +580,14 @@ void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, in
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   f32_to_act_kernel<<<grid, 256, 0, st>>>(src, rows, K, lds, dst, ldd, split);
+}
+
+void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, int n, void* dst, cudaStream_t st) {
+  ++g_launches;
+  ProfScope prof_(CAT_MISC, 0, st);
+  if (n <= 0) return;
+  gather_rows_kernel<<<row_grid(n, 8), 256, 0, st>>>(static_cast<const uint8_t*>(src), row_bytes, rows, n,
+                                                     static_cast<uint8_t*>(dst));
 }
 
 void launch_layernorm(const LNArgs& a, cudaStream_t st) {
