@@ -81,6 +81,10 @@ __global__ void add_one_kernel(int32_t* v, int n) {
 struct Layer {
   LinearW qkv, o, f1, f2;
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  // LayerNorm folded into the consuming linear (CLIP, bf16 persistent path): W' = gamma * W, bias' = b + W beta,
+  // s[n] = sum_k W'[n,k]
+  LinearW qkv_f, f1_f;
+  float *qkv_s = nullptr, *f1_s = nullptr;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -120,7 +124,8 @@ struct conzic_ctx {
   // bert id -> clip ids
   int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
   int max_tok_per_word = 1;
-  int chunk_rows = 75776;
+  int chunk_rows = 303104;
+  int ln_fold = 0;    // LayerNorm folded into QKV / fc1 of the CLIP tower (bf16 persistent path)
   int mlp_fused = 0;  // fc1 + fc2 of a CLIP block in one persistent launch (bf16 mode, CTA pairs)
   uint64_t launches0 = 0;
 
@@ -140,6 +145,26 @@ struct conzic_ctx {
     return d;
   }
   int ldw(int K) const { return split ? 2 * K : K; }
+  // Folded copy of `parts` stacked fp32 [n_i, K] blocks sharing one LayerNorm (gamma, beta) on their input.
+  bool make_folded(LinearW* L, float** s_out, const void* const* w_parts, const void* const* b_parts, const int* n_parts,
+                   int parts, int K, const float* gamma, const float* beta, cudaStream_t st) {
+    int N = 0;
+    for (int i = 0; i < parts; ++i) N += n_parts[i];
+    L->N = N; L->K = K;
+    L->w = dalloc<bf16>(static_cast<size_t>(N) * K);
+    float* bias = dalloc<float>(N);
+    float* sv = dalloc<float>(N);
+    if (!L->w || !bias || !sv) return false;
+    int r0 = 0;
+    for (int i = 0; i < parts; ++i) {
+      launch_fold_ln(static_cast<const float*>(w_parts[i]), b_parts ? static_cast<const float*>(b_parts[i]) : nullptr, gamma,
+                     beta, n_parts[i], K, L->w + static_cast<size_t>(r0) * K, sv + r0, bias + r0, st);
+      r0 += n_parts[i];
+    }
+    L->bias = bias;
+    *s_out = sv;
+    return make_tmap_bf16_2d(&L->tmap128, L->w, N, K, K, 128) && make_tmap_bf16_2d(&L->tmap256, L->w, N, K, K, 256);
+  }
   // Build a LinearW from `parts` row blocks of fp32 [n_i, K] (e.g. q, k, v stacked into one [3H, K]).
   bool make_linear(LinearW* L, const void* const* w_parts, const void* const* b_parts, const int* n_parts, int parts,
                    int K, cudaStream_t st) {
@@ -189,6 +214,8 @@ struct Plan {
   int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx, *pool_rows;
   // CLIP chunk
   float *cx, *cxe;
+  bf16* cxb;
+  float2* cstats;
   bf16 *ch, *cattn, *cffn, *cpool, *cscratch;
   void* cqkv;
   float* text;
@@ -238,6 +265,8 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   p.cscratch = b.take<bf16>(c->mlp_fused ? static_cast<size_t>(mlp_scratch_rows()) * Fc : 1);
   p.text = b.take<float>(BK * g.clip_proj);
   p.cxe = b.take<float>(BK * Hc);
+  p.cxb = b.take<bf16>(c->ln_fold ? Mc * Hc : 1);
+  p.cstats = b.take<float2>(c->ln_fold ? Mc * 4 : 1);
   p.bytes = align_up(b.off, 256);
   return p;
 }
@@ -330,19 +359,41 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     const int32_t* idp = P > 0 ? ids_prefix + static_cast<size_t>(b0) * P : nullptr;
     const int32_t* ids = ids_suffix + static_cast<size_t>(b0) * K * S;
     const int32_t* p0c = p0 ? p0 + b0 : nullptr;
-    launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, st);
+    const bool fold = c->ln_fold && !s;
+    launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, fold ? p.cxb : nullptr,
+                      fold ? p.cstats : nullptr, 4, st);
+    // folded-LN epilogues: a GEMM that writes the residual stream also writes its bf16 copy and row statistics;
+    // the GEMM that would consume LN(x) reads them instead (Epi in kernels.h)
+    auto epi_ln_consumer = [&](const LinearW& W, const float* sv, bf16* out, int ld, int act) {
+      Epi e;
+      e.bias = W.bias; e.out_act = out; e.ldo_act = ld; e.act = act;
+      e.ln_s = sv; e.ln_stats = p.cstats; e.ln_parts = 4; e.ln_width = H; e.ln_eps = g.clip_ln_eps;
+      return e;
+    };
+    auto epi_x_producer = [&](const LinearW& W, float* x, bool want_ln) {
+      Epi e = epi_f32_out(W, x, H, x, H, ACT_NONE);
+      if (want_ln) { e.out_act = p.cxb; e.ldo_act = H; e.stats_out = p.cstats; e.stats_parts = 4; }
+      return e;
+    };
     const int NE = nb * K;  // candidate captions of this chunk = rows that are pooled (one EOS row each)
     float* xe = p.cxe + static_cast<size_t>(b0) * K * H;
     for (size_t l = 0; l < c->clip.size(); ++l) {
       const Layer& ly = c->clip[l];
       const bool last = (l + 1 == c->clip.size());
-      LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
-      launch_layernorm(ln1, st);
-      Act h{p.ch, ldh, H};
-      Epi e;
-      if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
-      else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.cqkv), 3 * H, 0, ACT_NONE);
-      if (!launch_linear(h, M, ly.qkv, e, c->gopt, st, nullptr)) return false;
+      if (fold) {
+        Act xb{p.cxb, H, H};
+        if (!launch_linear(xb, M, ly.qkv_f, epi_ln_consumer(ly.qkv_f, ly.qkv_s, static_cast<bf16*>(p.cqkv), 3 * H, ACT_NONE),
+                           c->gopt, st, nullptr))
+          return false;
+      } else {
+        LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+        launch_layernorm(ln1, st);
+        Act h{p.ch, ldh, H};
+        Epi e;
+        if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
+        else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.cqkv), 3 * H, 0, ACT_NONE);
+        if (!launch_linear(h, M, ly.qkv, e, c->gopt, st, nullptr)) return false;
+      }
       AttnArgs at;
       at.qkv = p.cqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = p0c;
       at.B = nb; at.P = P; at.K = K; at.S = S; at.H = H; at.heads = g.clip_heads; at.causal = 1;
@@ -361,6 +412,17 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
         Mr = NE; x = xe; a_in = p.ch; h2 = p.cattn;
       }
       Act a{a_in, ldh, H};
+      if (fold) {
+        // O-proj writes x, bf16(x) and the row statistics; fc1 applies LN2 in its epilogue; fc2 does the same for
+        // the next block's LN1 (after the last block the plain final LayerNorm kernel follows)
+        if (!launch_linear(a, Mr, ly.o, epi_x_producer(ly.o, x, true), c->gopt, st, nullptr)) return false;
+        Act xb{p.cxb, H, H};
+        if (!launch_linear(xb, Mr, ly.f1_f, epi_ln_consumer(ly.f1_f, ly.f1_s, p.cffn, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
+          return false;
+        Act f{p.cffn, F, F};
+        if (!launch_linear(f, Mr, ly.f2, epi_x_producer(ly.f2, x, !last), c->gopt, st, nullptr)) return false;
+        continue;
+      }
       if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), c->gopt, st, nullptr)) return false;
       LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
       launch_layernorm(ln2, st);
@@ -442,13 +504,17 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->gopt.cg = 2;
   if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_CG")) c->gopt.cg = atoi(e);
+  // LayerNorm folded into the consuming GEMM's epilogue (no LN kernels, no normalised copy of x in HBM)
+  c->ln_fold = (c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
+  if (const char* e = getenv("CONZIC_LN_FOLD")) c->ln_fold = c->ln_fold && atoi(e);
   // fc1+fc2 in one launch (mlp_persist_kernel): measured equal to the two-launch path on B200 (the 78 MB of
   // per-CTA scratch tiles do not survive in L2 between fc1 and fc2), so it is opt-in: CONZIC_MLP_FUSED=1
   c->mlp_fused = 0;
   if (const char* e = getenv("CONZIC_MLP_FUSED"))
     c->mlp_fused = (atoi(e) && c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
-  // default: 4 x (148 SMs x 128 rows) token rows per pass -- whole waves of the persistent GEMM's 128-row tiles
-  c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 75776;
+  // default: 16 x (148 SMs x 128 rows) token rows per pass; measured on B200: the larger the pass the better
+  // (every kernel is a persistent or grid-stride launch; nothing stays L2 resident between kernels anyway)
+  c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 303104;
   if (const char* e = getenv("CONZIC_CLIP_CHUNK_ROWS")) c->chunk_rows = atoi(e);
   bool ok = true;
   if (cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ok = tma_init() && gemm_configure();
@@ -509,6 +575,10 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
     const void* wg[1] = {t[14]}; const void* bg[1] = {t[15]}; int ng[1] = {Hc};
     ok = ok && c->make_linear(&ly.f2, wg, bg, ng, 1, Fc, st);
     ok = ok && ly.ln1_g && ly.ln1_b && ly.ln2_g && ly.ln2_b;
+    if (ok && c->ln_fold) {
+      ok = c->make_folded(&ly.qkv_f, &ly.qkv_s, wq, bq, nq, 3, Hc, ly.ln1_g, ly.ln1_b, st) &&
+           c->make_folded(&ly.f1_f, &ly.f1_s, wf, bf, nf, 1, Hc, ly.ln2_g, ly.ln2_b, st);
+    }
     c->clip.push_back(ly);
   }
   ok = ok && cuda_ok(cudaStreamSynchronize(st), "ctx_create sync");

@@ -305,7 +305,7 @@ __device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, i
 // bias4 = this lane's slice of the warp's bias, chunk = index of the 16-column chunk inside the warp's 128.
 __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
                                                    float (&v)[16], const float4 (&rr)[4], const float4& bias4,
-                                                   int chunk) {
+                                                   int chunk, float (&st1)[4], float (&st2)[4]) {
   const Epi& e = p.e;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -329,6 +329,10 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
     if (grow < p.M) {
       const int col = n0 + pc * 4;
       x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
+      if (e.stats_out) {  // LayerNorm statistics of the values being written, for the next GEMM's folded LN
+        st1[i] += (x.x + x.y) + (x.z + x.w);
+        st2[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+      }
       if (e.out_f32) {
         float* dst = e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col;
         if (p.st_policy) st_global_v4f_hint(dst, x, p.st_policy);
@@ -345,17 +349,63 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
   __syncwarp();
 }
 
-// bf16-only path (no residual, no fp32 output): 32 columns [n0, n0+32) per chunk = 64-byte rows of bf16.
-__device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
-                                                    float (&v)[32], const float4& bias4, int chunk) {
-  const Epi& e = p.e;
+// After a warp's 8 chunks: lanes 4r..4r+3 hold partial sums of the same rows; fold them and let lane 4r write
+// the (sum, sum of squares) of this warp's 128 columns of rows (lane >> 2) + 8 i.
+__device__ __forceinline__ void flush_row_stats(const PGemmParams& p, int lane, int row0, int slice, float (&st1)[4],
+                                                float (&st2)[4]) {
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
-    const int src = chunk * 8 + jj;
-    v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
-    v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
-    v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
-    v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
+  for (int i = 0; i < 4; ++i) {
+    float a = st1[i], b = st2[i];
+    a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+    const int grow = row0 + (lane >> 2) + 8 * i;
+    if ((lane & 3) == 0 && grow < p.M)
+      p.e.stats_out[static_cast<size_t>(grow) * p.e.stats_parts + slice] = make_float2(a, b);
+  }
+}
+
+// Row statistics for the folded LayerNorm of a consumer GEMM: mean and 1/std of row `grow` from its partials.
+__device__ __forceinline__ void load_row_ln(const PGemmParams& p, int grow, float& rstd, float& t) {
+  rstd = 0.f; t = 0.f;
+  if (grow >= p.M) return;
+  float s1 = 0.f, s2 = 0.f;
+  const float2* st = p.e.ln_stats + static_cast<size_t>(grow) * p.e.ln_parts;
+  for (int j = 0; j < p.e.ln_parts; ++j) {
+    const float2 v = st[j];
+    s1 += v.x; s2 += v.y;
+  }
+  const float inv = 1.0f / static_cast<float>(p.e.ln_width);
+  const float mean = s1 * inv;
+  const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+  rstd = rsqrtf(var + p.e.ln_eps);
+  t = -rstd * mean;
+}
+
+// bf16-only path (no residual, no fp32 output): 32 columns [n0, n0+32) per chunk = 64-byte rows of bf16.
+// With a folded LayerNorm (e.ln_s): value = rstd * acc + (t * s[n] + bias[n]), t = -rstd * mean of this row.
+__device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
+                                                    float (&v)[32], const float4& bias4, int chunk,
+                                                    const float4& s4 = float4{0.f, 0.f, 0.f, 0.f}, float rstd = 1.f,
+                                                    float t = 0.f) {
+  const Epi& e = p.e;
+  if (e.ln_s) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int src = chunk * 8 + jj;
+      v[4 * jj] = fmaf(rstd, v[4 * jj], fmaf(t, __shfl_sync(0xffffffffu, s4.x, src), __shfl_sync(0xffffffffu, bias4.x, src)));
+      v[4 * jj + 1] = fmaf(rstd, v[4 * jj + 1], fmaf(t, __shfl_sync(0xffffffffu, s4.y, src), __shfl_sync(0xffffffffu, bias4.y, src)));
+      v[4 * jj + 2] = fmaf(rstd, v[4 * jj + 2], fmaf(t, __shfl_sync(0xffffffffu, s4.z, src), __shfl_sync(0xffffffffu, bias4.z, src)));
+      v[4 * jj + 3] = fmaf(rstd, v[4 * jj + 3], fmaf(t, __shfl_sync(0xffffffffu, s4.w, src), __shfl_sync(0xffffffffu, bias4.w, src)));
+    }
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
+      const int src = chunk * 8 + jj;
+      v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
+      v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+      v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+      v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
+    }
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
@@ -528,6 +578,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // this lane's 4 bias values of the warp's 128 columns (loaded while the tensor core is still busy)
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.e.bias && nbase + lane * 4 + 4 <= p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float ln_rstd = 1.f, ln_t = 0.f;
+      if (p.e.ln_s) {
+        if (nbase + lane * 4 + 4 <= p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.e.ln_s + nbase + lane * 4));
+        load_row_ln(p, row0 + lane, ln_rstd, ln_t);
+      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
@@ -550,9 +606,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c, s4, ln_rstd, ln_t);
         }
       } else if (nbase + PBN / 2 <= p.N) {
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           const int n0 = nbase + c * 16;
@@ -565,8 +622,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c);
+          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
         }
+        if (p.e.stats_out) flush_row_stats(p, lane, row0, nbase / (PBN / 2), st1, st2);
       } else {
         // ragged last n tile (N not a multiple of 128): plain row-per-thread epilogue
 #pragma unroll 1
@@ -803,6 +861,7 @@ mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
           if (lane == 0) mbar_arrive(&fready_bar[u]);
         } else {
           const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+          float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
             const int n0 = nbase + c * 16;
@@ -815,7 +874,7 @@ mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_f32_chunk(p2, stg, lane, row0, n0, v, rr, bias4, c);
+            epilogue_f32_chunk(p2, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
           }
         }
         acc ^= 1;

@@ -56,6 +56,18 @@ struct Epi {
   int ldo_act = 0;
   int out_K = 0;  // column offset of the lo plane when writing a split Act
   int act = ACT_NONE;
+  // LayerNorm folded into the GEMM (persistent kernel, bf16 mode).  Consumer side: A holds bf16(x) (NOT
+  // normalised), W holds bf16(gamma * W), `bias` holds b + W beta, ln_s[n] = sum_k W'[n,k]; with the row's
+  // mean and rstd from the partial sums in ln_stats the epilogue forms rstd*(acc - mean*ln_s[n]) + bias[n],
+  // which equals LN(x) W^T + b.  Producer side: stats_out receives per-row (sum, sum of squares) of the fp32
+  // values this GEMM writes, one float2 per 128-column slice: stats_out[row * stats_parts + slice].
+  const float* ln_s = nullptr;
+  const float2* ln_stats = nullptr;
+  int ln_parts = 0;
+  int ln_width = 0;     // number of columns the statistics cover (H)
+  float ln_eps = 0.f;
+  float2* stats_out = nullptr;
+  int stats_parts = 0;
 };
 
 struct GemmOpts {
@@ -102,8 +114,15 @@ void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, 
 void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st);
+// xb / stats optional: bf16 copy of the rows and their (sum, sum of squares) in stats[row * stats_parts + 0]
+// (the other slices are zeroed), for a consumer GEMM with folded LayerNorm.
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
-                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st);
+                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
+                       float2* stats, int stats_parts, cudaStream_t st);
+// Folds a LayerNorm into the linear layer that consumes it: w_out[n,k] = bf16(gamma[k] * w[n,k]),
+// s_out[n] = sum_k float(w_out[n,k]), bias_out[n] = bias[n] + sum_k beta[k] * w[n,k].
+void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,
+                    float* s_out, float* bias_out, cudaStream_t st);
 
 // Attention over packed token rows.  Row layout: B*P "prefix" rows (image b, position t) followed by
 // B*K*S "suffix" rows (image b, candidate k, offset s).  A suffix row attends to its image's first p0[b]

@@ -122,7 +122,8 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ inp, int rows, 
 __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const int32_t* __restrict__ ids_suffix,
                                   const int32_t* __restrict__ p0, int B, int P, int K, int S, int maxpos,
                                   const float* __restrict__ tok, const float* __restrict__ pos, int H,
-                                  float* __restrict__ x) {
+                                  float* __restrict__ x, bf16* __restrict__ xb, float2* __restrict__ stats,
+                                  int stats_parts) {
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_pre = B * P;
@@ -142,10 +143,43 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
     const float* te = tok + static_cast<size_t>(id) * H;
     const float* pe = pos + static_cast<size_t>(position) * H;
     float* o = x + static_cast<size_t>(r) * H;
+    float s1 = 0.f, s2 = 0.f;
     for (int c = lane * 4; c < H; c += 128) {
       float4 a = *reinterpret_cast<const float4*>(te + c);
       float4 b = *reinterpret_cast<const float4*>(pe + c);
-      *reinterpret_cast<float4*>(o + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      *reinterpret_cast<float4*>(o + c) = v;
+      if (xb) {
+        store_act4(xb + static_cast<size_t>(r) * H, H, 0, c, v);
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    }
+    if (stats) {
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane < stats_parts) stats[static_cast<size_t>(r) * stats_parts + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
+// LayerNorm -> Linear folding (see Epi in kernels.h).  One warp per output row n.
+__global__ void fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int N, int K, bf16* __restrict__ w_out,
+                               float* __restrict__ s_out, float* __restrict__ bias_out) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
+    const float* wr = w + static_cast<size_t>(n) * K;
+    float s = 0.f, bb = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const bf16 h = __float2bfloat16_rn(gamma[k] * wr[k]);
+      w_out[static_cast<size_t>(n) * K + k] = h;
+      s += __bfloat162float(h);
+      bb = fmaf(beta[k], wr[k], bb);
+    }
+    s = warp_sum(s); bb = warp_sum(bb);
+    if (lane == 0) {
+      s_out[n] = s;
+      bias_out[n] = (bias ? bias[n] : 0.f) + bb;
     }
   }
 }
@@ -618,13 +652,20 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 }
 
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
-                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st) {
+                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
+                       float2* stats, int stats_parts, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_EMBED, 0, st);
   const int rows = B * P + B * K * S;
   if (rows <= 0) return;
   clip_embed_kernel<<<row_grid(rows, 8), 256, 0, st>>>(ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
-                                                       x_f32);
+                                                       x_f32, xb, stats, stats_parts);
+}
+
+void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,
+                    float* s_out, float* bias_out, cudaStream_t st) {
+  ++g_launches;
+  fold_ln_kernel<<<row_grid(N, 8), 256, 0, st>>>(w, bias, gamma, beta, N, K, w_out, s_out, bias_out);
 }
 
 bool launch_attention(const AttnArgs& a, cudaStream_t st) {

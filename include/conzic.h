@@ -51,7 +51,7 @@ typedef struct conzic_config {
   int32_t clip_bos, clip_eos;  /* 49406 / 49407; pad id == eos id (clip/clip.py:71-72) */
   int32_t precision;           /* CONZIC_PREC_* */
   int32_t gemm_impl;           /* CONZIC_GEMM_* */
-  int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (75776 = 4 waves of 148 x 128-row tiles) */
+  int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (303104 = 16 waves of 148 x 128-row tiles) */
 } conzic_config;
 
 /* ---- weight tables: arrays of fp32 DEVICE pointers in this order (HF state-dict tensors) -------------

@@ -140,6 +140,36 @@ def test_clip_text_encode_vs_oracle(prec, tol):
         assert float((out - ref).abs().max()) < tol
 
 
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-4), ("bf16", 0.06)])
+def test_clip_text_encode_with_nontrivial_layernorm(prec, tol):
+    """The bf16 path folds every LayerNorm of the CLIP tower into the GEMM that consumes it (gamma into the
+    weights, beta into the bias, mean / rstd applied in the epilogue from statistics the previous GEMM wrote).
+    The synthetic checkpoint has gamma = 1, beta = 0, so perturb them here and compare with the oracle."""
+    from conzic_b200.engine import Engine
+    from oracle import conzic_oracle as orc
+    sd = {k: v.clone() for k, v in gc.weights("clip").items()}
+    g = torch.Generator().manual_seed(11)
+    for k in sd:
+        if "layer_norm" in k and k.startswith("text_model"):
+            if k.endswith(".weight"):
+                sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
+            else:
+                sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+    eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision=prec)
+    torch.manual_seed(3)
+    for N, T in ((300, 9), (41, 16)):
+        ids = torch.randint(300, 40000, (N, T))
+        ids[:, 0] = synth.CLIP_BOS
+        lens = torch.randint(2, T + 1, (N,))
+        for i in range(N):
+            ids[i, lens[i] - 1:] = synth.CLIP_EOS
+        with torch.no_grad():
+            ref = orc.clip_text_embeds(sd, ids)
+        out = eng.clip_text_encode(ids.int().cuda()).cpu()
+        assert float((out - ref).abs().max()) < tol
+    eng.close()
+
+
 def test_similarity_vs_oracle():
     from oracle import conzic_oracle as orc
     eng = gc.engine("bf16x3")
