@@ -21,6 +21,7 @@ EXPORTS = [
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
     "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_debug_mlp",
+    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode",
 ]
 
 
@@ -34,6 +35,11 @@ class Config(C.Structure):
         ("mask_id", C.c_int32), ("dot_id", C.c_int32), ("clip_bos", C.c_int32), ("clip_eos", C.c_int32),
         ("precision", C.c_int32), ("gemm_impl", C.c_int32), ("clip_chunk_rows", C.c_int32),
     ]
+
+
+class VisionConfig(C.Structure):
+    _fields_ = [("layers", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32), ("ffn", C.c_int32),
+                ("image_size", C.c_int32), ("patch", C.c_int32), ("proj", C.c_int32), ("ln_eps", C.c_float)]
 
 
 class StepArgs(C.Structure):
@@ -82,6 +88,12 @@ def _declare(lib):
     lib.conzic_debug_linear.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
     lib.conzic_debug_mlp.restype = C.c_int
     lib.conzic_debug_mlp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
+    lib.conzic_set_vision.restype = C.c_int
+    lib.conzic_set_vision.argtypes = [vp, C.POINTER(VisionConfig), C.POINTER(vp), i32, vp]
+    lib.conzic_vision_workspace_bytes.restype = sz
+    lib.conzic_vision_workspace_bytes.argtypes = [vp, i32]
+    lib.conzic_clip_image_encode.restype = C.c_int
+    lib.conzic_clip_image_encode.argtypes = [vp, vp, i32, vp, vp, sz, vp]
     lib.conzic_profile.restype = C.c_int
     lib.conzic_profile.argtypes = [vp, i32]
     lib.conzic_profile_read.restype = C.c_int

@@ -6,7 +6,6 @@ from typing import Dict, Optional
 
 import torch
 
-from .. import vision
 
 
 class CLIP:
@@ -25,7 +24,6 @@ class CLIP:
         self.tokenizer = tokenizer
         self.processor = processor
         self.device = torch.device("cpu")
-        self._vis_sd = None
 
     # nn.Module-ish surface used by run.py / demo.py
     def state_dict(self):
@@ -36,7 +34,6 @@ class CLIP:
 
     def to(self, device):
         self.device = torch.device(device)
-        self._vis_sd = None
         return self
 
     def _engine(self):
@@ -51,11 +48,8 @@ class CLIP:
 
     @torch.no_grad()
     def compute_image_representation_from_pixels(self, pixel_values):
-        eng = self._engine()
-        if self._vis_sd is None:
-            self._vis_sd = {k: v.to(eng.device, torch.float32) for k, v in self._sd.items()
-                            if k.startswith("vision_model.") or k == "visual_projection.weight"}
-        return vision.image_embeds(self._vis_sd, pixel_values.to(eng.device, torch.float32))
+        """Vision tower on the engine's own sm_100a kernels (conzic_clip_image_encode)."""
+        return self._engine().image_encode(pixel_values)
 
     @torch.no_grad()
     def compute_image_representation_from_image_path(self, image_path):

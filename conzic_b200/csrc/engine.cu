@@ -121,6 +121,12 @@ struct conzic_ctx {
   float *c_tok = nullptr, *c_pos = nullptr, *c_fln_g = nullptr, *c_fln_b = nullptr;
   LinearW c_proj;
   std::vector<Layer> clip;
+  // CLIP image tower (optional; conzic_set_vision)
+  conzic_vision_config vcfg{};
+  bool has_vision = false;
+  LinearW v_patch, v_proj;
+  float *v_cls = nullptr, *v_pos = nullptr, *v_pre_g = nullptr, *v_pre_b = nullptr, *v_post_g = nullptr, *v_post_b = nullptr;
+  std::vector<Layer> vis;
   // bert id -> clip ids
   int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
   int max_tok_per_word = 1;
@@ -255,7 +261,10 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   p.p0 = b.take<int32_t>(B);
   p.eos_idx = b.take<int32_t>(BK);
   p.pool_rows = b.take<int32_t>(BK);
-  const size_t Mc = chunk_cap_rows(c, K);
+  // rows of one pass: the configured chunk, but never more than B images can produce (77 * (K + 1) rows each)
+  size_t Mc = chunk_cap_rows(c, K);
+  const size_t most = static_cast<size_t>(B > 0 ? B : 1) * c->cfg.clip_maxpos * (K + 1);
+  if (Mc > most) Mc = most;
   p.cx = b.take<float>(Mc * Hc);
   p.ch = b.take<bf16>(Mc * Hc * (1 + s));
   p.cattn = b.take<bf16>(Mc * Hc * (1 + s));
@@ -504,9 +513,12 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->gopt.cg = 2;
   if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_CG")) c->gopt.cg = atoi(e);
-  // LayerNorm folded into the consuming GEMM's epilogue (no LN kernels, no normalised copy of x in HBM)
-  c->ln_fold = (c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
-  if (const char* e = getenv("CONZIC_LN_FOLD")) c->ln_fold = c->ln_fold && atoi(e);
+  // LayerNorm folded into the consuming GEMM's epilogue (no LN kernels).  Measured on B200 (profiles/r01f_ab.md):
+  // the stand-alone LN kernels stream at 5.3 TB/s while the same bytes moved by GEMM epilogues go slower, so the
+  // fold costs ~1 % of a step instead of saving time; it is therefore opt-in: CONZIC_LN_FOLD=1
+  c->ln_fold = 0;
+  if (const char* e = getenv("CONZIC_LN_FOLD"))
+    c->ln_fold = (atoi(e) && c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
   // fc1+fc2 in one launch (mlp_persist_kernel): measured equal to the two-launch path on B200 (the 78 MB of
   // per-CTA scratch tiles do not survive in L2 between fc1 and fc2), so it is opt-in: CONZIC_MLP_FUSED=1
   c->mlp_fused = 0;
@@ -765,6 +777,129 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
     ++g_launches;
   }
   return cuda_ok(cudaGetLastError(), "debug_linear") ? 0 : -4;
+}
+
+// ---- CLIP image tower -------------------------------------------------------------------------------
+namespace {
+struct VPlan {
+  bf16 *patches, *h, *attn, *ffn, *pool;
+  float *pe, *x;
+  void* qkv;
+  size_t bytes;
+};
+VPlan make_vplan(const conzic_ctx* c, void* ws, int B) {
+  const conzic_vision_config& v = c->vcfg;
+  const int s = c->split, H = v.hidden, F = v.ffn;
+  const int g2 = (v.image_size / v.patch) * (v.image_size / v.patch), T = g2 + 1, Kp = 3 * v.patch * v.patch;
+  const size_t M = static_cast<size_t>(B) * T;
+  Bump b(ws, 0);
+  VPlan p;
+  p.patches = b.take<bf16>(static_cast<size_t>(B) * g2 * Kp * (1 + s));
+  p.pe = b.take<float>(static_cast<size_t>(B) * g2 * H);
+  p.x = b.take<float>(M * H);
+  p.h = b.take<bf16>(M * H * (1 + s));
+  p.attn = b.take<bf16>(M * H * (1 + s));
+  p.ffn = b.take<bf16>(M * F * (1 + s));
+  p.qkv = b.take<char>(M * 3 * H * (s ? 4 : 2));
+  p.pool = b.take<bf16>(static_cast<size_t>(B) * H * (1 + s));
+  p.bytes = align_up(b.off, 256);
+  return p;
+}
+}  // namespace
+
+int conzic_set_vision(conzic_ctx* c, const conzic_vision_config* vc, const void* const* w, int n, void* stream) {
+  if (!c || !vc || !w) { set_error("set_vision: null argument"); return -1; }
+  if (n != 8 + CONZIC_PER_LAYER * vc->layers) { set_error("set_vision: weight table length does not match the layer count"); return -1; }
+  if (vc->hidden != vc->heads * 64 || (vc->patch % 4) || (vc->image_size % vc->patch)) { set_error("set_vision: unsupported shape"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  c->vcfg = *vc;
+  const int H = vc->hidden, F = vc->ffn, Kp = 3 * vc->patch * vc->patch;
+  const int T = (vc->image_size / vc->patch) * (vc->image_size / vc->patch) + 1;
+  bool ok = true;
+  { const void* wp[1] = {w[0]}; int np[1] = {H}; ok = c->make_linear(&c->v_patch, wp, nullptr, np, 1, Kp, st); }
+  c->v_cls = c->copy_f32(w[1], H, st);
+  c->v_pos = c->copy_f32(w[2], static_cast<size_t>(T) * H, st);
+  c->v_pre_g = c->copy_f32(w[3], H, st); c->v_pre_b = c->copy_f32(w[4], H, st);
+  c->v_post_g = c->copy_f32(w[5], H, st); c->v_post_b = c->copy_f32(w[6], H, st);
+  { const void* wp[1] = {w[7]}; int np[1] = {vc->proj}; ok = ok && c->make_linear(&c->v_proj, wp, nullptr, np, 1, H, st); }
+  ok = ok && c->v_cls && c->v_pos && c->v_pre_g && c->v_pre_b && c->v_post_g && c->v_post_b;
+  c->vis.clear();
+  for (int l = 0; ok && l < vc->layers; ++l) {
+    const void* const* t = w + 8 + CONZIC_PER_LAYER * l;
+    Layer ly;
+    ly.ln1_g = c->copy_f32(t[0], H, st); ly.ln1_b = c->copy_f32(t[1], H, st);
+    const void* wq[3] = {t[2], t[4], t[6]}; const void* bq[3] = {t[3], t[5], t[7]}; int nq[3] = {H, H, H};
+    ok = c->make_linear(&ly.qkv, wq, bq, nq, 3, H, st);
+    const void* wo[1] = {t[8]}; const void* bo[1] = {t[9]}; int no[1] = {H};
+    ok = ok && c->make_linear(&ly.o, wo, bo, no, 1, H, st);
+    ly.ln2_g = c->copy_f32(t[10], H, st); ly.ln2_b = c->copy_f32(t[11], H, st);
+    const void* wf[1] = {t[12]}; const void* bf[1] = {t[13]}; int nf[1] = {F};
+    ok = ok && c->make_linear(&ly.f1, wf, bf, nf, 1, H, st);
+    const void* wg[1] = {t[14]}; const void* bg[1] = {t[15]}; int ng[1] = {H};
+    ok = ok && c->make_linear(&ly.f2, wg, bg, ng, 1, F, st);
+    ok = ok && ly.ln1_g && ly.ln1_b && ly.ln2_g && ly.ln2_b;
+    c->vis.push_back(ly);
+  }
+  ok = ok && cuda_ok(cudaStreamSynchronize(st), "set_vision sync");
+  c->has_vision = ok;
+  return ok ? 0 : -3;
+}
+
+size_t conzic_vision_workspace_bytes(const conzic_ctx* c, int B) {
+  if (!c || !c->has_vision) return 0;
+  return make_vplan(c, nullptr, B).bytes;
+}
+
+int conzic_clip_image_encode(conzic_ctx* c, const float* pix, int B, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!c || !pix || !out || !ws) { set_error("clip_image_encode: null argument"); return -1; }
+  if (!c->has_vision) { set_error("clip_image_encode: conzic_set_vision has not been called"); return -1; }
+  if (B < 1) { set_error("clip_image_encode: B < 1"); return -1; }
+  VPlan p = make_vplan(c, ws, B);
+  if (ws_bytes < p.bytes) { set_error("clip_image_encode: workspace too small, need " + std::to_string(p.bytes)); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const conzic_vision_config& v = c->vcfg;
+  const int s = c->split, H = v.hidden, F = v.ffn, Kp = 3 * v.patch * v.patch;
+  const int g2 = (v.image_size / v.patch) * (v.image_size / v.patch), T = g2 + 1;
+  const int M = B * T, ldh = H * (1 + s), ldf = F * (1 + s);
+  // patch embedding = GEMM over unfolded patches (conv with stride = kernel, no bias)
+  launch_im2col(pix, B, v.image_size, v.patch, p.patches, Kp * (1 + s), s, st);
+  Act pa{p.patches, Kp * (1 + s), Kp};
+  Epi e0; e0.out_f32 = p.pe; e0.ldo_f32 = H;
+  if (!launch_linear(pa, B * g2, c->v_patch, e0, c->gopt, st, nullptr)) return -4;
+  launch_vision_embed(p.pe, c->v_cls, c->v_pos, B, T, H, p.x, st);
+  LNArgs pre{p.x, nullptr, M, H, c->v_pre_g, c->v_pre_b, v.ln_eps, p.x, nullptr, 0, 0};  // in place: a warp owns a row
+  launch_layernorm(pre, st);
+  for (size_t l = 0; l < c->vis.size(); ++l) {
+    const Layer& ly = c->vis[l];
+    LNArgs ln1{p.x, nullptr, M, H, ly.ln1_g, ly.ln1_b, v.ln_eps, nullptr, p.h, ldh, s};
+    launch_layernorm(ln1, st);
+    Act h{p.h, ldh, H};
+    Epi e;
+    if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.qkv), 3 * H, nullptr, 0, ACT_NONE);
+    else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.qkv), 3 * H, 0, ACT_NONE);
+    if (!launch_linear(h, M, ly.qkv, e, c->gopt, st, nullptr)) return -4;
+    AttnArgs at;
+    at.qkv = p.qkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = nullptr;
+    at.B = B; at.P = 0; at.K = 1; at.S = T; at.H = H; at.heads = v.heads; at.causal = 0;
+    at.scale = 0.125f; at.out_act = p.attn; at.ld_act = ldh; at.split = s;
+    if (!launch_attention(at, st)) return -4;
+    Act a{p.attn, ldh, H};
+    if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.x, H, p.x, H, ACT_NONE), c->gopt, st, nullptr)) return -4;
+    LNArgs ln2{p.x, nullptr, M, H, ly.ln2_g, ly.ln2_b, v.ln_eps, nullptr, p.h, ldh, s};
+    launch_layernorm(ln2, st);
+    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.ffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr)) return -4;
+    Act f{p.ffn, ldf, F};
+    if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.x, H, p.x, H, ACT_NONE), c->gopt, st, nullptr)) return -4;
+  }
+  // pooled = post_layernorm(hidden[:, 0]) (row stride T*H) -> visual_projection
+  LNArgs post{p.x, nullptr, B, H, c->v_post_g, c->v_post_b, v.ln_eps, nullptr, p.pool, ldh, s};
+  post.x_row_stride = static_cast<size_t>(T) * H;
+  launch_layernorm(post, st);
+  Act pooled{p.pool, ldh, H};
+  Epi e;
+  e.out_f32 = out; e.ldo_f32 = v.proj;
+  if (!launch_linear(pooled, B, c->v_proj, e, c->gopt, st, nullptr)) return -4;
+  return cuda_ok(cudaGetLastError(), "clip_image_encode") ? 0 : -4;
 }
 
 int conzic_debug_mlp(conzic_ctx* c, const float* X, const float* W1f, const float* b1, const float* W2f, const float* b2,

@@ -106,9 +106,15 @@ struct LNArgs {
   float* out_f32;      // optional [n_rows, H]
   bf16* out_act;       // optional Act [n_rows, ld]
   int ld_act, split;
+  size_t x_row_stride = 0;  // elements between input rows; 0 = H (dense)
 };
 void launch_layernorm(const LNArgs& a, cudaStream_t st);
 
+// Image patches as GEMM rows: pix f32[B,3,S,S] -> Act [B*g*g, 3*p*p] (channel, py, px order = conv weight layout)
+void launch_im2col(const float* pix, int B, int S, int p, bf16* dst, int ldd, int split, cudaStream_t st);
+// x[b,0,:] = cls + pos[0]; x[b,1+i,:] = patch[b*g2+i,:] + pos[1+i]    (HF:models/clip/modeling_clip.py:190-200)
+void launch_vision_embed(const float* patch, const float* cls, const float* pos, int B, int T, int H, float* x,
+                         cudaStream_t st);
 void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, int n, void* dst, cudaStream_t st);
 
 void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,

@@ -84,7 +84,7 @@ __global__ void layernorm_kernel(LNArgs a) {
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < a.n_rows; r += gridDim.x * warps) {
     const int src = a.rows ? a.rows[r] : r;
-    const float* x = a.x + static_cast<size_t>(src) * a.H;
+    const float* x = a.x + static_cast<size_t>(src) * (a.x_row_stride ? a.x_row_stride : static_cast<size_t>(a.H));
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
@@ -575,6 +575,37 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   }
 }
 
+__global__ void im2col_kernel(const float* __restrict__ pix, int B, int S, int p, bf16* __restrict__ dst, int ldd,
+                              int split) {
+  const int g = S / p, K = 3 * p * p;
+  const size_t total = static_cast<size_t>(B) * g * g * (K / 4);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % (K / 4)) * 4;
+    const size_t row = i / (K / 4);
+    const int b = static_cast<int>(row / (g * g)), pi = static_cast<int>(row % (g * g));
+    const int c = k / (p * p), rem = k % (p * p), py = rem / p, px = rem % p;  // px % 4 == 0 (p % 4 == 0)
+    const float4 v = *reinterpret_cast<const float4*>(
+        pix + ((static_cast<size_t>(b) * 3 + c) * S + (pi / g) * p + py) * S + (pi % g) * p + px);
+    store_act4(dst + row * ldd, K, split, k, v);
+  }
+}
+
+__global__ void vision_embed_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, int B, int T, int H, float* __restrict__ x) {
+  const size_t total = static_cast<size_t>(B) * T * (H / 4);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (H / 4)) * 4;
+    const size_t row = i / (H / 4);
+    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    const float4 a = t == 0 ? *reinterpret_cast<const float4*>(cls + c)
+                            : *reinterpret_cast<const float4*>(patch + (static_cast<size_t>(b) * (T - 1) + (t - 1)) * H + c);
+    const float4 q = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * H + c);
+    *reinterpret_cast<float4*>(x + row * H + c) = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
 // dst row r = src row rows[r]; rows of `row_bytes` bytes (a multiple of 16).  One warp per row.
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, size_t row_bytes, const int32_t* __restrict__ rows,
                                    int n, uint8_t* __restrict__ dst) {
@@ -614,6 +645,27 @@ void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, in
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   f32_to_act_kernel<<<grid, 256, 0, st>>>(src, rows, K, lds, dst, ldd, split);
+}
+
+void launch_im2col(const float* pix, int B, int S, int p, bf16* dst, int ldd, int split, cudaStream_t st) {
+  ++g_launches;
+  ProfScope prof_(CAT_EMBED, 0, st);
+  const size_t total = static_cast<size_t>(B) * (S / p) * (S / p) * (3 * p * p / 4);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  if (grid < 1) grid = 1;
+  im2col_kernel<<<grid, 256, 0, st>>>(pix, B, S, p, dst, ldd, split);
+}
+
+void launch_vision_embed(const float* patch, const float* cls, const float* pos, int B, int T, int H, float* x,
+                         cudaStream_t st) {
+  ++g_launches;
+  ProfScope prof_(CAT_EMBED, 0, st);
+  const size_t total = static_cast<size_t>(B) * T * (H / 4);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 16) grid = num_sms() * 16;
+  if (grid < 1) grid = 1;
+  vision_embed_kernel<<<grid, 256, 0, st>>>(patch, cls, pos, B, T, H, x);
 }
 
 void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, int n, void* dst, cudaStream_t st) {

@@ -116,7 +116,11 @@ class Engine:
         ls = clip_sd.get("logit_scale")
         self.logit_scale_exp = float(torch.as_tensor(ls).float().exp()) if ls is not None else 100.0
         self._ws = None
+        self._vws = None
+        self.vision_cfg = None
         self.has_table = False
+        if "vision_model.embeddings.patch_embedding.weight" in clip_sd:
+            self.set_vision(clip_sd)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -171,6 +175,56 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         self.max_tok_per_word = max(w, 1)
         self.has_table = True
+
+    # ------------------------------------------------------------------ image tower (once per call)
+    def set_vision(self, clip_sd: SD):
+        """Uploads the CLIP vision tower (clip/clip.py:48-62) from an HF CLIPModel state dict."""
+        v = "vision_model."
+        n = _count_layers(clip_sd, v + "encoder.layers.{}.layer_norm1.weight")
+        names = [v + "embeddings.patch_embedding.weight", v + "embeddings.class_embedding",
+                 v + "embeddings.position_embedding.weight", v + "pre_layrnorm.weight", v + "pre_layrnorm.bias",
+                 v + "post_layernorm.weight", v + "post_layernorm.bias", "visual_projection.weight"]
+        for i in range(n):
+            q = f"{v}encoder.layers.{i}."
+            names += [q + "layer_norm1.weight", q + "layer_norm1.bias",
+                      q + "self_attn.q_proj.weight", q + "self_attn.q_proj.bias",
+                      q + "self_attn.k_proj.weight", q + "self_attn.k_proj.bias",
+                      q + "self_attn.v_proj.weight", q + "self_attn.v_proj.bias",
+                      q + "self_attn.out_proj.weight", q + "self_attn.out_proj.bias",
+                      q + "layer_norm2.weight", q + "layer_norm2.bias",
+                      q + "mlp.fc1.weight", q + "mlp.fc1.bias", q + "mlp.fc2.weight", q + "mlp.fc2.bias"]
+        ts = [clip_sd[k].detach().to(self.device, torch.float32).contiguous() for k in names]
+        arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        patch = clip_sd[names[0]]
+        H, ps = patch.shape[0], patch.shape[-1]
+        tokens = clip_sd[names[2]].shape[0]
+        grid = int(round((tokens - 1) ** 0.5))
+        vc = _lib.VisionConfig()
+        vc.layers, vc.hidden, vc.heads = n, H, H // 64
+        vc.ffn = clip_sd[f"{v}encoder.layers.0.mlp.fc1.weight"].shape[0]
+        vc.image_size, vc.patch, vc.proj = grid * ps, ps, clip_sd["visual_projection.weight"].shape[0]
+        vc.ln_eps = _dims.CLIP_LN_EPS
+        _lib.check(self.lib.conzic_set_vision(self.ctx, C.byref(vc), arr, len(ts), self._stream()), "conzic_set_vision")
+        del ts
+        self.vision_cfg = vc
+        self._vws = None
+
+    def image_encode(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """CLIP.compute_image_representation_from_image_instance after the processor: f32[B,3,S,S] -> f32[B,proj]."""
+        if getattr(self, "vision_cfg", None) is None:
+            raise RuntimeError("Engine.set_vision has not been called (the checkpoint has no vision tower?)")
+        pix = pixel_values.to(self.device, torch.float32).contiguous()
+        B = pix.shape[0]
+        assert pix.shape[1:] == (3, self.vision_cfg.image_size, self.vision_cfg.image_size), pix.shape
+        out = torch.empty((B, self.vision_cfg.proj), dtype=torch.float32, device=self.device)
+        need = int(self.lib.conzic_vision_workspace_bytes(self.ctx, B))
+        if self._vws is None or self._vws.numel() < need:
+            self._vws = None
+            self._vws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self.lib.conzic_clip_image_encode(self.ctx, _ptr(pix), B, _ptr(out), _ptr(self._vws), self._vws.numel(),
+                                               self._stream())
+        _lib.check(rc, "conzic_clip_image_encode")
+        return out
 
     # ------------------------------------------------------------------ pieces
     def bert_mlm_row(self, inp: torch.Tensor, pos: int) -> torch.Tensor:

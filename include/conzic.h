@@ -171,6 +171,24 @@ int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev,
                         const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
 
+/* ---- CLIP image tower (clip/clip.py:48-62; HF:models/clip/modeling_clip.py:676-686): once per call, before the
+ * Gibbs loop.  Weight table (fp32 device pointers, n = 8 + 16*layers):
+ *   0 patch_embedding.weight[H,3,p,p] 1 class_embedding[H] 2 position_embedding[T,H] 3 pre_layrnorm g 4 b
+ *   5 post_layernorm g 6 b 7 visual_projection.weight[proj,H]
+ *   per layer l at 8+16*l: same 16 entries as the text tower (ln1.g ln1.b q.w q.b k.w k.b v.w v.b out.w out.b
+ *   ln2.g ln2.b fc1.w fc1.b fc2.w fc2.b). */
+typedef struct conzic_vision_config {
+  int32_t layers, hidden, heads, ffn, image_size, patch, proj;
+  float ln_eps;
+} conzic_vision_config;
+int conzic_set_vision(conzic_ctx* ctx, const conzic_vision_config* vc, const void* const* weights_dev, int n,
+                      void* stream);
+size_t conzic_vision_workspace_bytes(const conzic_ctx* ctx, int B);
+/* pixel_values f32[B,3,S,S] dev (already resized / normalised by the caller's processor) -> image_embeds
+ * f32[B,proj] dev (not L2-normalised, like compute_image_representation_from_image_instance). */
+int conzic_clip_image_encode(conzic_ctx* ctx, const float* pixel_values_dev, int B, float* image_embeds_dev,
+                             void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Fused MLP entry used by tests: out[M,H] = X + fc2(act(fc1(X))) with X f32[M,H] (the residual; its bf16
  * rounding is the GEMM operand), W1 f32[F,H], b1[F], W2 f32[H,F], b2[H] -- one launch of the persistent
  * fc1+fc2 kernel the CLIP tower uses (HF:models/clip/modeling_clip.py:347-351,380-384).  bf16 mode only. */

@@ -140,11 +140,15 @@ def test_clip_text_encode_vs_oracle(prec, tol):
         assert float((out - ref).abs().max()) < tol
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-4), ("bf16", 0.06)])
-def test_clip_text_encode_with_nontrivial_layernorm(prec, tol):
-    """The bf16 path folds every LayerNorm of the CLIP tower into the GEMM that consumes it (gamma into the
-    weights, beta into the bias, mean / rstd applied in the epilogue from statistics the previous GEMM wrote).
-    The synthetic checkpoint has gamma = 1, beta = 0, so perturb them here and compare with the oracle."""
+@pytest.mark.parametrize("prec,tol,env", [("bf16x3", 3e-4, {}), ("bf16", 0.06, {}),
+                                          ("bf16", 0.06, {"CONZIC_LN_FOLD": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_MLP_FUSED": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_GEMM_CG": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_GEMM_PERSIST": "0"})])
+def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch):
+    """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
+    the oracle, for the default path and every opt-in kernel variant: LayerNorm folded into the consuming GEMM
+    (CONZIC_LN_FOLD), fc1+fc2 in one launch (CONZIC_MLP_FUSED), single-CTA and non-persistent GEMMs."""
     from conzic_b200.engine import Engine
     from oracle import conzic_oracle as orc
     sd = {k: v.clone() for k, v in gc.weights("clip").items()}
@@ -155,6 +159,8 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol):
                 sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
             else:
                 sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+    for k, v in env.items():  # optional kernel variants are selected when the context is created
+        monkeypatch.setenv(k, v)
     eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision=prec)
     torch.manual_seed(3)
     for N, T in ((300, 9), (41, 16)):
@@ -167,6 +173,27 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol):
             ref = orc.clip_text_embeds(sd, ids)
         out = eng.clip_text_encode(ids.int().cuda()).cpu()
         assert float((out - ref).abs().max()) < tol
+    eng.close()
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+def test_clip_image_encode_vs_oracle(prec, tol):
+    """CLIP ViT-B/32 image tower on the engine's kernels (im2col + patch GEMM, pre-LN, 12 blocks with
+    bidirectional 50-token attention, post-LN of the class token, projection) against the oracle's
+    compute_image_representation (clip/clip.py:48-62)."""
+    from conzic_b200.engine import Engine
+    from oracle import conzic_oracle as orc
+    sd = synth.make_clip_state_dict(0, vision=True)
+    eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision=prec)
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(5)])
+    o = orc.Oracle(gc.weights("bert"), sd, synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(), full_logits=False)
+    with torch.no_grad():
+        ref = o.compute_image_representation(pix)
+    out = eng.image_encode(pix.cuda()).cpu()
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) < tol * float(ref.abs().max())
+    cos = torch.nn.functional.cosine_similarity(out, ref, dim=-1)
+    assert float((1 - cos).max()) < (1e-7 if prec == "bf16x3" else 2e-4)
     eng.close()
 
 
