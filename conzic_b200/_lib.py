@@ -52,6 +52,7 @@ class StepArgs(C.Structure):
         ("out_clip_ref", C.c_void_p), ("out_senti", C.c_void_p),
         ("tr_probs", C.c_void_p), ("tr_ids", C.c_void_p), ("tr_clip_score", C.c_void_p), ("tr_clip_ref", C.c_void_p),
         ("tr_final", C.c_void_p), ("tr_best", C.c_void_p), ("tr_logits", C.c_void_p),
+        ("logits_in", C.c_void_p),
     ]
 
 
@@ -112,7 +113,7 @@ def load(build_if_missing: bool = True):
         from . import build as _build
         _build.build()
     _lib = _declare(C.CDLL(LIB_PATH))
-    if _lib.conzic_abi_version() != 1:
+    if _lib.conzic_abi_version() != 2:
         raise RuntimeError("libconzic.so ABI version mismatch; rebuild with `python -m conzic_b200.build --force`")
     return _lib
 

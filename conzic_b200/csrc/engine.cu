@@ -712,7 +712,11 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   const conzic_config& g = c->cfg;
   launch_step_prologue(s->inp, B, L, pos, g.mask_id, s->token_mask, g.dot_id, s->dot_allowed, st);
   float* logits = s->tr_logits ? s->tr_logits : p.logits;
-  if (!bert_row_logits(c, s->inp, B, L, pos, logits, p.ldl, p, st)) return -4;
+  if (s->logits_in) {
+    logits = const_cast<float*>(s->logits_in);  // span order: scores from an earlier forward, no BERT here
+  } else if (!bert_row_logits(c, s->inp, B, L, pos, logits, p.ldl, p, st)) {
+    return -4;
+  }
   float* probs = s->tr_probs ? s->tr_probs : p.probs;
   int64_t* ids = s->tr_ids ? s->tr_ids : p.ids;
   if (!launch_topk(logits, p.ldl, B, g.bert_vocab, s->token_mask, s->temperature, K, probs, ids, st)) return -4;

@@ -238,6 +238,16 @@ class Engine:
         _lib.check(rc, "conzic_bert_mlm_row")
         return out[:, : self.V]
 
+    def bert_mlm_row_padded(self, inp: torch.Tensor, pos: int) -> torch.Tensor:
+        """Same as bert_mlm_row but returns the padded f32[B, ldl] buffer that gibbs_step(logits_in=...) takes."""
+        B, L = inp.shape
+        out = torch.empty((B, self.ldl), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, L, 1)
+        rc = self.lib.conzic_bert_mlm_row(self.ctx, _ptr(inp), B, L, int(pos), _ptr(out), self.ldl, _ptr(ws),
+                                          ws.numel(), self._stream())
+        _lib.check(rc, "conzic_bert_mlm_row")
+        return out
+
     def topk_mask(self, logits: torch.Tensor, token_mask: torch.Tensor, temperature: float, K: int):
         """generate_caption_step (gen_utils.py:33-49) on one row of logits per image."""
         B = logits.shape[0]
@@ -314,7 +324,8 @@ class Engine:
                    dot_allowed: bool, K: int, temperature: float, alpha: float, beta: float,
                    visited_before: int, visited_after: int, gamma: Optional[float] = None,
                    senti_table: Optional[torch.Tensor] = None, out_clip_ref: Optional[torch.Tensor] = None,
-                   out_senti: Optional[torch.Tensor] = None, trace: bool = False):
+                   out_senti: Optional[torch.Tensor] = None, trace: bool = False,
+                   logits_in: Optional[torch.Tensor] = None):
         """One position update, in place on `inp` (int64[B,L]) and `token_mask` (f32[1,V]); gen_utils.py:66-81,
         control_gen_utils.py:45-67.  Returns (clip_ref[B], senti[B] or None, trace dict or None) -- device tensors,
         nothing is synchronised."""
@@ -347,6 +358,9 @@ class Engine:
             a.tr_probs, a.tr_ids = tr["probs"].data_ptr(), tr["idxs"].data_ptr()
             a.tr_clip_score, a.tr_clip_ref = tr["clip_score"].data_ptr(), tr["clip_ref"].data_ptr()
             a.tr_final, a.tr_best, a.tr_logits = tr["final"].data_ptr(), tr["best"].data_ptr(), tr["logits"].data_ptr()
+        if logits_in is not None:  # span order: f32[B, ldl] rows from bert_mlm_row_padded
+            assert logits_in.dtype == torch.float32 and logits_in.shape == (B, self.ldl) and logits_in.is_contiguous()
+            a.logits_in = logits_in.data_ptr()
         ws = self.workspace(B, L, K)
         rc = self.lib.conzic_gibbs_step(self.ctx, C.byref(a), _ptr(ws), ws.numel(), self._stream())
         _lib.check(rc, "conzic_gibbs_step")

@@ -52,14 +52,15 @@ class _Chain:
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
 
-    def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None):
+    def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
         pos = self.seed_len + ii
         before = sum(self.holds_word[:pos])
         after = sum(self.holds_word[pos + 1:])
         self.eng.gibbs_step(self.inp, self.mask, self.image_embeds, pos, ii == self.max_len - 1, top_k,
                             1.0 if temperature is None else temperature, alpha, beta, before, after, gamma=gamma,
                             senti_table=senti_table, out_clip_ref=self.clip_slots[slot],
-                            out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
+                            out_senti=self.senti_slots[slot] if self.senti_slots is not None else None,
+                            logits_in=logits_in)
         self.holds_word[pos] = True
 
     def finish(self):
@@ -163,8 +164,46 @@ def random_generation(img_name, model, clip, tokenizer, image_instance, token_ma
     return texts, scores
 
 
-def span_generation(*args, **kwargs):
-    raise NotImplementedError("--order span is not part of the accelerated path yet (SURVEY.md section 8f, rank 3)")
+def span_generation(img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger,
+                    max_len=15, top_k=0, temperature=None, alpha=0.7, beta=1,
+                    max_iters=20, batch_size=1, verbose=True):
+    """Spans of two positions, left to right (gen_utils.py:148-195): both positions of a span are masked, BERT
+    runs once on that state, and each position is then scored from those logits (the second one from logits
+    that do not see the word just chosen for the first, exactly like the reference)."""
+    ch = _Chain(model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, False)
+    eng = ch.eng
+    span_len = 2
+    best_score, best_caption = [0] * batch_size, ["None"] * batch_size
+    texts, scores = [], []
+    cur_text = None
+    for it in range(max_iters):
+        slot = 0
+        for span_start in range(0, max_len, span_len):
+            span_end = min(span_start + span_len, max_len)
+            lo, hi = ch.seed_len + span_start, ch.seed_len + span_end
+            ch.inp[:, lo:hi] = eng.mask_id
+            for p in range(lo, hi):
+                ch.holds_word[p] = False
+            rows = [eng.bert_mlm_row_padded(ch.inp, p) for p in range(lo, hi)]  # same ids -> same forward
+            for ii in range(span_start, span_end):
+                ch.step(slot, ii, top_k, temperature, alpha, beta, logits_in=rows[ii - span_start])
+                slot += 1
+        ids = ch.inp.cpu()
+        cur_score = ch.clip_slots[slot - 1].cpu().numpy().tolist()
+        if verbose:
+            shown = tokenizer.batch_decode(ids)
+            cur_text = tokenizer.batch_decode(ids, skip_special_tokens=True)
+            for jj in range(batch_size):
+                if best_score[jj] < cur_score[jj]:
+                    best_score[jj], best_caption[jj] = cur_score[jj], cur_text[jj]
+                logger.info(f"iter {it + 1}, The {jj+1}-th image: {img_name[jj]},"
+                            f"clip score {cur_score[jj]:.3f}: " + shown[jj])
+        texts.append(cur_text)
+        scores.append(cur_score)
+    texts.append(best_caption)
+    scores.append(best_score)
+    ch.finish()
+    return texts, scores
 
 
 def parallel_generation(*args, **kwargs):
@@ -191,7 +230,8 @@ def generate_caption(img_name, model, clip, tokenizer, image_instance, token_mas
                                                         prompt, logger, max_iters=max_iter * max_len,
                                                         print_every=max_len, verbose=True, **common)
     elif generate_order == "span":
-        return span_generation()
+        generate_texts, clip_scores = span_generation(img_name, model, clip, tokenizer, image_instance, token_mask,
+                                                      prompt, logger, max_iters=max_iter, **common)
     elif generate_order == "parallel":
         return parallel_generation()
     else:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CONZIC_ABI_VERSION 1
+#define CONZIC_ABI_VERSION 2
 
 typedef struct conzic_ctx conzic_ctx;
 
@@ -148,6 +148,9 @@ typedef struct conzic_step_args {
   float* tr_final;
   int64_t* tr_best;
   float* tr_logits;   /* f32[B, ldl = roundup(V,4)] or NULL */
+  /* Span order (gen_utils.py:148-195): logits of row `pos` from an EARLIER forward, f32[B, ldl] from
+   * conzic_bert_mlm_row; when non-NULL the step skips its own BERT forward and scores these. */
+  const float* logits_in;
 } conzic_step_args;
 
 int conzic_gibbs_step(conzic_ctx* ctx, const conzic_step_args* args, void* ws_dev, size_t ws_bytes, void* stream);

@@ -214,13 +214,17 @@ class Oracle:
 
     # -- one Gibbs step: gen_utils.py:66-81 / control_gen_utils.py:45-67 --------------------
     def step(self, inp, image_embeds, token_mask, pos, ii, max_len, top_k, temperature, alpha, beta,
-             gamma=None, ctl_signal="positive"):
+             gamma=None, ctl_signal="positive", logits_row=None):
+        """`logits_row` (f32[B,V]): logits of row `pos` from an earlier forward (span order, gen_utils.py:162-165);
+        None = run BERT on the current ids."""
         tok = self.tokenizer
         token_mask = update_token_mask(tok, token_mask, max_len, ii)
         inp[:, pos] = tok.mask_token_id
         inp_ = inp.clone()
         t0 = time.perf_counter()
-        if self.full_logits:
+        if logits_row is not None:
+            probs, idxs = generate_caption_step(logits_row[:, None], 0, token_mask, temperature, top_k)
+        elif self.full_logits:
             out = bert_mlm_logits(self.bert_sd, inp)
             probs, idxs = generate_caption_step(out, pos, token_mask, temperature, top_k)
             logits_row = out[:, pos]
@@ -275,7 +279,23 @@ class Oracle:
         elif order == "shuffle" or (gamma is not None and order != "sequential"):
             positions = list(range(max_len))
             random.shuffle(positions)  # gen_utils.py:110-111, one permutation per call
-        if order == "random" and gamma is None:
+        if order == "span" and gamma is None:
+            # gen_utils.py:148-195: spans of 2 positions are masked together and scored from ONE forward
+            for _ in range(max_iters):
+                for span_start in range(0, max_len, 2):
+                    span_end = min(span_start + 2, max_len)
+                    inp[:, seed_len + span_start: seed_len + span_end] = tok.mask_token_id
+                    rows = bert_mlm_head(self.bert_sd, bert_encoder(self.bert_sd, inp)[:, seed_len + span_start: seed_len + span_end])
+                    for ii in range(span_start, span_end):
+                        cur, _ = self.step(inp, image_embeds, token_mask, seed_len + ii, ii, max_len, top_k, temperature,
+                                           alpha, beta, logits_row=rows[:, ii - span_start])
+                cur_text = tok.batch_decode(inp, skip_special_tokens=True)
+                for jj in range(B):
+                    if best_score[jj] < cur[jj]:
+                        best_score[jj], best_cap[jj] = cur[jj], cur_text[jj]
+                texts_list.append(cur_text)
+                scores_list.append(cur)
+        elif order == "random" and gamma is None:
             # gen_utils.py:197-242 with generate_caption's max_iter*=max_len, print_every=max_len
             for step in range(max_iters * max_len):
                 kk = np.random.randint(0, max_len)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libconzic.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.conzic_abi_version() == 1
+    assert lib.conzic_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -309,7 +309,7 @@ def _models(case):
 
 
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "random_b2_n3_k8", "senti_seq_b2_n4_k8",
-                                  "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32"])
+                                  "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32", "span_b2_n5_k8"])
 def test_free_running_call_matches_reference(name, monkeypatch):
     """generate_caption / control_generate_caption through the drop-in API under set_seed(42): same captions per
     sweep, same best list, same CLIP scores as the unmodified reference returned (bf16x3 mode)."""

@@ -65,7 +65,7 @@ def test_teacher_forced_steps(name, synth_weights):
                 assert torch.equal(inp[:, keep], nxt[:, keep])
 
 
-@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8"])
+@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8", "span_b2_n5_k8"])
 def test_free_running_call(name, synth_weights):
     """Whole ``generate_caption`` / ``control_generate_caption`` call under set_seed(42):
     same captions per sweep, same CLIP scores, same best list as the reference returned."""

@@ -81,14 +81,17 @@ class Recorder:
         rec = self
 
         def fwd(inp, *a, **k):
-            rec.cur = {"inp": inp.clone()}
             out = orig_fwd(inp, *a, **k)
-            rec.cur["_logits"] = out.logits
+            rec.fw = {"inp": inp.clone(), "logits": out.logits, "uses": 0}
             return out
 
         def step(out, gen_idx, mask, temperature=None, top_k=100):
             probs, ids = orig_step(out, gen_idx=gen_idx, mask=mask, temperature=temperature, top_k=top_k)
-            row = rec.cur.pop("_logits")[:, gen_idx]
+            # span order scores two positions from ONE forward: the second step's logits are stale w.r.t. the
+            # token chosen at the first; such records are marked and skipped by the teacher-forced replays
+            rec.cur = {"inp": rec.fw["inp"], "stale_logits": rec.fw["uses"] > 0}
+            rec.fw["uses"] += 1
+            row = rec.fw["logits"][:, gen_idx]
             cols = torch.cat([LOGIT_COLS.expand(row.shape[0], -1), ids], dim=1)
             rec.cur.update(pos=int(gen_idx), token_mask_dot=float(mask[0, synth.DOT_ID]),
                            logit_cols=cols.to(torch.int32), logit_vals=row.gather(1, cols).clone(),
@@ -127,6 +130,7 @@ CASES = [
     dict(name="senti_shuffle_neg_b2_n4_k8", order="shuffle", B=2, n=4, K=8, iters=2, gamma=5.0, style="negative"),
     dict(name="peaked_seq_b2_n4_k32", order="sequential", B=2, n=4, K=32, iters=2, peaked=True),
     dict(name="seq_b1_n10_k200", order="sequential", B=1, n=10, K=200, iters=1),
+    dict(name="span_b2_n5_k8", order="span", B=2, n=5, K=8, iters=2),
 ]
 
 
