@@ -318,19 +318,24 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
     else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.bqkv), 3 * H, 0, ACT_NONE);
     GemmOpts o = c->gopt;
     o.persist = 0;  // BERT has few token rows (B*L): the (n, m)-gridded kernel spreads them over more SMs
-    if (!launch_linear(h, M, ly.qkv, e, o, st, nullptr)) return false;
+    // These GEMMs are latency bound (<= 150 CTAs, 12-48 k blocks each): a deep TMA ring (6 x 32 KB in flight per
+    // CTA) matters more than a second resident CTA, except for fc1 whose grid exceeds one CTA per SM.
+    GemmOpts od = o;
+    if (!getenv("CONZIC_GEMM_STAGES")) od.stages = 6;
+    const bool one_wave = static_cast<long long>((M + 127) / 128) * ((F + o.bn - 1) / o.bn) <= 148;
+    if (!launch_linear(h, M, ly.qkv, e, od, st, nullptr)) return false;
     AttnArgs at;
     at.qkv = p.bqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = nullptr;
     at.B = B; at.P = 0; at.K = 1; at.S = L; at.H = H; at.heads = g.bert_heads; at.causal = 0;
     at.scale = 0.125f; at.out_act = p.battn; at.ld_act = ldh; at.split = s;
     if (!launch_attention(at, st)) return false;
     Act a{p.battn, ldh, H};
-    if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.by, H, p.bx, H, ACT_NONE), o, st, nullptr)) return false;
+    if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.by, H, p.bx, H, ACT_NONE), od, st, nullptr)) return false;
     LNArgs ln{p.by, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
     launch_layernorm(ln, st);
-    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), o, st, nullptr)) return false;
+    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), one_wave ? od : o, st, nullptr)) return false;
     Act f{p.bffn, ldf, F};
-    if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.by, H, p.bx, H, ACT_NONE), o, st, nullptr)) return false;
+    if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.by, H, p.bx, H, ACT_NONE), od, st, nullptr)) return false;
     LNArgs ln2{p.by, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
     launch_layernorm(ln2, st);
   }

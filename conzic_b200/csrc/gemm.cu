@@ -258,7 +258,19 @@ struct PGemmParams {
   Epi e;
   uint64_t st_policy = 0;  // non-zero: L2 eviction-priority hint for the output stores / residual loads
   uint64_t ld_policy = 0;
+  const bf16* a_ptr = nullptr;  // A operand in global memory (row stride lda elements), for L2 prefetch of the next tile
+  int lda = 0;
 };
+
+// Pull rows [r_lo, r_hi) x `bytes` of the A operand into L2 ahead of the TMA loads that will read them: the
+// smem ring only covers L2 latency, not HBM latency (~2 us under load).
+__device__ __forceinline__ void prefetch_a_rows(const PGemmParams& p, int r_lo, int r_hi, int bytes) {
+  if (!p.a_ptr) return;
+  r_hi = min(r_hi, p.M);
+  for (int r = r_lo; r < r_hi; ++r)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.a_ptr + static_cast<size_t>(r) * p.lda), "r"(bytes)
+                 : "memory");
+}
 
 template <int CG, bool ARES>
 struct PSmem {
@@ -515,6 +527,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int r = r_lo; r < r_hi; ++r)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr + c0),
                              "r"(nbytes) : "memory");
+          }
+          if (ARES && newm && m + 1 < p.m_tiles) {
+            // next m tile of this CTA: its A rows go to L2 now, one slice of rows per k block
+            const int rows_per_kb = (BM + nkb - 1) / nkb;
+            const int r_lo = ((m + 1) * CG + static_cast<int>(cta_rank)) * BM + kb * rows_per_kb;
+            prefetch_a_rows(p, r_lo, min(r_lo + rows_per_kb, ((m + 1) * CG + static_cast<int>(cta_rank) + 1) * BM), p.K * 2);
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
           const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
@@ -890,6 +908,173 @@ mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streamed-A variant for N = 512 (fc2 of the CLIP blocks, K = 2048): one unit = a 256-row pair tile x ALL 512
+// columns, i.e. both 256-column TMEM accumulators belong to the same unit.  The A tile (the [M, 2048] MLP
+// intermediate, 4 KB per token row) is then streamed from HBM ONCE instead of once per 256-column n tile --
+// measured with ncu, the second pass of gemm_persist_kernel<2,false> missed L2 and doubled the kernel's DRAM
+// reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
+// back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
+// ---------------------------------------------------------------------------------------------------
+struct WideSmem {
+  static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
+  static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
+  static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
+  static constexpr int STAGES = 4;
+  static constexpr int STG_OFF = STAGES * STAGE;
+  static constexpr int BAR_OFF = STG_OFF + P_EPI_WARPS * 2048;
+  static constexpr int N_BARS = 2 * STAGES + 4;
+  static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PGemmParams p) {
+  using SL = WideSmem;
+  constexpr int CG = 2;
+  constexpr int STAGES = SL::STAGES;
+  extern __shared__ __align__(1024) uint8_t psmem[];
+  uint8_t* smem = psmem;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [0]: both halves of the unit are complete
+  uint64_t* tempty_bar = tfull_bar + 2;       // [h]: half h has been read by every epilogue warp of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_groups = gridDim.x / CG;
+  const int group = blockIdx.x / CG;
+  const int nkb = p.K / BK;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], CG * P_EPI_WARPS); mbar_init(&tempty_bar[1], CG * P_EPI_WARPS);  // every warp reads both halves
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg<CG>(tmem_slot, 512);
+    tmem_relinquish_cg<CG>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int m = group; m < p.m_tiles; m += n_groups) {
+        const int arow = (m * CG + static_cast<int>(cta_rank)) * BM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (p.e.resid) {
+            const int rows_per_kb = (BM + nkb - 1) / nkb;
+            const int r_lo = arow + kb * rows_per_kb;
+            const int r_hi = min(min(r_lo + rows_per_kb, arow + BM), p.M);
+            for (int r = r_lo; r < r_hi; ++r)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr),
+                           "r"(2 * PBN * 4) : "memory");
+          }
+          if (m + n_groups < p.m_tiles) {
+            const int rows_per_kb = (BM + nkb - 1) / nkb;
+            const int nrow = ((m + n_groups) * CG + static_cast<int>(cta_rank)) * BM;
+            const int r_lo = nrow + kb * rows_per_kb;
+            prefetch_a_rows(p, r_lo, min(r_lo + rows_per_kb, nrow + BM), p.K * 2);
+          }
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * SL::STAGE);
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+          uint8_t* st = smem + s * SL::STAGE;
+          tma_load_2d_cg<CG>(st, &tmA, bar, kb * BK, arow);
+          tma_load_2d_cg<CG>(st + SL::A_SLOT, &tmB, bar, kb * BK, static_cast<int>(cta_rank) * BM);
+          tma_load_2d_cg<CG>(st + SL::A_SLOT + SL::B_SLOT, &tmB, bar, kb * BK, PBN + static_cast<int>(cta_rank) * BM);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, PBN);
+      int s = 0; uint32_t ph = 0; uint32_t uph = 0;
+      for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * SL::STAGE);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (kb == 0) {  // half h of the previous unit must have been drained
+              mbar_wait(&tempty_bar[h], uph ^ 1);
+              tc_fence_after();
+            }
+            const uint32_t b0 = a0 + SL::A_SLOT + h * SL::B_SLOT;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
+              const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
+              umma_bf16_cg<CG>(tmem_base + h * PBN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit_cg<CG>(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_cg<CG>(&tfull_bar[0]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // 8 warps: warp % 4 = TMEM lane quarter; (warp - 2) / 4 = which 128-column slice of EACH 256-column half
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;  // 0 / 1: columns [sub*128, sub*128+128) of each 256-column half
+    uint32_t uph = 0;
+    const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
+    for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
+      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      mbar_wait(&tfull_bar[0], uph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int nbase = h * PBN + sub * (PBN / 2);
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * PBN + sub * (PBN / 2);
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int n0 = nbase + c * 16;
+          float4 rr[4];
+          prefetch_resid(p, lane, row0, n0, rr);
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
+          tmem_ld_wait();
+          if (c == 7) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + h * 8);
+          }
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+        }
+        if (p.e.stats_out) flush_row_stats(p, lane, row0, nbase / (PBN / 2), st1, st2);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
 // Slow reference kernel on CUDA cores with the same operand format and epilogue (tests / bring-up only).
 __global__ void gemm_simt_debug_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw,
                                        const GemmParams p) {
@@ -1045,13 +1230,33 @@ bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W
   return cuda_ok(cudaLaunchKernelEx(&cfg, mlp_persist_kernel, th, W1.tmap128, tf, W2.tmap128, p), "mlp_persist launch");
 }
 
+static bool configure_wide() {
+  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem::DYN_BYTES),
+                 "cudaFuncSetAttribute(gemm_wide)");
+}
+static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, cudaStream_t st) {
+  int groups = sm_count() / 2;
+  if (groups > p.m_tiles) groups = p.m_tiles;
+  if (groups < 1) groups = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = WideSmem::DYN_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel, ta, tb, p), "gemm_wide launch");
+}
 static bool configure_mlp() {
   return cuda_ok(cudaFuncSetAttribute(mlp_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::DYN_BYTES),
                  "cudaFuncSetAttribute(mlp_persist)");
 }
 
 bool gemm_configure() {
-  if (!configure_mlp()) return false;
+  if (!configure_mlp() || !configure_wide()) return false;
   if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>()))
     return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
@@ -1069,7 +1274,9 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   p.M = M; p.N = W.N; p.K = W.K; p.split = o.split; p.e = epi;
   (void)launches;
   ++g_launches;
-  ProfScope prof_(CAT_GEMM, 2.0 * M * static_cast<double>(W.N) * W.K * (o.split ? 3 : 1), st);
+  // the persistent pair kernel (CLIP tower) and the gridded kernel (BERT, parity mode) are timed separately
+  ProfScope prof_((o.persist && !o.split && o.impl == 0) ? CAT_GEMM : CAT_GEMM_SMALL,
+                  2.0 * M * static_cast<double>(W.N) * W.K * (o.split ? 3 : 1), st);
   if ((epi.out_f32 && (epi.ldo_f32 & 3)) || (epi.resid && (epi.ldr & 3)) || (epi.out_act && (epi.ldo_act & 7)) ||
       (A.ld & 7)) {
     set_error("linear: leading dimensions must keep rows 16-byte aligned");
@@ -1095,6 +1302,14 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     PGemmParams pp;
     pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi;
     pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
+    static int allow_pf = -1;
+    if (allow_pf < 0) {
+      // measured on B200: prefetching the next tile's A rows into L2 makes the GEMMs 10-20 % SLOWER (the ring of
+      // TMA loads already keeps HBM busy and the prefetch only adds traffic), so this stays an experiment switch
+      const char* e = getenv("CONZIC_GEMM_APREFETCH");
+      allow_pf = e ? atoi(e) : 0;
+    }
+    if (allow_pf && ((W.K * 2) % 16) == 0 && ((static_cast<size_t>(A.ld) * 2) % 16) == 0) { pp.a_ptr = A.p; pp.lda = A.ld; }
     pp.n_tiles = (W.N + PBN - 1) / PBN;
     static int allow_ares = -1;
     if (allow_ares < 0) {
@@ -1103,6 +1318,16 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     }
     const bool ares = allow_ares && cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
     const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;
+    static int allow_wide = -1;
+    if (allow_wide < 0) {
+      const char* e = getenv("CONZIC_GEMM_WIDE");
+      allow_wide = e ? atoi(e) : 1;
+    }
+    // fp32-output GEMM with N == 512 and a streamed A (fc2): one 512-column unit per tile so A leaves HBM once
+    if (allow_wide && cg == 2 && !ares && W.N == 2 * PBN && (epi.out_f32 != nullptr) && W.K >= 1024) {
+      pp.n_tiles = 1;
+      return launch_wide(ta, tb, pp, st);
+    }
     if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
     return launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
   }

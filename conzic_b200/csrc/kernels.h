@@ -17,7 +17,7 @@ bool cuda_ok(cudaError_t e, const char* what);
 
 // Optional per-category device timing (CUDA events around each launch on the launching stream); off by default.
 enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_LN = 2, CAT_EMBED = 3, CAT_TOPK = 4, CAT_ASSEMBLE = 5, CAT_SELECT = 6,
-       CAT_MISC = 7, CAT_COUNT = 8 };
+       CAT_MISC = 7, CAT_GEMM_SMALL = 8, CAT_COUNT = 9 };
 struct ProfScope {
   int cat; cudaStream_t st; bool on;
   ProfScope(int cat, double work, cudaStream_t st);

@@ -148,7 +148,8 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.conzic_launch_count(self.ctx))
 
-    PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed", "topk", "assemble", "select", "misc")
+    PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed", "topk", "assemble", "select", "misc",
+                          "gemm_small")
 
     def profile(self, enable: bool):
         """CUDA-event timing of every launch by category (conzic_profile); off by default."""

@@ -159,8 +159,8 @@ int conzic_gibbs_step(conzic_ctx* ctx, const conzic_step_args* args, void* ws_de
 uint64_t conzic_launch_count(const conzic_ctx* ctx);
 
 /* Optional device timing by kernel category (CUDA events around each launch, on the launching stream).
- * Categories: 0 GEMM (work = executed FLOPs), 1 attention, 2 LayerNorm, 3 embeddings, 4 top-k, 5 CLIP-id
- * assembly, 6 score/select, 7 misc.  conzic_profile(ctx, 1) clears and enables, (ctx, 0) disables;
+ * Categories: 0 persistent pair GEMM (CLIP / vision towers; work = executed FLOPs), 1 attention, 2 LayerNorm,
+ * 3 embeddings, 4 top-k, 5 CLIP-id assembly, 6 score/select, 7 misc, 8 gridded GEMM (BERT, bf16x3 mode).  conzic_profile(ctx, 1) clears and enables, (ctx, 0) disables;
  * conzic_profile_read waits for the recorded events and returns summed milliseconds, work and launches. */
 int conzic_profile(conzic_ctx* ctx, int enable);
 int conzic_profile_read(conzic_ctx* ctx, int category, double* ms, double* work, int* launches);
