@@ -25,10 +25,13 @@ fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 600 --csv --log-file $OUT/launches_step.csv \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_step.log 2>&1; echo "ncu list rc=$?"
-  # layer 6 of the CLIP tower in the profiled step: QKV, O, fc1, fc2 launches of the persistent GEMM
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_persist -s 74 -c 4 -f -o $OUT/prof_gemm \
+  # profile_step runs 1 warm-up + 1 profiled step: per step 36 gemm_persist (QKV, O, fc1 x 12 blocks), 12 gemm_wide
+  # (fc2), 12 BERT + 12 CLIP attention launches
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_persist -s 51 -c 3 -f -o $OUT/prof_gemm \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_mma -s 30 -c 2 -f -o $OUT/prof_attn \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_wide -s 17 -c 1 -f -o $OUT/prof_gemm_wide \
+      python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm_wide.log 2>&1; echo "ncu gemm_wide rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_mma -s 41 -c 2 -f -o $OUT/prof_attn \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
   ls -la $OUT
 fi
