@@ -295,6 +295,25 @@ class Engine:
         _lib.check(rc, "conzic_image_text_similarity")
         return score, ref
 
+    def score_select(self, text_embeds, image_embeds, probs, ids_masked, inp, pos, alpha, beta, gamma=None,
+                     senti_raw=None, repeats=None, out_clip_ref=None, out_senti=None):
+        """Score fuse + argmax + write-back (gen_utils.py:77-81, control_gen_utils.py:59-65) on caller-built
+        candidate embeddings; `inp[:, pos]` receives the winners."""
+        B, K = probs.shape
+        if out_clip_ref is None:
+            out_clip_ref = torch.empty((B,), dtype=torch.float32, device=self.device)
+        ctl = gamma is not None
+        if ctl and out_senti is None:
+            out_senti = torch.empty((B,), dtype=torch.float32, device=self.device)
+        rc = self.lib.conzic_score_select(self.ctx, _ptr(text_embeds.contiguous()), _ptr(image_embeds.contiguous()), B, K,
+                                          self.logit_scale_exp, _ptr(probs.contiguous()), _ptr(ids_masked.contiguous()),
+                                          _ptr(senti_raw if ctl else None), _ptr(repeats if ctl else None),
+                                          float(alpha), float(beta), float(gamma) if ctl else 0.0, _ptr(inp),
+                                          inp.shape[1], int(pos), _ptr(out_clip_ref), _ptr(out_senti if ctl else None),
+                                          self._stream())
+        _lib.check(rc, "conzic_score_select")
+        return out_clip_ref, (out_senti if ctl else None)
+
     def debug_linear(self, A, W, bias=None, resid=None, act: int = 0):
         M, K = A.shape
         N = W.shape[0]

@@ -5,6 +5,7 @@ write-back -- is ONE call into libconzic.so (`conzic_gibbs_step`); the host only
 once per sweep, reads ids and scores back to build the strings the reference returns and logs."""
 from __future__ import annotations
 
+import os
 import random
 import time
 
@@ -34,6 +35,9 @@ class _Chain:
     def __init__(self, model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, ctl):
         self.eng = runtime.engine_for(model, clip, tokenizer)
         eng = self.eng
+        self.clip = clip
+        # '##' word pieces (real BERT vocabularies) need the host string path; CONZIC_STRING_PATH=1 forces it
+        self.string_path = bool(getattr(eng, "needs_host_ids", None)) or os.environ.get("CONZIC_STRING_PATH") == "1"
         self.tokenizer, self.max_len, self.B = tokenizer, max_len, batch_size
         self.seed_len = len(prompt.split()) + 1
         batch = get_init_text(tokenizer, prompt, max_len, batch_size)
@@ -52,7 +56,41 @@ class _Chain:
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
 
+    def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
+        """The same step with the reference's string round trip (gen_utils.py:66-81): candidate ids -> host ->
+        tokenizer.batch_decode -> CLIP tokenizer -> device.  Every arithmetic piece is still a libconzic kernel;
+        only the text handling runs on the host.  Used when the BERT vocabulary has '##' word pieces, whose merge
+        into the previous word changes the CLIP BPE of that word and cannot be tabulated per token."""
+        eng, tok = self.eng, self.tokenizer
+        pos = self.seed_len + ii
+        T = 1.0 if temperature is None else temperature
+        self.mask.view(-1)[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0  # utils.py:53-59
+        self.inp[:, pos] = eng.mask_id
+        row = logits_in[:, : eng.V] if logits_in is not None else eng.bert_mlm_row(self.inp, pos)
+        probs, idxs = eng.topk_mask(row, self.mask, T, top_k)
+        # ids * token_mask[ids] and the candidate id tensor (gen_utils.py:71-74), on the host with the strings
+        idxs_h = idxs.cpu()
+        ids_masked_h = (idxs_h * self.mask.view(-1).cpu()[idxs_h]).long()
+        cand = self.inp.cpu().unsqueeze(1).repeat(1, top_k, 1)
+        cand[:, :, pos] = ids_masked_h
+        flat = cand.view(-1, cand.shape[-1])
+        texts = tok.batch_decode(flat, skip_special_tokens=True)
+        text_embeds = self.clip.compute_text_representation(texts)
+        senti_raw = repeats = None
+        if gamma is not None:
+            special = torch.tensor(sorted({eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id}))
+            table = senti_table.cpu()
+            vis = ~torch.isin(flat, special)
+            senti_raw = (table[flat] * vis).sum(1).view(self.B, top_k).to(eng.device).contiguous()
+            repeats = ((ids_masked_h[:, :, None] == cand).float().sum(2) - 1).to(eng.device).contiguous()
+        eng.score_select(text_embeds, self.image_embeds, probs, ids_masked_h.to(eng.device), self.inp, pos, alpha, beta,
+                         gamma=gamma, senti_raw=senti_raw, repeats=repeats, out_clip_ref=self.clip_slots[slot],
+                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
+        self.holds_word[pos] = True
+
     def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
+        if self.string_path:
+            return self.step_via_strings(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in)
         pos = self.seed_len + ii
         before = sum(self.holds_word[:pos])
         after = sum(self.holds_word[pos + 1:])

@@ -342,6 +342,40 @@ def test_free_running_call_matches_reference(name, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "span_b2_n5_k8"])
+def test_host_string_path_matches_reference(name, monkeypatch):
+    """CONZIC_STRING_PATH=1: the fallback for vocabularies with '##' word pieces (candidate ids -> host ->
+    batch_decode -> CLIP tokenizer -> device, every arithmetic piece still a libconzic kernel) gives the
+    reference's captions and scores too."""
+    import logging
+    from conzic_b200 import control_gen_utils, gen_utils, runtime
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+    runtime.clear()
+    g = gc.load_golden(name)
+    case = g["case"]
+    bert, clip = _models(case)
+    B, n, K = case["B"], case["n"], case["K"]
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=case["iters"],
+              alpha=0.02, beta=2.0, generate_order=case["order"])
+    names = [f"img{i}.jpg" for i in range(B)]
+    set_seed(42)
+    if case.get("gamma") is None:
+        texts, scores = gen_utils.generate_caption(names, bert, clip, synth.SynthBertTokenizer(), pix,
+                                                   synth.make_token_mask("cuda"), logging.getLogger("test"), **kw)
+    else:
+        texts, scores = control_gen_utils.control_generate_caption(
+            names, bert, clip, synth.SynthBertTokenizer(), pix, synth.make_token_mask("cuda"), logging.getLogger("test"),
+            gamma=case["gamma"], ctl_type="sentiment", style_type=case["style"],
+            sentiment_table=synth.make_sentiment_table(), **kw)
+    runtime.clear()
+    assert texts == g["texts"]
+    for a, b in zip(scores, g["scores"]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
 def test_prefix_sharing_equals_dense_encode():
     """Size-independent property: encoding candidates as shared prefix + per-candidate suffix gives the same
     cosine as encoding every full caption densely (causal tower => prefix states do not depend on the suffix)."""
