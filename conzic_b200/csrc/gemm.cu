@@ -32,7 +32,8 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int BAR_OFF = STAGES * (A_BYTES + B_BYTES);
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int STG_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;  // 4 epilogue warps x 2 KB transpose buffers
+  static constexpr int TOTAL = STG_OFF + 16 + 4 * 2048;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
 
@@ -126,113 +127,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
         if (p.split) o[e.out_K + n] = __float2bfloat16_rn(x - __bfloat162float(h));
       }
     }
-  }
-}
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
-  using SL = SmemLayout<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * SL::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x;
-  const int m_blk = blockIdx.y;
-  const int nkb = p.K / BK;
-  const int iters = p.split ? 3 * nkb : nkb;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
-      }
-      mbar_init(accum_bar, 1);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, BN);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < iters; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int pass = i / nkb, kb = i - pass * nkb;
-        const int a_col = (pass == 1 ? p.K : 0) + kb * BK;
-        const int b_col = (pass == 2 ? p.K : 0) + kb * BK;
-        mbar_arrive_expect_tx(&full_bar[s], SL::A_BYTES + SL::B_BYTES);
-        tma_load_2d(sA + s * SL::A_BYTES, &tmA, &full_bar[s], a_col, m_blk * BM);
-        tma_load_2d(sB + s * SL::B_BYTES, &tmB, &full_bar[s], b_col, n_blk * BN);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      for (int i = 0; i < iters; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA + s * SL::A_BYTES);
-        const uint32_t b0 = smem_u32(sB + s * SL::B_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
-          const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
-          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
-      }
-      umma_commit(accum_bar);  // accumulator complete
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int row = m_blk * BM + q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + c0, r);
-      tmem_ld_wait();
-      const int n0 = n_blk * BN + c0;
-      if (row < p.M && n0 < p.N) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_chunk(p, row, n0, v);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
   }
 }
 
@@ -459,6 +353,151 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_
     }
   }
   __syncwarp();
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using SL = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * SL::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x;
+  const int m_blk = blockIdx.y;
+  const int nkb = p.K / BK;
+  const int iters = p.split ? 3 * nkb : nkb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(accum_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < iters; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int pass = i / nkb, kb = i - pass * nkb;
+        const int a_col = (pass == 1 ? p.K : 0) + kb * BK;
+        const int b_col = (pass == 2 ? p.K : 0) + kb * BK;
+        mbar_arrive_expect_tx(&full_bar[s], SL::A_BYTES + SL::B_BYTES);
+        tma_load_2d(sA + s * SL::A_BYTES, &tmA, &full_bar[s], a_col, m_blk * BM);
+        tma_load_2d(sB + s * SL::B_BYTES, &tmB, &full_bar[s], b_col, n_blk * BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      for (int i = 0; i < iters; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * SL::A_BYTES);
+        const uint32_t b0 = smem_u32(sB + s * SL::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
+          const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
+          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int row = m_blk * BM + q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (BN == 128 && !p.split && (n_blk + 1) * BN <= p.N) {
+      // bf16 mode, full tile: the smem-transposed, coalesced epilogue of the persistent kernel (the row-per-thread
+      // form below made these small, latency-bound launches spend most of their time in scattered accesses)
+      PGemmParams pp;
+      pp.M = p.M; pp.N = p.N; pp.K = p.K; pp.m_tiles = 0; pp.n_tiles = 0; pp.e = p.e;
+      uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem + SL::STG_OFF) + 15) & ~uintptr_t(15)) + q * 2048;
+      const int row0 = m_blk * BM + q * 32;
+      const int nbase = n_blk * BN;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
+      if (p.e.out_act && !p.e.out_f32 && !p.e.resid) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_bf16_chunk(pp, stg, lane, row0, nbase + c * 32, v, bias4, c);
+        }
+      } else {
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int n0 = nbase + c * 16;
+          float4 rr[4];
+          prefetch_resid(pp, lane, row0, n0, rr);
+          uint32_t r[16];
+          tmem_ld16(lane_addr + c * 16, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_f32_chunk(pp, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+        }
+      }
+    } else
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + c0, r);
+      tmem_ld_wait();
+      const int n0 = n_blk * BN + c0;
+      if (row < p.M && n0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_chunk(p, row, n0, v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
 }
 
 template <int CG, bool ARES>
