@@ -208,7 +208,7 @@ namespace {
 
 struct Plan {
   // BERT
-  float *bx, *by;
+  float *bx, *by, *bpart;
   bf16 *bh, *battn, *bffn;
   void* bqkv;
   float *bt, *logits;
@@ -242,6 +242,7 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   const int Hb = g.bert_hidden, Fb = g.bert_ffn, Hc = g.clip_hidden, Fc = g.clip_ffn;
   p.bx = b.take<float>(Mb * Hb);
   p.by = b.take<float>(Mb * Hb);
+  p.bpart = b.take<float>(Mb * Hb * 4);  // split-K partial sums of the O-proj / FFN-out GEMMs (<= 4 splits)
   p.bh = b.take<bf16>(Mb * Hb * (1 + s));
   p.battn = b.take<bf16>(Mb * Hb * (1 + s));
   p.bffn = b.take<bf16>(Mb * Fb * (1 + s));
@@ -330,14 +331,33 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
     at.scale = 0.125f; at.out_act = p.battn; at.ld_act = ldh; at.split = s;
     if (!launch_attention(at, st)) return false;
     Act a{p.battn, ldh, H};
-    if (!launch_linear(a, M, ly.o, epi_f32_out(ly.o, p.by, H, p.bx, H, ACT_NONE), od, st, nullptr)) return false;
-    LNArgs ln{p.by, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
-    launch_layernorm(ln, st);
+    // The two N = H GEMMs have few tiles (48 at 64 images): split K so ~148 CTAs stream the operands, write raw
+    // fp32 partial sums, and let the LayerNorm that follows add them to the residual and the bias.
+    const int tiles = ((M + 127) / 128) * ((H + od.bn - 1) / od.bn);
+    int ks = 148 / (tiles > 0 ? tiles : 1);
+    if (ks > 4) ks = 4;
+    if (ks < 1 || getenv("CONZIC_BERT_NO_SPLITK")) ks = 1;
+    GemmOpts osk = od;
+    osk.ksplit = ks;
+    auto nh_gemm = [&](const Act& in, const LinearW& W, const float* lg, const float* lb) -> bool {
+      if (ks > 1) {
+        Epi e2;
+        e2.out_f32 = p.bpart; e2.ldo_f32 = H;
+        if (!launch_linear(in, M, W, e2, osk, st, nullptr)) return false;
+        LNArgs ln{p.bx, nullptr, M, H, lg, lb, g.bert_ln_eps, p.bx, p.bh, ldh, s};
+        ln.partials = p.bpart; ln.n_parts = ks; ln.part_stride = static_cast<size_t>(M) * H; ln.add_bias = W.bias;
+        launch_layernorm(ln, st);
+        return true;
+      }
+      if (!launch_linear(in, M, W, epi_f32_out(W, p.by, H, p.bx, H, ACT_NONE), od, st, nullptr)) return false;
+      LNArgs ln{p.by, nullptr, M, H, lg, lb, g.bert_ln_eps, p.bx, p.bh, ldh, s};
+      launch_layernorm(ln, st);
+      return true;
+    };
+    if (!nh_gemm(a, ly.o, ly.ln1_g, ly.ln1_b)) return false;
     if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), one_wave ? od : o, st, nullptr)) return false;
     Act f{p.bffn, ldf, F};
-    if (!launch_linear(f, M, ly.f2, epi_f32_out(ly.f2, p.by, H, p.bx, H, ACT_NONE), od, st, nullptr)) return false;
-    LNArgs ln2{p.by, nullptr, M, H, ly.ln2_g, ly.ln2_b, g.bert_ln_eps, p.bx, p.bh, ldh, s};
-    launch_layernorm(ln2, st);
+    if (!nh_gemm(f, ly.f2, ly.ln2_g, ly.ln2_b)) return false;
   }
   // MLM head on row `pos` only: a strided view of the hidden states (row stride L*ldh) needs no gather.
   Act hrow{p.bh + static_cast<size_t>(pos) * ldh, L * ldh, H};

@@ -25,6 +25,8 @@ struct GemmParams {
   int M, N, K;  // K = logical reduction length (per plane)
   int split;
   Epi e;
+  int ksplit = 1;            // split-K: blockIdx.z = z reduces k blocks [z*nkb/ksplit, (z+1)*nkb/ksplit) ...
+  size_t part_stride = 0;    // ... into out_f32 + z * part_stride (summed by the LayerNorm kernel that follows)
 };
 
 template <int BN, int STAGES>
@@ -373,7 +375,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x;
   const int m_blk = blockIdx.y;
-  const int nkb = p.K / BK;
+  const int nkb_all = p.K / BK;
+  const int kb0 = static_cast<int>(blockIdx.z) * nkb_all / p.ksplit;
+  const int nkb = (static_cast<int>(blockIdx.z) + 1) * nkb_all / p.ksplit - kb0;  // k blocks of this split
   const int iters = p.split ? 3 * nkb : nkb;
 
   if (warp == 0 && lane == 0) {
@@ -404,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const int pass = i / nkb, kb = i - pass * nkb;
+        const int pass = i / nkb, kb = kb0 + (i - pass * nkb);
         const int a_col = (pass == 1 ? p.K : 0) + kb * BK;
         const int b_col = (pass == 2 ? p.K : 0) + kb * BK;
         mbar_arrive_expect_tx(&full_bar[s], SL::A_BYTES + SL::B_BYTES);
@@ -445,6 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // form below made these small, latency-bound launches spend most of their time in scattered accesses)
       PGemmParams pp;
       pp.M = p.M; pp.N = p.N; pp.K = p.K; pp.m_tiles = 0; pp.n_tiles = 0; pp.e = p.e;
+      if (p.ksplit > 1) pp.e.out_f32 += static_cast<size_t>(blockIdx.z) * p.part_stride;
       uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem + SL::STG_OFF) + 15) & ~uintptr_t(15)) + q * 2048;
       const int row0 = m_blk * BM + q * 32;
       const int nbase = n_blk * BN;
@@ -488,7 +493,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_chunk(p, row, n0, v);
+        if (p.ksplit > 1) {
+          GemmParams pz = p;
+          pz.e.out_f32 += static_cast<size_t>(blockIdx.z) * p.part_stride;
+          epilogue_chunk(pz, row, n0, v);
+        } else {
+          epilogue_chunk(p, row, n0, v);
+        }
       }
     }
     tc_fence_before();
@@ -1167,7 +1178,7 @@ bool configure_one() {
 
 template <int BN, int STAGES>
 void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.ksplit);
   gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, SmemLayout<BN, STAGES>::DYN_BYTES, st>>>(ta, tb, p);
 }
 
@@ -1322,6 +1333,14 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   }
   GemmParams p;
   p.M = M; p.N = W.N; p.K = W.K; p.split = o.split; p.e = epi;
+  if (o.ksplit > 1 && !o.persist && o.impl == 0) {
+    if (epi.bias || epi.resid || epi.out_act || epi.act != ACT_NONE || !epi.out_f32 || o.ksplit > W.K / BK) {
+      set_error("linear: split-K writes raw fp32 partial sums only");
+      return false;
+    }
+    p.ksplit = o.ksplit;
+    p.part_stride = static_cast<size_t>(M) * epi.ldo_f32;
+  }
   (void)launches;
   ++g_launches;
   // the persistent pair kernel (CLIP tower) and the gridded kernel (BERT, parity mode) are timed separately

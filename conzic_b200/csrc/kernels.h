@@ -77,6 +77,7 @@ struct GemmOpts {
   int stages = 3;   // smem pipeline depth
   int persist = 0;  // 1 = persistent A-resident kernel with double-buffered TMEM accumulators (bf16 mode only)
   int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
+  int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
@@ -107,6 +108,11 @@ struct LNArgs {
   bf16* out_act;       // optional Act [n_rows, ld]
   int ld_act, split;
   size_t x_row_stride = 0;  // elements between input rows; 0 = H (dense)
+  // split-K consumer: the row to normalise is x + add_bias + sum_z partials[z * part_stride + row * H ...]
+  const float* partials = nullptr;
+  int n_parts = 0;
+  size_t part_stride = 0;
+  const float* add_bias = nullptr;
 };
 void launch_layernorm(const LNArgs& a, cudaStream_t st);
 

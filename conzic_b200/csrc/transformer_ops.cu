@@ -88,6 +88,20 @@ __global__ void layernorm_kernel(LNArgs a) {
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    if (a.partials) {  // residual + bias + split-K partial sums of the GEMM that precedes this LayerNorm
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        if (a.add_bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.add_bias + col));
+          v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+        }
+        for (int z = 0; z < a.n_parts; ++z) {
+          const float4 q = *reinterpret_cast<const float4*>(a.partials + z * a.part_stride + static_cast<size_t>(r) * a.H + col);
+          v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+        }
+      }
+    }
     ln_row<NV>(v, a.H, a.gamma, a.beta, a.eps, lane, a.out_f32 ? a.out_f32 + static_cast<size_t>(r) * a.H : nullptr,
                a.out_act ? a.out_act + static_cast<size_t>(r) * a.ld_act : nullptr, a.split);
   }
