@@ -12,6 +12,8 @@ namespace conzic {
 
 static thread_local std::string g_err;
 uint64_t g_launches = 0;
+int g_pdl = 1;
+int g_pdl_now = 1;
 
 void set_error(const std::string& msg) { g_err = msg; }
 bool cuda_ok(cudaError_t e, const char* what) {
@@ -309,6 +311,7 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
   const int M = B * L;
   const int ldh = H * (1 + s), ldf = F * (1 + s);
   if (L > g.bert_maxpos) { set_error("bert: sequence longer than position table"); return false; }
+  g_pdl_now = 1;  // ~85 short launches: overlap their launch latencies
   launch_bert_embed_ln(inp, M, L, c->b_word, c->b_pos, c->b_type, c->b_eln_g, c->b_eln_b, g.bert_ln_eps, H, p.bx, p.bh,
                        ldh, s, st);
   for (size_t l = 0; l < c->bert.size(); ++l) {
@@ -393,6 +396,7 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     const int32_t* idp = P > 0 ? ids_prefix + static_cast<size_t>(b0) * P : nullptr;
     const int32_t* ids = ids_suffix + static_cast<size_t>(b0) * K * S;
     const int32_t* p0c = p0 ? p0 + b0 : nullptr;
+    g_pdl_now = (M < 50000) ? 1 : 0;
     const bool fold = c->ln_fold && !s;
     launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, fold ? p.cxb : nullptr,
                       fold ? p.cstats : nullptr, 4, st);
@@ -534,6 +538,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   if (const char* e = getenv("CONZIC_GEMM_BN")) c->gopt.bn = atoi(e);
   if (const char* e = getenv("CONZIC_GEMM_STAGES")) c->gopt.stages = atoi(e);
   // CLIP linears: persistent A-resident kernel (bf16 mode); CONZIC_GEMM_CG=2 pairs CTAs (tcgen05 cta_group::2)
+  if (const char* e = getenv("CONZIC_PDL")) g_pdl = atoi(e) ? 1 : 0;
   c->gopt.persist = c->split ? 0 : 1;
   c->gopt.cg = 2;
   if (const char* e = getenv("CONZIC_GEMM_PERSIST")) c->gopt.persist = c->split ? 0 : atoi(e);
@@ -750,6 +755,7 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan p = make_plan(c, ws, B, L, K);
   const conzic_config& g = c->cfg;
+  g_pdl_now = 1;
   launch_step_prologue(s->inp, B, L, pos, g.mask_id, s->token_mask, g.dot_id, s->dot_allowed, st);
   float* logits = s->tr_logits ? s->tr_logits : p.logits;
   if (s->logits_in) {
@@ -773,6 +779,7 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   a.ids_masked = p.ids_masked; a.repeats = ctl ? p.repeats : nullptr; a.senti = ctl ? p.senti : nullptr;
   launch_assemble(a, st);
   if (!clip_encode(c, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.text, p, st)) return -4;
+  g_pdl_now = 1;
   SelectArgs q{};
   q.text = p.text; q.image = s->image_embeds; q.B = B; q.K = K; q.D = g.clip_proj; q.scale = s->logit_scale_exp;
   q.probs = probs; q.ids_masked = p.ids_masked; q.senti = ctl ? p.senti : nullptr; q.repeats = ctl ? p.repeats : nullptr;

@@ -361,6 +361,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
+  PDL_ENTRY();
   using SL = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -515,6 +516,7 @@ template <int CG, bool ARES>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const PGemmParams p) {
+  PDL_ENTRY();
   using SL = PSmem<CG, ARES>;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
@@ -774,6 +776,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW2,
                    const MlpParams p) {
+  PDL_ENTRY();
   using SL = MlpSmem;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
@@ -990,6 +993,7 @@ struct WideSmem {
 
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PGemmParams p) {
+  PDL_ENTRY();
   using SL = WideSmem;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
@@ -1179,7 +1183,7 @@ bool configure_one() {
 template <int BN, int STAGES>
 void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.ksplit);
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, SmemLayout<BN, STAGES>::DYN_BYTES, st>>>(ta, tb, p);
+  launch_k(gemm_tcgen05_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), SmemLayout<BN, STAGES>::DYN_BYTES, st, ta, tb, p);
 }
 
 }  // namespace
@@ -1233,13 +1237,15 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   cfg.blockDim = dim3(P_THREADS);
   cfg.dynamicSmemBytes = PSmem<CG, ARES>::DYN_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
   return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, p), "gemm_persist launch");
 }
 
@@ -1283,11 +1289,13 @@ bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W
   cfg.blockDim = dim3(P_THREADS);
   cfg.dynamicSmemBytes = MlpSmem::DYN_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
   return cuda_ok(cudaLaunchKernelEx(&cfg, mlp_persist_kernel, th, W1.tmap128, tf, W2.tmap128, p), "mlp_persist launch");
 }
 
@@ -1304,11 +1312,13 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   cfg.blockDim = dim3(P_THREADS);
   cfg.dynamicSmemBytes = WideSmem::DYN_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
   return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel, ta, tb, p), "gemm_wide launch");
 }
 static bool configure_mlp() {

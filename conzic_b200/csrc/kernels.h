@@ -12,6 +12,35 @@ namespace conzic {
 typedef __nv_bfloat16 bf16;
 
 extern uint64_t g_launches;  // kernels launched by this library (all contexts)
+extern int g_pdl;            // 1 = launches may carry the programmatic-dependent-launch attribute (CONZIC_PDL, default 1)
+extern int g_pdl_now;        // set by the engine per section: measured on B200, PDL gains ~3.5 % on steps made of short
+                             // kernels (BERT, CLIP passes under ~50 k rows) and costs 1-2 % when the kernels are long
+
+// Programmatic dependent launch: every hot-path kernel starts with PDL_ENTRY() -- it lets the NEXT kernel in the
+// stream begin launching right away (griddepcontrol.launch_dependents) and then waits until everything the
+// PREVIOUS kernels wrote is complete and visible (griddepcontrol.wait), before touching any global memory.
+// The launch latency and block scheduling of kernel N+1 thereby overlap the execution of kernel N; a step is
+// ~180 dependent launches, many of them 5-20 us long.
+#define PDL_ENTRY()                                                   \
+  do {                                                                \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (g_pdl && g_pdl_now) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_kernel(const float* __restr
                                                             const float* __restrict__ mask, float temperature, int K,
                                                             int K2, float* __restrict__ probs,
                                                             int64_t* __restrict__ ids) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) unsigned char topk_smem[];
   unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(topk_smem);          // [K2]
   uint32_t* keys = reinterpret_cast<uint32_t*>(sortbuf + K2);                                // [V]
@@ -192,6 +193,7 @@ __device__ __forceinline__ bool is_special(const AssembleArgs& a, int64_t id) {
 }
 
 __global__ void assemble_kernel(AssembleArgs a) {
+  PDL_ENTRY();
   __shared__ int pre[MAX_BODY];
   __shared__ int tail[MAX_BODY];
   __shared__ int s_np, s_nt;
@@ -267,6 +269,7 @@ __global__ void assemble_kernel(AssembleArgs a) {
 
 __global__ void step_prologue_kernel(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                                      int dot_allowed) {
+  PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) inp[static_cast<size_t>(i) * L + pos] = mask_id;       // gen_utils.py:67
   if (i == 0 && token_mask && dot_id >= 0) token_mask[dot_id] = dot_allowed ? 1.0f : 0.0f;  // utils.py:53-59
@@ -278,6 +281,7 @@ __global__ void gather_rows_index_kernel(int32_t* rows, int B, int L, int pos) {
 }
 
 __global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S) {
+  PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * K) rows[i] = B * P + i * S + eos_idx[i];
 }
@@ -288,6 +292,7 @@ __global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int B, 
 constexpr int SEL_THREADS = 256;
 
 __global__ void __launch_bounds__(SEL_THREADS) score_select_kernel(SelectArgs a) {
+  PDL_ENTRY();
   extern __shared__ float sel_smem[];
   float* vhat = sel_smem;            // [D]
   float* logit = vhat + a.D;         // [K]
@@ -417,21 +422,21 @@ bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, 
     set_error("topk: vocabulary too large for the shared-memory row buffer");
     return false;
   }
-  topk_kernel<<<B, TOPK_THREADS, smem, st>>>(logits, ldl, V, mask, temperature, K, K2, probs, ids);
+  launch_k(topk_kernel, dim3(B), dim3(TOPK_THREADS), smem, st, logits, ldl, V, mask, temperature, K, K2, probs, ids);
   return cuda_ok(cudaGetLastError(), "topk launch");
 }
 
 void launch_assemble(const AssembleArgs& a, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_ASSEMBLE, 0, st);
-  assemble_kernel<<<a.B, 256, 0, st>>>(a);
+  launch_k(assemble_kernel, dim3(a.B), dim3(256), 0, st, a);
 }
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_MISC, 0, st);
-  step_prologue_kernel<<<(B + 255) / 256, 256, 0, st>>>(inp, B, L, pos, mask_id, token_mask, dot_id, dot_allowed);
+  launch_k(step_prologue_kernel, dim3((B + 255) / 256), dim3(256), 0, st, inp, B, L, pos, mask_id, token_mask, dot_id, dot_allowed);
 }
 
 void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t st) {
@@ -443,14 +448,14 @@ void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t
 void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_MISC, 0, st);
-  pool_index_kernel<<<(B * K + 255) / 256, 256, 0, st>>>(rows, eos_idx, B, P, K, S);
+  launch_k(pool_index_kernel, dim3((B * K + 255) / 256), dim3(256), 0, st, rows, eos_idx, B, P, K, S);
 }
 
 void launch_score_select(const SelectArgs& a, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_SELECT, 0, st);
   const size_t smem = static_cast<size_t>(a.D + 3 * a.K + 40) * sizeof(float);
-  score_select_kernel<<<a.B, SEL_THREADS, smem, st>>>(a);
+  launch_k(score_select_kernel, dim3(a.B), dim3(SEL_THREADS), smem, st, a);
 }
 
 }  // namespace conzic

@@ -80,6 +80,7 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int H, const float* __re
 
 template <int NV>
 __global__ void layernorm_kernel(LNArgs a) {
+  PDL_ENTRY();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < a.n_rows; r += gridDim.x * warps) {
@@ -113,6 +114,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ inp, int rows, 
                                      const float* __restrict__ pos, const float* __restrict__ type,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int H,
                                      float* __restrict__ x_f32, bf16* __restrict__ act, int ld_act, int split) {
+  PDL_ENTRY();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps) {
@@ -138,6 +140,7 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
                                   const float* __restrict__ tok, const float* __restrict__ pos, int H,
                                   float* __restrict__ x, bf16* __restrict__ xb, float2* __restrict__ stats,
                                   int stats_parts) {
+  PDL_ENTRY();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_pre = B * P;
@@ -219,6 +222,7 @@ __device__ __forceinline__ float2 load_pair(const void* base, size_t elem) {
 
 template <bool F32>
 __global__ void attention_kernel(AttnArgs a, int nk_cap) {
+  PDL_ENTRY();
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
@@ -394,6 +398,7 @@ __device__ __forceinline__ void att_put16(uint8_t* tile, int dst0, int n_rows, i
 
 template <int NT>  // NT key tiles of 8: up to NT*8 keys per tile
 __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
+  PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t att_smem[];
   constexpr int KV_BYTES = NT * 8 * 128;
   constexpr int WARP_BYTES = 2 * KV_BYTES + 16 * 128;
@@ -623,6 +628,7 @@ __global__ void vision_embed_kernel(const float* __restrict__ patch, const float
 // dst row r = src row rows[r]; rows of `row_bytes` bytes (a multiple of 16).  One warp per row.
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, size_t row_bytes, const int32_t* __restrict__ rows,
                                    int n, uint8_t* __restrict__ dst) {
+  PDL_ENTRY();
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < n; r += gridDim.x * warps) {
     const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(rows[r]) * row_bytes);
@@ -686,7 +692,7 @@ void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, 
   ++g_launches;
   ProfScope prof_(CAT_MISC, 0, st);
   if (n <= 0) return;
-  gather_rows_kernel<<<row_grid(n, 8), 256, 0, st>>>(static_cast<const uint8_t*>(src), row_bytes, rows, n,
+  launch_k(gather_rows_kernel, dim3(row_grid(n, 8)), dim3(256), 0, st, static_cast<const uint8_t*>(src), row_bytes, rows, n,
                                                      static_cast<uint8_t*>(dst));
 }
 
@@ -696,9 +702,9 @@ void launch_layernorm(const LNArgs& a, cudaStream_t st) {
   if (a.n_rows <= 0) return;
   const int grid = row_grid(a.n_rows, 8);
   switch (a.H / 128) {
-    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(a); break;
-    case 6: layernorm_kernel<6><<<grid, 256, 0, st>>>(a); break;
-    case 8: layernorm_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    case 4: launch_k(layernorm_kernel<4>, dim3(grid), dim3(256), 0, st, a); break;
+    case 6: launch_k(layernorm_kernel<6>, dim3(grid), dim3(256), 0, st, a); break;
+    case 8: launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), 0, st, a); break;
     default: set_error("layernorm: hidden size must be 512, 768 or 1024"); break;
   }
 }
@@ -710,9 +716,9 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
   ProfScope prof_(CAT_EMBED, static_cast<double>(rows) * H, st);
   const int grid = row_grid(rows, 8);
   switch (H / 128) {
-    case 4: bert_embed_ln_kernel<4><<<grid, 256, 0, st>>>(inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
-    case 6: bert_embed_ln_kernel<6><<<grid, 256, 0, st>>>(inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
-    case 8: bert_embed_ln_kernel<8><<<grid, 256, 0, st>>>(inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
+    case 4: launch_k(bert_embed_ln_kernel<4>, dim3(grid), dim3(256), 0, st, inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
+    case 6: launch_k(bert_embed_ln_kernel<6>, dim3(grid), dim3(256), 0, st, inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
+    case 8: launch_k(bert_embed_ln_kernel<8>, dim3(grid), dim3(256), 0, st, inp, rows, L, word, pos, type, gamma, beta, eps, H, x_f32, act, ld_act, split); break;
     default: set_error("bert_embed: hidden size must be 512, 768 or 1024"); break;
   }
 }
@@ -724,7 +730,7 @@ void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, con
   ProfScope prof_(CAT_EMBED, 0, st);
   const int rows = B * P + B * K * S;
   if (rows <= 0) return;
-  clip_embed_kernel<<<row_grid(rows, 8), 256, 0, st>>>(ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
+  launch_k(clip_embed_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, st, ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
                                                        x_f32, xb, stats, stats_parts);
 }
 
@@ -769,9 +775,9 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
       if (!cuda_ok(e, "cudaFuncSetAttribute(attention_mma)")) return false;
       configured[which_nt] = smem;
     }
-    if (nt == 4) attention_mma_kernel<4><<<grid, warps * 32, smem, st>>>(aa);
-    else if (nt == 8) attention_mma_kernel<8><<<grid, warps * 32, smem, st>>>(aa);
-    else attention_mma_kernel<12><<<grid, warps * 32, smem, st>>>(aa);
+    if (nt == 4) launch_k(attention_mma_kernel<4>, dim3(grid), dim3(warps * 32), smem, st, aa);
+    else if (nt == 8) launch_k(attention_mma_kernel<8>, dim3(grid), dim3(warps * 32), smem, st, aa);
+    else launch_k(attention_mma_kernel<12>, dim3(grid), dim3(warps * 32), smem, st, aa);
     return cuda_ok(cudaGetLastError(), "attention_mma launch");
   }
   if (nk_cap > 32 * MAX_SLOTS) {
@@ -799,9 +805,9 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     configured[which] = 220 * 1024;
   }
   if (a.qkv_f32)
-    attention_kernel<true><<<static_cast<int>(grid), warps * 32, smem, st>>>(a, nk_cap);
+    launch_k(attention_kernel<true>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap);
   else
-    attention_kernel<false><<<static_cast<int>(grid), warps * 32, smem, st>>>(a, nk_cap);
+    launch_k(attention_kernel<false>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap);
   return cuda_ok(cudaGetLastError(), "attention launch");
 }
 
