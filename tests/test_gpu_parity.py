@@ -376,6 +376,41 @@ def test_host_string_path_matches_reference(name, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
+def test_long_sentence_free_running_matches_oracle():
+    """sentence_len 25 (BASELINE config 5's longest): prefixes up to 29 tokens and candidate suffixes up to 27 rows
+    -> the 64-key attention tiles and the multi-tile query path; multi-token words.  One sweep of a free-running
+    call (bf16x3) against the CPU oracle on the same seeded inputs: identical token ids, scores within 2e-5."""
+    import logging
+    from conzic_b200 import gen_utils, runtime
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    from oracle import conzic_oracle as orc
+    import os
+    os.environ["CONZIC_PRECISION"] = "bf16x3"
+    try:
+        runtime.clear()
+        B, n, K = 2, 25, 24
+        bert_sd, clip_sd = gc.weights("bert"), synth.make_clip_state_dict(0, vision=True)
+        o = orc.Oracle(bert_sd, clip_sd, synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(True), full_logits=False)
+        pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+        with torch.no_grad():
+            ref_texts, ref_scores = o.generate(pix, synth.make_token_mask(), synth.SYNTH_PROMPT, order="sequential",
+                                               max_len=n, top_k=K, max_iters=1)
+        bert = BertMLM(bert_sd)
+        clip = CLIP(state_dict=clip_sd, tokenizer=synth.SynthCLIPTokenizer(True), processor=synth.SynthProcessor()).to("cuda:0")
+        texts, scores = gen_utils.generate_caption([f"img{i}.jpg" for i in range(B)], bert, clip, synth.SynthBertTokenizer(),
+                                                   pix, synth.make_token_mask("cuda"), logging.getLogger("test"),
+                                                   prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K,
+                                                   temperature=0.1, max_iter=1, alpha=0.02, beta=2.0,
+                                                   generate_order="sequential")
+        assert texts == ref_texts
+        for a, b in zip(scores, ref_scores):
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+    finally:
+        os.environ.pop("CONZIC_PRECISION", None)
+        runtime.clear()
+
+
 def test_prefix_sharing_equals_dense_encode():
     """Size-independent property: encoding candidates as shared prefix + per-candidate suffix gives the same
     cosine as encoding every full caption densely (causal tower => prefix states do not depend on the suffix)."""
