@@ -1,7 +1,7 @@
 """GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of libconzic.so;
 the CPU oracle and the golden fixtures recorded from the unmodified reference are the checkers.
 
-Tolerances (stated here, measured margins in profiles/r01_parity.md):
+Tolerances (stated here, measured margins in profiles/r01h_parity.md, from tools/parity_report.py):
   * bf16x3 mode (3-pass split operands, the parity mode): BERT row logits within 1e-3 of the reference,
     CLIP cosine within 2e-5, softmax_K score within 2e-4; top-k ids identical wherever the reference's
     probabilities are non-zero and distinct; chosen token ids identical.
