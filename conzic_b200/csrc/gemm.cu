@@ -591,11 +591,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr + c0),
                              "r"(nbytes) : "memory");
           }
-          if (ARES && newm && m + 1 < p.m_tiles) {
-            // next m tile of this CTA: its A rows go to L2 now, one slice of rows per k block
-            const int rows_per_kb = (BM + nkb - 1) / nkb;
-            const int r_lo = ((m + 1) * CG + static_cast<int>(cta_rank)) * BM + kb * rows_per_kb;
-            prefetch_a_rows(p, r_lo, min(r_lo + rows_per_kb, ((m + 1) * CG + static_cast<int>(cta_rank) + 1) * BM), p.K * 2);
+          if (ARES && p.a_ptr && n == p.n_tiles - 1 && m + 1 < p.m_tiles) {
+            // last unit of this m tile: the next m tile's A boxes (loaded one unit from now) go to L2
+            tma_prefetch_2d(&tmA, kb * BK, ((m + 1) * CG + static_cast<int>(cta_rank)) * BM);
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
           const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
@@ -1045,11 +1043,13 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr),
                            "r"(2 * PBN * 4) : "memory");
           }
-          if (m + n_groups < p.m_tiles) {
-            const int rows_per_kb = (BM + nkb - 1) / nkb;
-            const int nrow = ((m + n_groups) * CG + static_cast<int>(cta_rank)) * BM;
-            const int r_lo = nrow + kb * rows_per_kb;
-            prefetch_a_rows(p, r_lo, min(r_lo + rows_per_kb, nrow + BM), p.K * 2);
+          if (p.a_ptr) {
+            // A comes straight from HBM (it was written by the previous kernel and is far larger than L2): pull the
+            // box that will be loaded PF_DIST k blocks from now into L2, so the ring only has to cover L2 latency
+            constexpr int PF_DIST = 8;
+            int pk = kb + PF_DIST, pm = m;
+            if (pk >= nkb) { pk -= nkb; pm += n_groups; }
+            if (pm < p.m_tiles) tma_prefetch_2d(&tmA, pk * BK, (pm * CG + static_cast<int>(cta_rank)) * BM);
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * SL::STAGE);
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
@@ -1383,8 +1383,9 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
     static int allow_pf = -1;
     if (allow_pf < 0) {
-      // measured on B200: prefetching the next tile's A rows into L2 makes the GEMMs 10-20 % SLOWER (the ring of
-      // TMA loads already keeps HBM busy and the prefetch only adds traffic), so this stays an experiment switch
+      // measured on B200: prefetching upcoming A boxes into L2 (cp.async.bulk.prefetch.tensor, 8 k blocks or one
+      // unit ahead) makes the GEMMs 2-6 % SLOWER, row-wise bulk prefetch a whole tile ahead 10-20 % slower: the
+      // ring of TMA loads already keeps HBM busy.  Kept as an experiment switch only.
       const char* e = getenv("CONZIC_GEMM_APREFETCH");
       allow_pf = e ? atoi(e) : 0;
     }
