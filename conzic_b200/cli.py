@@ -98,6 +98,7 @@ def load_models(args):
         clip = CLIP(state_dict=synth.make_clip_state_dict(0), tokenizer=synth.SynthCLIPTokenizer(),
                     processor=synth.SynthProcessor())
         table = synth.make_sentiment_table()
+        control_gen_utils.set_pos_tagger(synth.synth_pos_tagger)  # --control_type pos without NLTK
     else:
         from transformers import AutoTokenizer
         lm_model = BertMLM.from_pretrained(args.lm_model)

@@ -734,14 +734,14 @@ int conzic_image_text_similarity(conzic_ctx* c, const float* text, const float* 
 int conzic_score_select(conzic_ctx* c, const float* text, const float* image, int B, int K, float scale,
                         const float* probs, const int64_t* ids_masked, const float* senti_raw, const float* repeats,
                         float alpha, float beta, float gamma, int64_t* inp, int L, int pos, float* out_clip_ref,
-                        float* out_senti, void* stream) {
+                        float* out_senti, int64_t* out_best, void* stream) {
   if (!c || !text || !image || !probs || !ids_masked || !inp || !out_clip_ref) { set_error("score_select: null argument"); return -1; }
   if (K < 1 || K > 1024 || pos < 0 || pos >= L) { set_error("score_select: bad K / pos"); return -1; }
   SelectArgs q{};
   q.text = text; q.image = image; q.B = B; q.K = K; q.D = c->cfg.clip_proj; q.scale = scale;
   q.probs = probs; q.ids_masked = ids_masked; q.senti = senti_raw; q.repeats = repeats;
   q.alpha = alpha; q.beta = beta; q.gamma = gamma;
-  q.inp = inp; q.L = L; q.pos = pos; q.out_clip_ref = out_clip_ref; q.out_senti = out_senti;
+  q.inp = inp; q.L = L; q.pos = pos; q.out_clip_ref = out_clip_ref; q.out_senti = out_senti; q.tr_best = out_best;
   launch_score_select(q, static_cast<cudaStream_t>(stream));
   return cuda_ok(cudaGetLastError(), "score_select") ? 0 : -4;
 }

@@ -296,9 +296,9 @@ class Engine:
         return score, ref
 
     def score_select(self, text_embeds, image_embeds, probs, ids_masked, inp, pos, alpha, beta, gamma=None,
-                     senti_raw=None, repeats=None, out_clip_ref=None, out_senti=None):
+                     senti_raw=None, repeats=None, out_clip_ref=None, out_senti=None, out_best=None):
         """Score fuse + argmax + write-back (gen_utils.py:77-81, control_gen_utils.py:59-65) on caller-built
-        candidate embeddings; `inp[:, pos]` receives the winners."""
+        candidate embeddings; `inp[:, pos]` receives the winners, `out_best` (int64[B], optional) their index."""
         B, K = probs.shape
         if out_clip_ref is None:
             out_clip_ref = torch.empty((B,), dtype=torch.float32, device=self.device)
@@ -310,7 +310,7 @@ class Engine:
                                           _ptr(senti_raw if ctl else None), _ptr(repeats if ctl else None),
                                           float(alpha), float(beta), float(gamma) if ctl else 0.0, _ptr(inp),
                                           inp.shape[1], int(pos), _ptr(out_clip_ref), _ptr(out_senti if ctl else None),
-                                          self._stream())
+                                          _ptr(out_best), self._stream())
         _lib.check(rc, "conzic_score_select")
         return out_clip_ref, (out_senti if ctl else None)
 

@@ -56,7 +56,8 @@ class _Chain:
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
 
-    def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
+    def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
+                         pos_scorer=None):
         """The same step with the reference's string round trip (gen_utils.py:66-81): candidate ids -> host ->
         tokenizer.batch_decode -> CLIP tokenizer -> device.  Every arithmetic piece is still a libconzic kernel;
         only the text handling runs on the host.  Used when the BERT vocabulary has '##' word pieces, whose merge
@@ -76,8 +77,15 @@ class _Chain:
         flat = cand.view(-1, cand.shape[-1])
         texts = tok.batch_decode(flat, skip_special_tokens=True)
         text_embeds = self.clip.compute_text_representation(texts)
-        senti_raw = repeats = None
-        if gamma is not None:
+        senti_raw = repeats = best = None
+        if pos_scorer is not None:
+            # POS template (control_gen_utils.py:164-168): softmax_K(score / 0.1), no repeat penalty; the winner's
+            # index comes back so its tag sequence and raw score can be reported (:171-178)
+            tags, raw = pos_scorer(texts)
+            raw = raw.to(torch.float32).view(self.B, top_k)
+            senti_raw = (raw / 0.1).to(eng.device).contiguous()
+            best = torch.empty((self.B,), dtype=torch.int64, device=eng.device)
+        elif gamma is not None:
             special = torch.tensor(sorted({eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id}))
             table = senti_table.cpu()
             vis = ~torch.isin(flat, special)
@@ -85,12 +93,18 @@ class _Chain:
             repeats = ((ids_masked_h[:, :, None] == cand).float().sum(2) - 1).to(eng.device).contiguous()
         eng.score_select(text_embeds, self.image_embeds, probs, ids_masked_h.to(eng.device), self.inp, pos, alpha, beta,
                          gamma=gamma, senti_raw=senti_raw, repeats=repeats, out_clip_ref=self.clip_slots[slot],
-                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
+                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None, out_best=best)
+        if best is not None:
+            win = best.cpu()
+            self.pos_scores = raw.gather(1, win.view(-1, 1)).squeeze(-1).numpy().tolist()
+            self.pos_tags = [tags[int(win[i]) + i * top_k] for i in range(self.B)]
         self.holds_word[pos] = True
 
-    def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
-        if self.string_path:
-            return self.step_via_strings(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in)
+    def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
+             pos_scorer=None):
+        if self.string_path or pos_scorer is not None:
+            return self.step_via_strings(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in,
+                                         pos_scorer)
         pos = self.seed_len + ii
         before = sum(self.holds_word[:pos])
         after = sum(self.holds_word[pos + 1:])
@@ -107,19 +121,23 @@ class _Chain:
 
 
 def _sweeps(name, img_name, model, clip, tokenizer, image_instance, token_mask, prompt, logger, max_len, top_k,
-            temperature, alpha, beta, max_iters, batch_size, verbose, order, gamma=None, senti_table=None):
-    """Sequential / shuffled sweeps (gen_utils.py:51-146, control_gen_utils.py:30-134)."""
+            temperature, alpha, beta, max_iters, batch_size, verbose, order, gamma=None, senti_table=None,
+            pos_scorer=None):
+    """Sequential / shuffled sweeps (gen_utils.py:51-146, control_gen_utils.py:30-195).  `pos_scorer(texts) ->
+    (tag sequences, f32[N] scores)` selects the POS-template formula, `senti_table` the sentiment one."""
     ch = _Chain(model, clip, tokenizer, image_instance, token_mask, prompt, max_len, batch_size, gamma is not None)
     best_score, best_caption = [0] * batch_size, ["None"] * batch_size
     texts, scores = [], []
     cur_text, cur_score = None, None
     for it in range(max_iters):
         for slot, ii in enumerate(order):
-            ch.step(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table)
+            ch.step(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, pos_scorer=pos_scorer)
         last = len(order) - 1
         ids = ch.inp.cpu()  # one device->host read per sweep
         cur_score = ch.clip_slots[last].cpu().numpy().tolist()
         cur_senti = ch.senti_slots[last].cpu().numpy().tolist() if gamma is not None else None
+        if pos_scorer is not None:
+            cur_senti = ch.pos_scores
         if verbose:
             shown = tokenizer.batch_decode(ids)
             cur_text = tokenizer.batch_decode(ids, skip_special_tokens=True)
@@ -132,6 +150,8 @@ def _sweeps(name, img_name, model, clip, tokenizer, image_instance, token_mask, 
                 else:
                     logger.info(f"iter {it + 1}, The {jj+1}-th image: {img_name[jj]}, clip score {cur_score[jj]:.3f}"
                                 f", ctl score {cur_senti[jj]:.3f}: " + shown[jj])
+                    if pos_scorer is not None:
+                        logger.info(ch.pos_tags[jj])
         texts.append(cur_text)
         scores.append(cur_score)
     texts.append(best_caption)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CONZIC_ABI_VERSION 2
+#define CONZIC_ABI_VERSION 3
 
 typedef struct conzic_ctx conzic_ctx;
 
@@ -120,12 +120,17 @@ int conzic_image_text_similarity(conzic_ctx* ctx, const float* text_embeds_dev, 
 /* Score fuse + argmax + write-back on its own (gen_utils.py:77-81, control_gen_utils.py:59-65), for callers that
  * build the candidate texts themselves (host string path for vocabularies with '##' word pieces):
  *   final = alpha*probs + beta*softmax_K(scale*cos) (+ gamma*softmax_K(senti_raw) + 0.1*(1-exp(repeats)));
- *   inp[b,pos] = ids_masked[b, argmax]; out_clip_ref[b] = cos of the winner; out_senti[b] = senti_raw of the winner.
+ *   inp[b,pos] = ids_masked[b, argmax]; out_clip_ref[b] = cos of the winner; out_senti[b] = senti_raw of the winner;
+ *   out_best[b] = argmax (int64, may be NULL) -- the POS-template path needs it to pick the winner's tag
+ *   sequence and raw score on the host (control_gen_utils.py:171-178).
+ * A control term with its own softmax temperature t (POS: 0.1, control_gen_utils.py:166) passes senti_raw = raw / t
+ * and repeats = NULL (no repeat penalty in that formula).
  * text f32[B*K,D], image f32[B,D], probs f32[B,K], ids_masked int64[B,K], senti_raw / repeats f32[B,K] or NULL. */
 int conzic_score_select(conzic_ctx* ctx, const float* text_embeds_dev, const float* image_embeds_dev, int B, int K,
                         float logit_scale_exp, const float* probs_dev, const int64_t* ids_masked_dev,
                         const float* senti_raw_dev, const float* repeats_dev, float alpha, float beta, float gamma,
-                        int64_t* inp_dev, int L, int pos, float* out_clip_ref_dev, float* out_senti_dev, void* stream);
+                        int64_t* inp_dev, int L, int pos, float* out_clip_ref_dev, float* out_senti_dev,
+                        int64_t* out_best_dev, void* stream);
 
 /* One whole Gibbs step (gen_utils.py:66-81, control_gen_utils.py:45-67) with no host round trip:
  *   token_mask[dot_id] = dot_allowed; inp[:,pos] = [MASK]; BERT row logits; top-K; candidates -> CLIP ids

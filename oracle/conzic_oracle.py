@@ -9,7 +9,8 @@ eager torch, so torch CPU ops are the faithful medium):
 
 * the reference's own loop code: ``gen_utils.py:33-49`` (``generate_caption_step``),
   ``gen_utils.py:51-96 / 98-146 / 197-242`` (sequential / shuffle / random order),
-  ``control_gen_utils.py:30-134`` (sentiment variants), ``utils.py:46-59`` (init text, '.' mask
+  ``control_gen_utils.py:30-134`` (sentiment variants), ``control_gen_utils.py:136-195`` +
+  ``POS_classifier.py:6-31`` (POS-template variant; the NLTK tagger itself is a plug-in), ``utils.py:46-59`` (init text, '.' mask
   rule), ``clip/clip.py:48-102`` (image / text representation, similarity);
 * the third-party arithmetic those call, which is NOT under ``/root/reference``:
   ``transformers`` (unpinned in ``requirements.txt:3``; 5.5.0 is what is installed here):
@@ -183,6 +184,25 @@ def table_sentiment(batch_texts: List[str], table: torch.Tensor, tokenizer, temp
     return F.softmax(scores / temperature, dim=1), scores
 
 
+def pos_template_scores(batch_texts: List[str], template, tagger):
+    """POS_classifier.py:6-31: tag every caption, fit the tag list to the template length (cut, or pad with ""),
+    count slots that are empty or contain the tag (Python ``in``), score = count / slots.  ``tagger(text)`` stands
+    in for ``nltk.pos_tag(word_tokenize(text), tagset="universal")``."""
+    scores = torch.zeros(len(batch_texts))
+    tags_out = []
+    for b, text in enumerate(batch_texts):
+        res = list(tagger(text))
+        total = len(template)
+        cur = res + [""] * (total - len(res)) if len(res) <= total else res[:total]
+        correct = 0
+        for w in range(len(cur)):
+            if template[w] == "" or cur[w] in template[w]:
+                correct += 1
+        tags_out.append(res)
+        scores[b] = correct / total
+    return tags_out, scores
+
+
 class Oracle:
     """Holds the two state dicts and the tokenizers; methods mirror the reference's callables."""
 
@@ -214,7 +234,7 @@ class Oracle:
 
     # -- one Gibbs step: gen_utils.py:66-81 / control_gen_utils.py:45-67 --------------------
     def step(self, inp, image_embeds, token_mask, pos, ii, max_len, top_k, temperature, alpha, beta,
-             gamma=None, ctl_signal="positive", logits_row=None):
+             gamma=None, ctl_signal="positive", logits_row=None, pos_template=None, pos_tagger=None):
         """`logits_row` (f32[B,V]): logits of row `pos` from an earlier forward (span order, gen_utils.py:162-165);
         None = run BERT on the current ids."""
         tok = self.tokenizer
@@ -242,7 +262,11 @@ class Oracle:
         clip_score, clip_ref = image_text_similarity(image_embeds, text_embeds, self.clip_sd["logit_scale"])
         final = alpha * probs + beta * clip_score
         senti_scores = None
-        if gamma is not None:
+        if pos_template is not None:  # control_gen_utils.py:164-168
+            _, pos_scores = pos_template_scores(texts, pos_template, pos_tagger)
+            senti_scores = pos_scores.view(inp.shape[0], -1)
+            final = final + gamma * torch.softmax(senti_scores / 0.1, dim=-1)
+        elif gamma is not None:
             repeats = (idxs_[:, :, None] == topk_inp).float().sum(2) - 1
             table = -self.sentiment_table if ctl_signal == "negative" else self.sentiment_table
             senti_probs, senti_scores = table_sentiment(texts, table, tok, 1, inp.shape[0])
@@ -262,7 +286,7 @@ class Oracle:
     # -- the loops: gen_utils.py:51-146,197-242; control_gen_utils.py:30-134 ---------------------
     def generate(self, pixel_values, token_mask, prompt, order="sequential", max_len=10, top_k=200,
                  temperature=0.1, alpha=0.02, beta=2.0, max_iters=5, gamma=None, ctl_signal="positive",
-                 image_embeds=None):
+                 image_embeds=None, pos_template=None, pos_tagger=None):
         """Returns (gen_texts_list, clip_score_sequence) with the reference's structure:
         one list per sweep plus the best-by-CLIP-score list last (gen_utils.py:93-96)."""
         tok = self.tokenizer
@@ -312,7 +336,8 @@ class Oracle:
             for _ in range(max_iters):
                 for ii in positions:
                     cur, _ = self.step(inp, image_embeds, token_mask, seed_len + ii, ii, max_len, top_k,
-                                       temperature, alpha, beta, gamma, ctl_signal)
+                                       temperature, alpha, beta, gamma, ctl_signal, pos_template=pos_template,
+                                       pos_tagger=pos_tagger)
                 cur_text = tok.batch_decode(inp, skip_special_tokens=True)
                 for jj in range(B):
                     if best_score[jj] < cur[jj]:

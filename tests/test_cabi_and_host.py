@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libconzic.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.conzic_abi_version() == 2
+    assert lib.conzic_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -98,8 +98,42 @@ def test_reference_api_surface():
     assert d == dict(max_len=15, top_k=100, temperature=None, alpha=0.7, beta=1, max_iters=20, batch_size=1, verbose=True)
     for name in ("shuffle_generation", "random_generation", "generate_caption_step"):
         assert hasattr(gen_utils, name)
-    for name in ("sentiment_sequential_generation", "sentiment_shuffle_generation", "generate_caption_step"):
+    for name in ("sentiment_sequential_generation", "sentiment_shuffle_generation", "generate_caption_step",
+                 "POS_sequential_generation"):
         assert hasattr(control_gen_utils, name)
+    sig = inspect.signature(control_gen_utils.POS_sequential_generation)  # control_gen_utils.py:136-139
+    d = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    assert d == dict(max_len=15, top_k=0, temperature=None, alpha=0.7, beta=1, gamma=0.1, max_iters=20, batch_size=1,
+                     ctl_signal=["DET"], verbose=True)
+
+
+def test_pos_template_scoring_matches_oracle_and_known_answers():
+    """POS_classifier.py:6-31 through the product's host scorer: hand-worked cases (cut, pad, empty slot, list
+    membership versus substring slots) and agreement with the oracle's restatement on synthetic captions."""
+    from conzic_b200 import control_gen_utils as cgu
+    from oracle import conzic_oracle as orc
+    canned = {"a": ["DET", "NOUN"], "b": ["DET", "NOUN", "VERB", "ADV"], "c": ["NOUN"], "d": []}
+    tagger = canned.__getitem__
+    tpl = [["DET"], "", ["VERB", "NOUN"]]
+    tags, sc = cgu.batch_texts_POS_analysis(["a", "b", "c", "d"], tpl, tagger=tagger)
+    assert tags == [canned[k] for k in "abcd"]
+    # a: DET ok, "" ok, pad "" not in list -> 2/3;  b: cut to 3, all ok -> 1;  c: NOUN not DET, "" ok, pad -> 1/3;  d: 1/3
+    np.testing.assert_array_equal(sc.numpy(), np.array([2 / 3, 1.0, 1 / 3, 1 / 3], dtype=np.float32))
+    # a string slot is a substring test, so the "" padding matches it (the reference's `in` quirk)
+    _, sc = cgu.batch_texts_POS_analysis(["c", "d"], ["NOUN", "ADV"], tagger=tagger)
+    np.testing.assert_array_equal(sc.numpy(), np.array([1.0, 1.0], dtype=np.float32))
+    texts = [" ".join(f"w{2000 + (i * 37 + j * 101) % 20000}" for j in range(3 + i % 6)) + (" ." if i % 3 == 0 else "")
+             for i in range(64)]
+    t1, s1 = cgu.batch_texts_POS_analysis(texts, synth.SYNTH_POS_TEMPLATE, tagger=synth.synth_pos_tagger)
+    t2, s2 = orc.pos_template_scores(texts, synth.SYNTH_POS_TEMPLATE, synth.synth_pos_tagger)
+    assert t1 == t2 and torch.equal(s1, s2) and len(set(s1.tolist())) > 2
+
+
+def test_pos_control_without_a_tagger_fails_loudly():
+    from conzic_b200 import control_gen_utils as cgu
+    cgu.set_pos_tagger(None)
+    with pytest.raises(RuntimeError, match="set_pos_tagger"):
+        cgu.batch_texts_POS_analysis(["w2000 w2001"], [["DET"]])
 
 
 def test_cli_flags_and_defaults_match_the_reference():

@@ -309,7 +309,8 @@ def _models(case):
 
 
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "random_b2_n3_k8", "senti_seq_b2_n4_k8",
-                                  "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32", "span_b2_n5_k8"])
+                                  "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32", "span_b2_n5_k8",
+                                  "pos_seq_b2_n5_k16"])
 def test_free_running_call_matches_reference(name, monkeypatch):
     """generate_caption / control_generate_caption through the drop-in API under set_seed(42): same captions per
     sweep, same best list, same CLIP scores as the unmodified reference returned (bf16x3 mode)."""
@@ -318,6 +319,7 @@ def test_free_running_call_matches_reference(name, monkeypatch):
     from conzic_b200.utils import set_seed
     monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
     runtime.clear()
+    control_gen_utils.set_pos_tagger(synth.synth_pos_tagger)  # POS control: the tagger is a plug-in
     g = gc.load_golden(name)
     case = g["case"]
     bert, clip = _models(case)
@@ -335,7 +337,8 @@ def test_free_running_call_matches_reference(name, monkeypatch):
     else:
         texts, scores = control_gen_utils.control_generate_caption(
             names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask, logger, gamma=case["gamma"],
-            ctl_type="sentiment", style_type=case["style"], sentiment_table=synth.make_sentiment_table(), **kw)
+            ctl_type=case.get("ctl", "sentiment"), style_type=case.get("style", "positive"),
+            pos_type=synth.SYNTH_POS_TEMPLATE, sentiment_table=synth.make_sentiment_table(), **kw)
     runtime.clear()
     assert texts == g["texts"]
     for a, b in zip(scores, g["scores"]):

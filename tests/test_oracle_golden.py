@@ -13,7 +13,14 @@ from conzic_b200 import synth
 from oracle import conzic_oracle as orc
 
 ALL = sorted(f[:-3] for f in os.listdir(GOLDEN) if f.endswith(".pt"))
-FAST = ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32"]
+FAST = ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32",
+        "pos_seq_b2_n5_k16"]
+
+
+def _pos(case):
+    if case.get("ctl") != "pos":
+        return {}
+    return dict(pos_template=synth.SYNTH_POS_TEMPLATE, pos_tagger=synth.synth_pos_tagger)
 
 
 def make_oracle(g, synth_weights, full_logits=False):
@@ -44,7 +51,7 @@ def test_teacher_forced_steps(name, synth_weights):
         token_mask = synth.make_token_mask()
         with torch.no_grad():
             o.step(inp, s["image_embeds"], token_mask, pos, ii, n, K, 0.1, 0.02, 2.0,
-                   gamma=case.get("gamma"), ctl_signal=case.get("style", "positive"))
+                   gamma=case.get("gamma"), ctl_signal=case.get("style", "positive"), **_pos(case))
         t = o.trace[-1]
         assert float(token_mask[0, synth.DOT_ID]) == s["token_mask_dot"]
         cols = s["logit_cols"].long()
@@ -65,7 +72,8 @@ def test_teacher_forced_steps(name, synth_weights):
                 assert torch.equal(inp[:, keep], nxt[:, keep])
 
 
-@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8", "span_b2_n5_k8"])
+@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8", "span_b2_n5_k8",
+                                  "pos_seq_b2_n5_k16"])
 def test_free_running_call(name, synth_weights):
     """Whole ``generate_caption`` / ``control_generate_caption`` call under set_seed(42):
     same captions per sweep, same CLIP scores, same best list as the reference returned."""
@@ -77,7 +85,7 @@ def test_free_running_call(name, synth_weights):
     with torch.no_grad():
         texts, scores = o.generate(pix, synth.make_token_mask(), synth.SYNTH_PROMPT, order=case["order"],
                                    max_len=case["n"], top_k=case["K"], max_iters=case["iters"],
-                                   gamma=case.get("gamma"), ctl_signal=case.get("style", "positive"))
+                                   gamma=case.get("gamma"), ctl_signal=case.get("style", "positive"), **_pos(case))
     assert texts == g["texts"]
     assert len(scores) == len(g["scores"])
     for a, b in zip(scores, g["scores"]):

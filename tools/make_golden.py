@@ -6,7 +6,8 @@
 The reference modules (``gen_utils``, ``control_gen_utils``, ``clip.clip``, ``utils``) are imported
 from /root/reference exactly as they are.  What is supplied around them:
 
-* a 1-line ``colorlog`` shim and stub ``sentiments_classifer`` / ``POS_classifier`` modules
+* a 1-line ``colorlog`` shim, a stub ``sentiments_classifer`` module, and stub ``nltk.pos_tag`` /
+  ``nltk.tokenize.word_tokenize`` callables under the unmodified ``POS_classifier``
   (NLTK / colorlog are not installed and there is no network; SURVEY.md 8(c));
 * HF ``BertForMaskedLM(BertConfig())`` / ``CLIPModel(CLIPConfig())`` loaded with the synthetic
   state dicts from ``conzic_b200.synth`` (no pretrained weights exist offline);
@@ -51,10 +52,23 @@ def import_reference(sentiment_table):
         return torch.softmax(sb / temperature, dim=1).to(device), sb, [], []
 
     sys.modules["sentiments_classifer"] = types.SimpleNamespace(batch_texts_POS_Sentiments_analysis=table_scorer)
-    sys.modules["POS_classifier"] = types.SimpleNamespace(batch_texts_POS_analysis=None)
+    # POS_classifier.py is imported UNMODIFIED; only the two NLTK callables it uses are supplied, backed by
+    # the synthetic tagger (NLTK and its corpora are not installed)
+    nltk = types.ModuleType("nltk")
+    nltk.tokenize = types.ModuleType("nltk.tokenize")
+    nltk.tokenize.word_tokenize = lambda text: text.replace(".", " . ").split()
+    nltk.pos_tag = lambda words, tagset=None: list(zip(words, synth.synth_pos_tagger(" ".join(words))))
+    sys.modules["nltk"], sys.modules["nltk.tokenize"] = nltk, nltk.tokenize
     import utils, gen_utils, control_gen_utils  # noqa: E401  (unmodified reference modules)
-    from clip.clip import CLIP
-    return utils, gen_utils, control_gen_utils, CLIP
+    # /root/reference/clip has no __init__.py, so this repo's root-level `clip` shim package would win the
+    # name; load the reference's file by path instead
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_clip_clip", os.path.join(REF, "clip", "clip.py"))
+    ref_clip = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_clip)
+    for m in (utils, gen_utils, control_gen_utils):
+        assert m.__file__.startswith(REF), m.__file__
+    return utils, gen_utils, control_gen_utils, ref_clip.CLIP
 
 
 def build_models(bert_sd, clip_sd, CLIP, multi):
@@ -131,6 +145,7 @@ CASES = [
     dict(name="peaked_seq_b2_n4_k32", order="sequential", B=2, n=4, K=32, iters=2, peaked=True),
     dict(name="seq_b1_n10_k200", order="sequential", B=1, n=10, K=200, iters=1),
     dict(name="span_b2_n5_k8", order="span", B=2, n=5, K=8, iters=2),
+    dict(name="pos_seq_b2_n5_k16", order="sequential", B=2, n=5, K=16, iters=2, gamma=5.0, ctl="pos"),
 ]
 
 
@@ -166,7 +181,8 @@ def main():
             else:
                 texts, scores = control_gen_utils.control_generate_caption(
                     names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask, logger, gamma=gamma,
-                    ctl_type="sentiment", style_type=case["style"], **kw)
+                    ctl_type=case.get("ctl", "sentiment"), style_type=case.get("style", "positive"),
+                    pos_type=synth.SYNTH_POS_TEMPLATE, **kw)
         rec.close()
         fixture = dict(case=case, steps=rec.steps, texts=texts, scores=scores,
                        bert_crc=synth.state_dict_checksum(bert_sd), clip_crc=synth.state_dict_checksum(clip_sd),
