@@ -58,10 +58,11 @@ def ncu_traffic():
     (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture has been summarised."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
-        return None
+        return None, None
     d = json.load(open(p))
-    return {"bytes_per_launch": d.get("dram_bytes_per_launch"), "kernel": d.get("kernel"), "shape": d.get("shape"),
-            "algorithmic_bytes_per_launch": d.get("algorithmic_bytes_per_launch"), "source": d.get("source")}
+    return d.get("dram_bytes_per_launch"), {"kernel": d.get("kernel"), "shape": d.get("shape"),
+                                            "algorithmic_bytes_per_launch": d.get("algorithmic_bytes_per_launch"),
+                                            "source": d.get("source")}
 
 
 class ClockSampler:
@@ -278,6 +279,7 @@ def run_ours(args, rank, local_rank, world):
     prof = eng.profile_read()
     eng.profile(False)
     pk = peaks()
+    traffic, traffic_detail = ncu_traffic()
     g_ms, g_flops, g_n = prof["gemm"]
     achieved = g_flops / (g_ms / 1000.0) / 1e12 if g_ms > 0 else 0.0
     total_ms = sum(v[0] for v in prof.values())
@@ -288,10 +290,12 @@ def run_ours(args, rank, local_rank, world):
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
-                "roofline": {"kernel": "gemm_persist_kernel<2,*> (CLIP linears; CTA pairs, tcgen05 cta_group::2) + "
-                                       "gemm_tcgen05_kernel (BERT linears)", "bound": "tensor",
+                "roofline": {"kernel": "gemm_persist_kernel<2,*> + gemm_wide_kernel (the CLIP towers' linears: CTA "
+                                       "pairs, tcgen05 cta_group::2, TMA-fed); average over the launches of one step",
+                             "bound": "tensor",
                              "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
-                             "peak_source": f"{pk['src']} sustained bf16", "traffic": ncu_traffic(),
+                             "peak_source": f"{pk['src']} sustained bf16", "traffic": traffic,
+                             "traffic_detail": traffic_detail,
                              "launches_profiled": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
                              "flops_per_launch": g_flops / max(g_n, 1),
                              "share_of_step": g_ms / total_ms if total_ms else None},

@@ -135,6 +135,9 @@ struct conzic_ctx {
   int chunk_rows = 303104;
   int ln_fold = 0;    // LayerNorm folded into QKV / fc1 of the CLIP tower (bf16 persistent path)
   int mlp_fused = 0;  // fc1 + fc2 of a CLIP block in one persistent launch (bf16 mode, CTA pairs)
+  int wide_ln_mode = 1;
+  int wide_ln = 0;    // CLIP tower: LayerNorm written by the epilogue of the GEMM that produces the residual stream
+                      // (gemm_wide_kernel): 1 = fc2 -> next block's LN1 / final LN, 2 = also O-proj -> LN2
   uint64_t launches0 = 0;
 
   ~conzic_ctx() {
@@ -415,6 +418,14 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     };
     const int NE = nb * K;  // candidate captions of this chunk = rows that are pooled (one EOS row each)
     float* xe = p.cxe + static_cast<size_t>(b0) * K * H;
+    // LayerNorm fused into the producer GEMM's epilogue (gemm_wide_kernel owns whole 512-column rows)
+    const int wl = (!fold && !c->mlp_fused && !s) ? c->wide_ln : 0;
+    bool h_ready = false, pooled_ready = false;
+    auto with_ln = [&](Epi e, bf16* out, const float* gamma, const float* beta) {
+      e.lnf_out = out; e.lnf_ld = ldh; e.lnf_g = gamma; e.lnf_b = beta; e.lnf_eps = g.clip_ln_eps;
+      e.lnf_mode = c->wide_ln_mode;
+      return e;
+    };
     for (size_t l = 0; l < c->clip.size(); ++l) {
       const Layer& ly = c->clip[l];
       const bool last = (l + 1 == c->clip.size());
@@ -424,8 +435,10 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
                            c->gopt, st, nullptr))
           return false;
       } else {
-        LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
-        launch_layernorm(ln1, st);
+        if (!h_ready) {  // otherwise the previous block's fc2 epilogue already wrote LN1(x) into ch
+          LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+          launch_layernorm(ln1, st);
+        }
         Act h{p.ch, ldh, H};
         Epi e;
         if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
@@ -461,9 +474,16 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
         if (!launch_linear(f, Mr, ly.f2, epi_x_producer(ly.f2, x, !last), c->gopt, st, nullptr)) return false;
         continue;
       }
-      if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), c->gopt, st, nullptr)) return false;
-      LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
-      launch_layernorm(ln2, st);
+      if (wl >= 2) {
+        GemmOpts ow = c->gopt;
+        ow.force_wide = 1;
+        if (!launch_linear(a, Mr, ly.o, with_ln(epi_f32_out(ly.o, x, H, x, H, ACT_NONE), h2, ly.ln2_g, ly.ln2_b), ow, st, nullptr))
+          return false;
+      } else {
+        if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), c->gopt, st, nullptr)) return false;
+        LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
+        launch_layernorm(ln2, st);
+      }
       Act hh{h2, ldh, H};
       if (c->mlp_fused) {
         if (!launch_mlp_fused(hh, Mr, ly.f1, ly.f2, p.cscratch, ACT_QUICK_GELU, x, H, x, H, nullptr, 0, st)) return false;
@@ -471,7 +491,15 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
         if (!launch_linear(hh, Mr, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), c->gopt, st, nullptr))
           return false;
         Act f{p.cffn, ldf, F};
-        if (!launch_linear(f, Mr, ly.f2, epi_f32_out(ly.f2, x, H, x, H, ACT_NONE), c->gopt, st, nullptr))
+        Epi e2 = epi_f32_out(ly.f2, x, H, x, H, ACT_NONE);
+        if (wl >= 1 && !last) {  // LN1 of the next block, straight into its QKV operand
+          e2 = with_ln(e2, p.ch, c->clip[l + 1].ln1_g, c->clip[l + 1].ln1_b);
+          h_ready = true;
+        } else if (wl >= 1) {    // last block (EOS rows only): the final LayerNorm, straight into the projection operand
+          e2 = with_ln(e2, p.cpool, c->c_fln_g, c->c_fln_b);
+          pooled_ready = true;
+        }
+        if (!launch_linear(f, Mr, ly.f2, e2, c->gopt, st, nullptr))
           return false;
       }
     }
@@ -480,8 +508,10 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
       launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
     }
     // pooled = final LN of the hidden state at the first EOS (already compacted); text_projection without bias
-    LNArgs lnf{xe, nullptr, NE, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
-    launch_layernorm(lnf, st);
+    if (!pooled_ready) {
+      LNArgs lnf{xe, nullptr, NE, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
+      launch_layernorm(lnf, st);
+    }
     Act pooled{p.cpool, ldh, H};
     Epi e;
     e.out_f32 = text + static_cast<size_t>(b0) * K * g.clip_proj;
@@ -551,6 +581,11 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
     c->ln_fold = (atoi(e) && c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;
   // fc1+fc2 in one launch (mlp_persist_kernel): measured equal to the two-launch path on B200 (the 78 MB of
   // per-CTA scratch tiles do not survive in L2 between fc1 and fc2), so it is opt-in: CONZIC_MLP_FUSED=1
+  c->wide_ln = 0;
+  if (const char* e = getenv("CONZIC_WIDE_LN_MODE")) c->wide_ln_mode = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("CONZIC_WIDE_LN"))
+    c->wide_ln = (c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 && !c->split &&
+                  cfg->clip_hidden == 512) ? atoi(e) : 0;
   c->mlp_fused = 0;
   if (const char* e = getenv("CONZIC_MLP_FUSED"))
     c->mlp_fused = (atoi(e) && c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05) ? 1 : 0;

@@ -213,7 +213,8 @@ __device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, i
 // bias4 = this lane's slice of the warp's bias, chunk = index of the 16-column chunk inside the warp's 128.
 __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
                                                    float (&v)[16], const float4 (&rr)[4], const float4& bias4,
-                                                   int chunk, float (&st1)[4], float (&st2)[4]) {
+                                                   int chunk, float (&st1)[4], float (&st2)[4],
+                                                   float4* xo = nullptr) {
   const Epi& e = p.e;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -237,10 +238,11 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
     if (grow < p.M) {
       const int col = n0 + pc * 4;
       x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
-      if (e.stats_out) {  // LayerNorm statistics of the values being written, for the next GEMM's folded LN
+      if (e.stats_out || e.lnf_out) {  // LayerNorm statistics of the values being written
         st1[i] += (x.x + x.y) + (x.z + x.w);
         st2[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
       }
+      if (xo) xo[i] = x;
       if (e.out_f32) {
         float* dst = e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col;
         if (p.st_policy) st_global_v4f_hint(dst, x, p.st_policy);
@@ -984,9 +986,11 @@ struct WideSmem {
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
   static constexpr int STAGES = 4;
   static constexpr int STG_OFF = STAGES * STAGE;
-  static constexpr int BAR_OFF = STG_OFF + P_EPI_WARPS * 2048;
+  static constexpr int LNS_OFF = STG_OFF + P_EPI_WARPS * 2048;  // fused LN: float2 [2 parities][2 column halves][128 rows]
+  static constexpr int BAR_OFF = LNS_OFF + 2 * 2 * BM * 8;
   static constexpr int N_BARS = 2 * STAGES + 4;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
+  static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
 };
 
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -1097,12 +1101,15 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;  // 0 / 1: columns [sub*128, sub*128+128) of each 256-column half
     uint32_t uph = 0;
+    const bool lnf = p.e.lnf_out != nullptr;
+    const bool keep = lnf && p.e.lnf_mode == 2;  // x stays in TMEM for the LayerNorm pass
     const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
+      float ls1[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};  // row sums over both halves (fused LN)
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int nbase = h * PBN + sub * (PBN / 2);
@@ -1118,7 +1125,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[16];
           tmem_ld16(taddr + c * 16, r);
           tmem_ld_wait();
-          if (c == 7) {
+          if (c == 7 && !keep) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + h * 8);
@@ -1126,9 +1133,112 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+          if (keep) {
+            // keep x = acc + bias + resid (as laid out after the transpose: 4 rows x 4 columns per lane) in the
+            // TMEM columns just read -- they are this warp's own and serve as scratch for the LayerNorm pass
+            float4 xo[4];
+            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2, xo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              r[4 * i] = __float_as_uint(xo[i].x); r[4 * i + 1] = __float_as_uint(xo[i].y);
+              r[4 * i + 2] = __float_as_uint(xo[i].z); r[4 * i + 3] = __float_as_uint(xo[i].w);
+            }
+            tmem_st16(taddr + c * 16, r);
+          } else {
+            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+          }
         }
         if (p.e.stats_out) flush_row_stats(p, lane, row0, nbase / (PBN / 2), st1, st2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ls1[i] += st1[i]; ls2[i] += st2[i]; }
+      }
+      if (lnf) {
+        // Fused LayerNorm of the rows just written.  This warp covered 256 of a row's 512 columns, the warp with
+        // the other `sub` the rest: exchange (sum, sum of squares) through shared memory, read the kept values
+        // back from TMEM, write bf16(LN(x) * g + b), and only then hand the accumulators back to the MMA warp.
+        const Epi& e = p.e;
+        float2* xs = reinterpret_cast<float2*>(smem + SL::LNS_OFF) + uph * (2 * BM);
+        float mean[4], rstd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = ls1[i], b = ls2[i];
+          a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+          b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+          mean[i] = a; rstd[i] = b;
+          if ((lane & 3) == 0) xs[sub * BM + q * 32 + (lane >> 2) + 8 * i] = make_float2(a, b);
+        }
+        if (keep) tmem_st_wait();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of TMEM lane quarter q
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 o = xs[(1 - sub) * BM + q * 32 + (lane >> 2) + 8 * i];
+          const float inv = 1.0f / static_cast<float>(2 * PBN);
+          const float mu = (mean[i] + o.x) * inv;
+          const float var = fmaxf((rstd[i] + o.y) * inv - mu * mu, 0.f);
+          rstd[i] = rsqrtf(var + e.lnf_eps);
+          mean[i] = -mu * rstd[i];  // y = x * rstd + (-mean * rstd)
+        }
+        const int pc = lane & 3;
+        auto write_ln = [&](int col, const float4& g4, const float4& b4, int i, float x0, float x1, float x2, float x3) {
+          const int grow = row0 + (lane >> 2) + 8 * i;
+          if (grow >= p.M) return;
+          const float y0 = fmaf(x0, rstd[i], mean[i]) * g4.x + b4.x, y1 = fmaf(x1, rstd[i], mean[i]) * g4.y + b4.y;
+          const float y2 = fmaf(x2, rstd[i], mean[i]) * g4.z + b4.z, y3 = fmaf(x3, rstd[i], mean[i]) * g4.w + b4.w;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + col) = u;
+        };
+        if (keep) {
+#pragma unroll 2
+          for (int hc = 0; hc < 16; ++hc) {
+            const int cbase = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16;  // first column of the chunk
+            const int col = cbase + pc * 4;
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.lnf_g + col));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.lnf_b + col));
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cbase, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              write_ln(col, g4, b4, i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster_relaxed(tempty_addr0);
+            mbar_arrive_cluster_relaxed(tempty_addr0 + 8);
+          }
+        } else {
+          // re-read what this lane stored (same addresses, program order; L2 hits mostly), 4 chunks = 16 loads
+          // in flight per lane so the pass is bandwidth- and not latency-bound; it overlaps the next unit's MMAs
+#pragma unroll 1
+          for (int g0 = 0; g0 < 16; g0 += 4) {
+            float4 x[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int hc = g0 + j;
+              const int col = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int grow = row0 + (lane >> 2) + 8 * i;
+                x[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < p.M)
+                  x[j][i] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int hc = g0 + j;
+              const int col = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.lnf_g + col));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.lnf_b + col));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) write_ln(col, g4, b4, i, x[j][i].x, x[j][i].y, x[j][i].z, x[j][i].w);
+            }
+          }
+        }
       }
     }
   }
@@ -1404,12 +1514,21 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       allow_wide = e ? atoi(e) : 1;
     }
     // fp32-output GEMM with N == 512 and a streamed A (fc2): one 512-column unit per tile so A leaves HBM once
-    if (allow_wide && cg == 2 && !ares && W.N == 2 * PBN && (epi.out_f32 != nullptr) && W.K >= 1024) {
+    const bool wide_ok = cg == 2 && W.N == 2 * PBN && epi.out_f32 != nullptr;
+    if (wide_ok && ((allow_wide && !ares && W.K >= 1024) || o.force_wide || epi.lnf_out)) {
       pp.n_tiles = 1;
       return launch_wide(ta, tb, pp, st);
     }
+    if (epi.lnf_out) {
+      set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");
+      return false;
+    }
     if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
     return launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
+  }
+  if (epi.lnf_out) {
+    set_error("linear: a fused LayerNorm output needs the persistent wide pair kernel");
+    return false;
   }
   const int key = o.bn * 10 + o.stages;
   switch (key) {

@@ -97,6 +97,16 @@ struct Epi {
   float ln_eps = 0.f;
   float2* stats_out = nullptr;
   int stats_parts = 0;
+  // LayerNorm of the rows this GEMM writes, applied by the SAME kernel (gemm_wide_kernel only: N == 512 == H, a
+  // CTA owns whole rows): after x = acc + bias + resid has been stored, lnf_out[m, :] = bf16(LN(x[m, :]) * g + b).
+  // Replaces the stand-alone LayerNorm launch that would re-read x from HBM (HF:models/clip/modeling_clip.py:369-384).
+  bf16* lnf_out = nullptr;
+  int lnf_ld = 0;
+  const float* lnf_g = nullptr;
+  const float* lnf_b = nullptr;
+  float lnf_eps = 0.f;
+  int lnf_mode = 1;  // 1: the LayerNorm pass re-reads the fp32 values the lane just stored (L2) and the accumulators are
+                     // handed back as soon as they are drained; 2: the values are kept in TMEM until the pass is done
 };
 
 struct GemmOpts {
@@ -107,6 +117,7 @@ struct GemmOpts {
   int persist = 0;  // 1 = persistent A-resident kernel with double-buffered TMEM accumulators (bf16 mode only)
   int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
   int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
+  int force_wide = 0;  // persistent pair path, N == 512, fp32 output: use gemm_wide_kernel whatever K is
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
@@ -181,6 +192,8 @@ struct AttnArgs {
   int ld_act, split;
   int cpt = 1;            // filled by launch_attention: candidates packed into one 16-row query tile
   int cand_per_task = 8;  // filled by launch_attention: candidates per warp task
+  int prefetch = 0;       // filled by launch_attention: fetch the next candidate tile's q/k/v rows into registers
+                          // before computing the current one (tiles of <= 16 own rows)
 };
 bool launch_attention(const AttnArgs& a, cudaStream_t st);
 

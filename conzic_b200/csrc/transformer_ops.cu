@@ -396,7 +396,7 @@ __device__ __forceinline__ void att_put16(uint8_t* tile, int dst0, int n_rows, i
   }
 }
 
-template <int NT>  // NT key tiles of 8: up to NT*8 keys per tile
+template <int NT, bool PIPE = false>  // NT key tiles of 8: up to NT*8 keys per tile; PIPE: register prefetch of the next tile
 __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t att_smem[];
@@ -461,6 +461,18 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   const int lm_r = lane & 7, lm_m = lane >> 3;  // ldmatrix: row within the 8x8 matrix, matrix index
   const float sl2 = a.scale * 1.4426950408889634f;
 
+  // Software pipeline over the candidate tiles of this task (tiles of <= 16 own rows, the usual case): the q / k / v
+  // rows of tile i+1 are requested into registers before tile i is computed, so the warp waits for global memory
+  // once per task instead of once per tile.
+  const bool pipe = PIPE && !is_prefix && cpt * nq <= 16;
+  uint4 pk[4], pv[4], pq[4];
+  if (pipe) {
+    const int n0 = min(cpt, k1 - k0) * nq;
+    const int base0 = n_pre_rows + (b * a.K + k0) * a.S;
+    att_fetch16(qkv, ld, col_k, base0, n0, lane, pk);
+    att_fetch16(qkv, ld, col_v, base0, n0, lane, pv);
+    att_fetch16(qkv, ld, col_q, base0, n0, lane, pq);
+  }
   for (int k = k0; k < k1; k += cpt) {
     const int nc = min(cpt, k1 - k);
     const int n_own = nc * nq;          // query rows = own key rows of this iteration (contiguous in memory)
@@ -468,7 +480,18 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
     const int own_base = is_prefix ? pre_base : n_pre_rows + (b * a.K + k) * a.S;
     const bool single = n_own <= 16;
     __syncwarp();
-    if (single) {
+    if (pipe) {
+      att_put16(sK, pl, n_own, lane, pk);
+      att_put16(sV, pl, n_own, lane, pv);
+      att_put16(sQ, 0, n_own, lane, pq);
+      if (k + cpt < k1) {
+        const int nn = min(cpt, k1 - (k + cpt)) * nq;
+        const int nbase = n_pre_rows + (b * a.K + k + cpt) * a.S;
+        att_fetch16(qkv, ld, col_k, nbase, nn, lane, pk);
+        att_fetch16(qkv, ld, col_v, nbase, nn, lane, pv);
+        att_fetch16(qkv, ld, col_q, nbase, nn, lane, pq);
+      }
+    } else if (single) {
       uint4 rk[4], rv[4], rq[4];
       att_fetch16(qkv, ld, col_k, own_base, n_own, lane, rk);
       att_fetch16(qkv, ld, col_v, own_base, n_own, lane, rv);
@@ -757,6 +780,8 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     AttnArgs aa = a;
     aa.cpt = (a.causal && a.S <= 8 && a.P + (16 / a.S) * a.S <= 96) ? 16 / a.S : 1;
     aa.cand_per_task = aa.cpt >= 4 ? 2 * aa.cpt : (aa.cpt > 1 ? ((8 + aa.cpt - 1) / aa.cpt) * aa.cpt : 8);
+    const char* pf = getenv("CONZIC_ATTN_PREFETCH");  // read per launch so tests can switch variants
+    aa.prefetch = pf ? atoi(pf) : 0;
     const int keys_cap = a.P + (aa.cpt > 1 ? aa.cpt * a.S : a.S);
     const int groups = (a.K + aa.cand_per_task - 1) / aa.cand_per_task;
     const long long tasks = (a.P > 0 ? static_cast<long long>(a.B) * a.heads : 0) +
@@ -774,6 +799,18 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
                               : cudaFuncSetAttribute(attention_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (!cuda_ok(e, "cudaFuncSetAttribute(attention_mma)")) return false;
       configured[which_nt] = smem;
+    }
+    if (nt <= 8 && aa.prefetch) {
+      static bool pipe_cfg = false;
+      if (!pipe_cfg) {
+        if (!cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 4 * 1024 + 2048)), "attr") ||
+            !cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 8 * 1024 + 2048)), "attr"))
+          return false;
+        pipe_cfg = true;
+      }
+      if (nt == 4) launch_k(attention_mma_kernel<4, true>, dim3(grid), dim3(warps * 32), smem, st, aa);
+      else launch_k(attention_mma_kernel<8, true>, dim3(grid), dim3(warps * 32), smem, st, aa);
+      return cuda_ok(cudaGetLastError(), "attention_mma launch");
     }
     if (nt == 4) launch_k(attention_mma_kernel<4>, dim3(grid), dim3(warps * 32), smem, st, aa);
     else if (nt == 8) launch_k(attention_mma_kernel<8>, dim3(grid), dim3(warps * 32), smem, st, aa);

@@ -143,12 +143,16 @@ def test_clip_text_encode_vs_oracle(prec, tol):
 @pytest.mark.parametrize("prec,tol,env", [("bf16x3", 3e-4, {}), ("bf16", 0.06, {}),
                                           ("bf16", 0.06, {"CONZIC_LN_FOLD": "1"}),
                                           ("bf16", 0.06, {"CONZIC_MLP_FUSED": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_WIDE_LN": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_WIDE_LN": "2"}),
+                                          ("bf16", 0.06, {"CONZIC_ATTN_PREFETCH": "1"}),
                                           ("bf16", 0.06, {"CONZIC_GEMM_CG": "1"}),
                                           ("bf16", 0.06, {"CONZIC_GEMM_PERSIST": "0"})])
 def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch):
     """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
     the oracle, for the default path and every opt-in kernel variant: LayerNorm folded into the consuming GEMM
-    (CONZIC_LN_FOLD), fc1+fc2 in one launch (CONZIC_MLP_FUSED), single-CTA and non-persistent GEMMs."""
+    (CONZIC_LN_FOLD), fc1+fc2 in one launch (CONZIC_MLP_FUSED), LayerNorm written by the producing wide GEMM's
+    epilogue (CONZIC_WIDE_LN), single-CTA and non-persistent GEMMs."""
     from conzic_b200.engine import Engine
     from oracle import conzic_oracle as orc
     sd = {k: v.clone() for k, v in gc.weights("clip").items()}
