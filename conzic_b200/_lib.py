@@ -21,7 +21,7 @@ EXPORTS = [
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
     "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_debug_mlp",
-    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select",
+    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_encode_candidates",
 ]
 
 
@@ -81,6 +81,9 @@ def _declare(lib):
     lib.conzic_clip_text_encode.argtypes = [vp, vp, i32, i32, vp, vp, sz, vp]
     lib.conzic_image_text_similarity.restype = C.c_int
     lib.conzic_image_text_similarity.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
+    lib.conzic_encode_candidates.restype = C.c_int
+    lib.conzic_encode_candidates.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                                             C.c_size_t, vp]
     lib.conzic_score_select.restype = C.c_int
     lib.conzic_score_select.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, f32, f32, f32, vp, i32, i32, vp, vp, vp, vp]
     lib.conzic_gibbs_step.restype = C.c_int
@@ -115,7 +118,7 @@ def load(build_if_missing: bool = True):
         from . import build as _build
         _build.build()
     _lib = _declare(C.CDLL(LIB_PATH))
-    if _lib.conzic_abi_version() != 3:
+    if _lib.conzic_abi_version() != 4:
         raise RuntimeError("libconzic.so ABI version mismatch; rebuild with `python -m conzic_b200.build --force`")
     return _lib
 

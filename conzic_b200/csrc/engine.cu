@@ -755,6 +755,37 @@ int conzic_clip_text_encode(conzic_ctx* c, const int32_t* clip_ids, int N, int T
                                  cudaMemcpyDeviceToDevice, st), "copy text embeds") ? 0 : -4;
 }
 
+int conzic_encode_candidates(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, const int64_t* ids,
+                             const float* token_mask, int K, int P, int S, const float* senti_table, float* text,
+                             int64_t* ids_masked, float* repeats, float* senti_raw, void* ws, size_t ws_bytes,
+                             void* stream) {
+  if (!c || !inp || !ids || !token_mask || !text || !ids_masked || !ws) { set_error("encode_candidates: null argument"); return -1; }
+  if (!c->b2c_off) { set_error("encode_candidates: conzic_set_bert2clip has not been called"); return -1; }
+  const int cap = c->cfg.clip_maxpos - 1;
+  if (B < 1 || K < 1 || K > 1024 || pos < 1 || pos >= L - 1 || P < 1 || P > cap || S < 2 || S > cap) {
+    set_error("encode_candidates: bad B / K / pos / P / S");
+    return -1;
+  }
+  if (!check_ws(c, ws_bytes, B, L, K)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan p = make_plan(c, ws, B, L, K);
+  if (static_cast<size_t>(P) + static_cast<size_t>(K) * S > static_cast<size_t>(c->cfg.clip_maxpos) * (K + 1)) {
+    set_error("encode_candidates: P + K * S exceeds the workspace plan");
+    return -1;
+  }
+  g_pdl_now = 1;
+  AssembleArgs a{};
+  fill_assemble(c, a);
+  a.inp = inp; a.ids = ids; a.token_mask = token_mask; a.senti_table = senti_table;
+  a.B = B; a.L = L; a.K = K; a.pos = pos;
+  a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
+  a.ids_masked = ids_masked; a.repeats = repeats; a.senti = senti_table ? senti_raw : nullptr;
+  launch_assemble(a, st);
+  if (!clip_encode(c, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.text, p, st)) return -4;
+  return cuda_ok(cudaMemcpyAsync(text, p.text, static_cast<size_t>(B) * K * c->cfg.clip_proj * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st), "copy text embeds") ? 0 : -4;
+}
+
 int conzic_image_text_similarity(conzic_ctx* c, const float* text, const float* image, int B, int K, float scale,
                                  float* clip_score, float* clip_ref, void* stream) {
   if (!c || !text || !image) { set_error("image_text_similarity: null argument"); return -1; }

@@ -283,6 +283,26 @@ class Engine:
         _lib.check(rc, "conzic_clip_text_encode")
         return out
 
+    def encode_candidates(self, inp: torch.Tensor, pos: int, ids: torch.Tensor, token_mask: torch.Tensor, P: int, S: int,
+                          senti_table: Optional[torch.Tensor] = None, want_repeats: bool = False):
+        """gen_utils.py:71-76 + clip/clip.py:71-83 without the string round trip: candidate ids -> CLIP ids via the
+        table (shared prefix of P rows per image, S rows per candidate) -> text tower.  Returns (text_embeds
+        f32[B*K, D], ids_masked int64[B,K], repeats f32[B,K] or None, senti_raw f32[B,K] or None) on the device."""
+        assert self.has_table, "call Engine.set_bert2clip first"
+        B, L = inp.shape
+        K = ids.shape[1]
+        text = torch.empty((B * K, self.D), dtype=torch.float32, device=self.device)
+        ids_masked = torch.empty((B, K), dtype=torch.int64, device=self.device)
+        repeats = torch.empty((B, K), dtype=torch.float32, device=self.device) if want_repeats else None
+        senti = torch.empty((B, K), dtype=torch.float32, device=self.device) if senti_table is not None else None
+        ws = self.workspace(B, L, K)
+        rc = self.lib.conzic_encode_candidates(self.ctx, _ptr(inp), B, L, int(pos), _ptr(ids.contiguous()),
+                                               _ptr(token_mask), K, int(P), int(S), _ptr(senti_table), _ptr(text),
+                                               _ptr(ids_masked), _ptr(repeats), _ptr(senti), _ptr(ws), ws.numel(),
+                                               self._stream())
+        _lib.check(rc, "conzic_encode_candidates")
+        return text, ids_masked, repeats, senti
+
     def image_text_similarity(self, image_embeds: torch.Tensor, text_embeds: torch.Tensor):
         """compute_image_text_similarity_via_embeddings (clip/clip.py:86-98)."""
         B = image_embeds.shape[0]

@@ -36,8 +36,11 @@ class _Chain:
         self.eng = runtime.engine_for(model, clip, tokenizer)
         eng = self.eng
         self.clip = clip
-        # '##' word pieces (real BERT vocabularies) need the host string path; CONZIC_STRING_PATH=1 forces it
-        self.string_path = bool(getattr(eng, "needs_host_ids", None)) or os.environ.get("CONZIC_STRING_PATH") == "1"
+        # CONZIC_STRING_PATH=1 forces the reference's string round trip for every candidate.  Vocabularies with '##'
+        # word pieces (real BERT vocabularies) take the hybrid step: table path on the device, plus a host string
+        # pass for just the captions that contain a piece
+        self.string_path = os.environ.get("CONZIC_STRING_PATH") == "1"
+        self.hybrid = bool(getattr(eng, "needs_host_ids", None)) and not self.string_path
         self.tokenizer, self.max_len, self.B = tokenizer, max_len, batch_size
         self.seed_len = len(prompt.split()) + 1
         batch = get_init_text(tokenizer, prompt, max_len, batch_size)
@@ -60,8 +63,8 @@ class _Chain:
                          pos_scorer=None):
         """The same step with the reference's string round trip (gen_utils.py:66-81): candidate ids -> host ->
         tokenizer.batch_decode -> CLIP tokenizer -> device.  Every arithmetic piece is still a libconzic kernel;
-        only the text handling runs on the host.  Used when the BERT vocabulary has '##' word pieces, whose merge
-        into the previous word changes the CLIP BPE of that word and cannot be tabulated per token."""
+        only the text handling runs on the host.  Used by POS-template control (the tagger needs every string) and
+        when CONZIC_STRING_PATH=1 asks for it; vocabularies with '##' word pieces use step_hybrid."""
         eng, tok = self.eng, self.tokenizer
         pos = self.seed_len + ii
         T = 1.0 if temperature is None else temperature
@@ -100,11 +103,46 @@ class _Chain:
             self.pos_tags = [tags[int(win[i]) + i * top_k] for i in range(self.B)]
         self.holds_word[pos] = True
 
+    def step_hybrid(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
+        """The step for vocabularies with '##' word pieces.  A piece merges into the previous word and changes
+        that word's CLIP BPE, so the per-token table is exact only for captions without pieces.  All candidates go
+        through the table path on the device (shared prefix, conzic_encode_candidates); the host reads the top-k
+        ids, finds the captions that contain a piece (tokens.plan_hybrid), builds exactly those strings like the
+        reference does (gen_utils.py:75), encodes them densely with the same kernels and patches their embeddings
+        in before the fused score / argmax.  One device->host read per step; the string work overlaps the main
+        encode on the GPU."""
+        from . import tokens
+        eng, tok = self.eng, self.tokenizer
+        pos = self.seed_len + ii
+        T = 1.0 if temperature is None else temperature
+        self.mask.view(-1)[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0  # utils.py:53-59
+        self.inp[:, pos] = eng.mask_id
+        row = logits_in[:, : eng.V] if logits_in is not None else eng.bert_mlm_row(self.inp, pos)
+        probs, idxs = eng.topk_mask(row, self.mask, T, top_k)
+        idxs_h, inp_h = idxs.cpu(), self.inp.cpu()
+        ids_masked_h = (idxs_h * self.mask.view(-1).cpu()[idxs_h]).long()  # gen_utils.py:72
+        flag, P, S = tokens.plan_hybrid(inp_h, pos, ids_masked_h, eng.piece_mask_h, eng.tok_len_h, eng.cfg.clip_maxpos)
+        text, ids_masked, repeats, senti_raw = eng.encode_candidates(
+            self.inp, pos, idxs, self.mask, P, S, senti_table=senti_table if gamma is not None else None,
+            want_repeats=gamma is not None)
+        if bool(flag.any()):  # host strings for the flagged captions only, while the GPU runs the main encode
+            bi, ki = flag.nonzero(as_tuple=True)
+            rows = inp_h[bi].clone()
+            rows[:, pos] = ids_masked_h[bi, ki]
+            emb = self.clip.compute_text_representation(tok.batch_decode(rows, skip_special_tokens=True))
+            text.index_copy_(0, (bi * top_k + ki).to(eng.device), emb)
+        eng.score_select(text, self.image_embeds, probs, ids_masked, self.inp, pos, alpha, beta, gamma=gamma,
+                         senti_raw=senti_raw, repeats=repeats, out_clip_ref=self.clip_slots[slot],
+                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
+        self.holds_word[pos] = True
+
     def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
              pos_scorer=None):
         if self.string_path or pos_scorer is not None:
             return self.step_via_strings(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in,
                                          pos_scorer)
+        if self.hybrid:
+            return self.step_hybrid(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in)
         pos = self.seed_len + ii
         before = sum(self.holds_word[:pos])
         after = sum(self.holds_word[pos + 1:])

@@ -69,7 +69,7 @@ def bind_tokenizers(eng: Engine, bert_tokenizer, clip_tokenizer):
     """Builds (once per tokenizer pair) and uploads the BERT-id -> CLIP-id table."""
     key = (id(bert_tokenizer), id(clip_tokenizer))
     if key not in _tables:
-        if isinstance(bert_tokenizer, synth.SynthBertTokenizer) and isinstance(clip_tokenizer, synth.SynthCLIPTokenizer):
+        if type(bert_tokenizer) is synth.SynthBertTokenizer and type(clip_tokenizer) is synth.SynthCLIPTokenizer:
             off, tok = synth.build_bert2clip_table(clip_tokenizer.multi)
             needs_host = []
         else:
@@ -80,6 +80,11 @@ def bind_tokenizers(eng: Engine, bert_tokenizer, clip_tokenizer):
     off, tok, needs_host = _tables[key]
     eng.set_bert2clip(off, tok)
     eng.needs_host_ids = needs_host
+    # host copies for the hybrid path of vocabularies with '##' pieces (tokens.plan_hybrid)
+    eng.piece_mask_h = torch.zeros(eng.V, dtype=torch.bool)
+    if needs_host:
+        eng.piece_mask_h[torch.tensor(needs_host, dtype=torch.long)] = True
+    eng.tok_len_h = (off[1:] - off[:-1])[: eng.V].to(torch.int32)
 
 
 def any_engine() -> Engine:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CONZIC_ABI_VERSION 3
+#define CONZIC_ABI_VERSION 4
 
 typedef struct conzic_ctx conzic_ctx;
 
@@ -110,6 +110,20 @@ int conzic_build_clip_ids(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L,
  * text_embeds f32[N,proj]. */
 int conzic_clip_text_encode(conzic_ctx* ctx, const int32_t* clip_ids_dev, int N, int T, float* text_embeds_dev,
                             void* ws_dev, size_t ws_bytes, void* stream);
+
+/* The middle of a Gibbs step on its own (gen_utils.py:71-76 + clip/clip.py:71-83): candidates -> CLIP ids through the
+ * BERT-id -> CLIP-id table (caption prefix before `pos` encoded once per image, the rest per candidate) -> CLIP text
+ * tower -> text_embeds f32[B*K, proj].  For callers that know the ids on the host (vocabularies with '##' word
+ * pieces: rows whose caption contains a piece are re-encoded from strings by the caller and patched into
+ * text_embeds before conzic_score_select).  P = prefix rows per image including BOS (>= 1 + the longest prefix in
+ * CLIP tokens), S = rows per candidate (>= the longest candidate word + tail in CLIP tokens, + 1 for EOS); both are
+ * capacities, shorter sequences are padded with EOS, longer ones are cut like truncation at 77 would.
+ * Also out: ids_masked int64[B,K] = ids * token_mask[ids]; repeats f32[B,K] (control_gen_utils.py:53) or NULL;
+ * senti_raw f32[B,K] = sum of senti_table over the caption's words, or NULL (needs senti_table). */
+int conzic_encode_candidates(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L, int pos, const int64_t* ids_dev,
+                             const float* token_mask_dev, int K, int P, int S, const float* senti_table_dev,
+                             float* text_embeds_dev, int64_t* ids_masked_dev, float* repeats_dev, float* senti_raw_dev,
+                             void* ws_dev, size_t ws_bytes, void* stream);
 
 /* compute_image_text_similarity_via_embeddings (clip/clip.py:86-98): text f32[B*K,D], image f32[B,D]
  * -> clip_score f32[B,K] (softmax over K of scale*cos) and clip_ref f32[B,K] (cos). */

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libconzic.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.conzic_abi_version() == 3
+    assert lib.conzic_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -160,3 +160,66 @@ def test_root_level_modules_mirror_the_reference_layout():
     for name, attr in (("gen_utils", "generate_caption"), ("control_gen_utils", "control_generate_caption"),
                        ("utils", "set_seed"), ("clip.clip", "CLIP")):
         assert hasattr(importlib.import_module(name), attr)
+
+
+def test_piece_vocabulary_decodes_like_hf_bert():
+    """'##' pieces join the previous word (HF convert_tokens_to_string); a leading piece stays literal; the CLIP side
+    tokenises a merged word as a whole, not as the concatenation of its parts."""
+    tok, ctok = synth.PieceBertTokenizer(), synth.PieceCLIPTokenizer()
+    assert synth.is_piece(2003) and not synth.is_piece(2004) and not synth.is_piece(synth.DOT_ID)
+    ids = [101, 3746, 2003, 2008, 2004, 103, 1012, 102]
+    assert tok.decode(ids) == "[CLS] w3746p2003p2008 w2004 [MASK] . [SEP]"
+    assert tok.decode(ids, skip_special_tokens=True) == "w3746p2003p2008 w2004 ."
+    assert tok.decode([2003, 2004], skip_special_tokens=True) == "##p2003 w2004"
+    assert tok.vocab["##p2003"] == 2003 and tok.convert_ids_to_tokens([2003, 2004]) == ["##p2003", "w2004"]
+    merged = ctok.tokens_of_text("w3746p2003")
+    assert merged != ctok.tokens_of_text("w3746") + ctok.tokens_of_text("w2003") and len(merged) == 1
+
+
+def test_plan_hybrid_against_string_tokenisation():
+    """tokens.plan_hybrid: a caption is flagged exactly when its decoded string had a piece merged in, and for every
+    unflagged caption the CLIP ids of the decoded string are prefix + candidate word + tail from the table, within
+    the planned capacities P and S."""
+    tok, ctok = synth.PieceBertTokenizer(), synth.PieceCLIPTokenizer(multi=True)
+    V = synth.BERT_VOCAB
+    off, tk, needs_host = tokens.build_bert2clip(tok, ctok, V, synth.SPECIAL_IDS)
+    piece = torch.zeros(V, dtype=torch.bool)
+    piece[torch.tensor(needs_host)] = True
+    assert all(synth.is_piece(v) for v in needs_host[:50]) and len(needs_host) == sum(synth.is_piece(v) for v in range(V))
+    tok_len = (off[1:] - off[:-1]).to(torch.int32)
+    assert int(tok_len[piece].max()) == 0
+    g = torch.Generator().manual_seed(5)
+    B, L, K, pos = 6, 12, 24, 6
+    inp = torch.randint(1996, V, (B, L), generator=g)
+    inp[:, 0], inp[:, -1] = synth.CLS_ID, synth.SEP_ID
+    for b in (0, 2, 3):  # these images hold no piece outside pos
+        inp[b] = torch.where(piece[inp[b]], inp[b] + 1, inp[b])
+    inp[1, 3] = 2003                                                         # image 1: a piece in the prefix
+    inp[2, 9] = synth.MASK_ID                                                # specials are skipped
+    inp[:, pos] = synth.MASK_ID
+    inp[:, -1] = synth.SEP_ID
+    ids = torch.randint(1996, V, (B, K), generator=g)
+    ids[:, 0] = 0  # a masked candidate ([PAD]): the word is dropped
+    flag, P, S = tokens.plan_hybrid(inp, pos, ids, piece, tok_len)
+    assert bool(flag[1].all()) and not bool(flag[0, 0])
+    n_unflagged = 0
+    for b in range(B):
+        pre_ids = [int(v) for v in inp[b, :pos] if int(v) not in synth.SPECIAL_IDS]
+        tail_ids = [int(v) for v in inp[b, pos + 1:] if int(v) not in synth.SPECIAL_IDS]
+        for k in range(K):
+            row = inp[b].clone()
+            row[pos] = ids[b, k]
+            kept = [int(v) for v in row if int(v) not in synth.SPECIAL_IDS]
+            has_piece = any(synth.is_piece(v) for v in kept)
+            assert bool(flag[b, k]) == has_piece
+            if has_piece:
+                continue
+            n_unflagged += 1
+            full = ctok.tokens_of_text(tok.decode(row, skip_special_tokens=True))
+            table = lambda v: tk[off[v]: off[v + 1]].tolist()
+            pre = [t for v in pre_ids for t in table(v)]
+            cand = table(int(ids[b, k])) if int(ids[b, k]) not in synth.SPECIAL_IDS else []
+            tail = [t for v in tail_ids for t in table(v)]
+            assert full == pre + cand + tail
+            assert 1 + len(pre) <= P and len(cand) + len(tail) + 1 <= S
+    assert n_unflagged > 40

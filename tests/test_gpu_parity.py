@@ -383,6 +383,43 @@ def test_host_string_path_matches_reference(name, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("name", ["pieces_seq_b2_n5_k16", "pieces_shuffle_b3_n6_k16_multi"])
+@pytest.mark.parametrize("path", ["hybrid", "strings"])
+def test_piece_vocabulary_matches_reference(name, path, monkeypatch):
+    """A BERT vocabulary with '##' word pieces (the shape of real bert-base-uncased): pieces among the candidates and,
+    once one wins, inside the caption.  Default = hybrid step (table path on the device + host strings for just the
+    captions that contain a piece, conzic_encode_candidates); CONZIC_STRING_PATH=1 = every candidate through
+    strings.  Both must reproduce the unmodified reference's captions and scores."""
+    import logging
+    from conzic_b200 import gen_utils, runtime
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    if path == "strings":
+        monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+    runtime.clear()
+    g = gc.load_golden(name)
+    case = g["case"]
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    bert = BertMLM(gc.weights("bert"))
+    clip = CLIP(state_dict=gc.weights("clip"), tokenizer=synth.PieceCLIPTokenizer(case.get("multi", False)),
+                processor=synth.SynthProcessor()).to("cuda:0")
+    B, n, K = case["B"], case["n"], case["K"]
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    set_seed(42)
+    texts, scores = gen_utils.generate_caption(
+        [f"img{i}.jpg" for i in range(B)], bert, clip, synth.PieceBertTokenizer(), pix, synth.make_token_mask("cuda"),
+        logging.getLogger("test"), prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1,
+        max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
+    eng = runtime.any_engine()
+    assert len(eng.needs_host_ids) > 5000 and int(eng.tok_len_h[eng.piece_mask_h].max()) == 0
+    runtime.clear()
+    assert any("p" in w[1:] for t in g["texts"] for c in t for w in c.split()), "fixture holds no merged word"
+    assert texts == g["texts"]
+    for a, b in zip(scores, g["scores"]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
 def test_long_sentence_free_running_matches_oracle():
     """sentence_len 25 (BASELINE config 5's longest): prefixes up to 29 tokens and candidate suffixes up to 27 rows
     -> the 64-key attention tiles and the multi-tile query path; multi-token words.  One sweep of a free-running

@@ -14,7 +14,7 @@ from oracle import conzic_oracle as orc
 
 ALL = sorted(f[:-3] for f in os.listdir(GOLDEN) if f.endswith(".pt"))
 FAST = ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32",
-        "pos_seq_b2_n5_k16"]
+        "pos_seq_b2_n5_k16", "pieces_shuffle_b3_n6_k16_multi"]
 
 
 def _pos(case):
@@ -29,8 +29,13 @@ def make_oracle(g, synth_weights, full_logits=False):
     clip_sd = synth_weights("clip")
     assert synth.state_dict_checksum(bert_sd) == g["bert_crc"], "synthetic BERT weights drifted"
     assert synth.state_dict_checksum(clip_sd) == g["clip_crc"], "synthetic CLIP weights drifted"
-    return orc.Oracle(bert_sd, clip_sd, synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(case.get("multi", False)),
-                      sentiment_table=synth.make_sentiment_table(), full_logits=full_logits)
+    multi = case.get("multi", False)
+    if case.get("pieces"):  # vocabulary with '##' word pieces
+        toks = synth.PieceBertTokenizer(), synth.PieceCLIPTokenizer(multi)
+    else:
+        toks = synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(multi)
+    return orc.Oracle(bert_sd, clip_sd, toks[0], toks[1], sentiment_table=synth.make_sentiment_table(),
+                      full_logits=full_logits)
 
 
 @pytest.mark.parametrize("name", FAST)
@@ -73,7 +78,7 @@ def test_teacher_forced_steps(name, synth_weights):
 
 
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8", "span_b2_n5_k8",
-                                  "pos_seq_b2_n5_k16"])
+                                  "pos_seq_b2_n5_k16", "pieces_seq_b2_n5_k16"])
 def test_free_running_call(name, synth_weights):
     """Whole ``generate_caption`` / ``control_generate_caption`` call under set_seed(42):
     same captions per sweep, same CLIP scores, same best list as the reference returned."""

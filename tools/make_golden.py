@@ -71,7 +71,7 @@ def import_reference(sentiment_table):
     return utils, gen_utils, control_gen_utils, ref_clip.CLIP
 
 
-def build_models(bert_sd, clip_sd, CLIP, multi):
+def build_models(bert_sd, clip_sd, CLIP, multi, pieces=False):
     from transformers import BertConfig, BertForMaskedLM, CLIPConfig, CLIPModel
     bert = BertForMaskedLM(BertConfig()).eval()
     missing = bert.load_state_dict(bert_sd, strict=False)
@@ -82,7 +82,8 @@ def build_models(bert_sd, clip_sd, CLIP, multi):
     clip = CLIP.__new__(CLIP)
     torch.nn.Module.__init__(clip)
     clip.model, clip.processor = clipm, synth.SynthProcessor()
-    clip.tokenizer, clip.cuda_has_been_checked = synth.SynthCLIPTokenizer(multi), False
+    clip.tokenizer = synth.PieceCLIPTokenizer(multi) if pieces else synth.SynthCLIPTokenizer(multi)
+    clip.cuda_has_been_checked = False
     return bert, clip
 
 
@@ -145,6 +146,8 @@ CASES = [
     dict(name="peaked_seq_b2_n4_k32", order="sequential", B=2, n=4, K=32, iters=2, peaked=True),
     dict(name="seq_b1_n10_k200", order="sequential", B=1, n=10, K=200, iters=1),
     dict(name="span_b2_n5_k8", order="span", B=2, n=5, K=8, iters=2),
+    dict(name="pieces_seq_b2_n5_k16", order="sequential", B=2, n=5, K=16, iters=3, pieces=True),
+    dict(name="pieces_shuffle_b3_n6_k16_multi", order="shuffle", B=3, n=6, K=16, iters=2, pieces=True, multi=True),
     dict(name="pos_seq_b2_n5_k16", order="sequential", B=2, n=5, K=16, iters=2, gamma=5.0, ctl="pos"),
 ]
 
@@ -163,7 +166,9 @@ def main():
             continue
         peaked, multi = case.get("peaked", False), case.get("multi", False)
         bert_sd = sds[peaked]
-        bert, clip = build_models(bert_sd, clip_sd, CLIP, multi)
+        pieces = case.get("pieces", False)
+        bert, clip = build_models(bert_sd, clip_sd, CLIP, multi, pieces)
+        bert_tok = synth.PieceBertTokenizer if pieces else synth.SynthBertTokenizer
         B, n, K = case["B"], case["n"], case["K"]
         pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
         token_mask = synth.make_token_mask()
@@ -176,11 +181,11 @@ def main():
                   max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
         with torch.no_grad():
             if gamma is None:
-                texts, scores = gen_utils.generate_caption(names, bert, clip, synth.SynthBertTokenizer(), pix,
+                texts, scores = gen_utils.generate_caption(names, bert, clip, bert_tok(), pix,
                                                            token_mask, logger, **kw)
             else:
                 texts, scores = control_gen_utils.control_generate_caption(
-                    names, bert, clip, synth.SynthBertTokenizer(), pix, token_mask, logger, gamma=gamma,
+                    names, bert, clip, bert_tok(), pix, token_mask, logger, gamma=gamma,
                     ctl_type=case.get("ctl", "sentiment"), style_type=case.get("style", "positive"),
                     pos_type=synth.SYNTH_POS_TEMPLATE, **kw)
         rec.close()
