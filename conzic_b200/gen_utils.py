@@ -58,6 +58,7 @@ class _Chain:
         self.clip_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device)
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
+        self.mask_h = None
 
     def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
                          pos_scorer=None):
@@ -120,7 +121,10 @@ class _Chain:
         row = logits_in[:, : eng.V] if logits_in is not None else eng.bert_mlm_row(self.inp, pos)
         probs, idxs = eng.topk_mask(row, self.mask, T, top_k)
         idxs_h, inp_h = idxs.cpu(), self.inp.cpu()
-        ids_masked_h = (idxs_h * self.mask.view(-1).cpu()[idxs_h]).long()  # gen_utils.py:72
+        if self.mask_h is None:  # host mirror of the token mask; only the '.' column changes between steps
+            self.mask_h = self.mask.view(-1).cpu()
+        self.mask_h[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0
+        ids_masked_h = (idxs_h * self.mask_h[idxs_h]).long()  # gen_utils.py:72
         flag, P, S = tokens.plan_hybrid(inp_h, pos, ids_masked_h, eng.piece_mask_h, eng.tok_len_h, eng.cfg.clip_maxpos)
         text, ids_masked, repeats, senti_raw = eng.encode_candidates(
             self.inp, pos, idxs, self.mask, P, S, senti_table=senti_table if gamma is not None else None,

@@ -414,7 +414,8 @@ def test_piece_vocabulary_matches_reference(name, path, monkeypatch):
     eng = runtime.any_engine()
     assert len(eng.needs_host_ids) > 5000 and int(eng.tok_len_h[eng.piece_mask_h].max()) == 0
     runtime.clear()
-    assert any("p" in w[1:] for t in g["texts"] for c in t for w in c.split()), "fixture holds no merged word"
+    if "shuffle" in name:  # in this fixture a piece wins a slot, so later steps see a merged word inside the caption
+        assert any("p" in w[1:] for t in g["texts"] for c in t for w in c.split()), "fixture holds no merged word"
     assert texts == g["texts"]
     for a, b in zip(scores, g["scores"]):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
