@@ -136,6 +136,7 @@ struct conzic_ctx {
   int ln_fold = 0;    // LayerNorm folded into QKV / fc1 of the CLIP tower (bf16 persistent path)
   int mlp_fused = 0;  // fc1 + fc2 of a CLIP block in one persistent launch (bf16 mode, CTA pairs)
   int wide_ln_mode = 1;
+  int oproj_wide = 0;  // CONZIC_OPROJ_WIDE=1: O-proj (K = N = 512) through gemm_wide_kernel
   int wide_ln = 0;    // CLIP tower: LayerNorm written by the epilogue of the GEMM that produces the residual stream
                       // (gemm_wide_kernel): 1 = fc2 -> next block's LN1 / final LN, 2 = also O-proj -> LN2
   uint64_t launches0 = 0;
@@ -474,7 +475,13 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
         if (!launch_linear(f, Mr, ly.f2, epi_x_producer(ly.f2, x, !last), c->gopt, st, nullptr)) return false;
         continue;
       }
-      if (wl >= 2) {
+      if (c->oproj_wide && wl < 2 && !s && c->gopt.persist && c->gopt.cg == 2 && H == 512) {
+        GemmOpts ow = c->gopt;  // experiment: O-proj through the wide kernel, LayerNorm still its own launch
+        ow.force_wide = 1;
+        if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), ow, st, nullptr)) return false;
+        LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
+        launch_layernorm(ln2, st);
+      } else if (wl >= 2) {
         GemmOpts ow = c->gopt;
         ow.force_wide = 1;
         if (!launch_linear(a, Mr, ly.o, with_ln(epi_f32_out(ly.o, x, H, x, H, ACT_NONE), h2, ly.ln2_g, ly.ln2_b), ow, st, nullptr))
@@ -582,6 +589,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   // fc1+fc2 in one launch (mlp_persist_kernel): measured equal to the two-launch path on B200 (the 78 MB of
   // per-CTA scratch tiles do not survive in L2 between fc1 and fc2), so it is opt-in: CONZIC_MLP_FUSED=1
   c->wide_ln = 0;
+  if (const char* e = getenv("CONZIC_OPROJ_WIDE")) c->oproj_wide = atoi(e) ? 1 : 0;
   if (const char* e = getenv("CONZIC_WIDE_LN_MODE")) c->wide_ln_mode = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("CONZIC_WIDE_LN"))
     c->wide_ln = (c->gopt.persist && c->gopt.cg == 2 && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 && !c->split &&
