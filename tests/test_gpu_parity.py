@@ -421,6 +421,74 @@ def test_piece_vocabulary_matches_reference(name, path, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("B,n,K", [(1, 1, 1), (2, 1, 1024), (1, 3, 5), (3, 2, 64)])
+def test_extreme_shapes_step_vs_oracle(B, n, K):
+    """Smallest and largest shapes the ABI accepts: one image / one candidate / one-word sentences (the only
+    position is also the last, so '.' is allowed), and candidate_k at the 1024 cap.  Every position of one sweep
+    is compared with the oracle in bf16x3 mode: top-k ids, cosines, winners."""
+    from oracle import conzic_oracle as orc
+    eng = gc.engine("bf16x3")
+    o = orc.Oracle(gc.weights("bert"), gc.weights("clip"), synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(),
+                   full_logits=False)
+    o.trace = []
+    tok = synth.SynthBertTokenizer()
+    inp_ref = torch.tensor([tok.encode(synth.SYNTH_PROMPT + "[MASK]" * n)] * B)
+    inp_dev = inp_ref.clone().cuda()
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=torch.Generator().manual_seed(21)), dim=-1)
+    tm_ref, tm_dev = synth.make_token_mask(), synth.make_token_mask("cuda")
+    for ii in range(n):
+        pos = 4 + ii
+        with torch.no_grad():
+            o.step(inp_ref, img, tm_ref, pos, ii, n, K, 0.1, 0.02, 2.0)
+        t = o.trace[-1]
+        _, _, tr = eng.gibbs_step(inp_dev, tm_dev, img.cuda(), pos, ii == n - 1, K, 0.1, 0.02, 2.0, 3 + ii, 0, trace=True)
+        torch.cuda.synchronize()
+        p = t["probs"]
+        rel = (p[:, :-1] - p[:, 1:]) / p[:, :-1].clamp_min(1e-30)
+        ok = torch.ones_like(p, dtype=torch.bool)
+        ok[:, :-1] &= rel > 1e-3
+        ok[:, 1:] &= rel > 1e-3
+        ok &= p > 0
+        assert torch.equal(tr["idxs"].cpu()[ok], t["idxs"][ok])
+        if torch.equal(tr["idxs"].cpu(), t["idxs"]):
+            assert float((tr["clip_ref"].cpu() - t["clip_ref"]).abs().max()) < 2e-5
+            assert torch.equal(inp_dev.cpu(), inp_ref)
+        else:  # a near tie at the top-k boundary reordered two candidates: re-align and carry on
+            inp_dev.copy_(inp_ref)
+        assert float(tm_dev[0, synth.DOT_ID]) == float(tm_ref[0, synth.DOT_ID])
+
+
+def test_cabi_rejects_bad_arguments():
+    """Error convention of include/conzic.h: a negative return code and a message in conzic_last_error(), surfaced
+    as RuntimeError by the binding; nothing is launched, the context stays usable."""
+    eng = gc.engine("bf16x3")
+    B, n = 2, 3
+    tok = synth.SynthBertTokenizer()
+    inp = torch.tensor([tok.encode(synth.SYNTH_PROMPT + "[MASK]" * n)] * B).cuda()
+    tm = synth.make_token_mask("cuda")
+    img = torch.randn(B, 512, device="cuda")
+    with pytest.raises(RuntimeError, match="bad B / K / pos"):
+        eng.gibbs_step(inp, tm, img, 4, False, 1025, 0.1, 0.02, 2.0, 3, 0)       # K over the 1024 cap
+    with pytest.raises(RuntimeError, match="bad B / K / pos"):
+        eng.gibbs_step(inp, tm, img, inp.shape[1] - 1, False, 8, 0.1, 0.02, 2.0, 3, 0)  # pos on [SEP]
+    with pytest.raises(RuntimeError, match="bad B / K / pos"):
+        eng.gibbs_step(inp, tm, img, 0, False, 8, 0.1, 0.02, 2.0, 0, 0)          # pos on [CLS]
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    out = torch.empty((B, eng.ldl), dtype=torch.float32, device="cuda")
+    rc = eng.lib.conzic_bert_mlm_row(eng.ctx, inp.data_ptr(), B, inp.shape[1], 4, out.data_ptr(), eng.ldl, ws.data_ptr(),
+                                     ws.numel(), None)
+    from conzic_b200 import _lib
+    assert rc < 0 and "workspace too small" in _lib.last_error()
+    with pytest.raises(RuntimeError, match=r"T must be in \[1, 77\]"):
+        eng.clip_text_encode(torch.full((2, 78), synth.CLIP_EOS, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="bad B / K / pos / P / S"):
+        eng.encode_candidates(inp, 4, torch.full((B, 4), 2000, device="cuda"), tm, 77, 4)
+    # still healthy afterwards
+    _, _, tr = eng.gibbs_step(inp, tm, img, 4, False, 8, 0.1, 0.02, 2.0, 3, 0, trace=True)
+    torch.cuda.synchronize()
+    assert bool((inp[:, 4] >= 1996).all())
+
+
 def test_long_sentence_free_running_matches_oracle():
     """sentence_len 25 (BASELINE config 5's longest): prefixes up to 29 tokens and candidate suffixes up to 27 rows
     -> the 64-key attention tiles and the multi-tile query path; multi-token words.  One sweep of a free-running
