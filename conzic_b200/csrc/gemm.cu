@@ -168,16 +168,16 @@ __device__ __forceinline__ void prefetch_a_rows(const PGemmParams& p, int r_lo, 
                  : "memory");
 }
 
-template <int CG, bool ARES>
+template <int CG, bool ARES, int EW = P_EPI_WARPS>
 struct PSmem {
   static constexpr int A_SLOT = BM * BK * 2;               // 16 KB
   static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
   static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
   static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
-  static constexpr int STAGES = ARES ? 5 : (CG == 1 ? 4 : 6);
+  static constexpr int STAGES = ARES ? (EW == 16 ? 4 : 5) : (CG == 1 ? 4 : 6);  // 16 warps: 16 KB more staging, one stage less
   static_assert(!ARES || CG == 2, "A-resident mode needs the CTA pair");
   static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 64 B transpose buffers
-  static constexpr int STG_BYTES = P_EPI_WARPS * 2048;
+  static constexpr int STG_BYTES = EW * 2048;
   static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int N_BARS = 2 * STAGES + P_MAX_KB + 4;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
@@ -514,12 +514,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int CG, bool ARES>
-__global__ void __launch_bounds__(P_THREADS, 1)
+// EW = epilogue warps.  8: each warp drains 128 columns of the 256-wide tile, every epilogue form.  16: 64 columns
+// each, fp32 (+ residual) output only -- for the GEMM whose epilogue is the critical path (O-proj: 5 KB of HBM
+// traffic per row for 0.5 MFLOP), where twice the warps mean twice the residual loads in flight.
+template <int CG, bool ARES, int EW = P_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const PGemmParams p) {
   PDL_ENTRY();
-  using SL = PSmem<CG, ARES>;
+  using SL = PSmem<CG, ARES, EW>;
+  constexpr int WCOLS = 2 * PBN / EW * 2;  // columns per epilogue warp: 128 (EW 8) or 64 (EW 16)
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
   uint8_t* smem = psmem;
@@ -555,7 +559,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int k = 0; k < P_MAX_KB; ++k) mbar_init(&empty_a[k], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], CG * P_EPI_WARPS);
+      mbar_init(&tempty_bar[b], CG * EW);
     }
     fence_mbar_init();
   }
@@ -647,15 +651,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ===== epilogue: 8 warps, warp%4 = TMEM lane quarter, (warp-2)/4 = column half of the 256-wide tile =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;  // which WCOLS-wide slice of the 256-column tile
     uint32_t acc = 0, acc_ph = 0;
     const uint32_t tempty_addr0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
-    const bool bf16_only = p.e.out_act && !p.e.out_f32 && !p.e.resid;
+    const bool bf16_only = EW == 8 && p.e.out_act && !p.e.out_f32 && !p.e.resid;
     for (long long u = u0; u < u1; ++u) {
       const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
-      const int nbase = n * PBN + half * (PBN / 2);
+      const int nbase = n * PBN + half * WCOLS;
       // this lane's 4 bias values of the warp's 128 columns (loaded while the tensor core is still busy)
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.e.bias && nbase + lane * 4 + 4 <= p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
@@ -667,7 +671,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * WCOLS;
       auto release = [&]() {
         // everything this warp needs from the accumulator is in registers: hand the buffer back to the MMA
         tc_fence_before();
@@ -677,6 +681,27 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else mbar_arrive_relaxed(&tempty_bar[acc]);
         }
       };
+      if constexpr (EW == 16) {
+        // fp32 (+ residual) output, N a multiple of 256 (checked by the launcher): 4 chunks of 16 columns per warp
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < WCOLS / 16; ++c) {
+          const int n0 = nbase + c * 16;
+          float4 rr[4];
+          prefetch_resid(p, lane, row0, n0, rr);
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
+          tmem_ld_wait();
+          if (c == WCOLS / 16 - 1) release();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+        continue;
+      }
       if (bf16_only && nbase + PBN / 2 <= p.N) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -980,23 +1005,26 @@ mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
 // reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
 // back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
 // ---------------------------------------------------------------------------------------------------
+template <int EW>  // EW epilogue warps: 8 (each drains 128 columns of BOTH halves; can fuse a LayerNorm) or 16
 struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
   static constexpr int STAGES = 4;
   static constexpr int STG_OFF = STAGES * STAGE;
-  static constexpr int LNS_OFF = STG_OFF + P_EPI_WARPS * 2048;  // fused LN: float2 [2 parities][2 column halves][128 rows]
-  static constexpr int BAR_OFF = LNS_OFF + 2 * 2 * BM * 8;
+  static constexpr int LNS_OFF = STG_OFF + EW * 2048;  // fused LN (EW == 8): float2 [2 parities][2 column halves][128 rows]
+  static constexpr int BAR_OFF = LNS_OFF + (EW == 8 ? 2 * 2 * BM * 8 : 0);
   static constexpr int N_BARS = 2 * STAGES + 4;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
+  static constexpr int THREADS = 64 + 32 * EW;
   static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
 };
 
-__global__ void __launch_bounds__(P_THREADS, 1)
+template <int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PGemmParams p) {
   PDL_ENTRY();
-  using SL = WideSmem;
+  using SL = WideSmem<EW>;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
@@ -1020,7 +1048,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], CG * P_EPI_WARPS); mbar_init(&tempty_bar[1], CG * P_EPI_WARPS);  // every warp reads both halves
+    // arrivals per half: EW == 8 -> all 8 warps of each CTA read both halves; EW == 16 -> 8 of the 16 read each half
+    mbar_init(&tempty_bar[0], CG * 8); mbar_init(&tempty_bar[1], CG * 8);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -1097,11 +1126,15 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // 8 warps: warp % 4 = TMEM lane quarter; (warp - 2) / 4 = which 128-column slice of EACH 256-column half
+    // warp % 4 = TMEM lane quarter.  EW == 8: (warp - 2) / 4 = which 128-column slice of EACH 256-column half;
+    // EW == 16: (warp - 2) / 4 = which 128-column slice of the 512 columns (one half per warp), which doubles the
+    // loads in flight of this latency-bound, non-overlapped epilogue
     const int q = warp & 3;
-    const int sub = (warp - 2) >> 2;  // 0 / 1: columns [sub*128, sub*128+128) of each 256-column half
+    const int slice = (warp - 2) >> 2;
+    const int sub = EW == 8 ? slice : (slice & 1);  // columns [sub*128, sub*128+128) of a 256-column half
+    const int h_lo = EW == 8 ? 0 : (slice >> 1), h_hi = EW == 8 ? 2 : (slice >> 1) + 1;
     uint32_t uph = 0;
-    const bool lnf = p.e.lnf_out != nullptr;
+    const bool lnf = EW == 8 && p.e.lnf_out != nullptr;
     const bool keep = lnf && p.e.lnf_mode == 2;  // x stays in TMEM for the LayerNorm pass
     const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
@@ -1111,7 +1144,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       float ls1[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};  // row sums over both halves (fused LN)
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int h = h_lo; h < h_hi; ++h) {
         const int nbase = h * PBN + sub * (PBN / 2);
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
@@ -1152,7 +1185,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ls1[i] += st1[i]; ls2[i] += st2[i]; }
       }
-      if (lnf) {
+      if constexpr (EW == 8) if (lnf) {
         // Fused LayerNorm of the rows just written.  This warp covered 256 of a row's 512 columns, the warp with
         // the other `sub` the rest: exchange (sum, sum of squares) through shared memory, read the kept values
         // back from TMEM, write bf16(LN(x) * g + b), and only then hand the accumulators back to the MMA warp.
@@ -1329,14 +1362,14 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return true;
 }
 
-template <int CG, bool ARES>
+template <int CG, bool ARES, int EW = P_EPI_WARPS>
 bool configure_persist() {
-  return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PSmem<CG, ARES>::DYN_BYTES),
+  return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PSmem<CG, ARES, EW>::DYN_BYTES),
                  "cudaFuncSetAttribute(gemm_persist)");
 }
 
-template <int CG, bool ARES>
+template <int CG, bool ARES, int EW = P_EPI_WARPS>
 bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int sms, cudaStream_t st) {
   const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
   long long groups = sms / CG;
@@ -1344,8 +1377,8 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   if (groups < 1) groups = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
-  cfg.blockDim = dim3(P_THREADS);
-  cfg.dynamicSmemBytes = PSmem<CG, ARES>::DYN_BYTES;
+  cfg.blockDim = dim3(64 + 32 * EW);
+  cfg.dynamicSmemBytes = PSmem<CG, ARES, EW>::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1356,7 +1389,7 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, p), "gemm_persist launch");
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES, EW>, ta, tb, p), "gemm_persist launch");
 }
 
 int g_sm_count = 0;
@@ -1410,17 +1443,22 @@ bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W
 }
 
 static bool configure_wide() {
-  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem::DYN_BYTES),
-                 "cudaFuncSetAttribute(gemm_wide)");
+  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<8>::DYN_BYTES),
+                 "cudaFuncSetAttribute(gemm_wide<8>)") &&
+         cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<16>::DYN_BYTES),
+                 "cudaFuncSetAttribute(gemm_wide<16>)");
 }
 static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
   if (groups < 1) groups = 1;
+  const char* e16 = getenv("CONZIC_WIDE_EPI16");  // read per launch so one process can compare both; default on
+  const bool w16 = (!e16 || atoi(e16)) && !p.e.lnf_out && !p.e.stats_out;
+
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
-  cfg.blockDim = dim3(P_THREADS);
-  cfg.dynamicSmemBytes = WideSmem::DYN_BYTES;
+  cfg.blockDim = dim3(w16 ? WideSmem<16>::THREADS : WideSmem<8>::THREADS);
+  cfg.dynamicSmemBytes = w16 ? WideSmem<16>::DYN_BYTES : WideSmem<8>::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1429,7 +1467,8 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel, ta, tb, p), "gemm_wide launch");
+  if (w16) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<16>, ta, tb, p), "gemm_wide<16> launch");
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<8>, ta, tb, p), "gemm_wide<8> launch");
 }
 static bool configure_mlp() {
   return cuda_ok(cudaFuncSetAttribute(mlp_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::DYN_BYTES),
@@ -1438,7 +1477,8 @@ static bool configure_mlp() {
 
 bool gemm_configure() {
   if (!configure_mlp() || !configure_wide()) return false;
-  if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>()))
+  if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>() &&
+        configure_persist<2, true, 16>()))
     return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
          configure_one<256, 2>() && configure_one<256, 4>();
@@ -1523,6 +1563,9 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");
       return false;
     }
+    const char* e16 = getenv("CONZIC_PERSIST_EPI16");  // read per launch so one process can compare both
+    if (cg == 2 && ares && e16 && atoi(e16) && epi.out_f32 && !epi.out_act && !epi.stats_out && !epi.ln_s && (W.N % PBN) == 0)
+      return launch_persist<2, true, 16>(ta, tb, pp, g_sm_count, st);
     if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
     return launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
   }
