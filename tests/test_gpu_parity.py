@@ -87,6 +87,28 @@ def test_persistent_pair_gemm_all_epilogues(mode, shape):
         assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("env,shape", [({"CONZIC_WIDE_EPI16": "0"}, (4096 + 77, 512, 2048)),
+                                       ({"CONZIC_PERSIST_EPI16": "1"}, (20000 + 33, 512, 512)),
+                                       ({"CONZIC_PERSIST_EPI16": "1"}, (700, 1536, 512))])
+def test_pair_gemm_epilogue_warp_variants_are_bit_identical(env, shape, monkeypatch):
+    """8 versus 16 epilogue warps (gemm_wide_kernel<8|16>, gemm_persist_kernel<2,true,8|16>) only change which warp
+    drains which accumulator columns: fp32 + residual outputs must be bit-identical to the default build's."""
+    M, N, K = shape
+    eng = gc.engine("bf16", "tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(M)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    base = eng.debug_linear(A, W, bias, resid, 0)
+    for k, v in env.items():  # read per launch
+        monkeypatch.setenv(k, v)
+    out = eng.debug_linear(A, W, bias, resid, 0)
+    assert torch.equal(out, base)
+    ref = _ref_linear(A, W, bias, resid, 0, True)
+    assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("M", [256, 1000, 37888 + 77])
 def test_fused_mlp_matches_fp64(M):
     """mlp_persist_kernel: x + fc2(quick_gelu(fc1(x))) with the bf16 intermediate kept in the per-CTA scratch
@@ -146,13 +168,17 @@ def test_clip_text_encode_vs_oracle(prec, tol):
                                           ("bf16", 0.06, {"CONZIC_WIDE_LN": "1"}),
                                           ("bf16", 0.06, {"CONZIC_WIDE_LN": "2"}),
                                           ("bf16", 0.06, {"CONZIC_ATTN_PREFETCH": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_WIDE_EPI16": "0"}),
+                                          ("bf16", 0.06, {"CONZIC_PERSIST_EPI16": "1"}),
+                                          ("bf16", 0.06, {"CONZIC_OPROJ_WIDE": "1"}),
                                           ("bf16", 0.06, {"CONZIC_GEMM_CG": "1"}),
                                           ("bf16", 0.06, {"CONZIC_GEMM_PERSIST": "0"})])
 def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch):
     """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
     the oracle, for the default path and every opt-in kernel variant: LayerNorm folded into the consuming GEMM
     (CONZIC_LN_FOLD), fc1+fc2 in one launch (CONZIC_MLP_FUSED), LayerNorm written by the producing wide GEMM's
-    epilogue (CONZIC_WIDE_LN), single-CTA and non-persistent GEMMs."""
+    epilogue (CONZIC_WIDE_LN), 8 / 16 epilogue warps, O-proj through the wide kernel, attention register prefetch,
+    single-CTA and non-persistent GEMMs."""
     from conzic_b200.engine import Engine
     from oracle import conzic_oracle as orc
     sd = {k: v.clone() for k, v in gc.weights("clip").items()}
