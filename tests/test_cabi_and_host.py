@@ -223,3 +223,27 @@ def test_plan_hybrid_against_string_tokenisation():
             assert full == pre + cand + tail
             assert 1 + len(pre) <= P and len(cand) + len(tail) + 1 <= S
     assert n_unflagged > 40
+
+
+def test_sentiment_table_export_follows_the_reference_scoring():
+    """tools/export_sentiment_table.py with stand-in NLTK callables: Penn tag -> WordNet class map and the mean of
+    pos - neg over the synsets (sentiments_classifer.py:14-30); pieces and special tokens score 0."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("export_sentiment_table", os.path.join(ROOT, "tools", "export_sentiment_table.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    tags = {"good": "JJ", "dog": "NN", "run": "VB", "the": "DT", "well": "RB"}
+    syn = lambda p, n: types.SimpleNamespace(pos_score=lambda: p, neg_score=lambda: n)
+    synsets = {("good", "a"): [syn(0.75, 0.0), syn(0.5, 0.25)], ("dog", "n"): [syn(0.0, 0.125)], ("run", "v"): [],
+               ("well", "r"): [syn(0.5, 0.0)], ("the", ""): [syn(0.9, 0.0)]}
+    calls = []
+
+    def senti_synsets(w, t):
+        calls.append((w, t))
+        return synsets.get((w, t), [])
+
+    tokens = ["[PAD]", "[unused5]", "good", "dog", "run", "the", "well", "##ing", "[MASK]"]
+    table = mod.build_table(tokens, lambda ws: [(w, tags[w]) for w in ws], senti_synsets)
+    np.testing.assert_allclose(table.numpy(), [0, 0, (0.75 + 0.25) / 2, -0.125, 0, 0.9, 0.5, 0, 0], atol=1e-7)
+    assert ("good", "a") in calls and ("the", "") in calls and all(w not in ("##ing", "[PAD]") for w, _ in calls)
