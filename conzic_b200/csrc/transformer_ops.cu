@@ -97,9 +97,18 @@ __global__ void layernorm_kernel(LNArgs a) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(a.add_bias + col));
           v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
         }
-        for (int z = 0; z < a.n_parts; ++z) {
-          const float4 q = *reinterpret_cast<const float4*>(a.partials + z * a.part_stride + static_cast<size_t>(r) * a.H + col);
-          v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+        // up to 4 split-K partial sums (launch_linear's cap): all loads are issued before the first add, so a row
+        // costs one memory latency instead of n_parts; the adds keep the order z = 0, 1, 2, 3
+        float4 q[4];
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          q[z] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (z < a.n_parts)
+            q[z] = *reinterpret_cast<const float4*>(a.partials + z * a.part_stride + static_cast<size_t>(r) * a.H + col);
+        }
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          if (z < a.n_parts) { v[i].x += q[z].x; v[i].y += q[z].y; v[i].z += q[z].z; v[i].w += q[z].w; }
         }
       }
     }
@@ -723,11 +732,14 @@ void launch_layernorm(const LNArgs& a, cudaStream_t st) {
   ++g_launches;
   ProfScope prof_(CAT_LN, static_cast<double>(a.n_rows) * a.H, st);
   if (a.n_rows <= 0) return;
-  const int grid = row_grid(a.n_rows, 8);
+  if (a.partials && a.n_parts > 4) { set_error("layernorm: at most 4 split-K partial sums"); return; }
+  // few rows (BERT: B * L ~ 1000): 4 warps per block so the rows spread over all SMs instead of 120 blocks
+  const int wpb = a.n_rows < 4096 ? 4 : 8;
+  const int grid = row_grid(a.n_rows, wpb);
   switch (a.H / 128) {
-    case 4: launch_k(layernorm_kernel<4>, dim3(grid), dim3(256), 0, st, a); break;
-    case 6: launch_k(layernorm_kernel<6>, dim3(grid), dim3(256), 0, st, a); break;
-    case 8: launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), 0, st, a); break;
+    case 4: launch_k(layernorm_kernel<4>, dim3(grid), dim3(wpb * 32), 0, st, a); break;
+    case 6: launch_k(layernorm_kernel<6>, dim3(grid), dim3(wpb * 32), 0, st, a); break;
+    case 8: launch_k(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, st, a); break;
     default: set_error("layernorm: hidden size must be 512, 768 or 1024"); break;
   }
 }
