@@ -17,7 +17,7 @@ from conzic_b200 import synth  # noqa: E402
 from conzic_b200.engine import Engine  # noqa: E402
 
 B, n, K = 64, 10, 200
-POSITIONS = (0, 5, 9)
+POSITIONS = tuple(int(x) for x in os.environ.get("EXP_POSITIONS", "0,5,9").split(","))
 
 
 def run(envspec, bert_sd, clip_sd, table, base):
