@@ -573,6 +573,72 @@ def test_prefix_sharing_equals_dense_encode():
     torch.testing.assert_close(score, tr["clip_score"], rtol=0, atol=3e-5)
 
 
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-5), ("bf16", 6e-3)])
+def test_full_size_prefix_sharing_equals_dense_encode(prec, tol):
+    """BASELINE config 2 sizes (B=64, K=200, len=10, middle position): the cosines of the shared-prefix step equal
+    those of encoding all 12 800 candidate captions densely, token by token, through conzic_clip_text_encode."""
+    eng = gc.engine(prec)
+    B, n, K, ii = 64, 10, 200, 4
+    pos = 4 + ii
+    g = torch.Generator().manual_seed(17)
+    words = torch.randint(2000, 30000, (B, n), generator=g)
+    inp = torch.cat([torch.tensor([[101, 3746, 1997, 1037]] * B), words, torch.tensor([[102]] * B)], dim=1).cuda()
+    inp[3, 6] = 0   # a dropped word in a prefix
+    inp[5, 11] = 0  # and in a tail
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).cuda()
+    tm = synth.make_token_mask("cuda")
+    inp0 = inp.clone()
+    _, _, tr = eng.gibbs_step(inp, tm, img, pos, False, K, 0.1, 0.02, 2.0, 3 + ii, n - 1 - ii, trace=True)
+    masked = inp0.clone()
+    masked[:, pos] = synth.MASK_ID
+    cids, clen, idm = eng.build_clip_ids(masked, pos, tr["idxs"], tm, n + 6)
+    assert int(clen.max()) <= n + 5 and int(clen.min()) >= n + 3
+    emb = eng.clip_text_encode(cids)
+    score, ref = eng.image_text_similarity(img, emb)
+    assert float((ref - tr["clip_ref"]).abs().max()) < tol
+    if prec == "bf16x3":
+        best_dense = (0.02 * tr["probs"] + 2.0 * score).argmax(dim=1)
+        assert torch.equal(best_dense, tr["best"])
+
+
+def test_full_size_sentiment_step_properties():
+    """BASELINE config 4 sizes (B=64 per GPU, sentence_len 12, K=200, sentiment gamma=5): legal winners, the control
+    term follows the table (softmax over K of the caption's table sum), repeats penalise duplicates, and the step
+    is deterministic."""
+    eng = gc.engine("bf16x3")
+    B, n, K, ii = 64, 12, 200, 5
+    pos = 4 + ii
+    g = torch.Generator().manual_seed(23)
+    words = torch.randint(2000, 30000, (B, n), generator=g)
+    inp0 = torch.cat([torch.tensor([[101, 3746, 1997, 1037]] * B), words, torch.tensor([[102]] * B)], dim=1).cuda()
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).cuda()
+    table = synth.make_sentiment_table().cuda()
+    runs = []
+    for _ in range(2):
+        inp = inp0.clone()
+        tm = synth.make_token_mask("cuda")
+        cr, se, tr = eng.gibbs_step(inp, tm, img, pos, False, K, 0.1, 0.02, 2.0, 3 + ii, n - 1 - ii, gamma=5.0,
+                                    senti_table=table, trace=True)
+        torch.cuda.synchronize()
+        runs.append((inp.clone(), cr.clone(), se.clone(), tr))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
+    inp, cr, se, tr = runs[0]
+    assert bool((inp[:, pos] >= 1996).all())
+    # rebuild the fused score from the traced pieces (control_gen_utils.py:53-59)
+    cand = inp0.unsqueeze(1).repeat(1, K, 1)
+    idm = (tr["idxs"] * synth.make_token_mask("cuda")[0][tr["idxs"]]).long()
+    cand[:, :, pos] = idm
+    special = torch.tensor(synth.SPECIAL_IDS, device="cuda")
+    vis = ~torch.isin(cand, special)
+    senti_raw = (table[cand] * vis).sum(-1)
+    repeats = (idm[:, :, None] == cand).float().sum(2) - 1
+    final = 0.02 * tr["probs"] + 2.0 * tr["clip_score"] + 5.0 * torch.softmax(senti_raw, dim=1) + 0.1 * (1 - torch.exp(repeats))
+    torch.testing.assert_close(final, tr["final"], rtol=0, atol=2e-5)
+    best = tr["best"]
+    assert torch.equal(idm.gather(1, best.view(-1, 1)).squeeze(1), inp[:, pos])
+    torch.testing.assert_close(se, senti_raw.gather(1, best.view(-1, 1)).squeeze(1), rtol=0, atol=1e-5)
+
+
 def test_full_size_step_properties():
     """BASELINE config 2 sizes (B=64, K=200, len=10): winners are legal (unmasked) ids, scores are cosines,
     the step is deterministic, and the bf16 path picks the same winner as bf16x3 on all but near ties."""
