@@ -405,16 +405,20 @@ __device__ __forceinline__ void att_put16(uint8_t* tile, int dst0, int n_rows, i
   }
 }
 
-template <int NT, bool PIPE = false>  // NT key tiles of 8: up to NT*8 keys per tile; PIPE: register prefetch of the next tile
-__global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
+// NT key tiles of 8: up to NT*8 keys per tile; PIPE: register prefetch of the next tile; MINB: resident blocks per SM the
+// register budget is sized for (the kernel is latency bound: 24 warps per SM instead of 16 when the tiles are small)
+template <int NT, bool PIPE = false, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) attention_mma_kernel(AttnArgs a) {
   PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t att_smem[];
   constexpr int KV_BYTES = NT * 8 * 128;
-  constexpr int WARP_BYTES = 2 * KV_BYTES + 16 * 128;
+  constexpr int VT = (NT + 1) / 2 * 2;  // P V consumes keys 16 at a time: the V tile is padded to an even tile count
+  constexpr int V_BYTES = VT * 8 * 128;
+  constexpr int WARP_BYTES = KV_BYTES + V_BYTES + 16 * 128;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sK = att_smem + wib * WARP_BYTES;
   uint8_t* sV = sK + KV_BYTES;
-  uint8_t* sQ = sV + KV_BYTES;  // 16 query rows; reused to stage the 16 output rows
+  uint8_t* sQ = sV + V_BYTES;  // 16 query rows; reused to stage the 16 output rows
   const uint32_t sK_a = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
   const uint32_t sV_a = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   const uint32_t sQ_a = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
   const int n_pre_rows = a.B * a.P;
 
   // V rows that hold no key must be finite: P = 0 there, and 0 * garbage could be NaN
-  for (int idx = lane; idx < (NT * 8 - pl) * 8; idx += 32)
+  for (int idx = lane; idx < (VT * 8 - pl) * 8; idx += 32)
     *reinterpret_cast<uint4*>(sV + sw_off(pl + (idx >> 3), idx & 7)) = make_uint4(0, 0, 0, 0);
   if (!is_prefix && pl > 0) {
     for (int r0 = 0; r0 < pl; r0 += 16) {
@@ -591,13 +595,17 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(AttnArgs a) {
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < NT / 2; ++ks) {
+      for (int ks = 0; ks < VT / 2; ++ks) {
         if (ks * 16 < nk) {
           uint32_t ph[4], plo[4];
           split_pair(sc[2 * ks][0] * i0, sc[2 * ks][1] * i0, ph[0], plo[0]);
           split_pair(sc[2 * ks][2] * i1, sc[2 * ks][3] * i1, ph[1], plo[1]);
-          split_pair(sc[2 * ks + 1][0] * i0, sc[2 * ks + 1][1] * i0, ph[2], plo[2]);
-          split_pair(sc[2 * ks + 1][2] * i1, sc[2 * ks + 1][3] * i1, ph[3], plo[3]);
+          if (2 * ks + 1 < NT) {
+            split_pair(sc[(2 * ks + 1) % NT][0] * i0, sc[(2 * ks + 1) % NT][1] * i0, ph[2], plo[2]);
+            split_pair(sc[(2 * ks + 1) % NT][2] * i1, sc[(2 * ks + 1) % NT][3] * i1, ph[3], plo[3]);
+          } else {  // odd NT: the last 8 keys of the padded V tile carry no probability
+            ph[2] = ph[3] = plo[2] = plo[3] = 0u;
+          }
 #pragma unroll
           for (int d2 = 0; d2 < 4; ++d2) {
             uint32_t v0, v1, v2, v3;
@@ -799,10 +807,26 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     const long long tasks = (a.P > 0 ? static_cast<long long>(a.B) * a.heads : 0) +
                             static_cast<long long>(a.B) * a.heads * groups;
     if (tasks <= 0) return true;
+    // Tiles of <= 16 keys (the long-suffix steps, where this kernel's share is largest): 2 key tiles, 80 registers and
+    // 48 KB per block -> 3 resident blocks (24 warps) per SM instead of 2; the kernel is latency bound, measured
+    // -12 % attention time, bit-identical.  With 17..32 keys the same trade (more warps, spills in the two-candidate
+    // tile loop) measured 2-3 % slower per step, so those keep 2 blocks of 128-register threads.
+    const char* e3 = getenv("CONZIC_ATTN_OCC3");  // read per launch so one process can compare both; default on
+    const bool occ3 = (!e3 || atoi(e3)) && keys_cap <= 16 && !aa.prefetch;
     const int warps = 8;
     const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
-    const int nt = keys_cap <= 32 ? 4 : (keys_cap <= 64 ? 8 : 12);
-    const size_t smem = static_cast<size_t>(warps) * (2 * nt * 1024 + 2048);
+    const int nt = occ3 ? 2 : (keys_cap <= 32 ? 4 : (keys_cap <= 64 ? 8 : 12));
+    const size_t smem = static_cast<size_t>(warps) * ((nt + (nt + 1) / 2 * 2) * 1024 + 2048);
+    if (occ3) {
+      static bool cfg3 = false;
+      if (!cfg3) {
+        if (!cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<2, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (4 * 1024 + 2048)), "attr"))
+          return false;
+        cfg3 = true;
+      }
+      launch_k(attention_mma_kernel<2, false, 3>, dim3(grid), dim3(warps * 32), smem, st, aa);
+      return cuda_ok(cudaGetLastError(), "attention_mma launch");
+    }
     static size_t configured[3] = {0, 0, 0};
     const int which_nt = nt == 4 ? 0 : (nt == 8 ? 1 : 2);
     if (smem > 48 * 1024 && smem > configured[which_nt]) {
