@@ -1138,23 +1138,32 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool keep = lnf && p.e.lnf_mode == 2;  // x stays in TMEM for the LayerNorm pass
     const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
+    // this warp's bias values (columns do not depend on the tile): fetched once, before the first accumulator is
+    // waited for -- inside the tile loop the load's latency sat on the un-overlapped epilogue's critical path
+    float4 bias_h[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    if (p.e.bias) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (h >= h_lo && h < h_hi) bias_h[h] = __ldg(reinterpret_cast<const float4*>(p.e.bias + h * PBN + sub * (PBN / 2) + lane * 4));
+    }
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      // the first chunk's residual does not depend on the accumulator either: request it before waiting for the MMAs
+      float4 rr[4];
+      prefetch_resid(p, lane, row0, h_lo * PBN + sub * (PBN / 2), rr);
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
       float ls1[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};  // row sums over both halves (fused LN)
 #pragma unroll 1
       for (int h = h_lo; h < h_hi; ++h) {
         const int nbase = h * PBN + sub * (PBN / 2);
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
+        const float4 bias4 = h == 0 ? bias_h[0] : bias_h[1];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * PBN + sub * (PBN / 2);
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           const int n0 = nbase + c * 16;
-          float4 rr[4];
-          prefetch_resid(p, lane, row0, n0, rr);
+          if (c > 0 || h > h_lo) prefetch_resid(p, lane, row0, n0, rr);
           uint32_t r[16];
           tmem_ld16(taddr + c * 16, r);
           tmem_ld_wait();
