@@ -516,6 +516,56 @@ def test_cabi_rejects_bad_arguments():
     assert bool((inp[:, 4] >= 1996).all())
 
 
+@pytest.mark.parametrize("mode", ["sentiment", "span", "random"])
+def test_piece_vocabulary_hybrid_equals_string_path(mode, monkeypatch):
+    """Piece vocabulary, modes the reference fixtures do not cover (its stub sentiment scorer cannot look up merged
+    words): the hybrid step and the all-strings step are two routes to the same numbers -- captions, CLIP scores and
+    (sentiment) the per-sweep log lines must agree exactly in bf16x3 mode."""
+    import logging
+    from conzic_b200 import control_gen_utils, gen_utils, runtime
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    B, n, K = 3, 5, 16
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    names = [f"img{i}.jpg" for i in range(B)]
+    results = {}
+    for path in ("hybrid", "strings"):
+        if path == "strings":
+            monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+        runtime.clear()
+        bert = BertMLM(gc.weights("bert"))
+        clip = CLIP(state_dict=gc.weights("clip"), tokenizer=synth.PieceCLIPTokenizer(True),
+                    processor=synth.SynthProcessor()).to("cuda:0")
+        lines = []
+        logger = logging.getLogger(f"pieces-{mode}-{path}")
+        logger.setLevel(logging.INFO)
+        logger.propagate = False
+        h = logging.Handler()
+        h.emit = lambda rec: lines.append(rec.getMessage())
+        logger.addHandler(h)
+        kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=2, alpha=0.02,
+                  beta=2.0)
+        set_seed(42)
+        if mode == "sentiment":
+            out = control_gen_utils.control_generate_caption(
+                names, bert, clip, synth.PieceBertTokenizer(), pix, synth.make_token_mask("cuda"), logger, gamma=5.0,
+                ctl_type="sentiment", style_type="positive", generate_order="shuffle",
+                sentiment_table=synth.make_sentiment_table(), **kw)
+        else:
+            out = gen_utils.generate_caption(names, bert, clip, synth.PieceBertTokenizer(), pix,
+                                             synth.make_token_mask("cuda"), logger, generate_order=mode, **kw)
+        results[path] = (out, [ln for ln in lines if ln.startswith("iter ")])
+    runtime.clear()
+    (ta, sa), la = results["hybrid"]
+    (tb, sb), lb = results["strings"]
+    assert ta == tb and la == lb and len(la) > 0
+    for a, b in zip(sa, sb):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+    assert any("p" in w[1:] for c in ta[-2] for w in c.split()) or mode != "sentiment"
+
+
 def test_long_sentence_free_running_matches_oracle():
     """sentence_len 25 (BASELINE config 5's longest): prefixes up to 29 tokens and candidate suffixes up to 27 rows
     -> the 64-key attention tiles and the multi-tile query path; multi-token words.  One sweep of a free-running
