@@ -82,8 +82,8 @@ def _declare(lib):
     lib.conzic_image_text_similarity.restype = C.c_int
     lib.conzic_image_text_similarity.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
     lib.conzic_encode_candidates.restype = C.c_int
-    lib.conzic_encode_candidates.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp,
-                                             C.c_size_t, vp]
+    lib.conzic_encode_candidates.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp,
+                                             vp, vp, C.c_size_t, vp]
     lib.conzic_score_select.restype = C.c_int
     lib.conzic_score_select.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, f32, f32, f32, vp, i32, i32, vp, vp, vp, vp]
     lib.conzic_gibbs_step.restype = C.c_int
@@ -118,7 +118,7 @@ def load(build_if_missing: bool = True):
         from . import build as _build
         _build.build()
     _lib = _declare(C.CDLL(LIB_PATH))
-    if _lib.conzic_abi_version() != 4:
+    if _lib.conzic_abi_version() != 5:
         raise RuntimeError("libconzic.so ABI version mismatch; rebuild with `python -m conzic_b200.build --force`")
     return _lib
 

@@ -765,9 +765,13 @@ int conzic_clip_text_encode(conzic_ctx* c, const int32_t* clip_ids, int N, int T
 
 int conzic_encode_candidates(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, const int64_t* ids,
                              const float* token_mask, int K, int P, int S, const float* senti_table, float* text,
-                             int64_t* ids_masked, float* repeats, float* senti_raw, void* ws, size_t ws_bytes,
-                             void* stream) {
+                             int64_t* ids_masked, float* repeats, float* senti_raw, const int32_t* ov_mask,
+                             const int32_t* ov_off, const int32_t* ov_tok, void* ws, size_t ws_bytes, void* stream) {
   if (!c || !inp || !ids || !token_mask || !text || !ids_masked || !ws) { set_error("encode_candidates: null argument"); return -1; }
+  if ((ov_mask != nullptr) != (ov_off != nullptr) || (ov_mask != nullptr) != (ov_tok != nullptr)) {
+    set_error("encode_candidates: ov_mask / ov_off / ov_tok go together");
+    return -1;
+  }
   if (!c->b2c_off) { set_error("encode_candidates: conzic_set_bert2clip has not been called"); return -1; }
   const int cap = c->cfg.clip_maxpos - 1;
   if (B < 1 || K < 1 || K > 1024 || pos < 1 || pos >= L - 1 || P < 1 || P > cap || S < 2 || S > cap) {
@@ -788,6 +792,7 @@ int conzic_encode_candidates(conzic_ctx* c, const int64_t* inp, int B, int L, in
   a.B = B; a.L = L; a.K = K; a.pos = pos;
   a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
   a.ids_masked = ids_masked; a.repeats = repeats; a.senti = senti_table ? senti_raw : nullptr;
+  a.ov_mask = ov_mask; a.ov_off = ov_off; a.ov_tok = ov_tok;
   launch_assemble(a, st);
   if (!clip_encode(c, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.text, p, st)) return -4;
   return cuda_ok(cudaMemcpyAsync(text, p.text, static_cast<size_t>(B) * K * c->cfg.clip_proj * sizeof(float),

@@ -221,6 +221,12 @@ struct AssembleArgs {
   int64_t* ids_masked;  // [B,K]
   float* repeats;       // [B,K] or null
   float* senti;         // [B,K] or null
+  // optional per-image override of the table walk (captions that hold a merged '##' word outside `pos`): for images
+  // with ov_mask[b] != 0 the prefix tokens are ov_tok[ov_off[2b] .. ov_off[2b+1]) and the tail tokens
+  // ov_tok[ov_off[2b+1] .. ov_off[2b+2]) -- what the host's tokenizers made of the decoded strings
+  const int32_t* ov_mask = nullptr;  // [B]
+  const int32_t* ov_off = nullptr;   // [2B+1]
+  const int32_t* ov_tok = nullptr;
 };
 void launch_assemble(const AssembleArgs& a, cudaStream_t st);
 

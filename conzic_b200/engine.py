@@ -284,10 +284,12 @@ class Engine:
         return out
 
     def encode_candidates(self, inp: torch.Tensor, pos: int, ids: torch.Tensor, token_mask: torch.Tensor, P: int, S: int,
-                          senti_table: Optional[torch.Tensor] = None, want_repeats: bool = False):
+                          senti_table: Optional[torch.Tensor] = None, want_repeats: bool = False, overrides=None):
         """gen_utils.py:71-76 + clip/clip.py:71-83 without the string round trip: candidate ids -> CLIP ids via the
         table (shared prefix of P rows per image, S rows per candidate) -> text tower.  Returns (text_embeds
-        f32[B*K, D], ids_masked int64[B,K], repeats f32[B,K] or None, senti_raw f32[B,K] or None) on the device."""
+        f32[B*K, D], ids_masked int64[B,K], repeats f32[B,K] or None, senti_raw f32[B,K] or None) on the device.
+        `overrides` = (ov_mask int32[B], ov_off int32[2B+1], ov_tok int32[n]) host tensors: host-tokenised prefix /
+        tail CLIP ids for the images whose caption holds a merged '##' word (see conzic.h)."""
         assert self.has_table, "call Engine.set_bert2clip first"
         B, L = inp.shape
         K = ids.shape[1]
@@ -296,10 +298,14 @@ class Engine:
         repeats = torch.empty((B, K), dtype=torch.float32, device=self.device) if want_repeats else None
         senti = torch.empty((B, K), dtype=torch.float32, device=self.device) if senti_table is not None else None
         ws = self.workspace(B, L, K)
+        ov = [None, None, None]
+        if overrides is not None:
+            ov = [t.to(self.device, torch.int32, non_blocking=True).contiguous() for t in overrides]
+            assert ov[0].numel() == B and ov[1].numel() == 2 * B + 1
         rc = self.lib.conzic_encode_candidates(self.ctx, _ptr(inp), B, L, int(pos), _ptr(ids.contiguous()),
                                                _ptr(token_mask), K, int(P), int(S), _ptr(senti_table), _ptr(text),
-                                               _ptr(ids_masked), _ptr(repeats), _ptr(senti), _ptr(ws), ws.numel(),
-                                               self._stream())
+                                               _ptr(ids_masked), _ptr(repeats), _ptr(senti), _ptr(ov[0]), _ptr(ov[1]),
+                                               _ptr(ov[2]), _ptr(ws), ws.numel(), self._stream())
         _lib.check(rc, "conzic_encode_candidates")
         return text, ids_masked, repeats, senti
 

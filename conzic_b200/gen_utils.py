@@ -59,6 +59,7 @@ class _Chain:
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
         self.mask_h = None
+        self._ov_memo = {}
 
     def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
                          pos_scorer=None):
@@ -104,14 +105,33 @@ class _Chain:
             self.pos_tags = [tags[int(win[i]) + i * top_k] for i in range(self.B)]
         self.holds_word[pos] = True
 
+    def _clip_ids_of(self, ids_row):
+        """CLIP ids (no BOS / EOS) of the decoded text of a run of BERT ids, as the reference would produce them
+        (batch_decode with skip_special_tokens, then the CLIP tokenizer); memoised per id tuple."""
+        key = tuple(int(v) for v in ids_row)
+        hit = self._ov_memo.get(key)
+        if hit is None:
+            text = self.tokenizer.decode(ids_row, skip_special_tokens=True)
+            ctok = self.clip.tokenizer
+            if not text:
+                hit = ()
+            elif hasattr(ctok, "tokens_of_text"):
+                hit = tuple(ctok.tokens_of_text(text))
+            else:
+                hit = tuple(ctok(text, add_special_tokens=False)["input_ids"])
+            self._ov_memo[key] = hit
+        return hit
+
     def step_hybrid(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
         """The step for vocabularies with '##' word pieces.  A piece merges into the previous word and changes
         that word's CLIP BPE, so the per-token table is exact only for captions without pieces.  All candidates go
         through the table path on the device (shared prefix, conzic_encode_candidates); the host reads the top-k
-        ids, finds the captions that contain a piece (tokens.plan_hybrid), builds exactly those strings like the
-        reference does (gen_utils.py:75), encodes them densely with the same kernels and patches their embeddings
-        in before the fused score / argmax.  One device->host read per step; the string work overlaps the main
-        encode on the GPU."""
+        ids and sorts the captions (tokens.hybrid_flags): a candidate that is itself a piece, or any candidate of an
+        image where a piece directly follows `pos`, is rebuilt as a string exactly like the reference does
+        (gen_utils.py:75), encoded densely with the same kernels and patched in before the fused score / argmax; an
+        image that merely holds a merged word elsewhere keeps the table path for its candidates and only has its
+        prefix / tail strings tokenised by the host (memoised).  One device->host read per step; the string work
+        overlaps the main encode on the GPU."""
         from . import tokens
         eng, tok = self.eng, self.tokenizer
         pos = self.seed_len + ii
@@ -125,10 +145,30 @@ class _Chain:
             self.mask_h = self.mask.view(-1).cpu()
         self.mask_h[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0
         ids_masked_h = (idxs_h * self.mask_h[idxs_h]).long()  # gen_utils.py:72
-        flag, P, S = tokens.plan_hybrid(inp_h, pos, ids_masked_h, eng.piece_mask_h, eng.tok_len_h, eng.cfg.clip_maxpos)
+        special = [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id]
+        flag, override = tokens.hybrid_flags(inp_h, pos, ids_masked_h, eng.piece_mask_h, special)
+        overrides, ov_lens = None, {}
+        if bool(override.any()):
+            # images whose caption already holds a merged word (away from `pos`): the host tokenises their prefix and
+            # tail strings (memoised per id run), the candidates stay on the table path
+            ov_mask = override.to(torch.int32)
+            ov_off, ov_tok = [0], []
+            for b in range(self.B):
+                if bool(override[b]):
+                    pre_t = self._clip_ids_of(inp_h[b, :pos])
+                    tail_t = self._clip_ids_of(inp_h[b, pos + 1:])
+                    ov_lens[b] = (len(pre_t), len(tail_t))
+                else:
+                    pre_t, tail_t = (), ()
+                ov_tok.extend(pre_t)
+                ov_off.append(len(ov_tok))
+                ov_tok.extend(tail_t)
+                ov_off.append(len(ov_tok))
+            overrides = (ov_mask, torch.tensor(ov_off, dtype=torch.int32), torch.tensor(ov_tok or [0], dtype=torch.int32))
+        P, S = tokens.hybrid_capacities(inp_h, pos, ids_masked_h, eng.tok_len_h, ov_lens, eng.cfg.clip_maxpos)
         text, ids_masked, repeats, senti_raw = eng.encode_candidates(
             self.inp, pos, idxs, self.mask, P, S, senti_table=senti_table if gamma is not None else None,
-            want_repeats=gamma is not None)
+            want_repeats=gamma is not None, overrides=overrides)
         if bool(flag.any()):  # host strings for the flagged captions only, while the GPU runs the main encode
             bi, ki = flag.nonzero(as_tuple=True)
             rows = inp_h[bi].clone()

@@ -38,24 +38,44 @@ def build_bert2clip(bert_tokenizer, clip_tokenizer, vocab_size: int, special_ids
     return torch.tensor(off, dtype=torch.int32), torch.tensor(toks, dtype=torch.int32), needs_host
 
 
-def plan_hybrid(inp_h: torch.Tensor, pos: int, ids_masked_h: torch.Tensor, piece: torch.Tensor, tok_len: torch.Tensor,
-                maxpos: int = 77):
-    """Host-side plan of one step for a vocabulary with '##' pieces.
+def hybrid_flags(inp_h: torch.Tensor, pos: int, ids_masked_h: torch.Tensor, piece: torch.Tensor, special_ids):
+    """Which candidate captions need the host string pass, and which images only need their prefix / tail re-tokenised.
 
-    inp_h int64[B,L] (column `pos` is ignored), ids_masked_h int64[B,K] (candidate ids, 0 where masked),
-    piece bool[V], tok_len int[V] (CLIP tokens per BERT id; 0 for special ids and pieces).
-    Returns (flag bool[B,K], P, S): flag marks the candidate captions that contain a piece anywhere -- the table
-    result is not valid for them; P / S are the exact row capacities of the shared prefix (BOS included) and of
-    the per-candidate part (EOS included) in CLIP tokens, clamped to what a 77-token caption can hold."""
+    A caption whose words outside `pos` hold a piece is still the space-joined sequence prefix + candidate + tail as
+    long as no piece follows `pos` directly (that one would merge INTO the candidate word, also across a dropped
+    candidate): such an image keeps the table path for its candidates once the host supplies the CLIP ids of its
+    prefix and tail strings.  Returns (flag bool[B,K], override bool[B]):
+      flag[b,k]   -- candidate k is a piece itself, or image b cannot be overridden (a piece right after `pos`);
+      override[b] -- image b holds a piece outside `pos` and can be handled by a prefix / tail override."""
     others = inp_h.clone()
-    others[:, pos] = 0  # [PAD]: special, no piece, no tokens
-    img_flag = piece[others].any(dim=1)
-    flag = piece[ids_masked_h] | img_flag[:, None]
+    others[:, pos] = int(special_ids[0])
+    pm = piece[others]
+    img_flag = pm.any(dim=1)
+    kept = ~torch.isin(others, torch.as_tensor(list(special_ids), dtype=others.dtype))
+    after = kept[:, pos + 1:]
+    if after.shape[1] > 0:
+        first = after.int().argmax(dim=1)
+        next_piece = after.any(dim=1) & pm[:, pos + 1:].gather(1, first.view(-1, 1)).squeeze(1)
+    else:
+        next_piece = torch.zeros_like(img_flag)
+    override = img_flag & ~next_piece
+    flag = piece[ids_masked_h] | (img_flag & ~override)[:, None]
+    return flag, override
+
+
+def hybrid_capacities(inp_h: torch.Tensor, pos: int, ids_masked_h: torch.Tensor, tok_len: torch.Tensor, ov_lens=None,
+                      maxpos: int = 77):
+    """Row capacities (P incl. BOS, S incl. EOS) for conzic_encode_candidates; `ov_lens` maps an overridden image
+    index to the (prefix, tail) token counts of its host-tokenised strings."""
+    others = inp_h.clone()
+    others[:, pos] = 0
     lens = tok_len[others].long()
     pre = 1 + lens[:, :pos].sum(dim=1)
     tail = lens[:, pos + 1:].sum(dim=1)
+    for b, (n_pre, n_tail) in (ov_lens or {}).items():
+        pre[b], tail[b] = 1 + n_pre, n_tail
     cand = tok_len[ids_masked_h].long()
     cap = maxpos - 1
     P = int(min(max(int(pre.max()), 1), cap))
     S = int(min(max(int((cand + tail[:, None]).max()) + 1, 2), cap))
-    return flag, P, S
+    return P, S

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CONZIC_ABI_VERSION 4
+#define CONZIC_ABI_VERSION 5
 
 typedef struct conzic_ctx conzic_ctx;
 
@@ -119,10 +119,15 @@ int conzic_clip_text_encode(conzic_ctx* ctx, const int32_t* clip_ids_dev, int N,
  * CLIP tokens), S = rows per candidate (>= the longest candidate word + tail in CLIP tokens, + 1 for EOS); both are
  * capacities, shorter sequences are padded with EOS, longer ones are cut like truncation at 77 would.
  * Also out: ids_masked int64[B,K] = ids * token_mask[ids]; repeats f32[B,K] (control_gen_utils.py:53) or NULL;
- * senti_raw f32[B,K] = sum of senti_table over the caption's words, or NULL (needs senti_table). */
+ * senti_raw f32[B,K] = sum of senti_table over the caption's words, or NULL (needs senti_table).
+ * Optional override (all three or none; int32 device arrays): for images with ov_mask[b] != 0 the CLIP ids of the
+ * words before `pos` are ov_tok[ov_off[2b] .. ov_off[2b+1]) and of the words after it ov_tok[ov_off[2b+1] ..
+ * ov_off[2b+2]) instead of the table's -- the caller tokenised those two strings itself because they hold a merged
+ * '##' word; the candidate word still comes from the table. */
 int conzic_encode_candidates(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L, int pos, const int64_t* ids_dev,
                              const float* token_mask_dev, int K, int P, int S, const float* senti_table_dev,
                              float* text_embeds_dev, int64_t* ids_masked_dev, float* repeats_dev, float* senti_raw_dev,
+                             const int32_t* ov_mask_dev, const int32_t* ov_off_dev, const int32_t* ov_tok_dev,
                              void* ws_dev, size_t ws_bytes, void* stream);
 
 /* compute_image_text_similarity_via_embeddings (clip/clip.py:86-98): text f32[B*K,D], image f32[B,D]

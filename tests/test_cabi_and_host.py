@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libconzic.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.conzic_abi_version() == 4
+    assert lib.conzic_abi_version() == 5
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -176,53 +176,72 @@ def test_piece_vocabulary_decodes_like_hf_bert():
     assert merged != ctok.tokens_of_text("w3746") + ctok.tokens_of_text("w2003") and len(merged) == 1
 
 
-def test_plan_hybrid_against_string_tokenisation():
-    """tokens.plan_hybrid: a caption is flagged exactly when its decoded string had a piece merged in, and for every
-    unflagged caption the CLIP ids of the decoded string are prefix + candidate word + tail from the table, within
-    the planned capacities P and S."""
+def test_hybrid_plan_against_string_tokenisation():
+    """tokens.hybrid_flags / hybrid_capacities against brute-force string work on the piece vocabulary: a caption is
+    flagged exactly when the candidate is a piece or a piece directly follows `pos`; every other caption's CLIP ids
+    (from decoding + tokenising the whole string, as the reference does) equal prefix + candidate word (table) +
+    tail, where prefix / tail come from the table or -- for images holding a merged word -- from tokenising the
+    prefix / tail strings; and the planned capacities P, S cover them."""
     tok, ctok = synth.PieceBertTokenizer(), synth.PieceCLIPTokenizer(multi=True)
     V = synth.BERT_VOCAB
     off, tk, needs_host = tokens.build_bert2clip(tok, ctok, V, synth.SPECIAL_IDS)
     piece = torch.zeros(V, dtype=torch.bool)
     piece[torch.tensor(needs_host)] = True
-    assert all(synth.is_piece(v) for v in needs_host[:50]) and len(needs_host) == sum(synth.is_piece(v) for v in range(V))
+    assert len(needs_host) == sum(synth.is_piece(v) for v in range(V))
     tok_len = (off[1:] - off[:-1]).to(torch.int32)
     assert int(tok_len[piece].max()) == 0
     g = torch.Generator().manual_seed(5)
-    B, L, K, pos = 6, 12, 24, 6
+    B, L, K, pos = 8, 12, 24, 6
     inp = torch.randint(1996, V, (B, L), generator=g)
-    inp[:, 0], inp[:, -1] = synth.CLS_ID, synth.SEP_ID
-    for b in (0, 2, 3):  # these images hold no piece outside pos
+    for b in (0, 1, 2, 3, 6, 7):  # start these images without pieces
         inp[b] = torch.where(piece[inp[b]], inp[b] + 1, inp[b])
-    inp[1, 3] = 2003                                                         # image 1: a piece in the prefix
-    inp[2, 9] = synth.MASK_ID                                                # specials are skipped
+    inp[:, 0], inp[:, -1] = synth.CLS_ID, synth.SEP_ID
+    inp[1, 3] = 2003               # image 1: a piece inside the prefix            -> override
+    inp[2, 9] = synth.MASK_ID      # specials are skipped
+    inp[3, 7] = 2008               # image 3: a piece right after pos              -> every candidate flagged
+    inp[6, 7] = synth.MASK_ID      # image 6: a dropped token, THEN a piece: it still follows pos directly
+    inp[6, 8] = 2013
+    inp[7, 9] = 2018               # image 7: a piece later in the tail            -> override
+    inp[7, 1] = 2023               #          and one leading the caption (stays literal)
     inp[:, pos] = synth.MASK_ID
-    inp[:, -1] = synth.SEP_ID
     ids = torch.randint(1996, V, (B, K), generator=g)
     ids[:, 0] = 0  # a masked candidate ([PAD]): the word is dropped
-    flag, P, S = tokens.plan_hybrid(inp, pos, ids, piece, tok_len)
-    assert bool(flag[1].all()) and not bool(flag[0, 0])
-    n_unflagged = 0
+    flag, override = tokens.hybrid_flags(inp, pos, ids, piece, synth.SPECIAL_IDS)
+    assert override.tolist()[:4] == [False, True, False, False] and bool(override[7]) and not bool(override[6])
+    assert bool(flag[3].all()) and bool(flag[6].all()) and not bool(flag[0, 0]) and not bool(flag[1, 0])
+    table = lambda v: tk[off[v]: off[v + 1]].tolist()
+    ov, ov_lens = {}, {}
+    for b in range(B):
+        if bool(override[b]):
+            ov[b] = (ctok.tokens_of_text(tok.decode(inp[b, :pos], skip_special_tokens=True)),
+                     ctok.tokens_of_text(tok.decode(inp[b, pos + 1:], skip_special_tokens=True)))
+            ov_lens[b] = (len(ov[b][0]), len(ov[b][1]))
+    P, S = tokens.hybrid_capacities(inp, pos, ids, tok_len, ov_lens)
+    n_table, n_override = 0, 0
     for b in range(B):
         pre_ids = [int(v) for v in inp[b, :pos] if int(v) not in synth.SPECIAL_IDS]
         tail_ids = [int(v) for v in inp[b, pos + 1:] if int(v) not in synth.SPECIAL_IDS]
         for k in range(K):
             row = inp[b].clone()
             row[pos] = ids[b, k]
-            kept = [int(v) for v in row if int(v) not in synth.SPECIAL_IDS]
-            has_piece = any(synth.is_piece(v) for v in kept)
-            assert bool(flag[b, k]) == has_piece
-            if has_piece:
+            cand_piece = synth.is_piece(int(ids[b, k]))
+            next_piece = bool(tail_ids) and synth.is_piece(tail_ids[0])
+            assert bool(flag[b, k]) == (cand_piece or next_piece)
+            if flag[b, k]:
                 continue
-            n_unflagged += 1
             full = ctok.tokens_of_text(tok.decode(row, skip_special_tokens=True))
-            table = lambda v: tk[off[v]: off[v + 1]].tolist()
-            pre = [t for v in pre_ids for t in table(v)]
             cand = table(int(ids[b, k])) if int(ids[b, k]) not in synth.SPECIAL_IDS else []
-            tail = [t for v in tail_ids for t in table(v)]
-            assert full == pre + cand + tail
+            if b in ov:
+                pre, tail = ov[b]
+                n_override += 1
+            else:
+                assert not any(synth.is_piece(v) for v in pre_ids + tail_ids)
+                pre = [t for v in pre_ids for t in table(v)]
+                tail = [t for v in tail_ids for t in table(v)]
+                n_table += 1
+            assert full == list(pre) + cand + list(tail)
             assert 1 + len(pre) <= P and len(cand) + len(tail) + 1 <= S
-    assert n_unflagged > 40
+    assert n_table > 40 and n_override > 20
 
 
 def test_sentiment_table_export_follows_the_reference_scoring():
