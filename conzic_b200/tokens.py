@@ -16,24 +16,31 @@ import torch
 
 def build_bert2clip(bert_tokenizer, clip_tokenizer, vocab_size: int, special_ids) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
     """Returns (off int32[V+1], tok int32[n], needs_host list of BERT ids that are '##' pieces)."""
-    off = [0]
-    toks: List[int] = []
     needs_host: List[int] = []
     special = set(int(s) for s in special_ids)
     conv = getattr(bert_tokenizer, "convert_ids_to_tokens", None)
+    pieces = conv(list(range(vocab_size))) if conv else [None] * vocab_size
+    texts: List[str] = []
+    owners: List[int] = []
     for v in range(vocab_size):
-        if v not in special:
-            piece = conv([v])[0] if conv else None
-            if piece is not None and piece.startswith("##"):
-                needs_host.append(v)
-                off.append(len(toks))
-                continue
-            text = bert_tokenizer.decode([v])
-            if hasattr(clip_tokenizer, "tokens_of_text"):
-                ids = clip_tokenizer.tokens_of_text(text)
-            else:
-                ids = clip_tokenizer(text, add_special_tokens=False)["input_ids"]
-            toks.extend(int(i) for i in ids)
+        if v in special:
+            continue
+        if pieces[v] is not None and pieces[v].startswith("##"):
+            needs_host.append(v)
+            continue
+        texts.append(bert_tokenizer.decode([v]))
+        owners.append(v)
+    if hasattr(clip_tokenizer, "tokens_of_text"):
+        rows = [clip_tokenizer.tokens_of_text(t) for t in texts]
+    else:  # one batched call: HF tokenizers take a list (30 k single calls cost tens of seconds)
+        rows = clip_tokenizer(texts, add_special_tokens=False)["input_ids"] if texts else []
+    per_id = [()] * vocab_size
+    for v, r in zip(owners, rows):
+        per_id[v] = r
+    off = [0]
+    toks: List[int] = []
+    for v in range(vocab_size):
+        toks.extend(int(i) for i in per_id[v])
         off.append(len(toks))
     return torch.tensor(off, dtype=torch.int32), torch.tensor(toks, dtype=torch.int32), needs_host
 

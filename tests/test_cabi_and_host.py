@@ -266,3 +266,82 @@ def test_sentiment_table_export_follows_the_reference_scoring():
     table = mod.build_table(tokens, lambda ws: [(w, tags[w]) for w in ws], senti_synsets)
     np.testing.assert_allclose(table.numpy(), [0, 0, (0.75 + 0.25) / 2, -0.125, 0, 0.9, 0.5, 0, 0], atol=1e-7)
     assert ("good", "a") in calls and ("the", "") in calls and all(w not in ("##ing", "[PAD]") for w, _ in calls)
+
+
+def test_table_and_hybrid_plan_with_real_hf_tokenizer_classes(tmp_path):
+    """The same decomposition with the REAL Hugging Face classes (BertTokenizer / CLIPTokenizer built from in-memory
+    vocabularies; no pretrained files exist offline): tokens.build_bert2clip walks the vocabulary through
+    BertTokenizer.decode + CLIPTokenizer, and for every unflagged caption the CLIP ids of the reference's string
+    round trip (batch_decode(skip_special_tokens=True) -> CLIPTokenizer, gen_utils.py:75 + clip/clip.py:71-72) equal
+    prefix + candidate + tail from the table / the host-tokenised override."""
+    import json
+    from transformers import BertTokenizer, CLIPTokenizer
+    base = ["[PAD]"] + [f"[unused{i}]" for i in range(1, 100)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    words = ["a", "dog", "cat", "run", "the", "girl", "red", "car", "tree", "walk", "small", "house", ".", "image", "of"]
+    pieces = ["##s", "##ning", "##ed", "##er"]
+    vocab = base + words + pieces
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab) + "\n")
+    bt = BertTokenizer(str(tmp_path / "vocab.txt"))
+    alphabet = list("abcdefghijklmnopqrstuvwxyz.")
+    cv = {}
+    for c in alphabet:
+        cv[c] = len(cv)
+    for c in alphabet:
+        cv[c + "</w>"] = len(cv)
+    merges = ["d o", "do g</w>", "c a", "ca t</w>", "t h", "th e</w>", "do g", "dog s</w>", "r e", "re d</w>", "e d</w>",
+              "c a", "ca r</w>", "ca r", "car s</w>", "e r</w>", "w a", "wa l", "wal k</w>", "wal k", "walk ed</w>"]
+    merges = list(dict.fromkeys(merges))
+    for m in merges:
+        cv[m.replace(" ", "")] = len(cv)
+    cv["<|startoftext|>"] = len(cv)
+    cv["<|endoftext|>"] = len(cv)
+    (tmp_path / "cv.json").write_text(json.dumps(cv))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(merges) + "\n")
+    ct = CLIPTokenizer(str(tmp_path / "cv.json"), str(tmp_path / "merges.txt"), model_max_length=77)
+    V = len(vocab)
+    special = [0, 100, 101, 102, 103]
+    off, tk, needs_host = tokens.build_bert2clip(bt, ct, V, special)
+    assert [vocab[v] for v in needs_host] == pieces
+    piece = torch.zeros(V, dtype=torch.bool)
+    piece[torch.tensor(needs_host)] = True
+    tok_len = (off[1:] - off[:-1]).to(torch.int32)
+    table = lambda v: tk[off[v]: off[v + 1]].tolist()
+    assert table(vocab.index("dog")) == ct("dog", add_special_tokens=False)["input_ids"]
+    w0 = len(base)
+    g = torch.Generator().manual_seed(3)
+    B, L, K, pos = 6, 10, V - w0, 5
+    inp = torch.randint(w0, w0 + len(words), (B, L), generator=g)
+    inp[:, 0], inp[:, -1] = 101, 102
+    inp[1, 3] = vocab.index("##s")      # merged word in the prefix
+    inp[2, 6] = vocab.index("##ed")     # piece right after pos: merges into every candidate
+    inp[3, 8] = vocab.index("##er")     # merged word in the tail
+    inp[4, 7] = 103                     # a [MASK] is skipped
+    inp[:, pos] = 103
+    ids = torch.arange(w0, V).repeat(B, 1)  # every word and every piece as a candidate
+    ids[:, 0] = 0
+    flag, override = tokens.hybrid_flags(inp, pos, ids, piece, special)
+    assert override.tolist() == [False, True, False, True, False, False] and bool(flag[2].all())
+    clip_ids = lambda text: ct(text, add_special_tokens=False)["input_ids"] if text else []
+    ov = {b: (clip_ids(bt.decode(inp[b, :pos], skip_special_tokens=True)),
+              clip_ids(bt.decode(inp[b, pos + 1:], skip_special_tokens=True))) for b in range(B) if bool(override[b])}
+    P, S = tokens.hybrid_capacities(inp, pos, ids, tok_len, {b: (len(p), len(t)) for b, (p, t) in ov.items()})
+    checked = 0
+    rows = inp.unsqueeze(1).repeat(1, K, 1)
+    rows[:, :, pos] = ids
+    texts = bt.batch_decode(rows.view(-1, L), skip_special_tokens=True)
+    for b in range(B):
+        for k in range(K):
+            if bool(flag[b, k]):
+                assert vocab[int(ids[b, k])].startswith("##") or b == 2
+                continue
+            full = clip_ids(texts[b * K + k])
+            cand = table(int(ids[b, k])) if int(ids[b, k]) not in special else []
+            if b in ov:
+                pre, tail = ov[b]
+            else:
+                pre = [t for v in inp[b, :pos].tolist() if v not in special for t in table(v)]
+                tail = [t for v in inp[b, pos + 1:].tolist() if v not in special for t in table(v)]
+            assert full == list(pre) + cand + list(tail), (b, k, texts[b * K + k])
+            assert 1 + len(pre) <= P and len(cand) + len(tail) + 1 <= S
+            checked += 1
+    assert checked > 60
