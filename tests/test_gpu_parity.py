@@ -516,6 +516,38 @@ def test_cabi_rejects_bad_arguments():
     assert bool((inp[:, 4] >= 1996).all())
 
 
+def test_real_hf_tokenizer_classes_match_reference(monkeypatch, tmp_path):
+    """generate_caption with the REAL transformers BertTokenizer / CLIPTokenizer classes (generated vocabulary files:
+    WordPiece decode with '##' joining and clean-up, byte-level BPE with merges, several CLIP tokens per word) against
+    the fixture the unmodified reference produced with the same tokenizers: the generic table builder
+    (tokens.build_bert2clip) and the hybrid step must reproduce its captions and scores."""
+    import logging
+    from conzic_b200 import gen_utils, runtime
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    runtime.clear()
+    g = gc.load_golden("hf_shuffle_b3_n5_k24")
+    case = g["case"]
+    bert_tok, clip_tok = synth.make_hf_tokenizers(str(tmp_path))
+    bert = BertMLM(gc.weights("bert"))
+    clip = CLIP(state_dict=gc.weights("clip"), tokenizer=clip_tok, processor=synth.SynthProcessor()).to("cuda:0")
+    B, n, K = case["B"], case["n"], case["K"]
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    set_seed(42)
+    texts, scores = gen_utils.generate_caption(
+        [f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix, synth.make_token_mask("cuda"),
+        logging.getLogger("test"), prompt=synth.hf_prompt(), batch_size=B, max_len=n, top_k=K, temperature=0.1,
+        max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
+    eng = runtime.any_engine()
+    assert len(eng.needs_host_ids) > 5000 and eng.max_tok_per_word > 3
+    runtime.clear()
+    assert texts == g["texts"]
+    for a, b in zip(scores, g["scores"]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
 @pytest.mark.parametrize("mode", ["sentiment", "span", "random"])
 def test_piece_vocabulary_hybrid_equals_string_path(mode, monkeypatch):
     """Piece vocabulary, modes the reference fixtures do not cover (its stub sentiment scorer cannot look up merged

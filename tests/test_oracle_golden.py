@@ -30,7 +30,10 @@ def make_oracle(g, synth_weights, full_logits=False):
     assert synth.state_dict_checksum(bert_sd) == g["bert_crc"], "synthetic BERT weights drifted"
     assert synth.state_dict_checksum(clip_sd) == g["clip_crc"], "synthetic CLIP weights drifted"
     multi = case.get("multi", False)
-    if case.get("pieces"):  # vocabulary with '##' word pieces
+    if case.get("hf"):  # the real transformers tokenizer classes over generated vocabulary files
+        import tempfile
+        toks = synth.make_hf_tokenizers(tempfile.mkdtemp())
+    elif case.get("pieces"):  # vocabulary with '##' word pieces
         toks = synth.PieceBertTokenizer(), synth.PieceCLIPTokenizer(multi)
     else:
         toks = synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(multi)
@@ -78,7 +81,7 @@ def test_teacher_forced_steps(name, synth_weights):
 
 
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8", "span_b2_n5_k8",
-                                  "pos_seq_b2_n5_k16", "pieces_seq_b2_n5_k16"])
+                                  "pos_seq_b2_n5_k16", "pieces_seq_b2_n5_k16", "hf_shuffle_b3_n5_k24"])
 def test_free_running_call(name, synth_weights):
     """Whole ``generate_caption`` / ``control_generate_caption`` call under set_seed(42):
     same captions per sweep, same CLIP scores, same best list as the reference returned."""
@@ -88,7 +91,8 @@ def test_free_running_call(name, synth_weights):
     random.seed(42); np.random.seed(42); torch.manual_seed(42)  # utils.py:37-44
     pix = torch.stack([synth.make_pixel_values(i) for i in range(case["B"])])
     with torch.no_grad():
-        texts, scores = o.generate(pix, synth.make_token_mask(), synth.SYNTH_PROMPT, order=case["order"],
+        prompt = synth.hf_prompt() if case.get("hf") else synth.SYNTH_PROMPT
+        texts, scores = o.generate(pix, synth.make_token_mask(), prompt, order=case["order"],
                                    max_len=case["n"], top_k=case["K"], max_iters=case["iters"],
                                    gamma=case.get("gamma"), ctl_signal=case.get("style", "positive"), **_pos(case))
     assert texts == g["texts"]

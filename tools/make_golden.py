@@ -148,6 +148,7 @@ CASES = [
     dict(name="span_b2_n5_k8", order="span", B=2, n=5, K=8, iters=2),
     dict(name="pieces_seq_b2_n5_k16", order="sequential", B=2, n=5, K=16, iters=3, pieces=True),
     dict(name="pieces_shuffle_b3_n6_k16_multi", order="shuffle", B=3, n=6, K=16, iters=2, pieces=True, multi=True),
+    dict(name="hf_shuffle_b3_n5_k24", order="shuffle", B=3, n=5, K=24, iters=2, hf=True),
     dict(name="pos_seq_b2_n5_k16", order="sequential", B=2, n=5, K=16, iters=2, gamma=5.0, ctl="pos"),
 ]
 
@@ -169,6 +170,13 @@ def main():
         pieces = case.get("pieces", False)
         bert, clip = build_models(bert_sd, clip_sd, CLIP, multi, pieces)
         bert_tok = synth.PieceBertTokenizer if pieces else synth.SynthBertTokenizer
+        prompt = synth.SYNTH_PROMPT
+        if case.get("hf"):  # the real transformers tokenizer classes over generated vocabulary files
+            import tempfile
+            hf_bert, hf_clip = synth.make_hf_tokenizers(tempfile.mkdtemp())
+            clip.tokenizer = hf_clip
+            bert_tok = lambda: hf_bert
+            prompt = synth.hf_prompt()
         B, n, K = case["B"], case["n"], case["K"]
         pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
         token_mask = synth.make_token_mask()
@@ -177,7 +185,7 @@ def main():
         rec = Recorder(bert, clip, mod, embed_stride=13 if K >= 100 else 1)
         utils.set_seed(42)
         names = [f"img{i}.jpg" for i in range(B)]
-        kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1,
+        kw = dict(prompt=prompt, batch_size=B, max_len=n, top_k=K, temperature=0.1,
                   max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
         with torch.no_grad():
             if gamma is None:
