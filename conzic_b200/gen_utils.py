@@ -166,6 +166,11 @@ class _Chain:
                 ov_off.append(len(ov_tok))
             overrides = (ov_mask, torch.tensor(ov_off, dtype=torch.int32), torch.tensor(ov_tok or [0], dtype=torch.int32))
         P, S = tokens.hybrid_capacities(inp_h, pos, ids_masked_h, eng.tok_len_h, ov_lens, eng.cfg.clip_maxpos)
+        if P + S > 96:
+            # the longest prefix and the longest suffix of the batch do not fit one attention tile together (each
+            # caption is still <= 77 tokens): every candidate takes the dense string pass for this step
+            flag = torch.ones_like(flag)
+            P, S = min(P, 48), min(S, 48)
         text, ids_masked, repeats, senti_raw = eng.encode_candidates(
             self.inp, pos, idxs, self.mask, P, S, senti_table=senti_table if gamma is not None else None,
             want_repeats=gamma is not None, overrides=overrides)

@@ -548,6 +548,40 @@ def test_real_hf_tokenizer_classes_match_reference(monkeypatch, tmp_path):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
+def test_long_token_heavy_captions_hybrid_equals_string_path(monkeypatch, tmp_path):
+    """Real tokenizer classes, 3-5 CLIP tokens per word, 22-word sentences: captions reach the 77-token truncation
+    and the longest prefix + longest suffix exceed one attention tile (the hybrid step then sends the whole step
+    through the dense string pass).  Hybrid and all-strings must still agree exactly."""
+    import logging
+    from conzic_b200 import gen_utils, runtime
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    bert_tok, clip_tok = synth.make_hf_tokenizers(str(tmp_path))
+    B, n, K = 2, 22, 8
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    out = {}
+    for path in ("hybrid", "strings"):
+        if path == "strings":
+            monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+        runtime.clear()
+        bert = BertMLM(gc.weights("bert"))
+        clip = CLIP(state_dict=gc.weights("clip"), tokenizer=clip_tok, processor=synth.SynthProcessor()).to("cuda:0")
+        set_seed(42)
+        out[path] = gen_utils.generate_caption(
+            [f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix, synth.make_token_mask("cuda"),
+            logging.getLogger("test"), prompt=synth.hf_prompt(), batch_size=B, max_len=n, top_k=K, temperature=0.1,
+            max_iter=2, alpha=0.02, beta=2.0, generate_order="sequential")
+    runtime.clear()
+    (ta, sa), (tb, sb) = out["hybrid"], out["strings"]
+    assert ta == tb
+    for a, b in zip(sa, sb):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+    n_tok = max(len(clip_tok(c, add_special_tokens=False)["input_ids"]) for c in ta[-2])
+    assert n_tok > 75, "captions are not token heavy enough to exercise truncation / the tile guard"
+
+
 @pytest.mark.parametrize("mode", ["sentiment", "span", "random"])
 def test_piece_vocabulary_hybrid_equals_string_path(mode, monkeypatch):
     """Piece vocabulary, modes the reference fixtures do not cover (its stub sentiment scorer cannot look up merged
