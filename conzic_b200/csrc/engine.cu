@@ -402,8 +402,14 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     const int32_t* p0c = p0 ? p0 + b0 : nullptr;
     g_pdl_now = (M < 50000) ? 1 : 0;
     const bool fold = c->ln_fold && !s;
+    // the embedding kernel holds each row in registers: it also writes LN1 of the first block (bit-identical to the
+    // stand-alone launch it replaces; CONZIC_EMBED_LN=0 keeps them separate)
+    const char* eel = getenv("CONZIC_EMBED_LN");  // read per call so one process can compare both
+    const bool embed_ln_on = !(eel && atoi(eel) == 0);
+    const bool embed_ln = embed_ln_on && !fold && !s && H == 512 && !c->clip.empty();
     launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, fold ? p.cxb : nullptr,
-                      fold ? p.cstats : nullptr, 4, st);
+                      fold ? p.cstats : nullptr, 4, st, embed_ln ? c->clip[0].ln1_g : nullptr,
+                      embed_ln ? c->clip[0].ln1_b : nullptr, g.clip_ln_eps, embed_ln ? p.ch : nullptr, ldh);
     // folded-LN epilogues: a GEMM that writes the residual stream also writes its bf16 copy and row statistics;
     // the GEMM that would consume LN(x) reads them instead (Epi in kernels.h)
     auto epi_ln_consumer = [&](const LinearW& W, const float* sv, bf16* out, int ld, int act) {
@@ -421,7 +427,7 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
     float* xe = p.cxe + static_cast<size_t>(b0) * K * H;
     // LayerNorm fused into the producer GEMM's epilogue (gemm_wide_kernel owns whole 512-column rows)
     const int wl = (!fold && !c->mlp_fused && !s) ? c->wide_ln : 0;
-    bool h_ready = false, pooled_ready = false;
+    bool h_ready = embed_ln, pooled_ready = false;
     auto with_ln = [&](Epi e, bf16* out, const float* gamma, const float* beta) {
       e.lnf_out = out; e.lnf_ld = ldh; e.lnf_g = gamma; e.lnf_b = beta; e.lnf_eps = g.clip_ln_eps;
       e.lnf_mode = c->wide_ln_mode;
@@ -436,10 +442,11 @@ bool clip_encode(conzic_ctx* c, const int32_t* ids_prefix, const int32_t* ids_su
                            c->gopt, st, nullptr))
           return false;
       } else {
-        if (!h_ready) {  // otherwise the previous block's fc2 epilogue already wrote LN1(x) into ch
+        if (!h_ready) {  // otherwise the embedding kernel / the previous block's fc2 epilogue already wrote LN1(x) into ch
           LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
           launch_layernorm(ln1, st);
         }
+        h_ready = false;  // consumed by this block's QKV
         Act h{p.ch, ldh, H};
         Epi e;
         if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);

@@ -170,7 +170,8 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 // (the other slices are zeroed), for a consumer GEMM with folded LayerNorm.
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
                        int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
-                       float2* stats, int stats_parts, cudaStream_t st);
+                       float2* stats, int stats_parts, cudaStream_t st, const float* ln_g = nullptr,
+                       const float* ln_b = nullptr, float ln_eps = 0.f, bf16* ln_out = nullptr, int ln_ld = 0);
 // Folds a LayerNorm into the linear layer that consumes it: w_out[n,k] = bf16(gamma[k] * w[n,k]),
 // s_out[n] = sum_k float(w_out[n,k]), bias_out[n] = bias[n] + sum_k beta[k] * w[n,k].
 void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,

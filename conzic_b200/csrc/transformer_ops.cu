@@ -148,7 +148,8 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
                                   const int32_t* __restrict__ p0, int B, int P, int K, int S, int maxpos,
                                   const float* __restrict__ tok, const float* __restrict__ pos, int H,
                                   float* __restrict__ x, bf16* __restrict__ xb, float2* __restrict__ stats,
-                                  int stats_parts) {
+                                  int stats_parts, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                  float ln_eps, bf16* __restrict__ ln_out, int ln_ld) {
   PDL_ENTRY();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,6 +185,19 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
     if (stats) {
       s1 = warp_sum(s1); s2 = warp_sum(s2);
       if (lane < stats_parts) stats[static_cast<size_t>(r) * stats_parts + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+    }
+    if (ln_out) {
+      // LayerNorm 1 of the first block on the row this warp just produced (H == 512): same arithmetic as
+      // layernorm_kernel<4> on the same fp32 values, without re-reading x from HBM
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 a = *reinterpret_cast<const float4*>(te + c);
+        const float4 b = *reinterpret_cast<const float4*>(pe + c);
+        v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      ln_row<4>(v, H, ln_g, ln_b, ln_eps, lane, nullptr, ln_out + static_cast<size_t>(r) * ln_ld, 0);
     }
   }
 }
@@ -768,13 +782,15 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
                        int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
-                       float2* stats, int stats_parts, cudaStream_t st) {
+                       float2* stats, int stats_parts, cudaStream_t st, const float* ln_g, const float* ln_b, float ln_eps,
+                       bf16* ln_out, int ln_ld) {
   ++g_launches;
   ProfScope prof_(CAT_EMBED, 0, st);
   const int rows = B * P + B * K * S;
   if (rows <= 0) return;
+  if (ln_out && H != 512) { set_error("clip_embed: the fused LayerNorm needs hidden size 512"); return; }
   launch_k(clip_embed_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, st, ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
-                                                       x_f32, xb, stats, stats_parts);
+                                                       x_f32, xb, stats, stats_parts, ln_g, ln_b, ln_eps, ln_out, ln_ld);
 }
 
 void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,

@@ -170,6 +170,7 @@ def test_clip_text_encode_vs_oracle(prec, tol):
                                           ("bf16", 0.06, {"CONZIC_ATTN_PREFETCH": "1"}),
                                           ("bf16", 0.06, {"CONZIC_WIDE_EPI16": "0"}),
                                           ("bf16", 0.06, {"CONZIC_ATTN_OCC3": "0"}),
+                                          ("bf16", 0.06, {"CONZIC_EMBED_LN": "0"}),
                                           ("bf16", 0.06, {"CONZIC_PERSIST_EPI16": "1"}),
                                           ("bf16", 0.06, {"CONZIC_OPROJ_WIDE": "1"}),
                                           ("bf16", 0.06, {"CONZIC_GEMM_CG": "1"}),
