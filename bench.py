@@ -1,26 +1,34 @@
 #!/usr/bin/env python
 """captions/sec of the Gibbs-BERT caption-polishing path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: a full generate_caption call on 64 synthetic images per
-GPU (BASELINE config 2: sequential order, sentence_len 10, candidate_k 200, 5 sweeps = 50 Gibbs steps, image
-encoding included, model load excluded).  Images are independent, so N GPUs process N x 64 images (weak
+GPU (default = BASELINE config 2: sequential order, sentence_len 10, candidate_k 200, 5 sweeps = 50 Gibbs steps,
+image encoding included, model load excluded).  Images are independent, so N GPUs process N x 64 images (weak
 scaling) with one NCCL all-gather of the final ids/scores per call.
 
-  value        captions/s with the pixel tensors already resident in HBM (device loop, no host reads);
+  precision    "certified" (default): BERT + image tower in bf16x3, CLIP text tower in bf16 over all candidates,
+               certified argmax with exact (bf16x3) re-score of every candidate the bf16 scores cannot rule out --
+               the same token ids and scores as the all-bf16x3 run; the `parity` key reports the check made in
+               this very run (one extra call in bf16x3 on the same inputs) and how many candidates were re-scored;
+  value        captions/s with the pixel tensors already resident in HBM (device loop, no host reads of results);
   e2e          captions/s through the public drop-in API conzic_b200.gen_utils.generate_caption with the pixels
                in pinned HOST memory: H2D copy, per-sweep D2H reads of ids/scores and string decoding included;
-  roofline     the dominant kernel (tcgen05 GEMM of the CLIP/BERT towers): executed FLOPs / CUDA-event time of
-               its launches during one extra profiled step, against the measured sustained bf16 peak;
-  cpu_baseline the CPU oracle (a torch-CPU restatement of the reference loop pinned against the unmodified
-               reference) on a bounded sample, all host cores;
-  --impl reference   the same CPU path as its own arm (the Python reference cannot travel to the GPU box).
+  roofline     the dominant kernel (tcgen05 GEMM of the CLIP tower): executed FLOPs / CUDA-event time of its
+               launches during one extra profiled step, against the measured sustained bf16 peak;
+  cpu_baseline the reference's CPU path on a bounded sample, all host cores: the UNMODIFIED reference modules from
+               oracle/_ref driving HF models (kind "reference") when that directory travelled with the snapshot,
+               else the torch-CPU oracle port (kind "port");
+  --impl reference   the same CPU path as its own arm;
+  --config     3: shuffle order, 3 samples per image (BASELINE config 3's per-GPU shard); 4: sentiment control,
+               gamma 5, sentence_len 12 (config 4's shard); 5: the K x sentence_len sweep (one line, `sweep` array).
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import logging
 import os
@@ -36,13 +44,48 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from conzic_b200 import dist as cdist  # noqa: E402
-from conzic_b200 import synth  # noqa: E402
+from synthetic import synth  # noqa: E402
 
-N_LEN, TOP_K, SWEEPS, BATCH = 10, 200, 5, 64
-TEMP, ALPHA, BETA = 0.1, 0.02, 2.0
-METRIC = "captions/sec (len=10, top_k=200, 5 iters)"
-# algorithmic FLOPs of one caption at n=10, K=200, 5 sweeps
-ALGO_TFLOP_PER_CAPTION = 10.806
+TEMP, ALPHA, BETA, GAMMA = 0.1, 0.02, 2.0, 5.0
+BATCH = 64
+
+
+class Workload:
+    """One BASELINE.json configuration, per GPU."""
+
+    def __init__(self, config: int, n_len=None, top_k=None):
+        self.config = config
+        self.order, self.samples, self.ctl = "sequential", 1, False
+        self.n_len, self.top_k, self.sweeps = 10, 200, 5
+        if config == 3:
+            self.order, self.samples = "shuffle", 3
+        elif config == 4:
+            self.ctl, self.n_len = True, 12
+        if n_len:
+            self.n_len = n_len
+        if top_k:
+            self.top_k = top_k
+        self.metric = f"captions/sec (len={self.n_len}, top_k={self.top_k}, {self.sweeps} iters)"
+
+    def algo_tflop_per_caption(self):
+        """reference-algorithm FLOPs (every candidate encoded in full, T = L = n + 5)."""
+        n, K = self.n_len, self.top_k
+        clip_tokens = n * (n + 11) / 2 + 4 * n * (n + 5)
+        steps = self.sweeps * n
+        clip = K * clip_tokens * (75497472 + 12288 * (n + 5)) + steps * K * 524288
+        bert = steps * ((n + 5) * (169869312 + 36864 * (n + 5)) + 48061440)
+        return (clip + bert) / 1e12
+
+    def describe(self, n_gpus):
+        what = {2: "BASELINE config 2", 3: "BASELINE config 3's per-GPU shard (512 images x 3 samples over 8 GPUs)",
+                4: "BASELINE config 4's per-GPU shard (256 images over 4 GPUs)", 5: "BASELINE config 5 sweep point"}
+        return {"workload": f"{BATCH}-image batch per GPU, {self.order} order, sentence_len {self.n_len}, candidate_k "
+                            f"{self.top_k}, {self.sweeps} sweeps, {self.samples} sample(s)"
+                            + (", sentiment control gamma 5 positive" if self.ctl else "")
+                            + f" ({what[self.config]}), bert-base + CLIP ViT-B/32 shapes, synthetic weights",
+                "images_per_gpu": BATCH, "samples": self.samples, "n_gpus": n_gpus,
+                "sharding": "images by global index, one all-gather per call",
+                "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 def peaks():
@@ -117,79 +160,120 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference loop)
+# CPU arm: the reference itself (oracle/_ref) when present, else the oracle port
 # ------------------------------------------------------------------------------------------------------
-def cpu_sample(B=2, threads=None):
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+_CPU = {}
+
+
+def _cpu_runner(wl: Workload):
+    """Returns (kind, run(B, sweeps) -> seconds): one generate call of B images for `sweeps` sweeps on the host."""
+    if "run" in _CPU:
+        return _CPU["kind"], _CPU["run"]
+    bert_sd, clip_sd = synth.make_bert_state_dict(0), synth.make_clip_state_dict(0, vision=True)
+    table = synth.make_sentiment_table()
+    logger = logging.getLogger("bench-ref")
+    logger.addHandler(logging.NullHandler())
+    logger.propagate = False
+    if os.path.exists(os.path.join(REF_DIR, "gen_utils.py")):
+        from oracle import ref_loader
+        tok = synth.SynthBertTokenizer()
+        utils, gen_utils, control_gen_utils, CLIP = ref_loader.load(REF_DIR, table, lambda w: tok.vocab[w],
+                                                                    synth.synth_pos_tagger)
+        bert, clip = ref_loader.build_models(bert_sd, clip_sd, CLIP, synth.SynthCLIPTokenizer(), synth.SynthProcessor())
+
+        def run(B, sweeps):
+            pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+            names = [f"img{i}.jpg" for i in range(B)]
+            kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=wl.n_len, top_k=wl.top_k, temperature=TEMP,
+                      max_iter=sweeps, alpha=ALPHA, beta=BETA, generate_order=wl.order)
+            utils.set_seed(42)
+            t0 = time.perf_counter()
+            # the reference prints its device check to stdout (clip/clip.py:20-33): keep stdout for the JSON line;
+            # its scripts call the generators under no_grad (run.py:176, demo.py:80)
+            with contextlib.redirect_stdout(sys.stderr), torch.no_grad():
+                if wl.ctl:
+                    control_gen_utils.control_generate_caption(names, bert, clip, tok, pix, synth.make_token_mask(), logger,
+                                                               gamma=GAMMA, ctl_type="sentiment", style_type="positive", **kw)
+                else:
+                    gen_utils.generate_caption(names, bert, clip, tok, pix, synth.make_token_mask(), logger, **kw)
+            return time.perf_counter() - t0
+        _CPU["kind"] = "reference"
+    else:
+        from oracle import conzic_oracle as orc
+        o = orc.Oracle(bert_sd, clip_sd, synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(), sentiment_table=table,
+                       full_logits=True)
+
+        def run(B, sweeps):
+            pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                o.generate(pix, synth.make_token_mask(), synth.SYNTH_PROMPT, order=wl.order, max_len=wl.n_len,
+                           top_k=wl.top_k, temperature=TEMP, alpha=ALPHA, beta=BETA, max_iters=sweeps,
+                           gamma=GAMMA if wl.ctl else None)
+            return time.perf_counter() - t0
+        _CPU["kind"] = "port"
+    _CPU["run"] = run
+    return _CPU["kind"], run
+
+
+def cpu_sample(wl: Workload, B=1, threads=None):
     """One bounded sample of the workload on the host cores: first sweep (growing captions) + one full-length
-    sweep for B images; captions/s for 5 sweeps = B / (t_first + 4 * t_full).  Returns (captions/s, seconds)."""
-    from oracle import conzic_oracle as orc
+    sweep for B images; captions/s for the full sweep count = B / (t_first + (sweeps-1) * t_full), the two sweeps
+    split by their CLIP token counts.  Returns (captions/s, seconds, kind)."""
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    global _CPU_ORACLE
-    if "_CPU_ORACLE" not in globals():
-        o = orc.Oracle(synth.make_bert_state_dict(0), synth.make_clip_state_dict(0, vision=True),
-                       synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(), full_logits=True)
-        _CPU_ORACLE = o
-    o = _CPU_ORACLE
-    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
-    tm = synth.make_token_mask()
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        o.generate(pix, tm, synth.SYNTH_PROMPT, order="sequential", max_len=N_LEN, top_k=TOP_K, temperature=TEMP,
-                   alpha=ALPHA, beta=BETA, max_iters=2)
-        t = time.perf_counter() - t0
-    # the two sweeps are timed together; split by CLIP token counts (105 vs 150 tokens per candidate, SURVEY 8d)
-    t_first, t_full = t * 105.0 / 255.0, t * 150.0 / 255.0
-    return B / (t_first + (SWEEPS - 1) * t_full), t
+    kind, run = _cpu_runner(wl)
+    t = run(B, 2)
+    n = wl.n_len
+    first, full = n * (n + 11) / 2.0, float(n * (n + 5))
+    t_first, t_full = t * first / (first + full), t * full / (first + full)
+    return B / (t_first + (wl.sweeps - 1) * t_full), t, kind
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, wl: Workload):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     B = 1
     for _ in range(args.warmup):
-        cpu_sample(B, cores)
-    vals, secs = [], []
+        cpu_sample(wl, B, cores)
+    vals, secs, kind = [], [], "port"
     for _ in range(args.steps):
-        v, s = cpu_sample(B, cores)
+        v, s, kind = cpu_sample(wl, B, cores)
         vals.append(v); secs.append(s)
     value = len(vals) / sum(1.0 / v for v in vals)  # harmonic mean = total captions / total time
-    sample = (f"{B} image(s) x (first sweep + one full-length sweep) of the len=10/K=200 workload per step, "
-              f"5-sweep time extrapolated as t_first + 4*t_full; CPU cost is linear in images (SURVEY.md 6)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": args.gpus,
+    what = ("the unmodified reference modules (oracle/_ref: gen_utils.generate_caption driving HF BertForMaskedLM / "
+            "CLIPModel on the host cores)" if kind == "reference" else "the torch-CPU oracle port of the reference loop")
+    sample = (f"{what}: {B} image(s) x (first sweep + one full-length sweep) of the workload per step, "
+              f"{wl.sweeps}-sweep time extrapolated as t_first + {wl.sweeps - 1}*t_full; CPU cost is linear in images "
+              f"(SURVEY.md 6)")
+    line = {"impl": "reference", "metric": wl.metric, "value": value, "unit": "captions/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": wl.describe(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "captions/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(n):
-    return {"workload": f"{BATCH}-image batch per GPU, sequential order, sentence_len {N_LEN}, candidate_k {TOP_K}, "
-                        f"{SWEEPS} sweeps (BASELINE config 2), bert-base + CLIP ViT-B/32 shapes, synthetic weights",
-            "images_per_gpu": BATCH, "n_gpus": n, "sharding": "images by global index, one all-gather per call",
-            "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
 class Job:
-    def __init__(self, rank, local_rank, world, precision):
+    def __init__(self, rank, local_rank, world, precision, wl: Workload):
         from conzic_b200 import runtime
         from conzic_b200.clip.clip import CLIP
         from conzic_b200.models import BertMLM
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.wl, self.precision = rank, world, wl, precision
         self.dev = torch.device("cuda", local_rank)
         torch.cuda.set_device(self.dev)
-        os.environ["CONZIC_PRECISION"] = precision
         self.bert = BertMLM(synth.make_bert_state_dict(0))
         self.clip = CLIP(state_dict=synth.make_clip_state_dict(0), tokenizer=synth.SynthCLIPTokenizer(),
                          processor=synth.SynthProcessor()).to(self.dev)
         self.tok = synth.SynthBertTokenizer()
-        self.eng = runtime.engine_for(self.bert, self.clip, self.tok, device=self.dev)
+        os.environ["CONZIC_PRECISION"] = precision
+        self.eng = runtime.engine_for(self.bert, self.clip, self.tok, precision=precision, device=self.dev)
         idx = range(rank * BATCH, (rank + 1) * BATCH)  # images keyed by global index
         self.pix_host = torch.stack([synth.make_pixel_values(i) for i in idx]).pin_memory()
         self.pix_dev = self.pix_host.to(self.dev)
@@ -197,38 +281,68 @@ class Job:
         self.logger = logging.getLogger("bench")
         self.logger.addHandler(logging.NullHandler())
         self.logger.propagate = False
-        self.L = N_LEN + 5
-        self.init_ids = torch.tensor([self.tok.encode(synth.SYNTH_PROMPT + "[MASK]" * N_LEN)] * BATCH, device=self.dev)
+        self.L = wl.n_len + 5
+        self.init_ids = torch.tensor([self.tok.encode(synth.SYNTH_PROMPT + "[MASK]" * wl.n_len)] * BATCH, device=self.dev)
         self.clip_ref = torch.zeros(BATCH, device=self.dev)
+        self.senti = torch.zeros(BATCH, device=self.dev)
+        self.table = synth.make_sentiment_table().to(self.dev)
+        self.orders = self._orders()
 
-    def device_step(self):
-        """Hot path only, everything resident: image encode + 50 Gibbs steps + the result gather."""
-        eng = self.eng
-        img = self.clip.compute_image_representation_from_pixels(self.pix_dev)
-        inp = self.init_ids.clone()
-        tm = synth.make_token_mask(self.dev)
-        holds = [True] * 4 + [False] * N_LEN + [False]
-        holds[0] = False
-        for _ in range(SWEEPS):
-            for ii in range(N_LEN):
-                pos = 4 + ii
-                eng.gibbs_step(inp, tm, img, pos, ii == N_LEN - 1, TOP_K, TEMP, ALPHA, BETA, sum(holds[:pos]),
-                               sum(holds[pos + 1:]), out_clip_ref=self.clip_ref)
-                holds[pos] = True
-        ids, sc = cdist.gather_ids_scores(inp.to(torch.int32), self.clip_ref, self.world)
-        return ids, sc
+    def _orders(self):
+        """One visiting order per sample, drawn like the reference draws them (gen_utils.py:110-111) under seed 42."""
+        import random
+        random.seed(42)
+        out = []
+        for _ in range(self.wl.samples):
+            o = list(range(self.wl.n_len))
+            if self.wl.order == "shuffle":
+                random.shuffle(o)
+            out.append(o)
+        return out
+
+    def device_step(self, eng=None):
+        """Hot path only, everything resident: per sample, image encode + sweeps x len Gibbs steps + the result gather."""
+        eng = eng or self.eng
+        wl = self.wl
+        last = None
+        for order in self.orders:
+            img = eng.image_encode(self.pix_dev)
+            inp = self.init_ids.clone()
+            tm = synth.make_token_mask(self.dev)
+            holds = [True] * 4 + [False] * wl.n_len + [False]
+            holds[0] = False
+            for _ in range(wl.sweeps):
+                for ii in order:
+                    pos = 4 + ii
+                    eng.gibbs_step(inp, tm, img, pos, ii == wl.n_len - 1, wl.top_k, TEMP, ALPHA, BETA, sum(holds[:pos]),
+                                   sum(holds[pos + 1:]), gamma=GAMMA if wl.ctl else None,
+                                   senti_table=self.table if wl.ctl else None, out_clip_ref=self.clip_ref,
+                                   out_senti=self.senti if wl.ctl else None)
+                    holds[pos] = True
+            last = cdist.gather_ids_scores(inp.to(torch.int32), self.clip_ref, self.world)
+        return last
 
     def api_step(self):
-        """The call a user makes: host pixels in, caption strings out."""
-        from conzic_b200 import gen_utils
-        tm = synth.make_token_mask(self.dev)
-        texts, scores = gen_utils.generate_caption(self.names, self.bert, self.clip, self.tok, self.pix_host, tm,
-                                                   self.logger, prompt=synth.SYNTH_PROMPT, batch_size=BATCH,
-                                                   max_len=N_LEN, top_k=TOP_K, temperature=TEMP, max_iter=SWEEPS,
-                                                   alpha=ALPHA, beta=BETA, generate_order="sequential")
-        if self.world > 1:  # rank 0 collects every rank's final captions (a few KB of strings)
-            cdist.gather_objects(texts[-2], self.world)
-        return texts, scores
+        """The call a user makes: host pixels in, caption strings out (one call per sample, run.py:180-190)."""
+        from conzic_b200 import control_gen_utils, gen_utils
+        from conzic_b200.utils import set_seed
+        wl = self.wl
+        set_seed(42)
+        out = None
+        for _ in range(wl.samples):
+            tm = synth.make_token_mask(self.dev)
+            kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=BATCH, max_len=wl.n_len, top_k=wl.top_k, temperature=TEMP,
+                      max_iter=wl.sweeps, alpha=ALPHA, beta=BETA, generate_order=wl.order)
+            if wl.ctl:
+                out = control_gen_utils.control_generate_caption(self.names, self.bert, self.clip, self.tok, self.pix_host,
+                                                                 tm, self.logger, gamma=GAMMA, ctl_type="sentiment",
+                                                                 style_type="positive", sentiment_table=self.table, **kw)
+            else:
+                out = gen_utils.generate_caption(self.names, self.bert, self.clip, self.tok, self.pix_host, tm,
+                                                 self.logger, **kw)
+            if self.world > 1:  # rank 0 collects every rank's final captions (a few KB of strings)
+                cdist.gather_objects(out[0][-2], self.world)
+        return out
 
 
 def timed(fn, steps, world, dev):
@@ -246,10 +360,34 @@ def timed(fn, steps, world, dev):
     return cdist.max_over_ranks(a.elapsed_time(b), world, dev)
 
 
-def run_ours(args, rank, local_rank, world):
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    job = Job(rank, local_rank, world, args.precision)
+def parity_check(job: Job):
+    """The certified run against an all-bf16x3 engine on the same inputs, in this process: token ids of every image
+    and the reported cosines must be identical.  Also how much exact re-scoring the certified run needed."""
+    from conzic_b200.engine import Engine
+    before = job.eng.cert_stats()
+    ids_c, sc_c = job.device_step()
+    st = {k: v - before[k] for k, v in job.eng.cert_stats().items()}
+    exact = Engine(job.bert.state_dict(), job.clip.state_dict(), device=job.dev, precision="bf16x3")
+    off, tok = synth.build_bert2clip_table(False)
+    exact.set_bert2clip(off, tok)
+    ids_x, sc_x = job.device_step(exact)
+    torch.cuda.synchronize(job.dev)
+    same_ids = bool(torch.equal(ids_c, ids_x))
+    same_sc = bool(torch.equal(sc_c, sc_x))
+    exact.close()
+    calls = max(st["calls"], 1)
+    return {"mode": "certified: BERT + image tower bf16x3, CLIP text tower bf16, certified argmax (bound on the bf16 "
+                    "cosine error: cert_dcos, include/conzic.h) with exact bf16x3 re-score",
+            "checked_against": "an all-bf16x3 engine run on the same inputs inside this bench process",
+            "ids_identical": same_ids, "scores_identical": same_sc,
+            "decisions": st["images"], "rescored_candidates_per_step": st["rescored_candidates"] / calls,
+            "images_with_several_unbeaten_per_step": st["images_multi"] / calls,
+            "images_fully_reencoded_per_step": st["images_full"] / calls,
+            "candidates_per_step": BATCH * job.wl.top_k}
+
+
+def measure(args, rank, local_rank, world, wl: Workload, full: bool):
+    job = Job(rank, local_rank, world, args.precision, wl)
     eng = job.eng
     for _ in range(max(args.warmup, 3)):
         job.device_step()
@@ -258,7 +396,8 @@ def run_ours(args, rank, local_rank, world):
         ms = timed(job.device_step, args.steps, world, job.dev)
     launches = (eng.launch_count() - l0) * world
     clocks = cs.summary()
-    value = world * BATCH * args.steps / (ms / 1000.0)
+    per_call = BATCH * wl.samples
+    value = world * per_call * args.steps / (ms / 1000.0)
     # end to end through the drop-in API (host pixels, strings out)
     job.api_step()
     t0 = time.perf_counter()
@@ -270,48 +409,79 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         torch.distributed.barrier()
     e2e_s = cdist.max_over_ranks(time.perf_counter() - t0, world, job.dev)
-    e2e = world * BATCH * args.steps / e2e_s
-    h2d = job.pix_host.numel() * 4
-    d2h = SWEEPS * (BATCH * job.L * 8 + BATCH * 4)
+    e2e = world * per_call * args.steps / e2e_s
+    h2d = job.pix_host.numel() * 4 * wl.samples
+    d2h = wl.samples * wl.sweeps * (BATCH * job.L * 8 + BATCH * 4 * (2 if wl.ctl else 1))
+    if args.precision == "certified":
+        d2h += wl.samples * wl.sweeps * wl.n_len * 2 * 64  # the two counter blocks the certified argmax reads per step
     # one extra profiled step: CUDA events around every launch, by category
     eng.profile(True)
     job.device_step()
     prof = eng.profile_read()
     eng.profile(False)
     pk = peaks()
-    traffic, traffic_detail = ncu_traffic()
     g_ms, g_flops, g_n = prof["gemm"]
     achieved = g_flops / (g_ms / 1000.0) / 1e12 if g_ms > 0 else 0.0
     total_ms = sum(v[0] for v in prof.values())
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.precision.replace("bf16x3", "bf16 (3-pass split)"),
-                "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches,
-                "roofline": {"kernel": "gemm_persist_kernel<2,*> + gemm_wide_kernel (the CLIP towers' linears: CTA "
-                                       "pairs, tcgen05 cta_group::2, TMA-fed); average over the launches of one step",
-                             "bound": "tensor",
-                             "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
-                             "peak_source": f"{pk['src']} sustained bf16", "traffic": traffic,
-                             "traffic_detail": traffic_detail,
-                             "launches_profiled": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
-                             "flops_per_launch": g_flops / max(g_n, 1),
-                             "share_of_step": g_ms / total_ms if total_ms else None},
-                "step_breakdown_ms": {k: round(v[0], 3) for k, v in prof.items()},
-                "algorithmic": {"tflop_per_caption": ALGO_TFLOP_PER_CAPTION,
-                                "tflops_per_gpu": value / world * ALGO_TFLOP_PER_CAPTION,
-                                "frac_of_peak": value / world * ALGO_TFLOP_PER_CAPTION / pk["tf"],
-                                "note": "reference-algorithm FLOPs (every candidate encoded in full); the engine "
-                                        "executes fewer because the caption prefix is encoded once per image"}}
-        if world == 1 and not args.no_cpu:
+    algo = wl.algo_tflop_per_caption()
+    rec = {"metric": wl.metric, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None,
+           "dtype": {"certified": "bf16 (CLIP text tower) + bf16 3-pass split (BERT, image tower, certified re-score)",
+                     "bf16x3": "bf16 (3-pass split)", "bf16": "bf16"}[args.precision],
+           "data": "synthetic", "config": wl.describe(world), "clocks": clocks,
+           "e2e": {"value": e2e, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": launches,
+           "roofline": {"kernel": "gemm_persist_kernel<2,*> + gemm_wide_kernel (the CLIP text tower's linears: CTA "
+                                  "pairs, tcgen05 cta_group::2, TMA-fed); average over the launches of one step",
+                        "bound": "tensor",
+                        "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
+                        "peak_source": f"{pk['src']} sustained bf16",
+                        "launches_profiled": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
+                        "flops_per_launch": g_flops / max(g_n, 1),
+                        "share_of_step": g_ms / total_ms if total_ms else None},
+           "step_breakdown_ms": {k: round(v[0], 3) for k, v in prof.items()},
+           "algorithmic": {"tflop_per_caption": algo,
+                           "tflops_per_gpu": value / world * algo,
+                           "frac_of_peak": value / world * algo / pk["tf"],
+                           "note": "reference-algorithm FLOPs (every candidate encoded in full); the engine "
+                                   "executes fewer because the caption prefix is encoded once per image"}}
+    if full:
+        traffic, traffic_detail = ncu_traffic()
+        rec["roofline"]["traffic"] = traffic
+        rec["roofline"]["traffic_detail"] = traffic_detail
+        if args.precision == "certified":
+            rec["parity"] = parity_check(job)
+    from conzic_b200 import runtime
+    runtime.clear()
+    return rec
+
+
+def run_ours(args, rank, local_rank, world):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if args.config == 5:
+        points = []
+        for n_len in (5, 10, 25):
+            for top_k in (50, 200, 512):
+                r = measure(args, rank, local_rank, world, Workload(5, n_len, top_k), full=False)
+                points.append({"sentence_len": n_len, "candidate_k": top_k, "value": r["value"], "e2e": r["e2e"]["value"],
+                               "ms_per_step": r["ms_per_step"], "gemm_frac": r["roofline"]["frac"],
+                               "algorithmic_frac": r["algorithmic"]["frac_of_peak"], "gpu_launches": r["gpu_launches"],
+                               "clocks": r["clocks"]})
+        line = measure(args, rank, local_rank, world, Workload(5, 10, 200), full=True)
+        line["sweep"] = points
+    else:
+        wl = Workload(args.config)
+        line = measure(args, rank, local_rank, world, wl, full=True)
+        if rank == 0 and world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            cpu_sample(2, cores)  # warm-up (cold first call is several times slower)
-            v, s = cpu_sample(2, cores)
-            line["cpu_baseline"] = {"value": v, "unit": "captions/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 images x (first sweep + one full-length sweep), {s:.1f} s of CPU work, "
-                                              "5-sweep time extrapolated as t_first + 4*t_full"}
+            cpu_sample(wl, 1, cores)  # warm-up (cold first call is several times slower)
+            v, s, kind = cpu_sample(wl, 1, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "captions/s", "cores": cores, "kind": kind,
+                                    "sample": f"1 image x (first sweep + one full-length sweep), {s:.1f} s of CPU work, "
+                                              f"{wl.sweeps}-sweep time extrapolated as t_first + {wl.sweeps - 1}*t_full"}
+    if rank == 0:
         print(json.dumps(line), flush=True)
 
 
@@ -321,12 +491,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="certified", choices=["certified", "bf16", "bf16x3"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank, local_rank, world = cdist.env_world()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, Workload(args.config if args.config != 5 else 2))
         return
     if world > 1:
         cdist.init("nccl")

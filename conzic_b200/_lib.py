@@ -11,7 +11,9 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libconzic.so")
 
-PREC_BF16, PREC_BF16X3 = 0, 1
+PREC_BF16, PREC_BF16X3, PREC_CERTIFIED = 0, 1, 2
+FLAG_NO_PDL, FLAG_LN_STANDALONE = 1, 2
+CERT_STATS = 8
 GEMM_TCGEN05, GEMM_SIMT_DEBUG = 0, 1
 BERT_GLOBALS, CLIP_GLOBALS, PER_LAYER = 10, 5, 16
 
@@ -20,7 +22,7 @@ EXPORTS = [
     "conzic_abi_version", "conzic_last_error", "conzic_ctx_create", "conzic_ctx_destroy", "conzic_set_bert2clip",
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
-    "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_debug_mlp",
+    "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_cert_stats",
     "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_encode_candidates",
 ]
 
@@ -34,6 +36,7 @@ class Config(C.Structure):
         ("pad_id", C.c_int32), ("unk_id", C.c_int32), ("cls_id", C.c_int32), ("sep_id", C.c_int32),
         ("mask_id", C.c_int32), ("dot_id", C.c_int32), ("clip_bos", C.c_int32), ("clip_eos", C.c_int32),
         ("precision", C.c_int32), ("gemm_impl", C.c_int32), ("clip_chunk_rows", C.c_int32),
+        ("cert_dcos", C.c_float), ("cert_fcap", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -85,15 +88,16 @@ def _declare(lib):
     lib.conzic_encode_candidates.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp,
                                              vp, vp, C.c_size_t, vp]
     lib.conzic_score_select.restype = C.c_int
-    lib.conzic_score_select.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, f32, f32, f32, vp, i32, i32, vp, vp, vp, vp]
+    lib.conzic_score_select.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, f32, f32, f32, vp, i32, i32,
+                                        vp, vp, vp, vp, sz, vp]
     lib.conzic_gibbs_step.restype = C.c_int
     lib.conzic_gibbs_step.argtypes = [vp, C.POINTER(StepArgs), vp, sz, vp]
     lib.conzic_launch_count.restype = C.c_uint64
     lib.conzic_launch_count.argtypes = [vp]
     lib.conzic_debug_linear.restype = C.c_int
     lib.conzic_debug_linear.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
-    lib.conzic_debug_mlp.restype = C.c_int
-    lib.conzic_debug_mlp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]
+    lib.conzic_cert_stats.restype = C.c_int
+    lib.conzic_cert_stats.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     lib.conzic_set_vision.restype = C.c_int
     lib.conzic_set_vision.argtypes = [vp, C.POINTER(VisionConfig), C.POINTER(vp), i32, vp]
     lib.conzic_vision_workspace_bytes.restype = sz
@@ -118,7 +122,7 @@ def load(build_if_missing: bool = True):
         from . import build as _build
         _build.build()
     _lib = _declare(C.CDLL(LIB_PATH))
-    if _lib.conzic_abi_version() != 5:
+    if _lib.conzic_abi_version() != 6:
         raise RuntimeError("libconzic.so ABI version mismatch; rebuild with `python -m conzic_b200.build --force`")
     return _lib
 

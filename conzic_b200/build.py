@@ -16,12 +16,13 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libconzic.so")
 STAMP = os.path.join(PKG, ".libconzic.stamp")
-SOURCES = ["engine.cu", "gemm.cu", "transformer_ops.cu", "select_ops.cu"]
-HEADERS = ["kernels.h", "ptx.cuh", os.path.join(ROOT, "include", "conzic.h")]
+OBJDIR = os.path.join(PKG, "_obj")
+SOURCES = ["engine.cu", "gemm.cu", "transformer_ops.cu", "select_ops.cu", "cert_ops.cu"]
+HEADERS = ["kernels.h", "ptx.cuh", "select_common.cuh", os.path.join(ROOT, "include", "conzic.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
 
 
@@ -46,13 +47,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    nvcc = find_nvcc()
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src):  # one translation unit per nvcc process, all of them at once
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for _, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+    if any(res.returncode != 0 for _, res in results):
         raise RuntimeError("nvcc failed building libconzic.so")
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] +
+                         [obj for obj, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libconzic.so")
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

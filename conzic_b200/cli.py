@@ -19,7 +19,17 @@ import time
 
 import torch
 
-from . import control_gen_utils, dist, gen_utils, synth
+from . import control_gen_utils, dist, gen_utils
+
+
+def _synth():
+    """The offline fixtures behind --synthetic (repo-level package `synthetic`, not part of the product package)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return importlib.import_module("synthetic.synth")
 from .clip.clip import CLIP
 from .models import BertMLM
 from .utils import create_logger, set_seed
@@ -93,12 +103,12 @@ def load_models(args):
     torch.cuda.set_device(dev)
     table = None
     if args.synthetic:
-        lm_model = BertMLM(synth.make_bert_state_dict(0))
-        lm_tokenizer = synth.SynthBertTokenizer()
-        clip = CLIP(state_dict=synth.make_clip_state_dict(0), tokenizer=synth.SynthCLIPTokenizer(),
-                    processor=synth.SynthProcessor())
-        table = synth.make_sentiment_table()
-        control_gen_utils.set_pos_tagger(synth.synth_pos_tagger)  # --control_type pos without NLTK
+        lm_model = BertMLM(_synth().make_bert_state_dict(0))
+        lm_tokenizer = _synth().SynthBertTokenizer()
+        clip = CLIP(state_dict=_synth().make_clip_state_dict(0), tokenizer=_synth().SynthCLIPTokenizer(),
+                    processor=_synth().SynthProcessor())
+        table = _synth().make_sentiment_table()
+        control_gen_utils.set_pos_tagger(_synth().synth_pos_tagger)  # --control_type pos without NLTK
     else:
         from transformers import AutoTokenizer
         lm_model = BertMLM.from_pretrained(args.lm_model)
@@ -115,7 +125,7 @@ def build_token_mask(args, tokenizer, dev):
     """ones(1, V) with the stop words zeroed (run.py:143-152).  --synthetic uses the id-range rule of
     SURVEY.md 8(d) (ids < 1996 are specials / [unused] / punctuation / digits in bert-base-uncased)."""
     if args.synthetic and not os.path.exists(args.stop_words_path):
-        return synth.make_token_mask(dev)
+        return _synth().make_token_mask(dev)
     with open(args.stop_words_path, "r", encoding="utf-8") as fh:
         words = [w.rstrip("\n") for w in fh.readlines()] + list(args.add_extra_stopwords)
     mask = torch.ones((1, tokenizer.vocab_size))
@@ -146,7 +156,7 @@ def demo_main(argv=None):
     token_mask = build_token_mask(args, lm_tokenizer, dev)
     logger.info(f"Processing: {args.caption_img_path}")
     if args.synthetic:
-        image, name = synth.make_pixel_values(0).unsqueeze(0), ["synthetic0.jpg"]
+        image, name = _synth().make_pixel_values(0).unsqueeze(0), ["synthetic0.jpg"]
     else:
         from PIL import Image
         image, name = Image.open(args.caption_img_path).convert("RGB"), [args.caption_img_path.split("/")[-1]]
@@ -174,7 +184,7 @@ def run_main(argv=None):
     token_mask = build_token_mask(args, lm_tokenizer, dev)
     if args.synthetic:
         names_all = [f"synthetic{i}.jpg" for i in range(args.synthetic_images)]
-        load = lambda idx: torch.stack([synth.make_pixel_values(i) for i in idx])
+        load = lambda idx: torch.stack([_synth().make_pixel_values(i) for i in idx])
     else:
         from PIL import Image
         names_all = os.listdir(args.caption_img_path)  # the reference's order (run.py:159)

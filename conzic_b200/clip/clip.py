@@ -57,11 +57,15 @@ class CLIP:
         return self.compute_image_representation_from_image_instance(Image.open(image_path))
 
     # ---- text side (clip/clip.py:64-102)
-    def compute_text_representation(self, text_list):
-        eng = self._engine()
+    def tokenize_texts(self, text_list):
+        """CLIP ids int64[N, T] of the texts, BOS ... EOS, right padded with EOS, truncated to 77 (clip/clip.py:71-72)."""
         t = self.tokenizer(text_list, padding=True, return_tensors="pt",
                            max_length=self.tokenizer.max_len_single_sentence + 2, truncation=True)
-        return eng.clip_text_encode(t["input_ids"].to(eng.device))
+        return t["input_ids"]
+
+    def compute_text_representation(self, text_list):
+        eng = self._engine()
+        return eng.clip_text_encode(self.tokenize_texts(text_list).to(eng.device))
 
     def compute_image_text_similarity_via_embeddings(self, image_embeds, text_embeds):
         return self._engine().image_text_similarity(image_embeds, text_embeds)

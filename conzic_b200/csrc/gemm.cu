@@ -152,32 +152,18 @@ struct PGemmParams {
   int m_tiles;  // per-CTA-group tiles of CG*128 rows
   int n_tiles;
   Epi e;
-  uint64_t st_policy = 0;  // non-zero: L2 eviction-priority hint for the output stores / residual loads
-  uint64_t ld_policy = 0;
-  const bf16* a_ptr = nullptr;  // A operand in global memory (row stride lda elements), for L2 prefetch of the next tile
-  int lda = 0;
 };
 
-// Pull rows [r_lo, r_hi) x `bytes` of the A operand into L2 ahead of the TMA loads that will read them: the
-// smem ring only covers L2 latency, not HBM latency (~2 us under load).
-__device__ __forceinline__ void prefetch_a_rows(const PGemmParams& p, int r_lo, int r_hi, int bytes) {
-  if (!p.a_ptr) return;
-  r_hi = min(r_hi, p.M);
-  for (int r = r_lo; r < r_hi; ++r)
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.a_ptr + static_cast<size_t>(r) * p.lda), "r"(bytes)
-                 : "memory");
-}
-
-template <int CG, bool ARES, int EW = P_EPI_WARPS>
+template <int CG, bool ARES>
 struct PSmem {
   static constexpr int A_SLOT = BM * BK * 2;               // 16 KB
   static constexpr int B_STAGE = (PBN / CG) * BK * 2;      // 32 KB or 16 KB (each CTA of a pair holds half)
   static constexpr int STAGE = ARES ? B_STAGE : (A_SLOT + B_STAGE);
   static constexpr int A_BYTES = ARES ? P_MAX_KB * A_SLOT : 0;
-  static constexpr int STAGES = ARES ? (EW == 16 ? 4 : 5) : (CG == 1 ? 4 : 6);  // 16 warps: 16 KB more staging, one stage less
+  static constexpr int STAGES = ARES ? 5 : (CG == 1 ? 4 : 6);
   static_assert(!ARES || CG == 2, "A-resident mode needs the CTA pair");
   static constexpr int STG_OFF = A_BYTES + STAGES * STAGE;  // per-epilogue-warp 32 x 64 B transpose buffers
-  static constexpr int STG_BYTES = EW * 2048;
+  static constexpr int STG_BYTES = P_EPI_WARPS * 2048;
   static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int N_BARS = 2 * STAGES + P_MAX_KB + 4;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
@@ -204,7 +190,7 @@ __device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, i
     rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.resid && grow < p.M) {
       const float* src = e.resid + static_cast<size_t>(grow) * e.ldr + n0 + pc * 4;
-      rr[i] = p.ld_policy ? ld_global_v4f_hint(src, p.ld_policy) : *reinterpret_cast<const float4*>(src);
+      rr[i] = *reinterpret_cast<const float4*>(src);
     }
   }
 }
@@ -213,8 +199,7 @@ __device__ __forceinline__ void prefetch_resid(const PGemmParams& p, int lane, i
 // bias4 = this lane's slice of the warp's bias, chunk = index of the 16-column chunk inside the warp's 128.
 __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
                                                    float (&v)[16], const float4 (&rr)[4], const float4& bias4,
-                                                   int chunk, float (&st1)[4], float (&st2)[4],
-                                                   float4* xo = nullptr) {
+                                                   int chunk, float (&st1)[4], float (&st2)[4]) {
   const Epi& e = p.e;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -238,15 +223,13 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
     if (grow < p.M) {
       const int col = n0 + pc * 4;
       x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
-      if (e.stats_out || e.lnf_out) {  // LayerNorm statistics of the values being written
+      if (e.lnf_out) {  // LayerNorm statistics of the values being written
         st1[i] += (x.x + x.y) + (x.z + x.w);
         st2[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
       }
-      if (xo) xo[i] = x;
       if (e.out_f32) {
         float* dst = e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + col;
-        if (p.st_policy) st_global_v4f_hint(dst, x, p.st_policy);
-        else *reinterpret_cast<float4*>(dst) = x;
+        *reinterpret_cast<float4*>(dst) = x;
       }
       if (e.out_act) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
@@ -259,63 +242,17 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
   __syncwarp();
 }
 
-// After a warp's 8 chunks: lanes 4r..4r+3 hold partial sums of the same rows; fold them and let lane 4r write
-// the (sum, sum of squares) of this warp's 128 columns of rows (lane >> 2) + 8 i.
-__device__ __forceinline__ void flush_row_stats(const PGemmParams& p, int lane, int row0, int slice, float (&st1)[4],
-                                                float (&st2)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a = st1[i], b = st2[i];
-    a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
-    b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
-    const int grow = row0 + (lane >> 2) + 8 * i;
-    if ((lane & 3) == 0 && grow < p.M)
-      p.e.stats_out[static_cast<size_t>(grow) * p.e.stats_parts + slice] = make_float2(a, b);
-  }
-}
-
-// Row statistics for the folded LayerNorm of a consumer GEMM: mean and 1/std of row `grow` from its partials.
-__device__ __forceinline__ void load_row_ln(const PGemmParams& p, int grow, float& rstd, float& t) {
-  rstd = 0.f; t = 0.f;
-  if (grow >= p.M) return;
-  float s1 = 0.f, s2 = 0.f;
-  const float2* st = p.e.ln_stats + static_cast<size_t>(grow) * p.e.ln_parts;
-  for (int j = 0; j < p.e.ln_parts; ++j) {
-    const float2 v = st[j];
-    s1 += v.x; s2 += v.y;
-  }
-  const float inv = 1.0f / static_cast<float>(p.e.ln_width);
-  const float mean = s1 * inv;
-  const float var = fmaxf(s2 * inv - mean * mean, 0.f);
-  rstd = rsqrtf(var + p.e.ln_eps);
-  t = -rstd * mean;
-}
-
 // bf16-only path (no residual, no fp32 output): 32 columns [n0, n0+32) per chunk = 64-byte rows of bf16.
-// With a folded LayerNorm (e.ln_s): value = rstd * acc + (t * s[n] + bias[n]), t = -rstd * mean of this row.
 __device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_t* stg, int lane, int row0, int n0,
-                                                    float (&v)[32], const float4& bias4, int chunk,
-                                                    const float4& s4 = float4{0.f, 0.f, 0.f, 0.f}, float rstd = 1.f,
-                                                    float t = 0.f) {
+                                                    float (&v)[32], const float4& bias4, int chunk) {
   const Epi& e = p.e;
-  if (e.ln_s) {
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int src = chunk * 8 + jj;
-      v[4 * jj] = fmaf(rstd, v[4 * jj], fmaf(t, __shfl_sync(0xffffffffu, s4.x, src), __shfl_sync(0xffffffffu, bias4.x, src)));
-      v[4 * jj + 1] = fmaf(rstd, v[4 * jj + 1], fmaf(t, __shfl_sync(0xffffffffu, s4.y, src), __shfl_sync(0xffffffffu, bias4.y, src)));
-      v[4 * jj + 2] = fmaf(rstd, v[4 * jj + 2], fmaf(t, __shfl_sync(0xffffffffu, s4.z, src), __shfl_sync(0xffffffffu, bias4.z, src)));
-      v[4 * jj + 3] = fmaf(rstd, v[4 * jj + 3], fmaf(t, __shfl_sync(0xffffffffu, s4.w, src), __shfl_sync(0xffffffffu, bias4.w, src)));
-    }
-  } else {
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
-      const int src = chunk * 8 + jj;
-      v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
-      v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
-      v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
-      v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
-    }
+  for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
+    const int src = chunk * 8 + jj;
+    v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
+    v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+    v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+    v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
   }
   if (e.act == ACT_QUICK_GELU) {
     // x * sigmoid(1.702 x) = x * (0.5 * tanh(0.851 x) + 0.5), written as three passes over the 32 values so the
@@ -352,8 +289,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_
     const uint4 x = *reinterpret_cast<const uint4*>(stg + stg_off(r, pc));
     if (grow < p.M) {
       bf16* dst = e.out_act + static_cast<size_t>(grow) * e.ldo_act + n0 + pc * 8;
-      if (p.st_policy) st_global_v4_hint(dst, x, p.st_policy);
-      else *reinterpret_cast<uint4*>(dst) = x;
+      *reinterpret_cast<uint4*>(dst) = x;
     }
   }
   __syncwarp();
@@ -514,16 +450,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// EW = epilogue warps.  8: each warp drains 128 columns of the 256-wide tile, every epilogue form.  16: 64 columns
-// each, fp32 (+ residual) output only -- for the GEMM whose epilogue is the critical path (O-proj: 5 KB of HBM
-// traffic per row for 0.5 MFLOP), where twice the warps mean twice the residual loads in flight.
-template <int CG, bool ARES, int EW = P_EPI_WARPS>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+template <int CG, bool ARES>
+__global__ void __launch_bounds__(P_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const PGemmParams p) {
   PDL_ENTRY();
-  using SL = PSmem<CG, ARES, EW>;
-  constexpr int WCOLS = 2 * PBN / EW * 2;  // columns per epilogue warp: 128 (EW 8) or 64 (EW 16)
+  using SL = PSmem<CG, ARES>;
+  constexpr int EW = P_EPI_WARPS;
+  constexpr int WCOLS = PBN / 2;  // columns per epilogue warp
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
   uint8_t* smem = psmem;
@@ -597,10 +531,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr + c0),
                              "r"(nbytes) : "memory");
           }
-          if (ARES && p.a_ptr && n == p.n_tiles - 1 && m + 1 < p.m_tiles) {
-            // last unit of this m tile: the next m tile's A boxes (loaded one unit from now) go to L2
-            tma_prefetch_2d(&tmA, kb * BK, ((m + 1) * CG + static_cast<int>(cta_rank)) * BM);
-          }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
           const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
           uint8_t* st = sStage + s * SL::STAGE;
@@ -655,7 +585,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc = 0, acc_ph = 0;
     const uint32_t tempty_addr0 = (CG == 2) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
-    const bool bf16_only = EW == 8 && p.e.out_act && !p.e.out_f32 && !p.e.resid;
+    const bool bf16_only = p.e.out_act && !p.e.out_f32 && !p.e.resid;
     for (long long u = u0; u < u1; ++u) {
       const int m = static_cast<int>(u / p.n_tiles), n = static_cast<int>(u % p.n_tiles);
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
@@ -663,12 +593,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // this lane's 4 bias values of the warp's 128 columns (loaded while the tensor core is still busy)
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.e.bias && nbase + lane * 4 + 4 <= p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nbase + lane * 4));
-      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float ln_rstd = 1.f, ln_t = 0.f;
-      if (p.e.ln_s) {
-        if (nbase + lane * 4 + 4 <= p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.e.ln_s + nbase + lane * 4));
-        load_row_ln(p, row0 + lane, ln_rstd, ln_t);
-      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * WCOLS;
@@ -681,27 +605,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else mbar_arrive_relaxed(&tempty_bar[acc]);
         }
       };
-      if constexpr (EW == 16) {
-        // fp32 (+ residual) output, N a multiple of 256 (checked by the launcher): 4 chunks of 16 columns per warp
-        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int c = 0; c < WCOLS / 16; ++c) {
-          const int n0 = nbase + c * 16;
-          float4 rr[4];
-          prefetch_resid(p, lane, row0, n0, rr);
-          uint32_t r[16];
-          tmem_ld16(taddr + c * 16, r);
-          tmem_ld_wait();
-          if (c == WCOLS / 16 - 1) release();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
-        }
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
-        continue;
-      }
       if (bf16_only && nbase + PBN / 2 <= p.N) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -712,7 +615,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c, s4, ln_rstd, ln_t);
+          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
         }
       } else if (nbase + PBN / 2 <= p.N) {
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -730,7 +633,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
         }
-        if (p.e.stats_out) flush_row_stats(p, lane, row0, nbase / (PBN / 2), st1, st2);
       } else {
         // ragged last n tile (N not a multiple of 128): plain row-per-thread epilogue
 #pragma unroll 1
@@ -756,241 +658,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_cg<CG>(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Fused MLP of one transformer block: x += fc2(act(fc1(h))) in ONE persistent launch.
-// Each CTA pair takes 256-row tiles; per tile it runs the F/256 fc1 units (h x W1^T, bias, activation) whose
-// bf16 results go to a per-CTA scratch tile [128, F] that is re-used for every tile (it stays in L2: the
-// [M, F] intermediate, 8 KB of HBM traffic per token row, never exists), then the H/256 fc2 units read that
-// scratch tile back through TMA as their A operand (bias, + residual, fp32 out).  fc2's k blocks 4j..4j+3 only
-// need fc1 unit j, so the producer waits on per-unit "ready" barriers and the tensor core never idles between
-// the two GEMMs.  Same pipeline as gemm_persist_kernel<2, false>: 6-stage TMA ring of (A 16 KB | B 16 KB),
-// tcgen05 cta_group::2 256x256x16 MMAs, two 256-column TMEM accumulators, 8 epilogue warps.
-// ---------------------------------------------------------------------------------------------------
-constexpr int MLP_MAX_N1 = 16;
-
-struct MlpParams {
-  int M, m_tiles, H, F;
-  const float* bias1;
-  const float* bias2;
-  bf16* scratch;       // [gridDim.x * 128, F]
-  const float* resid;  // x, fp32 [M, ldr]
-  int ldr;
-  float* out_f32;      // new x (may alias resid)
-  int ldo_f32;
-  bf16* out_act;       // optional bf16 copy of the new x
-  int ldo_act;
-  int act;
-};
-
-struct MlpSmem {
-  static constexpr int STAGE = 2 * BM * BK * 2;  // A 16 KB + B 16 KB
-  static constexpr int STAGES = 6;
-  static constexpr int STG_OFF = STAGES * STAGE;
-  static constexpr int BAR_OFF = STG_OFF + P_EPI_WARPS * 2048;
-  static constexpr int N_BARS = 2 * STAGES + 4 + MLP_MAX_N1;
-  static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
-};
-
-__global__ void __launch_bounds__(P_THREADS, 1)
-mlp_persist_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
-                   const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW2,
-                   const MlpParams p) {
-  PDL_ENTRY();
-  using SL = MlpSmem;
-  constexpr int CG = 2;
-  constexpr int STAGES = SL::STAGES;
-  extern __shared__ __align__(1024) uint8_t psmem[];
-  uint8_t* smem = psmem;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sStage = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* fready_bar = tempty_bar + 2;  // [n1]: fc1 unit j of the current tile is in the scratch tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fready_bar + MLP_MAX_N1);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool leader = cta_rank == 0;
-  const int n_groups = gridDim.x / CG;
-  const int group = blockIdx.x / CG;
-  const int n1 = p.F / PBN, n2 = p.H / PBN;      // fc1 / fc2 units per tile
-  const int nkb1 = p.H / BK, nkb2 = p.F / BK;    // k blocks of fc1 / fc2
-  const int kb_per_unit1 = PBN / BK;             // fc2 k blocks produced by one fc1 unit (4)
-  const int srow0 = blockIdx.x * BM;             // this CTA's rows of the scratch tensor
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmF); tma_prefetch_desc(&tmW2);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], CG * P_EPI_WARPS); }
-    for (int j = 0; j < MLP_MAX_N1; ++j) mbar_init(&fready_bar[j], P_EPI_WARPS);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc_cg<CG>(tmem_slot, 512);
-    tmem_relinquish_cg<CG>();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0; uint32_t tile_it = 0;
-      for (int m = group; m < p.m_tiles; m += n_groups, ++tile_it) {
-        const int arow = (m * CG + static_cast<int>(cta_rank)) * BM;
-        for (int u = 0; u < n1 + n2; ++u) {
-          const bool is1 = u < n1;
-          const int n = is1 ? u : u - n1;
-          const int nkb = is1 ? nkb1 : nkb2;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            if (!is1 && (kb % kb_per_unit1) == 0) {
-              // scratch columns [64 kb, 64 kb + 256) were written by the epilogue of fc1 unit kb / 4 (generic
-              // proxy); make them visible to the TMA (async proxy) read below
-              mbar_wait(&fready_bar[kb / kb_per_unit1], tile_it & 1);
-              asm volatile("fence.proxy.async.global;" ::: "memory");
-            }
-            if (!is1 && p.resid) {
-              const int rows_per_kb = (BM + nkb - 1) / nkb;
-              const int r_lo = arow + kb * rows_per_kb;
-              const int r_hi = min(min(r_lo + rows_per_kb, arow + BM), p.M);
-              for (int r = r_lo; r < r_hi; ++r)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.resid + static_cast<size_t>(r) * p.ldr + n * PBN),
-                             "r"(PBN * 4) : "memory");
-            }
-            if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * SL::STAGE);
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
-            uint8_t* st = sStage + s * SL::STAGE;
-            // L2 priorities: the scratch tile and the weights are the re-used data; h streams through once
-            if (is1) {
-              tma_load_2d_pair_hint(st, &tmH, bar, kb * BK, arow, L2_EVICT_FIRST);
-              tma_load_2d_pair_hint(st + SL::STAGE / 2, &tmW1, bar, kb * BK, n * PBN + static_cast<int>(cta_rank) * BM, L2_EVICT_LAST);
-            } else {
-              tma_load_2d_pair_hint(st, &tmF, bar, kb * BK, srow0, L2_EVICT_LAST);
-              tma_load_2d_pair_hint(st + SL::STAGE / 2, &tmW2, bar, kb * BK, n * PBN + static_cast<int>(cta_rank) * BM, L2_EVICT_LAST);
-            }
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, PBN);
-      int s = 0; uint32_t ph = 0; uint32_t acc = 0, acc_ph = 0;
-      for (int m = group; m < p.m_tiles; m += n_groups) {
-        for (int u = 0; u < n1 + n2; ++u) {
-          const int nkb = u < n1 ? nkb1 : nkb2;
-          mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + acc * PBN;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full_bar[s], ph);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sStage + s * SL::STAGE);
-            const uint32_t b0 = a0 + SL::STAGE / 2;
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = make_smem_desc_sw128(a0 + k * (UMMA_K * 2));
-              const uint64_t db = make_smem_desc_sw128(b0 + k * (UMMA_K * 2));
-              umma_bf16_cg<CG>(d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit_cg<CG>(&empty_bar[s]);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-          umma_commit_cg<CG>(&tfull_bar[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_ph ^= 1;
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    uint32_t acc = 0, acc_ph = 0;
-    const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
-    uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
-    // fc1 epilogue: bf16 into this CTA's scratch tile; fc2 epilogue: fp32 (+ residual) into x
-    PGemmParams p1{}, p2{};
-    p1.M = 0x7fffffff; p1.N = p.F; p1.K = p.H;
-    p1.e.out_act = p.scratch; p1.e.ldo_act = p.F; p1.e.act = p.act;
-    p2.M = p.M; p2.N = p.H; p2.K = p.F;
-    p2.e.resid = p.resid; p2.e.ldr = p.ldr; p2.e.out_f32 = p.out_f32; p2.e.ldo_f32 = p.ldo_f32;
-    p2.e.out_act = p.out_act; p2.e.ldo_act = p.ldo_act; p2.e.act = ACT_NONE;
-    p1.st_policy = L2_EVICT_LAST;                                   // scratch tile: keep in L2 until fc2 has read it
-    p2.st_policy = L2_EVICT_FIRST; p2.ld_policy = L2_EVICT_FIRST;   // the residual stream passes through once
-    for (int m = group; m < p.m_tiles; m += n_groups) {
-      for (int u = 0; u < n1 + n2; ++u) {
-        const bool is1 = u < n1;
-        const int n = is1 ? u : u - n1;
-        const int nbase = n * PBN + half * (PBN / 2);
-        const float* bias = is1 ? p.bias1 : p.bias2;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) bias4 = __ldg(reinterpret_cast<const float4*>(bias + nbase + lane * 4));
-        mbar_wait(&tfull_bar[acc], acc_ph);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PBN + half * (PBN / 2);
-        auto release = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + acc * 8);
-        };
-        if (is1) {
-          const int row0 = srow0 + q * 32;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c * 32, r);
-            tmem_ld_wait();
-            if (c == 3) release();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_bf16_chunk(p1, stg, lane, row0, nbase + c * 32, v, bias4, c);
-          }
-          // publish this warp's part of fc1 unit u to the TMA reads of the fc2 units
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&fready_bar[u]);
-        } else {
-          const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
-          float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            const int n0 = nbase + c * 16;
-            float4 rr[4];
-            prefetch_resid(p2, lane, row0, n0, rr);
-            uint32_t r[16];
-            tmem_ld16(taddr + c * 16, r);
-            tmem_ld_wait();
-            if (c == 7) release();
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_f32_chunk(p2, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
-          }
-        }
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
-      }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_cg<CG>(tmem_base, 512);
@@ -1076,14 +743,6 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.e.resid + static_cast<size_t>(r) * p.e.ldr),
                            "r"(2 * PBN * 4) : "memory");
           }
-          if (p.a_ptr) {
-            // A comes straight from HBM (it was written by the previous kernel and is far larger than L2): pull the
-            // box that will be loaded PF_DIST k blocks from now into L2, so the ring only has to cover L2 latency
-            constexpr int PF_DIST = 8;
-            int pk = kb + PF_DIST, pm = m;
-            if (pk >= nkb) { pk -= nkb; pm += n_groups; }
-            if (pm < p.m_tiles) tma_prefetch_2d(&tmA, pk * BK, (pm * CG + static_cast<int>(cta_rank)) * BM);
-          }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * SL::STAGE);
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
           uint8_t* st = smem + s * SL::STAGE;
@@ -1135,7 +794,6 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int h_lo = EW == 8 ? 0 : (slice >> 1), h_hi = EW == 8 ? 2 : (slice >> 1) + 1;
     uint32_t uph = 0;
     const bool lnf = EW == 8 && p.e.lnf_out != nullptr;
-    const bool keep = lnf && p.e.lnf_mode == 2;  // x stays in TMEM for the LayerNorm pass
     const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
     // this warp's bias values (columns do not depend on the tile): fetched once, before the first accumulator is
@@ -1167,7 +825,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[16];
           tmem_ld16(taddr + c * 16, r);
           tmem_ld_wait();
-          if (c == 7 && !keep) {
+          if (c == 7) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + h * 8);
@@ -1175,22 +833,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (keep) {
-            // keep x = acc + bias + resid (as laid out after the transpose: 4 rows x 4 columns per lane) in the
-            // TMEM columns just read -- they are this warp's own and serve as scratch for the LayerNorm pass
-            float4 xo[4];
-            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2, xo);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              r[4 * i] = __float_as_uint(xo[i].x); r[4 * i + 1] = __float_as_uint(xo[i].y);
-              r[4 * i + 2] = __float_as_uint(xo[i].z); r[4 * i + 3] = __float_as_uint(xo[i].w);
-            }
-            tmem_st16(taddr + c * 16, r);
-          } else {
-            epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
-          }
+          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
         }
-        if (p.e.stats_out) flush_row_stats(p, lane, row0, nbase / (PBN / 2), st1, st2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ls1[i] += st1[i]; ls2[i] += st2[i]; }
       }
@@ -1209,7 +853,6 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mean[i] = a; rstd[i] = b;
           if ((lane & 3) == 0) xs[sub * BM + q * 32 + (lane >> 2) + 8 * i] = make_float2(a, b);
         }
-        if (keep) tmem_st_wait();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of TMEM lane quarter q
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1231,28 +874,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
           *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + col) = u;
         };
-        if (keep) {
-#pragma unroll 2
-          for (int hc = 0; hc < 16; ++hc) {
-            const int cbase = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16;  // first column of the chunk
-            const int col = cbase + pc * 4;
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.lnf_g + col));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.lnf_b + col));
-            uint32_t r[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cbase, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              write_ln(col, g4, b4, i, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_cluster_relaxed(tempty_addr0);
-            mbar_arrive_cluster_relaxed(tempty_addr0 + 8);
-          }
-        } else {
+        {
           // re-read what this lane stored (same addresses, program order; L2 hits mostly), 4 chunks = 16 loads
           // in flight per lane so the pass is bandwidth- and not latency-bound; it overlaps the next unit's MMAs
 #pragma unroll 1
@@ -1371,14 +993,14 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return true;
 }
 
-template <int CG, bool ARES, int EW = P_EPI_WARPS>
+template <int CG, bool ARES>
 bool configure_persist() {
-  return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PSmem<CG, ARES, EW>::DYN_BYTES),
+  return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PSmem<CG, ARES>::DYN_BYTES),
                  "cudaFuncSetAttribute(gemm_persist)");
 }
 
-template <int CG, bool ARES, int EW = P_EPI_WARPS>
+template <int CG, bool ARES>
 bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int sms, cudaStream_t st) {
   const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
   long long groups = sms / CG;
@@ -1386,8 +1008,8 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   if (groups < 1) groups = 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
-  cfg.blockDim = dim3(64 + 32 * EW);
-  cfg.dynamicSmemBytes = PSmem<CG, ARES, EW>::DYN_BYTES;
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = PSmem<CG, ARES>::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1397,8 +1019,8 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES, EW>, ta, tb, p), "gemm_persist launch");
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, p), "gemm_persist launch");
 }
 
 int g_sm_count = 0;
@@ -1412,58 +1034,19 @@ int sm_count() {
   return g_sm_count;
 }
 
-int mlp_scratch_rows() { return (sm_count() / 2) * 2 * BM; }
-
-bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W2, bf16* scratch, int act,
-                      const float* resid, int ldr, float* out_f32, int ldo_f32, bf16* out_act, int ldo_act,
-                      cudaStream_t st) {
-  if (M <= 0) return true;
-  const int H = W1.K, F = W1.N;
-  if (W2.K != F || W2.N != H || Hin.K != H || (H % PBN) || (F % PBN) || F / PBN > MLP_MAX_N1) {
-    set_error("mlp_fused: unsupported shape");
-    return false;
-  }
-  ++g_launches;
-  ProfScope prof_(CAT_GEMM, 4.0 * M * static_cast<double>(H) * F, st);
-  const int grid = (sm_count() / 2) * 2;
-  CUtensorMap th, tf;
-  if (!make_tmap_bf16_2d(&th, Hin.p, static_cast<uint64_t>(M), static_cast<uint64_t>(H), static_cast<uint64_t>(Hin.ld), BM))
-    return false;
-  if (!make_tmap_bf16_2d(&tf, scratch, static_cast<uint64_t>(grid) * BM, static_cast<uint64_t>(F), static_cast<uint64_t>(F), BM))
-    return false;
-  MlpParams p;
-  p.M = M; p.m_tiles = (M + 2 * BM - 1) / (2 * BM); p.H = H; p.F = F;
-  p.bias1 = W1.bias; p.bias2 = W2.bias; p.scratch = scratch;
-  p.resid = resid; p.ldr = ldr; p.out_f32 = out_f32; p.ldo_f32 = ldo_f32; p.out_act = out_act; p.ldo_act = ldo_act;
-  p.act = act;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(P_THREADS);
-  cfg.dynamicSmemBytes = MlpSmem::DYN_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, mlp_persist_kernel, th, W1.tmap128, tf, W2.tmap128, p), "mlp_persist launch");
-}
-
 static bool configure_wide() {
   return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<8>::DYN_BYTES),
                  "cudaFuncSetAttribute(gemm_wide<8>)") &&
          cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<16>::DYN_BYTES),
                  "cudaFuncSetAttribute(gemm_wide<16>)");
 }
+// 16 epilogue warps (twice the residual loads in flight) unless the epilogue also writes a LayerNorm, which needs the
+// 8-warp form where one warp pair covers whole rows
 static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
   if (groups < 1) groups = 1;
-  const char* e16 = getenv("CONZIC_WIDE_EPI16");  // read per launch so one process can compare both; default on
-  const bool w16 = (!e16 || atoi(e16)) && !p.e.lnf_out && !p.e.stats_out;
-
+  const bool w16 = !p.e.lnf_out;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
   cfg.blockDim = dim3(w16 ? WideSmem<16>::THREADS : WideSmem<8>::THREADS);
@@ -1475,26 +1058,19 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (g_pdl && g_pdl_now) ? 2 : 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (w16) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<16>, ta, tb, p), "gemm_wide<16> launch");
   return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<8>, ta, tb, p), "gemm_wide<8> launch");
 }
-static bool configure_mlp() {
-  return cuda_ok(cudaFuncSetAttribute(mlp_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::DYN_BYTES),
-                 "cudaFuncSetAttribute(mlp_persist)");
-}
 
 bool gemm_configure() {
-  if (!configure_mlp() || !configure_wide()) return false;
-  if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>() &&
-        configure_persist<2, true, 16>()))
-    return false;
+  if (!configure_wide()) return false;
+  if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>())) return false;
   return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
          configure_one<256, 2>() && configure_one<256, 4>();
 }
 
-bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st,
-                   uint64_t* launches) {
+bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st) {
   if (M <= 0) return true;
   if (A.K != W.K || (W.K % BK) != 0) {
     set_error("linear: K mismatch or K not a multiple of 64");
@@ -1510,9 +1086,8 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     p.ksplit = o.ksplit;
     p.part_stride = static_cast<size_t>(M) * epi.ldo_f32;
   }
-  (void)launches;
-  ++g_launches;
-  // the persistent pair kernel (CLIP tower) and the gridded kernel (BERT, parity mode) are timed separately
+  count_launch();
+  // the persistent pair kernel (CLIP tower) and the gridded kernel (BERT, bf16x3 passes) are timed separately
   ProfScope prof_((o.persist && !o.split && o.impl == 0) ? CAT_GEMM : CAT_GEMM_SMALL,
                   2.0 * M * static_cast<double>(W.N) * W.K * (o.split ? 3 : 1), st);
   if ((epi.out_f32 && (epi.ldo_f32 & 3)) || (epi.resid && (epi.ldr & 3)) || (epi.out_act && (epi.ldo_act & 7)) ||
@@ -1530,41 +1105,17 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
                          static_cast<uint64_t>(A.ld), BM))
     return false;
   if (o.persist && !o.split) {
-    if (g_sm_count == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-      if (g_sm_count <= 0) g_sm_count = 148;
-    }
     const int cg = o.cg == 2 ? 2 : 1;
     PGemmParams pp;
     pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi;
     pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
-    static int allow_pf = -1;
-    if (allow_pf < 0) {
-      // measured on B200: prefetching upcoming A boxes into L2 (cp.async.bulk.prefetch.tensor, 8 k blocks or one
-      // unit ahead) makes the GEMMs 2-6 % SLOWER, row-wise bulk prefetch a whole tile ahead 10-20 % slower: the
-      // ring of TMA loads already keeps HBM busy.  Kept as an experiment switch only.
-      const char* e = getenv("CONZIC_GEMM_APREFETCH");
-      allow_pf = e ? atoi(e) : 0;
-    }
-    if (allow_pf && ((W.K * 2) % 16) == 0 && ((static_cast<size_t>(A.ld) * 2) % 16) == 0) { pp.a_ptr = A.p; pp.lda = A.ld; }
     pp.n_tiles = (W.N + PBN - 1) / PBN;
-    static int allow_ares = -1;
-    if (allow_ares < 0) {
-      const char* e = getenv("CONZIC_GEMM_ARES");
-      allow_ares = e ? atoi(e) : 1;
-    }
-    const bool ares = allow_ares && cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
+    const bool ares = cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
     const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;
-    static int allow_wide = -1;
-    if (allow_wide < 0) {
-      const char* e = getenv("CONZIC_GEMM_WIDE");
-      allow_wide = e ? atoi(e) : 1;
-    }
-    // fp32-output GEMM with N == 512 and a streamed A (fc2): one 512-column unit per tile so A leaves HBM once
+    // fp32-output GEMM with N == 512: one 512-column unit per tile, so a streamed A (fc2, K = 2048) leaves HBM once
+    // and a CTA pair owns whole rows (which is what a LayerNorm written by the same epilogue needs)
     const bool wide_ok = cg == 2 && W.N == 2 * PBN && epi.out_f32 != nullptr;
-    if (wide_ok && ((allow_wide && !ares && W.K >= 1024) || o.force_wide || epi.lnf_out)) {
+    if (wide_ok && ((!ares && W.K >= 1024) || epi.lnf_out)) {
       pp.n_tiles = 1;
       return launch_wide(ta, tb, pp, st);
     }
@@ -1572,11 +1123,8 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");
       return false;
     }
-    const char* e16 = getenv("CONZIC_PERSIST_EPI16");  // read per launch so one process can compare both
-    if (cg == 2 && ares && e16 && atoi(e16) && epi.out_f32 && !epi.out_act && !epi.stats_out && !epi.ln_s && (W.N % PBN) == 0)
-      return launch_persist<2, true, 16>(ta, tb, pp, g_sm_count, st);
-    if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, g_sm_count, st) : launch_persist<2, false>(ta, tb, pp, g_sm_count, st);
-    return launch_persist<1, false>(ta, tb, pp, g_sm_count, st);
+    if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, sm_count(), st) : launch_persist<2, false>(ta, tb, pp, sm_count(), st);
+    return launch_persist<1, false>(ta, tb, pp, sm_count(), st);
   }
   if (epi.lnf_out) {
     set_error("linear: a fused LayerNorm output needs the persistent wide pair kernel");

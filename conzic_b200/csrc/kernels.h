@@ -6,15 +6,28 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 namespace conzic {
 
 typedef __nv_bfloat16 bf16;
 
-extern uint64_t g_launches;  // kernels launched by this library (all contexts)
-extern int g_pdl;            // 1 = launches may carry the programmatic-dependent-launch attribute (CONZIC_PDL, default 1)
-extern int g_pdl_now;        // set by the engine per section: measured on B200, PDL gains ~3.5 % on steps made of short
-                             // kernels (BERT, CLIP passes under ~50 k rows) and costs 1-2 % when the kernels are long
+// Per-context launch state.  Every extern "C" entry point binds the calling thread to its context's state for the
+// duration of the call (StateScope in engine.cu), so two contexts -- or two threads with a context each -- do not
+// share counters, the PDL switch or profiling records.
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct CtxState {
+  uint64_t launches = 0;  // kernels launched for this context (bench.py "gpu_launches")
+  int pdl = 1;            // launches may carry the programmatic-dependent-launch attribute (conzic_config.no_pdl clears it)
+  int pdl_now = 1;        // set by the engine per section: measured on B200, PDL gains ~3.5 % on steps made of short
+                          // kernels (BERT, CLIP passes under ~50 k rows) and costs 1-2 % when the kernels are long
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+};
+extern thread_local CtxState* t_state;
+inline void count_launch() { if (t_state) ++t_state->launches; }
+inline bool pdl_enabled() { return t_state && t_state->pdl && t_state->pdl_now; }
+inline void set_pdl_now(int v) { if (t_state) t_state->pdl_now = v; }
 
 // Programmatic dependent launch: every hot-path kernel starts with PDL_ENTRY() -- it lets the NEXT kernel in the
 // stream begin launching right away (griddepcontrol.launch_dependents) and then waits until everything the
@@ -38,7 +51,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = (g_pdl && g_pdl_now) ? 1 : 0;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 void set_error(const std::string& msg);
@@ -52,8 +65,8 @@ struct ProfScope {
   ProfScope(int cat, double work, cudaStream_t st);
   ~ProfScope();
 };
-void prof_enable(bool on);
-bool prof_read(int cat, double* ms, double* work, int* n);
+void prof_enable(CtxState* s, bool on);
+bool prof_read(CtxState* s, int cat, double* ms, double* work, int* n);
 
 // A GEMM-input activation matrix.  bf16 mode: [rows, K].  bf16x3 mode: [rows, 2K], the bf16 "hi" plane in
 // columns [0,K) and the residual "lo" plane (x - float(hi)) in [K,2K).
@@ -85,18 +98,6 @@ struct Epi {
   int ldo_act = 0;
   int out_K = 0;  // column offset of the lo plane when writing a split Act
   int act = ACT_NONE;
-  // LayerNorm folded into the GEMM (persistent kernel, bf16 mode).  Consumer side: A holds bf16(x) (NOT
-  // normalised), W holds bf16(gamma * W), `bias` holds b + W beta, ln_s[n] = sum_k W'[n,k]; with the row's
-  // mean and rstd from the partial sums in ln_stats the epilogue forms rstd*(acc - mean*ln_s[n]) + bias[n],
-  // which equals LN(x) W^T + b.  Producer side: stats_out receives per-row (sum, sum of squares) of the fp32
-  // values this GEMM writes, one float2 per 128-column slice: stats_out[row * stats_parts + slice].
-  const float* ln_s = nullptr;
-  const float2* ln_stats = nullptr;
-  int ln_parts = 0;
-  int ln_width = 0;     // number of columns the statistics cover (H)
-  float ln_eps = 0.f;
-  float2* stats_out = nullptr;
-  int stats_parts = 0;
   // LayerNorm of the rows this GEMM writes, applied by the SAME kernel (gemm_wide_kernel only: N == 512 == H, a
   // CTA owns whole rows): after x = acc + bias + resid has been stored, lnf_out[m, :] = bf16(LN(x[m, :]) * g + b).
   // Replaces the stand-alone LayerNorm launch that would re-read x from HBM (HF:models/clip/modeling_clip.py:369-384).
@@ -105,8 +106,6 @@ struct Epi {
   const float* lnf_g = nullptr;
   const float* lnf_b = nullptr;
   float lnf_eps = 0.f;
-  int lnf_mode = 1;  // 1: the LayerNorm pass re-reads the fp32 values the lane just stored (L2) and the accumulators are
-                     // handed back as soon as they are drained; 2: the values are kept in TMEM until the pass is done
 };
 
 struct GemmOpts {
@@ -117,22 +116,13 @@ struct GemmOpts {
   int persist = 0;  // 1 = persistent A-resident kernel with double-buffered TMEM accumulators (bf16 mode only)
   int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
   int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
-  int force_wide = 0;  // persistent pair path, N == 512, fp32 output: use gemm_wide_kernel whatever K is
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
 bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                        uint32_t box_rows);
 bool gemm_configure();  // opt-in to large dynamic shared memory for every instantiation
-bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st,
-                   uint64_t* launches);
-
-// Fused MLP (bf16 mode): x_out = resid + fc2(act(fc1(Hin))) in one persistent launch; `scratch` is a bf16
-// buffer of mlp_scratch_rows() x W1.N elements that holds the per-CTA fc1 tiles (L2 resident, re-used per tile).
-int mlp_scratch_rows();
-bool launch_mlp_fused(const Act& Hin, int M, const LinearW& W1, const LinearW& W2, bf16* scratch, int act,
-                      const float* resid, int ldr, float* out_f32, int ldo_f32, bf16* out_act, int ldo_act,
-                      cudaStream_t st);
+bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const GemmOpts& o, cudaStream_t st);
 
 // ---- transformer pieces (transformer_ops.cu) ---------------------------------------------------------
 void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, int ldd, int split, cudaStream_t st);
@@ -166,16 +156,11 @@ void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, 
 void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st);
-// xb / stats optional: bf16 copy of the rows and their (sum, sum of squares) in stats[row * stats_parts + 0]
-// (the other slices are zeroed), for a consumer GEMM with folded LayerNorm.
+// ln_out optional (H == 512, bf16 operands): LayerNorm 1 of the first block written by the same kernel.
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
-                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
-                       float2* stats, int stats_parts, cudaStream_t st, const float* ln_g = nullptr,
-                       const float* ln_b = nullptr, float ln_eps = 0.f, bf16* ln_out = nullptr, int ln_ld = 0);
-// Folds a LayerNorm into the linear layer that consumes it: w_out[n,k] = bf16(gamma[k] * w[n,k]),
-// s_out[n] = sum_k float(w_out[n,k]), bias_out[n] = bias[n] + sum_k beta[k] * w[n,k].
-void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,
-                    float* s_out, float* bias_out, cudaStream_t st);
+                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st,
+                       const float* ln_g = nullptr, const float* ln_b = nullptr, float ln_eps = 0.f,
+                       bf16* ln_out = nullptr, int ln_ld = 0);
 
 // Attention over packed token rows.  Row layout: B*P "prefix" rows (image b, position t) followed by
 // B*K*S "suffix" rows (image b, candidate k, offset s).  A suffix row attends to its image's first p0[b]
@@ -193,9 +178,8 @@ struct AttnArgs {
   int ld_act, split;
   int cpt = 1;            // filled by launch_attention: candidates packed into one 16-row query tile
   int cand_per_task = 8;  // filled by launch_attention: candidates per warp task
-  int prefetch = 0;       // filled by launch_attention: fetch the next candidate tile's q/k/v rows into registers
-                          // before computing the current one (tiles of <= 16 own rows)
 };
+bool attention_configure();  // opt-in to large dynamic shared memory for every instantiation (current device)
 bool launch_attention(const AttnArgs& a, cudaStream_t st);
 
 // ---- selection pieces (select_ops.cu) -----------------------------------------------------------------
@@ -233,13 +217,11 @@ void launch_assemble(const AssembleArgs& a, cudaStream_t st);
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st);
-void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t st);
 void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st);
 
 struct SelectArgs {
-  const float* text;   // [B*K, D]
-  const float* image;  // [B, D]
-  int B, K, D;
+  const float* logit;  // [B,K] scale * cos(text, image) from launch_clip_logits
+  int B, K;
   float scale;
   const float* probs;        // [B,K] or null (similarity only)
   const int64_t* ids_masked; // [B,K]
@@ -251,6 +233,55 @@ struct SelectArgs {
   float* out_senti;          // [B] or null
   float* tr_clip_score; float* tr_clip_ref; float* tr_final; int64_t* tr_best;
 };
+// logit[r] = scale * cos(text row r, image row b) with b = (row_bk ? row_bk[r] : r) / K
+void launch_clip_logits(const float* text, const float* image, const int32_t* row_bk, int n_rows, int K, int D,
+                        float scale, float* logit, cudaStream_t st);
 void launch_score_select(const SelectArgs& a, cudaStream_t st);
+
+// ---- certified argmax (cert_ops.cu): the winner the exact (bf16x3) tower would pick, from a bf16 tower plus an
+// exact re-score of the few candidates that are not provably beaten.  See the file header for the bound.
+struct CertArgs {
+  SelectArgs q;        // q.logit = main-tower logits [B,K]; round 2 patches the listed candidates in place
+  float eps;           // bound on |main-tower logit - exact logit| of one candidate (scale * bound on the cosine error)
+  float tau;           // slack for the fp rounding of the comparisons themselves
+  int fcap;            // an image with more than fcap unbeaten candidates goes straight to the full exact re-encode
+  int32_t* img_nflag;  // [B] unbeaten candidates of image b (its winner included); -1 = full re-encode
+  int32_t* img_k;      // [B,fcap] their candidate indices, ascending
+  int32_t* flag_list;  // [<= B*fcap] b * K + k of every listed candidate; image b's occupy img_slot0[b] ... + img_nflag[b]
+  int32_t* img_slot0;  // [B]
+  int32_t* full_list;  // [B] images that need the full exact re-encode
+  int32_t* counters;   // [0] listed candidates, [1] images in full_list, [2] images with more than one unbeaten
+                       // candidate, [3] images sent to full_list by round 1
+  const float* logit3; // round 2: exact logits of the listed candidates, [counters[0]]
+};
+void launch_cert_round1(const CertArgs& a, cudaStream_t st);
+void launch_cert_round2(const CertArgs& a, cudaStream_t st);
+// dense CLIP id rows of the listed candidates: out_ids[n, T] = prefix[b][0:p0[b]] + suffix[b,k][0:S], EOS padded;
+// out_eos[n] = index of the first EOS
+void launch_cert_gather_ids(const int32_t* flag_list, int n, const int32_t* ids_prefix, const int32_t* ids_suffix,
+                            const int32_t* p0, const int32_t* eos_idx, int P, int K, int S, int T, int eos_id,
+                            int32_t* out_ids, int32_t* out_eos, cudaStream_t st);
+// Full re-encode of n images: compact copies of their per-image inputs (image i of the copy = image full_list[i]) ...
+struct CertCompact {
+  const int32_t* full_list; int n;
+  int B, K, P, S, D;
+  const int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx;
+  const float* probs; const int64_t* ids_masked; const float* senti; const float* repeats; const float* image;
+  int32_t *c_ids_prefix, *c_ids_suffix, *c_p0, *c_eos_idx;
+  float* c_probs; int64_t* c_ids_masked; float* c_senti; float* c_repeats; float* c_image;
+};
+void launch_cert_compact(const CertCompact& a, cudaStream_t st);
+// ... and the way back: winners / scores / trace rows of the compact run scattered to the images they belong to
+struct CertScatter {
+  const int32_t* full_list; int n;
+  int K, L, pos;
+  const int64_t* c_inp; int64_t* inp;                // [n,L] / [B,L], column pos
+  const float* c_clip_ref; float* clip_ref;          // [n] / [B]
+  const float* c_senti; float* senti;                // [n] / [B] or null
+  const float *c_tr_score, *c_tr_ref, *c_tr_final;   // [n,K] or null
+  float *tr_score, *tr_ref, *tr_final;               // [B,K] or null
+  const int64_t* c_tr_best; int64_t* tr_best;        // [n] / [B] or null
+};
+void launch_cert_scatter(const CertScatter& a, cudaStream_t st);
 
 }  // namespace conzic

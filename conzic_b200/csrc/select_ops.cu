@@ -2,50 +2,11 @@
 // candidate -> CLIP id assembly, cosine / softmax / score fuse / argmax.  HBM-bandwidth or latency bound:
 // coalesced vector loads, warp-shuffle reductions, everything stays on the device.
 #include "kernels.h"
+#include "select_common.cuh"
 
 namespace conzic {
 
 namespace {
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-// Block-wide reductions with a fixed tree (deterministic run to run).  scratch: >= 33 floats.
-__device__ float block_sum(float v, float* scratch) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    float t = lane < nw ? scratch[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
-__device__ float block_max(float v, float* scratch) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) scratch[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    float t = lane < nw ? scratch[lane] : -INFINITY;
-    t = warp_max(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
 
 // ---------------------------------------------------------------------------------------------------
 // generate_caption_step (gen_utils.py:33-49): one CTA per image row.  The whole vocabulary row lives in
@@ -279,11 +240,6 @@ __global__ void step_prologue_kernel(int64_t* inp, int B, int L, int pos, int ma
   if (i == 0 && token_mask && dot_id >= 0) token_mask[dot_id] = dot_allowed ? 1.0f : 0.0f;  // utils.py:53-59
 }
 
-__global__ void gather_rows_index_kernel(int32_t* rows, int B, int L, int pos) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) rows[i] = i * L + pos;
-}
-
 __global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S) {
   PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,116 +247,58 @@ __global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int B, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// clip/clip.py:86-98 + gen_utils.py:77-81 + control_gen_utils.py:59-65.  One CTA per image.
+// clip/clip.py:86-98 + gen_utils.py:77-81 + control_gen_utils.py:59-65, in two launches:
+//   clip_logits_kernel   one WARP per candidate caption, grid over all B*K of them: scale * cos(text, image) --
+//                        the only part that touches the [B*K, D] embeddings (HBM bound: B*K*D*4 bytes);
+//   score_select_kernel  one CTA per image over its K logits: softmax_K, score fuse, argmax, write-back.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 256;
+
+__global__ void __launch_bounds__(256) clip_logits_kernel(const float* __restrict__ text, const float* __restrict__ image,
+                                                          const int32_t* __restrict__ row_bk, int n_rows, int K, int D,
+                                                          float scale, float* __restrict__ logit) {
+  PDL_ENTRY();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int b = (row_bk ? row_bk[r] : r) / K;
+  const float l = sel_logit(text + static_cast<size_t>(r) * D, image + static_cast<size_t>(b) * D, D, scale, lane);
+  if (lane == 0) logit[r] = l;
+}
 
 __global__ void __launch_bounds__(SEL_THREADS) score_select_kernel(SelectArgs a) {
   PDL_ENTRY();
   extern __shared__ float sel_smem[];
-  float* vhat = sel_smem;            // [D]
-  float* logit = vhat + a.D;         // [K]
+  float* logit = sel_smem;           // [K]
   float* cscore = logit + a.K;       // [K]
   float* sprob = cscore + a.K;       // [K]
   float* scratch = sprob + a.K;      // [40]
-  __shared__ float s_bestv;
-  __shared__ int s_besti;
 
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = SEL_THREADS >> 5;
-  const float* v = a.image + static_cast<size_t>(b) * a.D;
-  float ss = 0.f;
-  for (int i = tid; i < a.D; i += SEL_THREADS) ss += v[i] * v[i];
-  const float vn = sqrtf(block_sum(ss, scratch));
-  for (int i = tid; i < a.D; i += SEL_THREADS) vhat[i] = v[i] / vn;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < a.K; k += SEL_THREADS) logit[k] = a.logit[static_cast<size_t>(b) * a.K + k];
   __syncthreads();
-
-  for (int k = w; k < a.K; k += nw) {
-    const float* e = a.text + (static_cast<size_t>(b) * a.K + k) * a.D;
-    float s2 = 0.f;
-    for (int i = lane * 4; i < a.D; i += 128) {
-      float4 x = *reinterpret_cast<const float4*>(e + i);
-      s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-    }
-    const float en = sqrtf(warp_sum(s2));
-    float dot = 0.f;
-    for (int i = lane * 4; i < a.D; i += 128) {
-      float4 x = *reinterpret_cast<const float4*>(e + i);
-      float4 y = *reinterpret_cast<const float4*>(vhat + i);
-      dot += ((x.x / en) * y.x + (x.y / en) * y.y) + ((x.z / en) * y.z + (x.w / en) * y.w);
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) logit[k] = dot * a.scale;
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int k = tid; k < a.K; k += SEL_THREADS) mx = fmaxf(mx, logit[k]);
-  mx = block_max(mx, scratch);
-  float sum = 0.f;
+  sel_softmax(logit, a.K, cscore, scratch);
   for (int k = tid; k < a.K; k += SEL_THREADS) {
-    const float e = expf(logit[k] - mx);
-    cscore[k] = e;
-    sum += e;
-  }
-  sum = block_sum(sum, scratch);
-  for (int k = tid; k < a.K; k += SEL_THREADS) {
-    const float c = cscore[k] / sum;
-    cscore[k] = c;
     const size_t o = static_cast<size_t>(b) * a.K + k;
-    if (a.tr_clip_score) a.tr_clip_score[o] = c;
+    if (a.tr_clip_score) a.tr_clip_score[o] = cscore[k];
     if (a.tr_clip_ref) a.tr_clip_ref[o] = logit[k] / a.scale;
   }
   if (!a.probs) return;
-
-  if (a.senti) {  // softmax over K of the raw control scores (sentiments_classifer.py:46-47, temperature 1)
-    float smx = -INFINITY;
-    for (int k = tid; k < a.K; k += SEL_THREADS) smx = fmaxf(smx, a.senti[static_cast<size_t>(b) * a.K + k]);
-    smx = block_max(smx, scratch);
-    float ssum = 0.f;
-    for (int k = tid; k < a.K; k += SEL_THREADS) {
-      const float e = expf(a.senti[static_cast<size_t>(b) * a.K + k] - smx);
-      sprob[k] = e;
-      ssum += e;
-    }
-    ssum = block_sum(ssum, scratch);
-    for (int k = tid; k < a.K; k += SEL_THREADS) sprob[k] = sprob[k] / ssum;
-  }
+  if (a.senti) sel_softmax(a.senti + static_cast<size_t>(b) * a.K, a.K, sprob, scratch);
   __syncthreads();
 
   float bestv = -INFINITY;
   int besti = 0x7fffffff;
   for (int k = tid; k < a.K; k += SEL_THREADS) {
     const size_t o = static_cast<size_t>(b) * a.K + k;
-    float f = a.alpha * a.probs[o] + a.beta * cscore[k];
-    if (a.senti) {
-      f = f + a.gamma * sprob[k];
-      f = f + 0.1f * (1.0f - expf(a.repeats ? a.repeats[o] : 0.f));
-    }
+    const float f = sel_fuse(a, o, cscore[k], a.senti ? sprob[k] : 0.f);
     if (a.tr_final) a.tr_final[o] = f;
     if (f > bestv || (f == bestv && k < besti)) { bestv = f; besti = k; }
   }
-  // argmax, first index on ties (torch.argmax on CPU)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
-  }
-  float* rv = scratch;
-  int* ri = reinterpret_cast<int*>(scratch + 16);
-  __syncthreads();
-  if (lane == 0) { rv[w] = bestv; ri[w] = besti; }
-  __syncthreads();
+  int bi = sel_block_argmax(bestv, besti, scratch);  // first index on ties (torch.argmax on CPU)
   if (tid == 0) {
-    float bv = rv[0]; int bi = ri[0];
-    for (int ww = 1; ww < nw; ++ww)
-      if (rv[ww] > bv || (rv[ww] == bv && ri[ww] < bi)) { bv = rv[ww]; bi = ri[ww]; }
-    s_bestv = bv; s_besti = bi;
     if (bi < 0 || bi >= a.K) bi = 0;  // all-NaN row: fall back to candidate 0 like argmax of NaNs is undefined
-    const size_t o = static_cast<size_t>(b) * a.K + bi;
-    if (a.inp) a.inp[static_cast<size_t>(b) * a.L + a.pos] = a.ids_masked[o];    // gen_utils.py:79
-    if (a.out_clip_ref) a.out_clip_ref[b] = logit[bi] / a.scale;                  // gen_utils.py:80
-    if (a.out_senti && a.senti) a.out_senti[b] = a.senti[o];                      // control_gen_utils.py:63
-    if (a.tr_best) a.tr_best[b] = bi;
+    sel_write_winner(a, b, bi, logit[bi]);
   }
 }
 
@@ -413,7 +311,7 @@ bool topk_configure() {
 
 bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, float temperature, int K, float* probs,
                  int64_t* ids, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_TOPK, static_cast<double>(B) * V, st);
   if (K < 1 || K > 1024 || K > V) {
     set_error("topk: K must be in [1, min(1024, V)]");
@@ -431,34 +329,36 @@ bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, 
 }
 
 void launch_assemble(const AssembleArgs& a, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_ASSEMBLE, 0, st);
   launch_k(assemble_kernel, dim3(a.B), dim3(256), 0, st, a);
 }
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_MISC, 0, st);
   launch_k(step_prologue_kernel, dim3((B + 255) / 256), dim3(256), 0, st, inp, B, L, pos, mask_id, token_mask, dot_id, dot_allowed);
 }
 
-void launch_gather_rows_index(int32_t* rows, int B, int L, int pos, cudaStream_t st) {
-  ++g_launches;
-  ProfScope prof_(CAT_MISC, 0, st);
-  gather_rows_index_kernel<<<(B + 255) / 256, 256, 0, st>>>(rows, B, L, pos);
-}
-
 void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_MISC, 0, st);
   launch_k(pool_index_kernel, dim3((B * K + 255) / 256), dim3(256), 0, st, rows, eos_idx, B, P, K, S);
 }
 
+void launch_clip_logits(const float* text, const float* image, const int32_t* row_bk, int n_rows, int K, int D,
+                        float scale, float* logit, cudaStream_t st) {
+  count_launch();
+  ProfScope prof_(CAT_SELECT, static_cast<double>(n_rows) * D * 4, st);
+  if (n_rows <= 0) return;
+  launch_k(clip_logits_kernel, dim3((n_rows + 7) / 8), dim3(256), 0, st, text, image, row_bk, n_rows, K, D, scale, logit);
+}
+
 void launch_score_select(const SelectArgs& a, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_SELECT, 0, st);
-  const size_t smem = static_cast<size_t>(a.D + 3 * a.K + 40) * sizeof(float);
+  const size_t smem = static_cast<size_t>(3 * a.K + 40) * sizeof(float);
   launch_k(score_select_kernel, dim3(a.B), dim3(SEL_THREADS), smem, st, a);
 }
 

@@ -147,8 +147,7 @@ __global__ void bert_embed_ln_kernel(const int64_t* __restrict__ inp, int rows, 
 __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const int32_t* __restrict__ ids_suffix,
                                   const int32_t* __restrict__ p0, int B, int P, int K, int S, int maxpos,
                                   const float* __restrict__ tok, const float* __restrict__ pos, int H,
-                                  float* __restrict__ x, bf16* __restrict__ xb, float2* __restrict__ stats,
-                                  int stats_parts, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                  float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                   float ln_eps, bf16* __restrict__ ln_out, int ln_ld) {
   PDL_ENTRY();
   const int warps = blockDim.x >> 5;
@@ -170,21 +169,10 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
     const float* te = tok + static_cast<size_t>(id) * H;
     const float* pe = pos + static_cast<size_t>(position) * H;
     float* o = x + static_cast<size_t>(r) * H;
-    float s1 = 0.f, s2 = 0.f;
     for (int c = lane * 4; c < H; c += 128) {
       float4 a = *reinterpret_cast<const float4*>(te + c);
       float4 b = *reinterpret_cast<const float4*>(pe + c);
-      const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      *reinterpret_cast<float4*>(o + c) = v;
-      if (xb) {
-        store_act4(xb + static_cast<size_t>(r) * H, H, 0, c, v);
-        s1 += (v.x + v.y) + (v.z + v.w);
-        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      }
-    }
-    if (stats) {
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane < stats_parts) stats[static_cast<size_t>(r) * stats_parts + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+      *reinterpret_cast<float4*>(o + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
     }
     if (ln_out) {
       // LayerNorm 1 of the first block on the row this warp just produced (H == 512): same arithmetic as
@@ -198,28 +186,6 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
         v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
       }
       ln_row<4>(v, H, ln_g, ln_b, ln_eps, lane, nullptr, ln_out + static_cast<size_t>(r) * ln_ld, 0);
-    }
-  }
-}
-
-// LayerNorm -> Linear folding (see Epi in kernels.h).  One warp per output row n.
-__global__ void fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, int N, int K, bf16* __restrict__ w_out,
-                               float* __restrict__ s_out, float* __restrict__ bias_out) {
-  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
-    const float* wr = w + static_cast<size_t>(n) * K;
-    float s = 0.f, bb = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const bf16 h = __float2bfloat16_rn(gamma[k] * wr[k]);
-      w_out[static_cast<size_t>(n) * K + k] = h;
-      s += __bfloat162float(h);
-      bb = fmaf(beta[k], wr[k], bb);
-    }
-    s = warp_sum(s); bb = warp_sum(bb);
-    if (lane == 0) {
-      s_out[n] = s;
-      bias_out[n] = (bias ? bias[n] : 0.f) + bb;
     }
   }
 }
@@ -419,9 +385,9 @@ __device__ __forceinline__ void att_put16(uint8_t* tile, int dst0, int n_rows, i
   }
 }
 
-// NT key tiles of 8: up to NT*8 keys per tile; PIPE: register prefetch of the next tile; MINB: resident blocks per SM the
-// register budget is sized for (the kernel is latency bound: 24 warps per SM instead of 16 when the tiles are small)
-template <int NT, bool PIPE = false, int MINB = 2>
+// NT key tiles of 8: up to NT*8 keys per tile; MINB: resident blocks per SM the register budget is sized for (the
+// kernel is latency bound: 24 warps per SM instead of 16 when the tiles are small)
+template <int NT, int MINB = 2>
 __global__ void __launch_bounds__(256, MINB) attention_mma_kernel(AttnArgs a) {
   PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t att_smem[];
@@ -488,18 +454,6 @@ __global__ void __launch_bounds__(256, MINB) attention_mma_kernel(AttnArgs a) {
   const int lm_r = lane & 7, lm_m = lane >> 3;  // ldmatrix: row within the 8x8 matrix, matrix index
   const float sl2 = a.scale * 1.4426950408889634f;
 
-  // Software pipeline over the candidate tiles of this task (tiles of <= 16 own rows, the usual case): the q / k / v
-  // rows of tile i+1 are requested into registers before tile i is computed, so the warp waits for global memory
-  // once per task instead of once per tile.
-  const bool pipe = PIPE && !is_prefix && cpt * nq <= 16;
-  uint4 pk[4], pv[4], pq[4];
-  if (pipe) {
-    const int n0 = min(cpt, k1 - k0) * nq;
-    const int base0 = n_pre_rows + (b * a.K + k0) * a.S;
-    att_fetch16(qkv, ld, col_k, base0, n0, lane, pk);
-    att_fetch16(qkv, ld, col_v, base0, n0, lane, pv);
-    att_fetch16(qkv, ld, col_q, base0, n0, lane, pq);
-  }
   for (int k = k0; k < k1; k += cpt) {
     const int nc = min(cpt, k1 - k);
     const int n_own = nc * nq;          // query rows = own key rows of this iteration (contiguous in memory)
@@ -507,18 +461,7 @@ __global__ void __launch_bounds__(256, MINB) attention_mma_kernel(AttnArgs a) {
     const int own_base = is_prefix ? pre_base : n_pre_rows + (b * a.K + k) * a.S;
     const bool single = n_own <= 16;
     __syncwarp();
-    if (pipe) {
-      att_put16(sK, pl, n_own, lane, pk);
-      att_put16(sV, pl, n_own, lane, pv);
-      att_put16(sQ, 0, n_own, lane, pq);
-      if (k + cpt < k1) {
-        const int nn = min(cpt, k1 - (k + cpt)) * nq;
-        const int nbase = n_pre_rows + (b * a.K + k + cpt) * a.S;
-        att_fetch16(qkv, ld, col_k, nbase, nn, lane, pk);
-        att_fetch16(qkv, ld, col_v, nbase, nn, lane, pv);
-        att_fetch16(qkv, ld, col_q, nbase, nn, lane, pq);
-      }
-    } else if (single) {
+    if (single) {
       uint4 rk[4], rv[4], rq[4];
       att_fetch16(qkv, ld, col_k, own_base, n_own, lane, rk);
       att_fetch16(qkv, ld, col_v, own_base, n_own, lane, rv);
@@ -711,7 +654,7 @@ int row_grid(int rows, int warps_per_block) {
 }  // namespace
 
 void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, int ldd, int split, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_MISC, 0, st);
   const size_t total = static_cast<size_t>(rows) * (K / 4);
   int grid = static_cast<int>((total + 255) / 256);
@@ -722,7 +665,7 @@ void launch_f32_to_act(const float* src, int rows, int K, int lds, bf16* dst, in
 }
 
 void launch_im2col(const float* pix, int B, int S, int p, bf16* dst, int ldd, int split, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_EMBED, 0, st);
   const size_t total = static_cast<size_t>(B) * (S / p) * (S / p) * (3 * p * p / 4);
   int grid = static_cast<int>((total + 255) / 256);
@@ -733,7 +676,7 @@ void launch_im2col(const float* pix, int B, int S, int p, bf16* dst, int ldd, in
 
 void launch_vision_embed(const float* patch, const float* cls, const float* pos, int B, int T, int H, float* x,
                          cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_EMBED, 0, st);
   const size_t total = static_cast<size_t>(B) * T * (H / 4);
   int grid = static_cast<int>((total + 255) / 256);
@@ -743,7 +686,7 @@ void launch_vision_embed(const float* patch, const float* cls, const float* pos,
 }
 
 void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, int n, void* dst, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_MISC, 0, st);
   if (n <= 0) return;
   launch_k(gather_rows_kernel, dim3(row_grid(n, 8)), dim3(256), 0, st, static_cast<const uint8_t*>(src), row_bytes, rows, n,
@@ -751,7 +694,7 @@ void launch_gather_rows(const void* src, size_t row_bytes, const int32_t* rows, 
 }
 
 void launch_layernorm(const LNArgs& a, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_LN, static_cast<double>(a.n_rows) * a.H, st);
   if (a.n_rows <= 0) return;
   if (a.partials && a.n_parts > 4) { set_error("layernorm: at most 4 split-K partial sums"); return; }
@@ -769,7 +712,7 @@ void launch_layernorm(const LNArgs& a, cudaStream_t st) {
 void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word, const float* pos, const float* type,
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_EMBED, static_cast<double>(rows) * H, st);
   const int grid = row_grid(rows, 8);
   switch (H / 128) {
@@ -781,43 +724,48 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 }
 
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
-                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, bf16* xb,
-                       float2* stats, int stats_parts, cudaStream_t st, const float* ln_g, const float* ln_b, float ln_eps,
-                       bf16* ln_out, int ln_ld) {
-  ++g_launches;
+                       int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st,
+                       const float* ln_g, const float* ln_b, float ln_eps, bf16* ln_out, int ln_ld) {
+  count_launch();
   ProfScope prof_(CAT_EMBED, 0, st);
   const int rows = B * P + B * K * S;
   if (rows <= 0) return;
   if (ln_out && H != 512) { set_error("clip_embed: the fused LayerNorm needs hidden size 512"); return; }
   launch_k(clip_embed_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, st, ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
-                                                       x_f32, xb, stats, stats_parts, ln_g, ln_b, ln_eps, ln_out, ln_ld);
+                                                       x_f32, ln_g, ln_b, ln_eps, ln_out, ln_ld);
 }
 
-void launch_fold_ln(const float* w, const float* bias, const float* gamma, const float* beta, int N, int K, bf16* w_out,
-                    float* s_out, float* bias_out, cudaStream_t st) {
-  ++g_launches;
-  fold_ln_kernel<<<row_grid(N, 8), 256, 0, st>>>(w, bias, gamma, beta, N, K, w_out, s_out, bias_out);
+constexpr int ATT_WARPS = 8;
+constexpr size_t att_smem_bytes(int nt) { return static_cast<size_t>(ATT_WARPS) * ((nt + (nt + 1) / 2 * 2) * 1024 + 2048); }
+
+bool attention_configure() {
+  const int big = 220 * 1024;
+  return cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(att_smem_bytes(2))), "cudaFuncSetAttribute(attention_mma<2>)") &&
+         cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(att_smem_bytes(4))), "cudaFuncSetAttribute(attention_mma<4>)") &&
+         cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(att_smem_bytes(8))), "cudaFuncSetAttribute(attention_mma<8>)") &&
+         cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(att_smem_bytes(12))), "cudaFuncSetAttribute(attention_mma<12>)") &&
+         cuda_ok(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big),
+                 "cudaFuncSetAttribute(attention<f32>)") &&
+         cuda_ok(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big),
+                 "cudaFuncSetAttribute(attention<bf16>)");
 }
 
 bool launch_attention(const AttnArgs& a, cudaStream_t st) {
-  ++g_launches;
+  count_launch();
   ProfScope prof_(CAT_ATTN, 0, st);
   if (a.H != a.heads * HD) {
     set_error("attention: head_dim must be 64");
     return false;
   }
   const int nk_cap = a.P + a.S;
-  static int use_mma = -1;
-  if (use_mma < 0) {
-    const char* e = getenv("CONZIC_ATTN_MMA");
-    use_mma = e ? atoi(e) : 1;
-  }
-  if (!a.qkv_f32 && !a.split && use_mma && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
+  if (!a.qkv_f32 && !a.split && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
     AttnArgs aa = a;
     aa.cpt = (a.causal && a.S <= 8 && a.P + (16 / a.S) * a.S <= 96) ? 16 / a.S : 1;
     aa.cand_per_task = aa.cpt >= 4 ? 2 * aa.cpt : (aa.cpt > 1 ? ((8 + aa.cpt - 1) / aa.cpt) * aa.cpt : 8);
-    const char* pf = getenv("CONZIC_ATTN_PREFETCH");  // read per launch so tests can switch variants
-    aa.prefetch = pf ? atoi(pf) : 0;
     const int keys_cap = a.P + (aa.cpt > 1 ? aa.cpt * a.S : a.S);
     const int groups = (a.K + aa.cand_per_task - 1) / aa.cand_per_task;
     const long long tasks = (a.P > 0 ? static_cast<long long>(a.B) * a.heads : 0) +
@@ -827,46 +775,13 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     // 48 KB per block -> 3 resident blocks (24 warps) per SM instead of 2; the kernel is latency bound, measured
     // -12 % attention time, bit-identical.  With 17..32 keys the same trade (more warps, spills in the two-candidate
     // tile loop) measured 2-3 % slower per step, so those keep 2 blocks of 128-register threads.
-    const char* e3 = getenv("CONZIC_ATTN_OCC3");  // read per launch so one process can compare both; default on
-    const bool occ3 = (!e3 || atoi(e3)) && keys_cap <= 16 && !aa.prefetch;
-    const int warps = 8;
-    const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
-    const int nt = occ3 ? 2 : (keys_cap <= 32 ? 4 : (keys_cap <= 64 ? 8 : 12));
-    const size_t smem = static_cast<size_t>(warps) * ((nt + (nt + 1) / 2 * 2) * 1024 + 2048);
-    if (occ3) {
-      static bool cfg3 = false;
-      if (!cfg3) {
-        if (!cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<2, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (4 * 1024 + 2048)), "attr"))
-          return false;
-        cfg3 = true;
-      }
-      launch_k(attention_mma_kernel<2, false, 3>, dim3(grid), dim3(warps * 32), smem, st, aa);
-      return cuda_ok(cudaGetLastError(), "attention_mma launch");
-    }
-    static size_t configured[3] = {0, 0, 0};
-    const int which_nt = nt == 4 ? 0 : (nt == 8 ? 1 : 2);
-    if (smem > 48 * 1024 && smem > configured[which_nt]) {
-      cudaError_t e = nt == 4 ? cudaFuncSetAttribute(attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                    : nt == 8 ? cudaFuncSetAttribute(attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                              : cudaFuncSetAttribute(attention_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (!cuda_ok(e, "cudaFuncSetAttribute(attention_mma)")) return false;
-      configured[which_nt] = smem;
-    }
-    if (nt <= 8 && aa.prefetch) {
-      static bool pipe_cfg = false;
-      if (!pipe_cfg) {
-        if (!cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 4 * 1024 + 2048)), "attr") ||
-            !cuda_ok(cudaFuncSetAttribute(attention_mma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 8 * 1024 + 2048)), "attr"))
-          return false;
-        pipe_cfg = true;
-      }
-      if (nt == 4) launch_k(attention_mma_kernel<4, true>, dim3(grid), dim3(warps * 32), smem, st, aa);
-      else launch_k(attention_mma_kernel<8, true>, dim3(grid), dim3(warps * 32), smem, st, aa);
-      return cuda_ok(cudaGetLastError(), "attention_mma launch");
-    }
-    if (nt == 4) launch_k(attention_mma_kernel<4>, dim3(grid), dim3(warps * 32), smem, st, aa);
-    else if (nt == 8) launch_k(attention_mma_kernel<8>, dim3(grid), dim3(warps * 32), smem, st, aa);
-    else launch_k(attention_mma_kernel<12>, dim3(grid), dim3(warps * 32), smem, st, aa);
+    const unsigned grid = static_cast<unsigned>((tasks + ATT_WARPS - 1) / ATT_WARPS);
+    const int nt = keys_cap <= 16 ? 2 : (keys_cap <= 32 ? 4 : (keys_cap <= 64 ? 8 : 12));
+    const size_t smem = att_smem_bytes(nt);
+    if (nt == 2) launch_k(attention_mma_kernel<2, 3>, dim3(grid), dim3(ATT_WARPS * 32), smem, st, aa);
+    else if (nt == 4) launch_k(attention_mma_kernel<4>, dim3(grid), dim3(ATT_WARPS * 32), smem, st, aa);
+    else if (nt == 8) launch_k(attention_mma_kernel<8>, dim3(grid), dim3(ATT_WARPS * 32), smem, st, aa);
+    else launch_k(attention_mma_kernel<12>, dim3(grid), dim3(ATT_WARPS * 32), smem, st, aa);
     return cuda_ok(cudaGetLastError(), "attention_mma launch");
   }
   if (nk_cap > 32 * MAX_SLOTS) {
@@ -885,14 +800,6 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  static size_t configured[2] = {0, 0};
-  const int which = a.qkv_f32 ? 1 : 0;
-  if (smem > 48 * 1024 && smem > configured[which]) {
-    cudaError_t e = a.qkv_f32 ? cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
-                              : cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (!cuda_ok(e, "cudaFuncSetAttribute(attention)")) return false;
-    configured[which] = 220 * 1024;
-  }
   if (a.qkv_f32)
     launch_k(attention_kernel<true>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap);
   else

@@ -6,12 +6,15 @@ below lands in a hand-written sm_100a kernel.  Nothing here falls back to torch 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
 
 from . import _lib
-from . import synth as _dims
+from . import defaults as _dims
+
+PRECISIONS = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "certified": _lib.PREC_CERTIFIED}
 
 SD = Dict[str, torch.Tensor]
 
@@ -65,15 +68,24 @@ class Engine:
     `generate_caption_step` and `CLIP.compute_text_representation / ..._similarity_via_embeddings` compute in the
     reference (gen_utils.py:64-81, clip/clip.py:64-98)."""
 
-    def __init__(self, bert_sd: SD, clip_sd: SD, device="cuda:0", precision: str = "bf16",
+    def __init__(self, bert_sd: SD, clip_sd: SD, device="cuda:0", precision: str = "certified",
                  gemm_impl: str = "tcgen05", special_ids: Sequence[int] = _dims.SPECIAL_IDS,
                  dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
-                 clip_chunk_rows: int = 0):
+                 clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_fcap: Optional[int] = None,
+                 ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None):
+        """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
+        in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
+        are read once, here: cert_dcos / cert_fcap (CONZIC_CERT_DCOS / CONZIC_CERT_FCAP), ln_standalone
+        (CONZIC_LN_STANDALONE=1) and pdl (CONZIC_PDL=0) exist for A/B measurements."""
         if not torch.cuda.is_available():
             raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
+        if self.device.index is None:  # clip.to("cuda") in the reference's scripts
+            self.device = torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
         self.precision = precision
         nb = _count_layers(bert_sd, "bert.encoder.layer.{}.attention.self.query.weight")
         nc = _count_layers(clip_sd, "text_model.encoder.layers.{}.layer_norm1.weight")
@@ -93,9 +105,17 @@ class Engine:
         cfg.clip_ln_eps = _dims.CLIP_LN_EPS
         cfg.pad_id, cfg.unk_id, cfg.cls_id, cfg.sep_id, cfg.mask_id = [int(x) for x in special_ids]
         cfg.dot_id, cfg.clip_bos, cfg.clip_eos = int(dot_id), int(clip_bos), int(clip_eos)
-        cfg.precision = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}[precision]
+        cfg.precision = PRECISIONS[precision]
         cfg.gemm_impl = {"tcgen05": _lib.GEMM_TCGEN05, "simt_debug": _lib.GEMM_SIMT_DEBUG}[gemm_impl]
         cfg.clip_chunk_rows = int(clip_chunk_rows)
+        env = os.environ.get
+        cfg.cert_dcos = float(cert_dcos if cert_dcos is not None else env("CONZIC_CERT_DCOS", 0.0))
+        cfg.cert_fcap = int(cert_fcap if cert_fcap is not None else env("CONZIC_CERT_FCAP", 0))
+        if ln_standalone is None:
+            ln_standalone = env("CONZIC_LN_STANDALONE", "0") == "1"
+        if pdl is None:
+            pdl = env("CONZIC_PDL", "1") != "0"
+        cfg.flags = (_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL)
         self.cfg = cfg
         self.V, self.D = cfg.bert_vocab, cfg.clip_proj
         self.ldl = (self.V + 3) & ~3
@@ -147,6 +167,14 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.conzic_launch_count(self.ctx))
+
+    CERT_STAT_NAMES = ("calls", "images", "rescored_candidates", "images_multi", "images_full_overflow", "images_full")
+
+    def cert_stats(self) -> Dict[str, int]:
+        """Certified-argmax bookkeeping since the engine was created (conzic_cert_stats); zeros in other modes."""
+        arr = (C.c_uint64 * _lib.CERT_STATS)()
+        _lib.check(self.lib.conzic_cert_stats(self.ctx, arr, _lib.CERT_STATS), "conzic_cert_stats")
+        return {n: int(arr[i]) for i, n in enumerate(self.CERT_STAT_NAMES)}
 
     PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed", "topk", "assemble", "select", "misc",
                           "gemm_small")
@@ -322,21 +350,31 @@ class Engine:
         return score, ref
 
     def score_select(self, text_embeds, image_embeds, probs, ids_masked, inp, pos, alpha, beta, gamma=None,
-                     senti_raw=None, repeats=None, out_clip_ref=None, out_senti=None, out_best=None):
+                     senti_raw=None, repeats=None, out_clip_ref=None, out_senti=None, out_best=None, clip_ids=None):
         """Score fuse + argmax + write-back (gen_utils.py:77-81, control_gen_utils.py:59-65) on caller-built
-        candidate embeddings; `inp[:, pos]` receives the winners, `out_best` (int64[B], optional) their index."""
+        candidate embeddings; `inp[:, pos]` receives the winners, `out_best` (int64[B], optional) their index.
+        `clip_ids` int32[B*K, T]: the CLIP id rows `text_embeds` was encoded from -- required by the certified
+        precision (candidates the bf16 scores cannot rule out are re-encoded exactly), ignored otherwise."""
         B, K = probs.shape
+        T = 0
+        if clip_ids is not None:
+            clip_ids = clip_ids.to(self.device, torch.int32).contiguous()
+            T = int(clip_ids.shape[1])
+        elif self.precision == "certified":
+            raise ValueError("score_select: the certified precision needs clip_ids")
+        ws = self.workspace(B, inp.shape[1], K)
         if out_clip_ref is None:
             out_clip_ref = torch.empty((B,), dtype=torch.float32, device=self.device)
         ctl = gamma is not None
         if ctl and out_senti is None:
             out_senti = torch.empty((B,), dtype=torch.float32, device=self.device)
-        rc = self.lib.conzic_score_select(self.ctx, _ptr(text_embeds.contiguous()), _ptr(image_embeds.contiguous()), B, K,
+        rc = self.lib.conzic_score_select(self.ctx, _ptr(text_embeds.contiguous()), _ptr(image_embeds.contiguous()),
+                                          _ptr(clip_ids), T, B, K,
                                           self.logit_scale_exp, _ptr(probs.contiguous()), _ptr(ids_masked.contiguous()),
                                           _ptr(senti_raw if ctl else None), _ptr(repeats if ctl else None),
                                           float(alpha), float(beta), float(gamma) if ctl else 0.0, _ptr(inp),
                                           inp.shape[1], int(pos), _ptr(out_clip_ref), _ptr(out_senti if ctl else None),
-                                          _ptr(out_best), self._stream())
+                                          _ptr(out_best), _ptr(ws), ws.numel(), self._stream())
         _lib.check(rc, "conzic_score_select")
         return out_clip_ref, (out_senti if ctl else None)
 
@@ -350,19 +388,6 @@ class Engine:
                                           _ptr(resid), M, N, K, int(act), _ptr(out), _ptr(ws), ws.numel(),
                                           self._stream())
         _lib.check(rc, "conzic_debug_linear")
-        return out
-
-    def debug_mlp(self, X, W1, b1, W2, b2, act: int = 1):
-        """X + fc2(act(fc1(X))) through the fused persistent MLP kernel (bf16 mode)."""
-        M, H = X.shape
-        F = W1.shape[0]
-        out = torch.empty((M, H), dtype=torch.float32, device=self.device)
-        need = (M * H + 2 * H * F + 160 * 128 * F) * 2 + 8192
-        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        rc = self.lib.conzic_debug_mlp(self.ctx, _ptr(X.contiguous()), _ptr(W1.contiguous()), _ptr(b1),
-                                       _ptr(W2.contiguous()), _ptr(b2), M, H, F, int(act), _ptr(out), _ptr(ws),
-                                       ws.numel(), self._stream())
-        _lib.check(rc, "conzic_debug_mlp")
         return out
 
     # ------------------------------------------------------------------ the fused step

@@ -41,6 +41,10 @@ class _Chain:
         # pass for just the captions that contain a piece
         self.string_path = os.environ.get("CONZIC_STRING_PATH") == "1"
         self.hybrid = bool(getattr(eng, "needs_host_ids", None)) and not self.string_path
+        if self.hybrid and eng.precision == "certified":
+            # the hybrid step patches host-encoded rows into the embedding matrix and has no CLIP ids for the certified
+            # re-score: vocabularies with '##' pieces take the string path under the certified precision
+            self.hybrid, self.string_path = False, True
         self.tokenizer, self.max_len, self.B = tokenizer, max_len, batch_size
         self.seed_len = len(prompt.split()) + 1
         batch = get_init_text(tokenizer, prompt, max_len, batch_size)
@@ -81,7 +85,8 @@ class _Chain:
         cand[:, :, pos] = ids_masked_h
         flat = cand.view(-1, cand.shape[-1])
         texts = tok.batch_decode(flat, skip_special_tokens=True)
-        text_embeds = self.clip.compute_text_representation(texts)
+        clip_ids = self.clip.tokenize_texts(texts).to(eng.device, torch.int32)
+        text_embeds = eng.clip_text_encode(clip_ids)
         senti_raw = repeats = best = None
         if pos_scorer is not None:
             # POS template (control_gen_utils.py:164-168): softmax_K(score / 0.1), no repeat penalty; the winner's
@@ -98,7 +103,8 @@ class _Chain:
             repeats = ((ids_masked_h[:, :, None] == cand).float().sum(2) - 1).to(eng.device).contiguous()
         eng.score_select(text_embeds, self.image_embeds, probs, ids_masked_h.to(eng.device), self.inp, pos, alpha, beta,
                          gamma=gamma, senti_raw=senti_raw, repeats=repeats, out_clip_ref=self.clip_slots[slot],
-                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None, out_best=best)
+                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None, out_best=best,
+                         clip_ids=clip_ids)
         if best is not None:
             win = best.cpu()
             self.pos_scores = raw.gather(1, win.view(-1, 1)).squeeze(-1).numpy().tolist()

@@ -1,23 +1,38 @@
 """Binds the caller's (model, clip, tokenizer) objects -- duck-typed exactly as loosely as the reference
-treats them -- to one libconzic context per weight pair, and caches it."""
+treats them -- to one libconzic context per (weights, tokenizer, device, precision), and caches it."""
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import synth, tokens
+from . import defaults, tokens
 from .engine import Engine
 
-_engines: Dict[Tuple[int, int, str], Engine] = {}
+_engines: Dict[tuple, Engine] = {}
 _last: Optional[Engine] = None
 _tables: Dict[Tuple[int, int], tuple] = {}
 
 
 def default_precision() -> str:
-    """bf16 operands by default; CONZIC_PRECISION=bf16x3 selects the 3-pass split mode used for id parity."""
-    return os.environ.get("CONZIC_PRECISION", "bf16")
+    """"certified" unless CONZIC_PRECISION says otherwise (read when an engine is created):
+    certified -- BERT / image tower in bf16x3, CLIP text tower in bf16 + exact re-score of every candidate the bf16
+                 scores cannot rule out: the reference's token ids at close to bf16 speed;
+    bf16x3    -- everything in the 3-pass split mode (fp32-grade; what `certified` is checked against);
+    bf16      -- everything in bf16 (tolerance-only parity)."""
+    return os.environ.get("CONZIC_PRECISION", "certified")
+
+
+def resolve_device(dev) -> torch.device:
+    """`clip.to("cuda")` in the reference gives an index-less device; the engine needs a concrete one."""
+    d = torch.device(dev) if dev is not None else torch.device("cuda")
+    if d.type != "cuda":
+        d = torch.device("cuda")
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
 
 
 def _dummy_bert_sd():
@@ -31,37 +46,56 @@ def _dummy_bert_sd():
             "bert.encoder.layer.0.intermediate.dense.weight": z(H, H)}
 
 
+def _evict(key):
+    global _last
+    eng = _engines.pop(key, None)
+    if eng is not None:
+        if _last is eng:
+            _last = None
+        eng.close()
+
+
 def engine_for(model, clip, tokenizer=None, precision: Optional[str] = None, device=None) -> Engine:
     """The engine holding `model`'s BERT weights and `clip`'s text tower.  Either may be None when only the
     other side is needed (the missing side is replaced by a 0-layer placeholder, or by the last engine that
-    already holds the side that is present)."""
+    already holds the side that is present).  Engines are evicted when their model / clip object is collected."""
     global _last
     precision = precision or default_precision()
+    dev = resolve_device(device or getattr(clip, "device", None))
     if model is None or clip is None:
-        for (mid, cid, pr), e in _engines.items():
-            if pr == precision and ((model is None and cid == id(clip)) or (clip is None and mid == id(model))):
+        for (mid, cid, tid, pr, dv), e in _engines.items():
+            if pr == precision and dv == str(dev) and ((model is None and cid == id(clip)) or
+                                                       (clip is None and mid == id(model))):
                 return e
-    key = (id(model), id(clip), precision)
+    tid = id(tokenizer) if tokenizer is not None else 0
+    key = (id(model), id(clip), tid, precision, str(dev))
     if key in _engines:
         return _engines[key]
     if clip is None:
         raise RuntimeError("no engine holds this model yet; call generate_caption or engine_for(model, clip) first")
+    if tokenizer is None:  # any engine of these weights will do for tokenizer-free calls (CLIP-only methods)
+        for k, e in _engines.items():
+            if k[0] == id(model) and k[1] == id(clip) and k[3] == precision and k[4] == str(dev):
+                return e
     bert_sd = model.state_dict() if model is not None else _dummy_bert_sd()
-    dev = device or getattr(clip, "device", None) or "cuda:0"
-    if torch.device(dev).type != "cuda":
-        dev = "cuda:0"
     kw = {}
     if tokenizer is not None:
-        sp = [getattr(tokenizer, n, d) for n, d in (("pad_token_id", synth.PAD_ID), ("unk_token_id", synth.UNK_ID),
-                                                    ("cls_token_id", synth.CLS_ID), ("sep_token_id", synth.SEP_ID),
-                                                    ("mask_token_id", synth.MASK_ID))]
-        kw["special_ids"] = [synth.SPECIAL_IDS[i] if s is None else int(s) for i, s in enumerate(sp)]
+        sp = [getattr(tokenizer, n, d) for n, d in (("pad_token_id", defaults.PAD_ID), ("unk_token_id", defaults.UNK_ID),
+                                                    ("cls_token_id", defaults.CLS_ID), ("sep_token_id", defaults.SEP_ID),
+                                                    ("mask_token_id", defaults.MASK_ID))]
+        kw["special_ids"] = [defaults.SPECIAL_IDS[i] if s is None else int(s) for i, s in enumerate(sp)]
         kw["dot_id"] = int(tokenizer.vocab["."])
     eng = Engine(bert_sd, clip.state_dict(), device=dev, precision=precision, **kw)
     if tokenizer is not None and model is not None:
         bind_tokenizers(eng, tokenizer, clip.tokenizer)
     _engines[key] = eng
     _last = eng
+    for obj in (model, clip, tokenizer):  # id() values are reused after collection: drop the engine with its owners
+        if obj is not None:
+            try:
+                weakref.finalize(obj, _evict, key)
+            except TypeError:
+                pass
     return eng
 
 
@@ -69,18 +103,13 @@ def bind_tokenizers(eng: Engine, bert_tokenizer, clip_tokenizer):
     """Builds (once per tokenizer pair) and uploads the BERT-id -> CLIP-id table."""
     key = (id(bert_tokenizer), id(clip_tokenizer))
     if key not in _tables:
-        if type(bert_tokenizer) is synth.SynthBertTokenizer and type(clip_tokenizer) is synth.SynthCLIPTokenizer:
-            off, tok = synth.build_bert2clip_table(clip_tokenizer.multi)
-            needs_host = []
-        else:
-            off, tok, needs_host = tokens.build_bert2clip(bert_tokenizer, clip_tokenizer, eng.V,
-                                                          [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id,
-                                                           eng.cfg.sep_id, eng.cfg.mask_id])
-        _tables[key] = (off, tok, needs_host)
+        _tables[key] = tokens.build_bert2clip(bert_tokenizer, clip_tokenizer, eng.V,
+                                              [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id,
+                                               eng.cfg.mask_id])
     off, tok, needs_host = _tables[key]
     eng.set_bert2clip(off, tok)
     eng.needs_host_ids = needs_host
-    # host copies for the hybrid path of vocabularies with '##' pieces (tokens.plan_hybrid)
+    # host copies for the hybrid path of vocabularies with '##' pieces (tokens.hybrid_flags)
     eng.piece_mask_h = torch.zeros(eng.V, dtype=torch.bool)
     if needs_host:
         eng.piece_mask_h[torch.tensor(needs_host, dtype=torch.long)] = True
@@ -95,7 +124,8 @@ def any_engine() -> Engine:
 
 def clear():
     global _last
-    for e in _engines.values():
+    for e in list(_engines.values()):
         e.close()
     _engines.clear()
+    _tables.clear()
     _last = None

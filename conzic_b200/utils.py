@@ -56,10 +56,7 @@ def update_token_mask(tokenizer, token_mask, max_len, index):
 
 
 def format_output(sample_num, FinalCaption, BestCaption):
-    """Same dictionary layout the reference's demo prints (utils.py:61-74)."""
-    if sample_num == 1:
-        return {"FinalCaption": FinalCaption[0], "BestCaption": BestCaption[0]}
-    out = {}
-    for i in range(sample_num):
-        out[f"Sample{i + 1}"] = {"FinalCaption": FinalCaption[i], "BestCaption": BestCaption[i]}
-    return out
+    """(final, best): the first `sample_num` captions of each list joined by newlines, at most five -- the two
+    strings the reference's Gradio front end shows (utils.py:61-74)."""
+    n = min(max(int(sample_num), 1), 5)
+    return "\n".join(f"{c}" for c in FinalCaption[:n]), "\n".join(f"{c}" for c in BestCaption[:n])

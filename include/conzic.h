@@ -9,7 +9,9 @@
  *   - every pointer marked "dev" is a DEVICE pointer owned by the caller (PyTorch tensors in practice);
  *     "host" pointers are ordinary host memory; nothing here allocates or frees caller memory;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the
- *     device, no call copies device->host;
+ *     device or copies device->host -- with ONE exception: in CONZIC_PREC_CERTIFIED mode conzic_gibbs_step and
+ *     conzic_score_select read two 64-byte counter blocks back per call (how many candidates need the exact
+ *     re-score) and wait for the stream each time;
  *   - scratch memory is one caller-owned device buffer `ws` of at least conzic_workspace_bytes();
  *   - return value: 0 = ok, negative = error; conzic_last_error() gives the message (thread local);
  *   - integer ids are int64 where the reference holds torch.long tensors, int32 for CLIP ids.
@@ -25,14 +27,31 @@
 extern "C" {
 #endif
 
-#define CONZIC_ABI_VERSION 5
+#define CONZIC_ABI_VERSION 6
 
 typedef struct conzic_ctx conzic_ctx;
 
 /* arithmetic mode of the GEMM operands (accumulation, LayerNorm, softmax, scores are always fp32) */
 enum {
-  CONZIC_PREC_BF16 = 0,      /* bf16 operands, one tcgen05.mma per k-step (throughput mode)            */
-  CONZIC_PREC_BF16X3 = 1     /* each fp32 operand split hi+lo bf16, 3 MMAs per k-step (parity mode)   */
+  CONZIC_PREC_BF16 = 0,      /* bf16 operands everywhere, one tcgen05.mma per k-step (tolerance-only parity)      */
+  CONZIC_PREC_BF16X3 = 1,    /* every fp32 operand split hi+lo bf16, 3 MMAs per k-step: fp32-grade, the reference's
+                                token ids (the exact mode the other two are judged against)                        */
+  CONZIC_PREC_CERTIFIED = 2  /* the default of the Python layer: BERT and the image tower in bf16x3 (so the top-K set,
+                                its probabilities and the image embedding are the exact ones), the CLIP text tower in
+                                bf16 over all K candidates, then a certified argmax: every candidate the bf16 scores
+                                cannot rule out (error bound cert_dcos) is re-encoded by a bf16x3 copy of the tower and
+                                the decision is taken on exact scores -- same winners and same reported cosines as
+                                CONZIC_PREC_BF16X3 (gen_utils.py:77-80), at close to bf16 speed                     */
+};
+#define CONZIC_CERT_DCOS_DEFAULT 4e-3f   /* bound on |cos(bf16 tower) - cos(bf16x3 tower)| of one candidate; measured
+                                            maximum on the config-2 workload x safety factor */
+#define CONZIC_CERT_STATS 8
+
+/* conzic_config.flags */
+enum {
+  CONZIC_FLAG_NO_PDL = 1,         /* launch without programmatic dependent launch (A/B measurements)                */
+  CONZIC_FLAG_LN_STANDALONE = 2   /* CLIP bf16 tower: LayerNorm as its own kernel instead of in the O-proj / fc2
+                                     epilogues (A/B measurements; HF:models/clip/modeling_clip.py:369-384)          */
 };
 
 /* GEMM implementation: 0 is the product path; 1 is a slow SIMT kernel kept for cross-checking in tests */
@@ -52,6 +71,9 @@ typedef struct conzic_config {
   int32_t precision;           /* CONZIC_PREC_* */
   int32_t gemm_impl;           /* CONZIC_GEMM_* */
   int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (303104 = 16 waves of 148 x 128-row tiles) */
+  float cert_dcos;             /* CERTIFIED: bound on the cosine error of the bf16 tower; 0 = CONZIC_CERT_DCOS_DEFAULT */
+  int32_t cert_fcap;           /* CERTIFIED: an image with more unbeaten candidates than this is re-encoded in full; 0 = 16 */
+  int32_t flags;               /* CONZIC_FLAG_* */
 } conzic_config;
 
 /* ---- weight tables: arrays of fp32 DEVICE pointers in this order (HF state-dict tensors) -------------
@@ -137,19 +159,23 @@ int conzic_image_text_similarity(conzic_ctx* ctx, const float* text_embeds_dev, 
                                  void* stream);
 
 /* Score fuse + argmax + write-back on its own (gen_utils.py:77-81, control_gen_utils.py:59-65), for callers that
- * build the candidate texts themselves (host string path for vocabularies with '##' word pieces):
+ * build the candidate texts themselves (host string path: POS-template control needs every caption as a string):
  *   final = alpha*probs + beta*softmax_K(scale*cos) (+ gamma*softmax_K(senti_raw) + 0.1*(1-exp(repeats)));
  *   inp[b,pos] = ids_masked[b, argmax]; out_clip_ref[b] = cos of the winner; out_senti[b] = senti_raw of the winner;
  *   out_best[b] = argmax (int64, may be NULL) -- the POS-template path needs it to pick the winner's tag
  *   sequence and raw score on the host (control_gen_utils.py:171-178).
  * A control term with its own softmax temperature t (POS: 0.1, control_gen_utils.py:166) passes senti_raw = raw / t
  * and repeats = NULL (no repeat penalty in that formula).
- * text f32[B*K,D], image f32[B,D], probs f32[B,K], ids_masked int64[B,K], senti_raw / repeats f32[B,K] or NULL. */
-int conzic_score_select(conzic_ctx* ctx, const float* text_embeds_dev, const float* image_embeds_dev, int B, int K,
-                        float logit_scale_exp, const float* probs_dev, const int64_t* ids_masked_dev,
-                        const float* senti_raw_dev, const float* repeats_dev, float alpha, float beta, float gamma,
-                        int64_t* inp_dev, int L, int pos, float* out_clip_ref_dev, float* out_senti_dev,
-                        int64_t* out_best_dev, void* stream);
+ * text f32[B*K,D] (from conzic_clip_text_encode), image f32[B,D], probs f32[B,K], ids_masked int64[B,K],
+ * senti_raw / repeats f32[B,K] or NULL.  clip_ids int32[B*K,T] = the rows text was encoded from: required in
+ * CERTIFIED mode (unbeaten candidates are re-encoded from them by the exact tower), ignored otherwise.
+ * ws: conzic_workspace_bytes(ctx, B, L, K). */
+int conzic_score_select(conzic_ctx* ctx, const float* text_embeds_dev, const float* image_embeds_dev,
+                        const int32_t* clip_ids_dev, int T, int B, int K, float logit_scale_exp,
+                        const float* probs_dev, const int64_t* ids_masked_dev, const float* senti_raw_dev,
+                        const float* repeats_dev, float alpha, float beta, float gamma, int64_t* inp_dev, int L,
+                        int pos, float* out_clip_ref_dev, float* out_senti_dev, int64_t* out_best_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
 
 /* One whole Gibbs step (gen_utils.py:66-81, control_gen_utils.py:45-67) with no host round trip:
  *   token_mask[dot_id] = dot_allowed; inp[:,pos] = [MASK]; BERT row logits; top-K; candidates -> CLIP ids
@@ -189,8 +215,15 @@ typedef struct conzic_step_args {
 
 int conzic_gibbs_step(conzic_ctx* ctx, const conzic_step_args* args, void* ws_dev, size_t ws_bytes, void* stream);
 
-/* Counters: kernels launched by this library since the context was created (bench.py "gpu_launches"). */
+/* Counters: kernels launched for this context since it was created (bench.py "gpu_launches"). */
 uint64_t conzic_launch_count(const conzic_ctx* ctx);
+
+/* CERTIFIED mode bookkeeping since the context was created, out[0..n): 0 selection calls, 1 images decided,
+ * 2 candidates re-encoded exactly (one per image at least: the winner's reported cosine is always the exact one),
+ * 3 images with more than one unbeaten candidate after the bf16 pass, 4 images sent to the full exact re-encode
+ * because more than cert_fcap candidates were unbeaten, 5 images fully re-encoded in total (4 + those the exact
+ * re-score of the unbeaten candidates still could not order).  Zeros in the other modes. */
+int conzic_cert_stats(const conzic_ctx* ctx, uint64_t* out, int n);
 
 /* Optional device timing by kernel category (CUDA events around each launch, on the launching stream).
  * Categories: 0 persistent pair GEMM (CLIP / vision towers; work = executed FLOPs), 1 attention, 2 LayerNorm,
@@ -202,8 +235,9 @@ int conzic_profile_read(conzic_ctx* ctx, int category, double* ms, double* work,
 /* Plain GEMM entry used by tests and the roofline microbench:
  *   out[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ resid), A/W fp32 dev, converted internally to the
  *   context's operand format; exercises exactly the kernel the towers use.  act: 0 none, 1 quick_gelu,
- *   2 erf-gelu; act | 16 routes the result through the kernel's bf16 activation output (bf16 mode, no
- *   residual) before it is widened into out.  out fp32[M,N]. */
+ *   2 erf-gelu; act | 16 routes the result through the kernel's bf16 activation output (bf16 operands, no
+ *   residual) before it is widened into out; act | 32 (CERTIFIED contexts) uses the exact tower's operand format and
+ *   kernel instead of the bf16 one.  out fp32[M,N]. */
 int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev, const float* bias_dev,
                         const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
@@ -225,13 +259,6 @@ size_t conzic_vision_workspace_bytes(const conzic_ctx* ctx, int B);
  * f32[B,proj] dev (not L2-normalised, like compute_image_representation_from_image_instance). */
 int conzic_clip_image_encode(conzic_ctx* ctx, const float* pixel_values_dev, int B, float* image_embeds_dev,
                              void* ws_dev, size_t ws_bytes, void* stream);
-
-/* Fused MLP entry used by tests: out[M,H] = X + fc2(act(fc1(X))) with X f32[M,H] (the residual; its bf16
- * rounding is the GEMM operand), W1 f32[F,H], b1[F], W2 f32[H,F], b2[H] -- one launch of the persistent
- * fc1+fc2 kernel the CLIP tower uses (HF:models/clip/modeling_clip.py:347-351,380-384).  bf16 mode only. */
-int conzic_debug_mlp(conzic_ctx* ctx, const float* X_dev, const float* W1_dev, const float* b1_dev,
-                     const float* W2_dev, const float* b2_dev, int M, int H, int F, int act, float* out_dev,
-                     void* ws_dev, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def synth_weights():
     """Synthetic HF-keyed state dicts, generated once per session (about 10 s)."""
-    from conzic_b200 import synth
+    from synthetic import synth
     cache = {}
 
     def get(kind, peaked=False):

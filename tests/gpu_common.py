@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from conzic_b200 import synth  # noqa: E402
+from synthetic import synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 _SD = {}
@@ -25,12 +25,13 @@ def weights(kind, peaked=False):
     return _SD[key]
 
 
-def engine(precision="bf16x3", impl="tcgen05", peaked=False, multi=False):
-    """Engines are cached per configuration (weights upload takes a few seconds)."""
+def engine(precision="bf16x3", impl="tcgen05", peaked=False, multi=False, **kw):
+    """Engines are cached per configuration (weights upload takes a few seconds).  `kw`: Engine keyword
+    arguments (cert_dcos, cert_fcap, ln_standalone ...)."""
     from conzic_b200.engine import Engine
-    key = (precision, impl, peaked, multi)
+    key = (precision, impl, peaked, multi, tuple(sorted(kw.items())))
     if key not in _ENG:
-        e = Engine(weights("bert", peaked), weights("clip"), device="cuda:0", precision=precision, gemm_impl=impl)
+        e = Engine(weights("bert", peaked), weights("clip"), device="cuda:0", precision=precision, gemm_impl=impl, **kw)
         off, tok = synth.build_bert2clip_table(multi)
         e.set_bert2clip(off, tok)
         _ENG[key] = e
@@ -59,7 +60,9 @@ def visible_counts(inp_row_batch: torch.Tensor, pos: int):
 
 def replay_fixture(eng, g, max_steps=None):
     """Teacher-forced replay of every recorded step of a golden fixture through conzic_gibbs_step.
-    Returns a dict of worst-case error magnitudes and mismatch counts."""
+    Returns a dict of worst-case error magnitudes and mismatch counts.  CLIP cosines are compared candidate by
+    candidate wherever the same id is in both top-k lists (the cosine depends on the caption only); the softmax
+    score and the winner of an image are compared whenever that image's top-k id SET matches the reference's."""
     case = g["case"]
     n, K = case["n"], case["K"]
     gamma = case.get("gamma")
@@ -69,7 +72,8 @@ def replay_fixture(eng, g, max_steps=None):
     dev = eng.device
     table_d = table.to(dev) if gamma is not None else None
     m = dict(steps=0, logit_err=0.0, prob_relerr=0.0, topk_id_mismatch=0, clip_ref_err=0.0, clip_score_err=0.0,
-             final_err=0.0, winner_mismatch=0, winner_checked=0, min_margin_at_mismatch=None, dot_mismatch=0)
+             winner_cos_err=0.0, winner_mismatch=0, winner_checked=0, min_margin_at_mismatch=None, dot_mismatch=0,
+             cos_checked=0)
     steps = g["steps"][:max_steps] if max_steps else g["steps"]
     for si, s in enumerate(steps):
         inp = s["inp"].clone().to(dev)
@@ -82,6 +86,7 @@ def replay_fixture(eng, g, max_steps=None):
                                              gamma=gamma, senti_table=table_d, trace=True)
         torch.cuda.synchronize()
         tr = {k: v.cpu() for k, v in tr.items()}
+        clip_ref = clip_ref.cpu()
         m["steps"] += 1
         if float(token_mask[0, synth.DOT_ID]) != s["token_mask_dot"]:
             m["dot_mismatch"] += 1
@@ -101,19 +106,35 @@ def replay_fixture(eng, g, max_steps=None):
         if bool((same & nz).any()):
             pr = ((tr["probs"] - s["probs"]).abs() / s["probs"].clamp_min(1e-30))[same & nz]
             m["prob_relerr"] = max(m["prob_relerr"], float(pr.max()))
-        if bool(same.all()):
-            m["clip_ref_err"] = max(m["clip_ref_err"], float((tr["clip_ref"] - s["clip_ref"]).abs().max()))
-            m["clip_score_err"] = max(m["clip_score_err"], float((tr["clip_score"] - s["clip_score"]).abs().max()))
+        has_next = si + 1 < len(g["steps"]) and g["steps"][si + 1]["pos"] != pos
+        for b in range(inp.shape[0]):
+            ref_ids, got_ids = s["idxs"][b].tolist(), tr["idxs"][b].tolist()
+            where = {}
+            for k, v in enumerate(ref_ids):
+                where.setdefault(v, k)  # masked candidates repeat id 0: first slot
+            pairs = [(k, where[v]) for k, v in enumerate(got_ids) if v in where]
+            if pairs:
+                gk = torch.tensor([a for a, _ in pairs])
+                rk = torch.tensor([c for _, c in pairs])
+                if eng.precision != "certified":  # certified: only re-scored candidates carry exact cosines
+                    m["clip_ref_err"] = max(m["clip_ref_err"], float((tr["clip_ref"][b][gk] - s["clip_ref"][b][rk]).abs().max()))
+                    m["cos_checked"] += len(pairs)
+            if sorted(ref_ids) != sorted(got_ids):
+                continue
+            if bool(same[b].all()) and eng.precision != "certified":
+                m["clip_score_err"] = max(m["clip_score_err"], float((tr["clip_score"][b] - s["clip_score"][b]).abs().max()))
             # the reference's winner is visible in the next recorded step's inp
-            if si + 1 < len(g["steps"]) and g["steps"][si + 1]["pos"] != pos:
-                nxt = g["steps"][si + 1]["inp"][:, pos]
-                got = inp[:, pos].cpu()
-                m["winner_checked"] += int(nxt.numel())
-                bad = got != nxt
-                if bool(bad.any()):
-                    m["winner_mismatch"] += int(bad.sum())
-                    top2 = tr["final"].topk(2, dim=1).values
-                    marg = float((top2[:, 0] - top2[:, 1])[bad].min())
+            if has_next:
+                nxt = int(g["steps"][si + 1]["inp"][b, pos])
+                got = int(inp[b, pos])
+                m["winner_checked"] += 1
+                if got != nxt:
+                    m["winner_mismatch"] += 1
+                    top2 = tr["final"][b].topk(min(2, K)).values
+                    marg = float(top2[0] - top2[-1])
                     m["min_margin_at_mismatch"] = marg if m["min_margin_at_mismatch"] is None else min(
                         m["min_margin_at_mismatch"], marg)
+                elif gamma is None:  # the reported cosine of the winner (gen_utils.py:80)
+                    rw = int((0.02 * s["probs"][b] + 2.0 * s["clip_score"][b]).argmax())
+                    m["winner_cos_err"] = max(m["winner_cos_err"], float((clip_ref[b] - s["clip_ref"][b][rw]).abs()))
     return m

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 from conftest import ROOT
-from conzic_b200 import _lib, synth, tokens, utils
+from conzic_b200 import _lib, tokens, utils
+from synthetic import synth
 
 
 def test_library_exports_every_declared_symbol():
@@ -21,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libconzic.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.conzic_abi_version() == 5
+    assert lib.conzic_abi_version() == 6
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -1,12 +1,15 @@
 """GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of libconzic.so;
 the CPU oracle and the golden fixtures recorded from the unmodified reference are the checkers.
 
-Tolerances (stated here, measured margins in profiles/r01h_parity.md, from tools/parity_report.py):
-  * bf16x3 mode (3-pass split operands, the parity mode): BERT row logits within 1e-3 of the reference,
+Tolerances (stated here; measured margins in profiles/r01h_parity.md and profiles/r02*_parity.md, from
+tools/parity_report.py):
+  * bf16x3 mode (3-pass split operands, the exact mode): BERT row logits within 1e-3 of the reference,
     CLIP cosine within 2e-5, softmax_K score within 2e-4; top-k ids identical wherever the reference's
     probabilities are non-zero and distinct; chosen token ids identical.
-  * bf16 mode (throughput mode): logits within 0.08, cosine within 4e-3; chosen ids must agree whenever
-    the reference's own top-2 margin exceeds what a 4e-3 cosine error can move.
+  * certified mode (the default: BERT bf16x3, CLIP bf16 + certified argmax with exact re-score): top-k ids,
+    chosen token ids and the reported cosines identical to bf16x3's, hence to the reference's.
+  * bf16 mode (everything bf16): logits within 0.04, cosine within 1.6e-3 (2x the measured maxima 1.8e-2 / 7.9e-4);
+    chosen ids must agree whenever the reference's own top-2 margin exceeds what that cosine error can move.
 """
 import random
 
@@ -15,7 +18,7 @@ import pytest
 import torch
 
 import gpu_common as gc
-from conzic_b200 import synth
+from synthetic import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -87,12 +90,10 @@ def test_persistent_pair_gemm_all_epilogues(mode, shape):
         assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("env,shape", [({"CONZIC_WIDE_EPI16": "0"}, (4096 + 77, 512, 2048)),
-                                       ({"CONZIC_PERSIST_EPI16": "1"}, (20000 + 33, 512, 512)),
-                                       ({"CONZIC_PERSIST_EPI16": "1"}, (700, 1536, 512))])
-def test_pair_gemm_epilogue_warp_variants_are_bit_identical(env, shape, monkeypatch):
-    """8 versus 16 epilogue warps (gemm_wide_kernel<8|16>, gemm_persist_kernel<2,true,8|16>) only change which warp
-    drains which accumulator columns: fp32 + residual outputs must be bit-identical to the default build's."""
+@pytest.mark.parametrize("shape", [(4096 + 77, 512, 2048), (20000 + 33, 512, 512), (300, 512, 512)])
+def test_wide_pair_gemm_with_fused_layernorm_inputs(shape):
+    """gemm_wide_kernel (one 512-column unit per CTA pair, the kernel that also writes the LayerNorm of its rows on
+    the CLIP tower's default path): fp32 + residual output against fp64, ragged M."""
     M, N, K = shape
     eng = gc.engine("bf16", "tcgen05")
     g = torch.Generator(device="cuda").manual_seed(M)
@@ -100,38 +101,31 @@ def test_pair_gemm_epilogue_warp_variants_are_bit_identical(env, shape, monkeypa
     W = torch.randn(N, K, device="cuda", generator=g) * 0.05
     bias = torch.randn(N, device="cuda", generator=g)
     resid = torch.randn(M, N, device="cuda", generator=g)
-    base = eng.debug_linear(A, W, bias, resid, 0)
-    for k, v in env.items():  # read per launch
-        monkeypatch.setenv(k, v)
     out = eng.debug_linear(A, W, bias, resid, 0)
-    assert torch.equal(out, base)
     ref = _ref_linear(A, W, bias, resid, 0, True)
     assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("M", [256, 1000, 37888 + 77])
-def test_fused_mlp_matches_fp64(M):
-    """mlp_persist_kernel: x + fc2(quick_gelu(fc1(x))) with the bf16 intermediate kept in the per-CTA scratch
-    tile, against fp64 with the same bf16 rounding points (operands and intermediate)."""
-    eng = gc.engine("bf16", "tcgen05")
-    H, F = 512, 2048
-    g = torch.Generator(device="cuda").manual_seed(M)
-    X = torch.randn(M, H, device="cuda", generator=g)
-    W1 = torch.randn(F, H, device="cuda", generator=g) * 0.04
-    W2 = torch.randn(H, F, device="cuda", generator=g) * 0.02
-    b1 = torch.randn(F, device="cuda", generator=g) * 0.1
-    b2 = torch.randn(H, device="cuda", generator=g) * 0.1
-    out = eng.debug_mlp(X, W1, b1, W2, b2, act=1)
-    xb, w1, w2 = X.bfloat16().double(), W1.bfloat16().double(), W2.bfloat16().double()
-    h = xb @ w1.t() + b1.double()
-    h = (h * torch.sigmoid(1.702 * h)).float().bfloat16().double()
-    ref = (X.double() + h @ w2.t() + b2.double()).float()
-    # the intermediate is rounded to bf16 from slightly different fp32 values: allow a few flipped roundings
-    assert float((out - ref).abs().max()) < 2e-2
-    assert float((out - ref).abs().mean()) < 1e-3
+@pytest.mark.parametrize("shape", [(200, 512, 512, 1), (333, 2048, 512, 1), (1000, 512, 2048, 0)])
+def test_certified_context_exact_tower_linear(shape):
+    """A CERTIFIED context holds the CLIP linears twice: act | 32 routes debug_linear through the exact (bf16x3)
+    copy's operand format and kernel, which must be as accurate as the bf16x3 context's."""
+    M, N, K, act = shape
+    eng = gc.engine("certified", "tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    out = eng.debug_linear(A, W, bias, resid, act | 32)
+    ref = _ref_linear(A, W, bias, resid, act, False)
+    assert float((out - ref).abs().max()) < 3e-4 * float(ref.abs().max())
+    fast = eng.debug_linear(A, W, bias, resid, act)
+    ref16 = _ref_linear(A, W, bias, resid, act, True)
+    assert float((fast - ref16).abs().max()) < 3e-4 * float(ref16.abs().max())
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-3), ("bf16", 0.08)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-3), ("certified", 1e-3), ("bf16", 0.04)])
 def test_bert_row_logits_vs_oracle(prec, tol):
     from oracle import conzic_oracle as orc
     sd = gc.weights("bert")
@@ -144,7 +138,7 @@ def test_bert_row_logits_vs_oracle(prec, tol):
     assert float((out - ref).abs().max()) < tol
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 0.05)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 0.03), ("certified", 0.03)])
 def test_clip_text_encode_vs_oracle(prec, tol):
     """Ragged lengths, EOS padding, T up to the 77-token cap."""
     from oracle import conzic_oracle as orc
@@ -162,25 +156,12 @@ def test_clip_text_encode_vs_oracle(prec, tol):
         assert float((out - ref).abs().max()) < tol
 
 
-@pytest.mark.parametrize("prec,tol,env", [("bf16x3", 3e-4, {}), ("bf16", 0.06, {}),
-                                          ("bf16", 0.06, {"CONZIC_LN_FOLD": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_MLP_FUSED": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_WIDE_LN": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_WIDE_LN": "2"}),
-                                          ("bf16", 0.06, {"CONZIC_ATTN_PREFETCH": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_WIDE_EPI16": "0"}),
-                                          ("bf16", 0.06, {"CONZIC_ATTN_OCC3": "0"}),
-                                          ("bf16", 0.06, {"CONZIC_EMBED_LN": "0"}),
-                                          ("bf16", 0.06, {"CONZIC_PERSIST_EPI16": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_OPROJ_WIDE": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_GEMM_CG": "1"}),
-                                          ("bf16", 0.06, {"CONZIC_GEMM_PERSIST": "0"})])
-def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch):
+@pytest.mark.parametrize("prec,tol,kw", [("bf16x3", 3e-4, {}), ("bf16", 0.04, {}),
+                                         ("bf16", 0.04, {"ln_standalone": True}), ("bf16", 0.04, {"pdl": False})])
+def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
     """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
-    the oracle, for the default path and every opt-in kernel variant: LayerNorm folded into the consuming GEMM
-    (CONZIC_LN_FOLD), fc1+fc2 in one launch (CONZIC_MLP_FUSED), LayerNorm written by the producing wide GEMM's
-    epilogue (CONZIC_WIDE_LN), 8 / 16 epilogue warps, O-proj through the wide kernel, attention register prefetch,
-    single-CTA and non-persistent GEMMs."""
+    the oracle: the default path (LayerNorm written by the O-proj / fc2 epilogues of the wide pair kernel and by the
+    embedding kernel), the stand-alone LayerNorm kernels (ln_standalone) and launches without PDL."""
     from conzic_b200.engine import Engine
     from oracle import conzic_oracle as orc
     sd = {k: v.clone() for k, v in gc.weights("clip").items()}
@@ -191,9 +172,7 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch)
                 sd[k] = 1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)
             else:
                 sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
-    for k, v in env.items():  # optional kernel variants are selected when the context is created
-        monkeypatch.setenv(k, v)
-    eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision=prec)
+    eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision=prec, **kw)
     torch.manual_seed(3)
     for N, T in ((300, 9), (41, 16)):
         ids = torch.randint(300, 40000, (N, T))
@@ -208,7 +187,7 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, env, monkeypatch)
     eng.close()
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("certified", 1e-4), ("bf16", 2e-2)])
 def test_clip_image_encode_vs_oracle(prec, tol):
     """CLIP ViT-B/32 image tower on the engine's kernels (im2col + patch GEMM, pre-LN, 12 blocks with
     bidirectional 50-token attention, post-LN of the class token, projection) against the oracle's
@@ -225,7 +204,7 @@ def test_clip_image_encode_vs_oracle(prec, tol):
     assert out.shape == ref.shape
     assert float((out - ref).abs().max()) < tol * float(ref.abs().max())
     cos = torch.nn.functional.cosine_similarity(out, ref, dim=-1)
-    assert float((1 - cos).max()) < (1e-7 if prec == "bf16x3" else 2e-4)
+    assert float((1 - cos).max()) < (2e-4 if prec == "bf16" else 1e-7)
     eng.close()
 
 
@@ -318,17 +297,45 @@ def test_gibbs_step_teacher_forced_bf16x3(name):
     assert m["clip_score_err"] < 2e-4
     assert m["winner_mismatch"] == 0
     assert m["winner_checked"] > 0
+    assert m["winner_cos_err"] < 2e-5
 
 
-@pytest.mark.parametrize("name", ["seq_b2_n4_k8", "random_b2_n3_k8", "senti_seq_b2_n4_k8"])
+@pytest.mark.parametrize("kw", [{}, {"cert_dcos": 1.0}, {"cert_dcos": 0.05, "cert_fcap": 2}, {"cert_dcos": 0.02, "cert_fcap": 64}])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_gibbs_step_teacher_forced_certified(name, kw):
+    """The default precision, teacher-forced on every recorded step of the unmodified reference: exact logits and
+    top-k ids (BERT runs in bf16x3), the reference's winner and its cosine (certified argmax).  Besides the default
+    error bound: a bound so loose that every image takes the full exact re-encode (cert_dcos 1.0), a loose bound with
+    a tiny survivor cap (round 2 and the overflow route), and a loose bound with a large cap (round 2 orders many
+    survivors) -- every route must land on the same winners."""
+    g = gc.load_golden(name)
+    case = g["case"]
+    eng = gc.engine("certified", "tcgen05", case.get("peaked", False), case.get("multi", False), **kw)
+    before = eng.cert_stats()
+    m = gc.replay_fixture(eng, g)
+    st = {k: v - before[k] for k, v in eng.cert_stats().items()}
+    assert m["dot_mismatch"] == 0
+    assert m["logit_err"] < 1e-3
+    assert m["topk_id_mismatch"] == 0
+    assert m["winner_mismatch"] == 0
+    assert m["winner_checked"] > 0
+    assert m["winner_cos_err"] < 2e-5
+    assert st["calls"] == m["steps"] and st["rescored_candidates"] >= 0
+    if kw.get("cert_dcos") == 1.0 and case["K"] > 1:
+        assert st["images_full"] > 0  # nothing can be ruled out with a bound that loose
+
+
+@pytest.mark.parametrize("name", FIXTURES)
 def test_gibbs_step_teacher_forced_bf16(name):
     g = gc.load_golden(name)
-    eng = gc.engine("bf16", "tcgen05")
+    case = g["case"]
+    eng = gc.engine("bf16", "tcgen05", case.get("peaked", False), case.get("multi", False))
     m = gc.replay_fixture(eng, g)
-    assert m["logit_err"] < 0.08
-    assert m["clip_ref_err"] < 4e-3
-    # a flipped winner is only acceptable on a near tie of the fused score
-    assert m["winner_mismatch"] == 0 or m["min_margin_at_mismatch"] < 2.0 * 100 * 4e-3
+    assert m["logit_err"] < 0.04
+    assert m["cos_checked"] > 0 and m["clip_ref_err"] < 1.6e-3
+    # winners are checked image by image wherever the top-k id set matches the reference's; a flipped winner is only
+    # acceptable on a near tie of the fused score: beta * (softmax change a 1.6e-3 cosine error can cause) < 0.7
+    assert m["winner_mismatch"] == 0 or m["min_margin_at_mismatch"] < 0.7
 
 
 def _models(case):
@@ -343,13 +350,15 @@ def _models(case):
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "random_b2_n3_k8", "senti_seq_b2_n4_k8",
                                   "senti_shuffle_neg_b2_n4_k8", "peaked_seq_b2_n4_k32", "span_b2_n5_k8",
                                   "pos_seq_b2_n5_k16"])
-def test_free_running_call_matches_reference(name, monkeypatch):
+@pytest.mark.parametrize("prec", ["certified", "bf16x3"])
+def test_free_running_call_matches_reference(name, prec, monkeypatch):
     """generate_caption / control_generate_caption through the drop-in API under set_seed(42): same captions per
-    sweep, same best list, same CLIP scores as the unmodified reference returned (bf16x3 mode)."""
+    sweep, same best list, same CLIP scores as the unmodified reference returned -- in the default (certified)
+    precision and in bf16x3."""
     import logging
     from conzic_b200 import control_gen_utils, gen_utils, runtime
     from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    monkeypatch.setenv("CONZIC_PRECISION", prec)
     runtime.clear()
     control_gen_utils.set_pos_tagger(synth.synth_pos_tagger)  # POS control: the tagger is a plug-in
     g = gc.load_golden(name)
@@ -378,14 +387,15 @@ def test_free_running_call_matches_reference(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["seq_b2_n4_k8", "shuffle_b3_n5_k16_multi", "senti_shuffle_neg_b2_n4_k8", "span_b2_n5_k8"])
-def test_host_string_path_matches_reference(name, monkeypatch):
-    """CONZIC_STRING_PATH=1: the fallback for vocabularies with '##' word pieces (candidate ids -> host ->
-    batch_decode -> CLIP tokenizer -> device, every arithmetic piece still a libconzic kernel) gives the
-    reference's captions and scores too."""
+@pytest.mark.parametrize("prec", ["certified", "bf16x3"])
+def test_host_string_path_matches_reference(name, prec, monkeypatch):
+    """CONZIC_STRING_PATH=1: candidate ids -> host -> batch_decode -> CLIP tokenizer -> device, every arithmetic
+    piece still a libconzic kernel (conzic_score_select with the candidates' CLIP ids for the certified re-score)
+    gives the reference's captions and scores too."""
     import logging
     from conzic_b200 import control_gen_utils, gen_utils, runtime
     from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    monkeypatch.setenv("CONZIC_PRECISION", prec)
     monkeypatch.setenv("CONZIC_STRING_PATH", "1")
     runtime.clear()
     g = gc.load_golden(name)
@@ -758,29 +768,113 @@ def test_full_size_sentiment_step_properties():
 
 
 def test_full_size_step_properties():
-    """BASELINE config 2 sizes (B=64, K=200, len=10): winners are legal (unmasked) ids, scores are cosines,
-    the step is deterministic, and the bf16 path picks the same winner as bf16x3 on all but near ties."""
+    """BASELINE config 2 sizes (B=64, K=200, len=10): winners are legal (unmasked) ids, scores are cosines, the step
+    is deterministic; the certified precision gives bf16x3's winners and bit-identical reported cosines; the all-bf16
+    precision picks the same winner on all but near ties."""
     B, n, K = 64, 10, 200
     img = torch.nn.functional.normalize(torch.randn(B, 512, generator=torch.Generator().manual_seed(9)), dim=-1).cuda()
     base = torch.tensor([[101, 3746, 1997, 1037] + [2000 + 7 * j for j in range(n)] + [102]] * B).cuda()
     outs = {}
-    for prec in ("bf16x3", "bf16"):
+    for prec in ("bf16x3", "certified", "bf16"):
         eng = gc.engine(prec)
         runs = []
         for _ in range(2):
             inp = base.clone()
             tm = synth.make_token_mask("cuda")
             cr, _, tr = eng.gibbs_step(inp, tm, img, 9, False, K, 0.1, 0.02, 2.0, 8, 4, trace=True)
-            runs.append((inp.cpu(), cr.cpu(), tr["final"].cpu()))
+            runs.append((inp.cpu(), cr.cpu(), tr["final"].cpu(), tr["idxs"].cpu()))
         assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
         w = runs[0][0][:, 9]
         assert bool((w >= 1996).all()) and bool((runs[0][1].abs() <= 1.0).all())
         outs[prec] = runs[0]
+    assert torch.equal(outs["certified"][3], outs["bf16x3"][3]), "top-k ids differ (BERT must run in bf16x3)"
+    assert torch.equal(outs["certified"][0], outs["bf16x3"][0]), "certified argmax picked another winner"
+    assert torch.equal(outs["certified"][1], outs["bf16x3"][1]), "reported cosine is not the exact tower's"
+    st = gc.engine("certified").cert_stats()
+    assert st["rescored_candidates"] >= st["images"] > 0
     same = outs["bf16"][0][:, 9] == outs["bf16x3"][0][:, 9]
     top2 = outs["bf16x3"][2].topk(2, dim=1).values
     margin = top2[:, 0] - top2[:, 1]
-    assert bool(same[margin > 0.8].all()), "bf16 flipped a winner whose fp32 margin was large"
+    assert bool(same[margin > 0.7].all()), "bf16 flipped a winner whose fp32 margin was large"
     gc.drop_engines()
+
+
+def _run_generate(prec, B, n, K, sweeps, order, monkeypatch):
+    import logging
+    from conzic_b200 import gen_utils, runtime
+    from conzic_b200.clip.clip import CLIP
+    from conzic_b200.models import BertMLM
+    from conzic_b200.utils import set_seed
+    monkeypatch.setenv("CONZIC_PRECISION", prec)
+    runtime.clear()
+    bert = BertMLM(gc.weights("bert"))
+    clip = CLIP(state_dict=synth.make_clip_state_dict(0, vision=True), tokenizer=synth.SynthCLIPTokenizer(),
+                processor=synth.SynthProcessor()).to("cuda")  # index-less device, like the reference's scripts
+    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    set_seed(42)
+    out = gen_utils.generate_caption([f"img{i}.jpg" for i in range(B)], bert, clip, synth.SynthBertTokenizer(), pix,
+                                     synth.make_token_mask("cuda"), logging.getLogger("test"), prompt=synth.SYNTH_PROMPT,
+                                     batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=sweeps, alpha=0.02,
+                                     beta=2.0, generate_order=order)
+    stats = runtime.any_engine().cert_stats()
+    runtime.clear()
+    return out, stats
+
+
+@pytest.mark.parametrize("order", ["sequential", "shuffle"])
+def test_config2_free_running_certified_equals_bf16x3(order, monkeypatch):
+    """BASELINE config 2 / 3 at full size (64 images, sentence_len 10, candidate_k 200, 5 sweeps), free running through
+    the public generate_caption: the default (certified) precision returns the same captions in every sweep, the
+    same best list and bit-identical CLIP scores as the all-bf16x3 run -- 3 200 argmax decisions over 200
+    candidates each."""
+    (t3, s3), _ = _run_generate("bf16x3", 64, 10, 200, 5, order, monkeypatch)
+    (tc, sc), st = _run_generate("certified", 64, 10, 200, 5, order, monkeypatch)
+    assert tc == t3
+    assert sc == s3
+    assert st["calls"] == 50 and st["images"] == 3200 and st["rescored_candidates"] >= 3200
+    # the point of the bound: almost every candidate is ruled out by the bf16 scores alone
+    assert st["rescored_candidates"] < 0.05 * 3200 * 200, st
+
+
+def test_config2_certified_lockstep_with_cpu_oracle():
+    """B = 8 images, sentence_len 10, candidate_k 200, two sweeps (20 Gibbs steps, 160 decisions over 200 candidates):
+    the certified engine in lockstep with the CPU oracle (the restatement pinned against the unmodified reference).
+    Token ids must be identical after every step; a divergence is tolerated once, and only where the oracle's own
+    top-2 fused scores are closer than 1e-4 (an fp32 tie no arithmetic can call)."""
+    from oracle import conzic_oracle as orc
+    B, n, K, sweeps = 8, 10, 200, 2
+    eng = gc.engine("certified")
+    o = orc.Oracle(gc.weights("bert"), gc.weights("clip"), synth.SynthBertTokenizer(), synth.SynthCLIPTokenizer(),
+                   full_logits=False)
+    o.trace = []
+    tok = synth.SynthBertTokenizer()
+    inp_ref = torch.tensor([tok.encode(synth.SYNTH_PROMPT + "[MASK]" * n)] * B)
+    inp_dev = inp_ref.clone().cuda()
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=torch.Generator().manual_seed(33)), dim=-1)
+    img_dev = img.cuda()
+    tm_ref, tm_dev = synth.make_token_mask(), synth.make_token_mask("cuda")
+    holds = [False] + [True] * 3 + [False] * (n + 1)
+    near_ties = 0
+    for it in range(sweeps):
+        for ii in range(n):
+            pos = 4 + ii
+            with torch.no_grad():
+                cur, _ = o.step(inp_ref, img, tm_ref, pos, ii, n, K, 0.1, 0.02, 2.0)
+            cr, _, _ = eng.gibbs_step(inp_dev, tm_dev, img_dev, pos, ii == n - 1, K, 0.1, 0.02, 2.0, sum(holds[:pos]),
+                                      sum(holds[pos + 1:]))
+            holds[pos] = True
+            got = inp_dev.cpu()
+            if not torch.equal(got, inp_ref):
+                t = o.trace[-1]
+                top2 = t["final"].topk(2, dim=1).values
+                bad = (got[:, pos] != inp_ref[:, pos])
+                assert float((top2[:, 0] - top2[:, 1])[bad].max()) < 1e-4, "winner differs from the oracle's off a tie"
+                near_ties += int(bad.sum())
+                inp_dev.copy_(inp_ref)
+            else:
+                np.testing.assert_allclose(cr.cpu().numpy(), np.array(cur, dtype=np.float32), rtol=0, atol=2e-5)
+            o.trace.clear()
+    assert near_ties <= 1
 
 
 def test_run_py_cli_synthetic_writes_reference_result_layout(tmp_path, monkeypatch):

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, load_golden
-from conzic_b200 import synth
+from synthetic import synth
 from oracle import conzic_oracle as orc
 
 ALL = sorted(f[:-3] for f in os.listdir(GOLDEN) if f.endswith(".pt"))

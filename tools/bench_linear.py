@@ -2,7 +2,7 @@
 """One linear-layer shape through conzic_debug_linear, GEMM-only device time from the library's CUDA events.
 Used for A/B runs in one process and as the short command behind ncu captures of the persistent GEMM.
 
-    python tools/bench_linear.py --M 75776 --N 1536 --K 512 --mode bf16 [--reps 10] [--env CONZIC_GEMM_CG=1]
+    python tools/bench_linear.py --M 75776 --N 1536 --K 512 --mode bf16 [--reps 10]
 """
 import argparse
 import json
@@ -22,11 +22,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["f32", "f32+resid", "bf16", "bf16+gelu"])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
-    ap.add_argument("--env", action="append", default=[])
     a = ap.parse_args()
-    for kv in a.env:
-        k, v = kv.split("=", 1)
-        os.environ[k] = v
     import torch
     import gpu_common as gc
     eng = gc.engine("bf16", "tcgen05")
@@ -53,7 +49,7 @@ def main():
         eng.debug_linear(A, W, bias, resid, act)
     ms, work, n = eng.profile_read()["gemm"]
     eng.profile(False)
-    print(json.dumps(dict(M=a.M, N=a.N, K=a.K, mode=a.mode, env=a.env, ms=round(ms / n, 4),
+    print(json.dumps(dict(M=a.M, N=a.N, K=a.K, mode=a.mode, ms=round(ms / n, 4),
                           tflops=round(work / (ms / 1e3) / 1e12, 1), cublas_8192_tflops=round(ref_tf, 1))))
 
 

@@ -17,7 +17,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from conzic_b200 import gen_utils, runtime, synth  # noqa: E402
+from conzic_b200 import gen_utils, runtime  # noqa: E402
+from synthetic import synth  # noqa: E402
 from conzic_b200.clip.clip import CLIP  # noqa: E402
 from conzic_b200.models import BertMLM  # noqa: E402
 

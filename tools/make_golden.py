@@ -10,8 +10,8 @@ from /root/reference exactly as they are.  What is supplied around them:
   ``nltk.tokenize.word_tokenize`` callables under the unmodified ``POS_classifier``
   (NLTK / colorlog are not installed and there is no network; SURVEY.md 8(c));
 * HF ``BertForMaskedLM(BertConfig())`` / ``CLIPModel(CLIPConfig())`` loaded with the synthetic
-  state dicts from ``conzic_b200.synth`` (no pretrained weights exist offline);
-* the synthetic string tokenizers of ``conzic_b200.synth``.
+  state dicts from ``synthetic.synth`` (no pretrained weights exist offline);
+* the synthetic string tokenizers of ``synthetic.synth``.
 
 Recording is done by wrapping callables at run time (the model's forward, ``generate_caption_step``
 and ``compute_image_text_similarity_via_raw_text``); no reference file is edited or copied.
@@ -22,14 +22,13 @@ import logging
 import os
 import random
 import sys
-import types
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from conzic_b200 import synth  # noqa: E402
+from synthetic import synth  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -37,54 +36,15 @@ LOGIT_COLS = torch.arange(0, synth.BERT_VOCAB, 61)  # 501 strided vocabulary col
 
 
 def import_reference(sentiment_table):
-    sys.path.insert(0, REF)
-    sys.modules["colorlog"] = types.SimpleNamespace(
-        ColoredFormatter=lambda *a, **k: logging.Formatter("%(message)s"))
+    from oracle import ref_loader
     tok = synth.SynthBertTokenizer()
-
-    def table_scorer(batch_texts, temperature, device, sentiment_ctl=None, batch_size_image=1):
-        # same maths as sentiments_classifer.py:35-48 with a per-word table for SentiWordNet
-        s = torch.zeros(len(batch_texts))
-        for i, t in enumerate(batch_texts):
-            v = sum(float(sentiment_table[tok.vocab[w]]) for w in t.split())
-            s[i] = -v if sentiment_ctl == "negative" else v
-        sb = s.view(batch_size_image, -1).to(device)
-        return torch.softmax(sb / temperature, dim=1).to(device), sb, [], []
-
-    sys.modules["sentiments_classifer"] = types.SimpleNamespace(batch_texts_POS_Sentiments_analysis=table_scorer)
-    # POS_classifier.py is imported UNMODIFIED; only the two NLTK callables it uses are supplied, backed by
-    # the synthetic tagger (NLTK and its corpora are not installed)
-    nltk = types.ModuleType("nltk")
-    nltk.tokenize = types.ModuleType("nltk.tokenize")
-    nltk.tokenize.word_tokenize = lambda text: text.replace(".", " . ").split()
-    nltk.pos_tag = lambda words, tagset=None: list(zip(words, synth.synth_pos_tagger(" ".join(words))))
-    sys.modules["nltk"], sys.modules["nltk.tokenize"] = nltk, nltk.tokenize
-    import utils, gen_utils, control_gen_utils  # noqa: E401  (unmodified reference modules)
-    # /root/reference/clip has no __init__.py, so this repo's root-level `clip` shim package would win the
-    # name; load the reference's file by path instead
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("reference_clip_clip", os.path.join(REF, "clip", "clip.py"))
-    ref_clip = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ref_clip)
-    for m in (utils, gen_utils, control_gen_utils):
-        assert m.__file__.startswith(REF), m.__file__
-    return utils, gen_utils, control_gen_utils, ref_clip.CLIP
+    return ref_loader.load(REF, sentiment_table, lambda w: tok.vocab[w], synth.synth_pos_tagger)
 
 
 def build_models(bert_sd, clip_sd, CLIP, multi, pieces=False):
-    from transformers import BertConfig, BertForMaskedLM, CLIPConfig, CLIPModel
-    bert = BertForMaskedLM(BertConfig()).eval()
-    missing = bert.load_state_dict(bert_sd, strict=False)
-    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
-    clipm = CLIPModel(CLIPConfig()).eval()
-    missing = clipm.load_state_dict(clip_sd, strict=False)
-    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
-    clip = CLIP.__new__(CLIP)
-    torch.nn.Module.__init__(clip)
-    clip.model, clip.processor = clipm, synth.SynthProcessor()
-    clip.tokenizer = synth.PieceCLIPTokenizer(multi) if pieces else synth.SynthCLIPTokenizer(multi)
-    clip.cuda_has_been_checked = False
-    return bert, clip
+    from oracle import ref_loader
+    ctok = synth.PieceCLIPTokenizer(multi) if pieces else synth.SynthCLIPTokenizer(multi)
+    return ref_loader.build_models(bert_sd, clip_sd, CLIP, ctok, synth.SynthProcessor())
 
 
 class Recorder:

@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from conzic_b200 import synth  # noqa: E402
+from synthetic import synth  # noqa: E402
 from conzic_b200.engine import Engine  # noqa: E402
 
 
@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--topk", type=int, default=200)
     ap.add_argument("--len", type=int, default=10)
-    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--precision", default="certified")
     ap.add_argument("--breakdown", action="store_true")
     a = ap.parse_args()
     B, n, K = a.batch, a.len, a.topk
