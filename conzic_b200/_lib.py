@@ -23,7 +23,7 @@ EXPORTS = [
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
     "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_cert_stats",
-    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_encode_candidates",
+    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_set_text_vocab",
 ]
 
 
@@ -38,6 +38,12 @@ class Config(C.Structure):
         ("precision", C.c_int32), ("gemm_impl", C.c_int32), ("clip_chunk_rows", C.c_int32),
         ("cert_dcos", C.c_float), ("cert_fcap", C.c_int32), ("flags", C.c_int32),
     ]
+
+
+class TextVocab(C.Structure):
+    _fields_ = [("tok_off", C.c_void_p), ("tok_bytes", C.c_void_p), ("tok_cls", C.c_void_p), ("tok_flags", C.c_void_p),
+                ("byte_sym", C.c_void_p), ("merge_keys", C.c_void_p), ("merge_vals", C.c_void_p),
+                ("n_bytes", C.c_int32), ("merge_bits", C.c_int32)]
 
 
 class VisionConfig(C.Structure):
@@ -84,9 +90,8 @@ def _declare(lib):
     lib.conzic_clip_text_encode.argtypes = [vp, vp, i32, i32, vp, vp, sz, vp]
     lib.conzic_image_text_similarity.restype = C.c_int
     lib.conzic_image_text_similarity.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
-    lib.conzic_encode_candidates.restype = C.c_int
-    lib.conzic_encode_candidates.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp,
-                                             vp, vp, C.c_size_t, vp]
+    lib.conzic_set_text_vocab.restype = C.c_int
+    lib.conzic_set_text_vocab.argtypes = [vp, C.POINTER(TextVocab), vp]
     lib.conzic_score_select.restype = C.c_int
     lib.conzic_score_select.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, f32, f32, f32, vp, i32, i32,
                                         vp, vp, vp, vp, sz, vp]

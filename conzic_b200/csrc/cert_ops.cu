@@ -14,6 +14,9 @@
 // than `fcap` of them -- is re-encoded in full by the exact tower and decided by the plain score_select_kernel, so
 // every decision equals the bf16x3 mode's.  Candidates that are the same caption (masked ids, gen_utils.py:72) have
 // identical logits in any arithmetic and are ordered by their exact terms alone.
+// Round 2's only uncertainty is the part of Z that still comes from bf16 logits, so round 1 also lists the "heavy"
+// candidates (softmax weight >= 1/128, doubled until the list fits fcap): they cannot win, but with their exact
+// logits Z is known to a fraction of a percent and round 2 almost never has to give an image up.
 #include "kernels.h"
 #include "select_common.cuh"
 
@@ -22,6 +25,7 @@ namespace conzic {
 namespace {
 
 constexpr int CERT_THREADS = 256;
+constexpr int CERT_HEAVY_BIT = 1 << 30;  // img_k entry: listed for its weight in Z only, already ruled out as a winner
 
 // lower bound of f_w - f_k given logits relative to a common maximum (ew = exp(a_w - m), ek likewise), their error
 // bounds, and bounds on the softmax denominator (same reference m)
@@ -52,7 +56,6 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
   const SelectArgs& a = c.q;
   const int K = a.K;
   CertSmem sm(cert_smem, K);
-  __shared__ int s_w;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t o0 = static_cast<size_t>(b) * K;
 
@@ -81,7 +84,6 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
   }
   int w = sel_block_argmax(bestv, besti, sm.scratch);
   if (w < 0 || w >= K) w = 0;
-  if (tid == 0) s_w = w;
   __syncthreads();
 
   const float zlo = Z * expf(-c.eps), zhi = Z * expf(c.eps);
@@ -102,11 +104,29 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
     sm.flag[k] = alive ? 1 : 0;
   }
   __syncthreads();
+  float cnt = 0.f;
+  for (int k = tid; k < K; k += CERT_THREADS) cnt += sm.flag[k] ? 1.f : 0.f;
+  const int n_alive = static_cast<int>(block_sum(cnt, sm.scratch));
+  if (n_alive <= c.fcap) {
+    float theta = (1.0f / 128.0f) * Z;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it, theta *= 2.0f) {
+      float add = 0.f;
+      for (int k = tid; k < K; k += CERT_THREADS) add += (!sm.flag[k] && sm.e[k] >= theta) ? 1.f : 0.f;
+      const int n_add = static_cast<int>(block_sum(add, sm.scratch));
+      if (n_alive + n_add <= c.fcap) {
+        for (int k = tid; k < K; k += CERT_THREADS)
+          if (!sm.flag[k] && sm.e[k] >= theta) sm.flag[k] = 2;
+        break;
+      }
+    }
+  }
+  __syncthreads();
   if (tid == 0) {
     int n = 0;
-    for (int k = 0; k < K; ++k) n += sm.flag[k];
-    if (n > 1) atomicAdd(&c.counters[2], 1);
-    if (n > c.fcap) {
+    for (int k = 0; k < K; ++k) n += sm.flag[k] != 0;
+    if (n_alive > 1) atomicAdd(&c.counters[2], 1);
+    if (n_alive > c.fcap) {
       c.img_nflag[b] = -1;
       c.full_list[atomicAdd(&c.counters[1], 1)] = b;
       atomicAdd(&c.counters[3], 1);
@@ -117,7 +137,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
       int i = 0;
       for (int k = 0; k < K; ++k)
         if (sm.flag[k]) {
-          c.img_k[b * c.fcap + i] = k;
+          c.img_k[b * c.fcap + i] = sm.flag[k] == 2 ? (k | CERT_HEAVY_BIT) : k;
           c.flag_list[slot0 + i] = b * K + k;
           ++i;
         }
@@ -140,7 +160,11 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round2_kernel(CertArgs c) {
 
   for (int k = tid; k < K; k += CERT_THREADS) { sm.logit[k] = a.logit[o0 + k]; sm.flag[k] = 0; }
   __syncthreads();
-  for (int i = tid; i < n; i += CERT_THREADS) { sm.logit[ks[i]] = c.logit3[slot0 + i]; sm.flag[ks[i]] = 1; }
+  for (int i = tid; i < n; i += CERT_THREADS) {
+    const int k = ks[i] & ~CERT_HEAVY_BIT;
+    sm.logit[k] = c.logit3[slot0 + i];
+    sm.flag[k] = 1;
+  }
   __syncthreads();
   float mx = -INFINITY;
   for (int k = tid; k < K; k += CERT_THREADS) mx = fmaxf(mx, sm.logit[k]);
@@ -168,16 +192,18 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round2_kernel(CertArgs c) {
   }
   __syncthreads();
   if (tid == 0) {
-    int w = ks[0];
-    for (int i = 1; i < n; ++i)
-      if (sm.sprob[ks[i]] > sm.sprob[w]) w = ks[i];  // ks ascending: the lowest index wins ties
+    int w = -1;
+    for (int i = 0; i < n; ++i) {
+      if (ks[i] & CERT_HEAVY_BIT) continue;  // ruled out in round 1
+      if (w < 0 || sm.sprob[ks[i]] > sm.sprob[w]) w = ks[i];  // ks ascending: the lowest index wins ties
+    }
     const float zfl = Z - Zrest;  // exact part of the denominator
     const float zlo = zfl + Zrest * expf(-c.eps), zhi = zfl + Zrest * expf(c.eps);
     bool ok = true;
     const int64_t idw = a.ids_masked[o0 + w];
     for (int i = 0; i < n && ok; ++i) {
       const int k = ks[i];
-      if (k == w) continue;
+      if (k == w || (k & CERT_HEAVY_BIT)) continue;
       const float dE = sm.exact[w] - sm.exact[k];
       if (a.ids_masked[o0 + k] == idw) ok = dE > c.tau || (a.probs[o0 + k] == a.probs[o0 + w] && k > w);
       else ok = cert_lower_bound(dE, a.beta, sm.e[w], 0.f, sm.e[k], 0.f, zlo, zhi) > c.tau;

@@ -75,6 +75,11 @@ __global__ void bf16_to_f32_kernel(const bf16* src, float* dst, size_t n) {
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __bfloat162float(src[i]);
 }
+__global__ void pad_eos_kernel(int32_t* ids, const int32_t* len, int N, int T, int eos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * T) return;
+  if (i % T >= len[i / T]) ids[i] = eos;
+}
 __global__ void add_one_kernel(int32_t* v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] += 1;
@@ -131,7 +136,7 @@ struct conzic_ctx {
   Tower clip, clip3;
   bool certified = false;
   float cert_dcos = 0.f;
-  int cert_fcap = 16;
+  int cert_fcap = 64;
   int32_t* cert_host = nullptr;  // pinned, 16 ints: the counters read back twice per certified step
   uint64_t cert_stats[CONZIC_CERT_STATS] = {};
   // CLIP image tower (optional; conzic_set_vision)
@@ -143,6 +148,12 @@ struct conzic_ctx {
   // bert id -> clip ids
   int32_t *b2c_off = nullptr, *b2c_tok = nullptr;
   int max_tok_per_word = 1;
+  // device text pipeline (conzic_set_text_vocab): vocabularies with '##' pieces
+  TextVocab text{};
+  bool has_text = false;
+  int32_t* dims_host = nullptr;  // pinned, 4 ints: the row capacities a text-path step reads back
+  int32_t* aux = nullptr;        // small device scratch for conzic_build_clip_ids on the text path
+  int aux_n = 0;
   int chunk_rows = 303104;
   int chunk_rows3 = 16384;
   int wide_ln = 0;  // CLIP bf16 tower: LayerNorm written by the epilogue of the GEMM that produces the residual stream
@@ -151,6 +162,7 @@ struct conzic_ctx {
     prof_enable(&state, false);
     for (void* p : owned) cudaFree(p);
     if (cert_host) cudaFreeHost(cert_host);
+    if (dims_host) cudaFreeHost(dims_host);
   }
   template <typename T>
   T* dalloc(size_t n) {
@@ -240,6 +252,7 @@ struct Plan {
   float *probs, *repeats, *senti, *clogit;
   int64_t *ids, *ids_masked;
   int32_t *ids_prefix, *ids_suffix, *p0, *eos_idx;
+  int32_t *seq, *seq_len, *dims;  // text path: every candidate's full CLIP id sequence
   ClipBufs main;
   // certified mode
   ClipBufs exact;
@@ -300,6 +313,9 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
   p.ids_suffix = b.take<int32_t>(BK * g.clip_maxpos);
   p.p0 = b.take<int32_t>(B);
   p.eos_idx = b.take<int32_t>(BK);
+  p.seq = b.take<int32_t>(c->has_text ? BK * g.clip_maxpos : 1);
+  p.seq_len = b.take<int32_t>(c->has_text ? BK : 1);
+  p.dims = b.take<int32_t>(4);
   take_clip_bufs(b, p.main, tower_rows_cap(c, c->chunk_rows, B, K), BK, Hc, Fc, g.clip_proj, c->clip.split);
   if (c->certified) {
     take_clip_bufs(b, p.exact, tower_rows_cap(c, c->chunk_rows3, B, K), BK, Hc, Fc, g.clip_proj, 1);
@@ -702,7 +718,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->wide_ln = (!(cfg->flags & CONZIC_FLAG_LN_STANDALONE) && c->clip.gopt.persist && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 &&
                 cfg->clip_hidden == 512) ? 1 : 0;
   c->cert_dcos = cfg->cert_dcos > 0.f ? cfg->cert_dcos : CONZIC_CERT_DCOS_DEFAULT;
-  c->cert_fcap = cfg->cert_fcap > 0 ? cfg->cert_fcap : 16;
+  c->cert_fcap = cfg->cert_fcap > 0 ? cfg->cert_fcap : 64;
   // default: 16 x (148 SMs x 128 rows) token rows per pass; measured on B200: the larger the pass the better
   // (every kernel is a persistent or grid-stride launch; nothing stays L2 resident between kernels anyway)
   c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 303104;
@@ -792,6 +808,39 @@ int conzic_set_bert2clip(conzic_ctx* c, const int32_t* off, const int32_t* tok, 
   return ok ? 0 : -3;
 }
 
+int conzic_set_text_vocab(conzic_ctx* c, const conzic_text_vocab* tv, void* stream) {
+  if (!c || !tv || !tv->tok_off || !tv->tok_bytes || !tv->tok_cls || !tv->tok_flags || !tv->byte_sym || !tv->merge_keys ||
+      !tv->merge_vals) { set_error("set_text_vocab: null argument"); return -1; }
+  if (!c->b2c_off) { set_error("set_text_vocab: conzic_set_bert2clip must come first (per-token ids of whole words)"); return -1; }
+  if (tv->merge_bits < 1 || tv->merge_bits > 24 || tv->n_bytes < 0) { set_error("set_text_vocab: bad table sizes"); return -1; }
+  StateScope scope(&c->state);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int V = c->cfg.bert_vocab;
+  const size_t nb = tv->n_bytes > 0 ? tv->n_bytes : 1, nm = static_cast<size_t>(1) << tv->merge_bits;
+  int32_t* off = c->dalloc<int32_t>(V + 1);
+  uint8_t* bytes = c->dalloc<uint8_t>(nb);
+  uint8_t* cls = c->dalloc<uint8_t>(nb);
+  uint8_t* flags = c->dalloc<uint8_t>(V);
+  int32_t* sym = c->dalloc<int32_t>(512);
+  uint64_t* keys = c->dalloc<uint64_t>(nm);
+  uint32_t* vals = c->dalloc<uint32_t>(nm);
+  if (!off || !bytes || !cls || !flags || !sym || !keys || !vals) return -3;
+  auto cp = [&](void* d, const void* s_, size_t n) {
+    return cuda_ok(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, st), "copy text vocab");
+  };
+  bool ok = cp(off, tv->tok_off, (V + 1) * sizeof(int32_t)) && cp(bytes, tv->tok_bytes, nb) && cp(cls, tv->tok_cls, nb) &&
+            cp(flags, tv->tok_flags, V) && cp(sym, tv->byte_sym, 512 * sizeof(int32_t)) &&
+            cp(keys, tv->merge_keys, nm * sizeof(uint64_t)) && cp(vals, tv->merge_vals, nm * sizeof(uint32_t));
+  if (ok && !c->dims_host)
+    ok = cuda_ok(cudaHostAlloc(reinterpret_cast<void**>(&c->dims_host), 4 * sizeof(int32_t), cudaHostAllocDefault),
+                 "cudaHostAlloc(text dims)");
+  ok = ok && cuda_ok(cudaStreamSynchronize(st), "set_text_vocab sync");
+  if (!ok) return -3;
+  c->text = TextVocab{off, bytes, cls, flags, c->b2c_off, c->b2c_tok, sym, keys, vals, tv->merge_bits, V};
+  c->has_text = true;
+  return 0;
+}
+
 size_t conzic_workspace_bytes(const conzic_ctx* c, int B, int L, int K) {
   if (!c) return 0;
   return make_plan(c, nullptr, B, L, K).bytes;
@@ -840,6 +889,29 @@ int conzic_build_clip_ids(conzic_ctx* c, const int64_t* inp, int B, int L, int p
   if (!c->b2c_off) { set_error("build_clip_ids: conzic_set_bert2clip has not been called"); return -1; }
   StateScope scope(&c->state);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->has_text) {
+    // device text pipeline: the sequences are written straight into clip_ids, which must have full-length rows
+    if (T != c->cfg.clip_maxpos || L > TXT_MAX_TOK) { set_error("build_clip_ids: with a text vocabulary T must be 77 and L <= 96"); return -1; }
+    if (c->aux_n < B + 4) {
+      c->aux = c->dalloc<int32_t>(B + 4);
+      c->aux_n = c->aux ? B + 4 : 0;
+      if (!c->aux) return -3;
+    }
+    const conzic_config& g = c->cfg;
+    TextAssembleArgs t{};
+    t.vocab = c->text;
+    t.inp = inp; t.ids = ids; t.token_mask = token_mask; t.senti_table = nullptr;
+    t.B = B; t.L = L; t.K = K; t.pos = pos;
+    t.special[0] = g.pad_id; t.special[1] = g.unk_id; t.special[2] = g.cls_id; t.special[3] = g.sep_id; t.special[4] = g.mask_id;
+    t.bos = g.clip_bos; t.eos = g.clip_eos; t.maxlen = T;
+    t.seq = clip_ids; t.len = clip_len; t.p0 = c->aux; t.dims = c->aux + B;
+    t.ids_masked = ids_masked;
+    if (!cuda_ok(cudaMemsetAsync(t.dims, 0, 4 * sizeof(int32_t), st), "memset(text dims)")) return -4;
+    launch_text_tokenize(t, st);
+    pad_eos_kernel<<<(B * K * T + 255) / 256, 256, 0, st>>>(clip_ids, clip_len, B * K, T, g.clip_eos);
+    count_launch();
+    return cuda_ok(cudaGetLastError(), "build_clip_ids") ? 0 : -4;
+  }
   AssembleArgs a{};
   fill_assemble(c, a);
   a.inp = inp; a.ids = ids; a.token_mask = token_mask; a.senti_table = nullptr;
@@ -865,44 +937,6 @@ int conzic_clip_text_encode(conzic_ctx* c, const int32_t* clip_ids, int N, int T
   if (!clip_encode(c, c->clip, p.main, c->chunk_rows, nullptr, clip_ids, nullptr, p.eos_idx, N, 0, 1, T, p.main.text, st))
     return -4;
   return cuda_ok(cudaMemcpyAsync(text, p.main.text, static_cast<size_t>(N) * c->cfg.clip_proj * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, st), "copy text embeds") ? 0 : -4;
-}
-
-int conzic_encode_candidates(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, const int64_t* ids,
-                             const float* token_mask, int K, int P, int S, const float* senti_table, float* text,
-                             int64_t* ids_masked, float* repeats, float* senti_raw, const int32_t* ov_mask,
-                             const int32_t* ov_off, const int32_t* ov_tok, void* ws, size_t ws_bytes, void* stream) {
-  if (!c || !inp || !ids || !token_mask || !text || !ids_masked || !ws) { set_error("encode_candidates: null argument"); return -1; }
-  if ((ov_mask != nullptr) != (ov_off != nullptr) || (ov_mask != nullptr) != (ov_tok != nullptr)) {
-    set_error("encode_candidates: ov_mask / ov_off / ov_tok go together");
-    return -1;
-  }
-  if (!c->b2c_off) { set_error("encode_candidates: conzic_set_bert2clip has not been called"); return -1; }
-  const int cap = c->cfg.clip_maxpos - 1;
-  if (B < 1 || K < 1 || K > 1024 || pos < 1 || pos >= L - 1 || P < 1 || P > cap || S < 2 || S > cap) {
-    set_error("encode_candidates: bad B / K / pos / P / S");
-    return -1;
-  }
-  if (!check_ws(c, ws_bytes, B, L, K)) return -1;
-  StateScope scope(&c->state);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  Plan p = make_plan(c, ws, B, L, K);
-  if (static_cast<size_t>(P) + static_cast<size_t>(K) * S > static_cast<size_t>(c->cfg.clip_maxpos) * (K + 1)) {
-    set_error("encode_candidates: P + K * S exceeds the workspace plan");
-    return -1;
-  }
-  set_pdl_now(1);
-  AssembleArgs a{};
-  fill_assemble(c, a);
-  a.inp = inp; a.ids = ids; a.token_mask = token_mask; a.senti_table = senti_table;
-  a.B = B; a.L = L; a.K = K; a.pos = pos;
-  a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
-  a.ids_masked = ids_masked; a.repeats = repeats; a.senti = senti_table ? senti_raw : nullptr;
-  a.ov_mask = ov_mask; a.ov_off = ov_off; a.ov_tok = ov_tok;
-  launch_assemble(a, st);
-  if (!clip_encode(c, c->clip, p.main, c->chunk_rows, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.main.text, st))
-    return -4;
-  return cuda_ok(cudaMemcpyAsync(text, p.main.text, static_cast<size_t>(B) * K * c->cfg.clip_proj * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st), "copy text embeds") ? 0 : -4;
 }
 
@@ -975,13 +1009,46 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   int P = 1 + W * s->visited_before; if (P > cap) P = cap;
   int S = W * (1 + s->visited_after) + 1; if (S > cap) S = cap;
   const bool ctl = s->senti_table != nullptr;
-  AssembleArgs a{};
-  fill_assemble(c, a);
-  a.inp = s->inp; a.ids = ids; a.token_mask = s->token_mask; a.senti_table = s->senti_table;
-  a.B = B; a.L = L; a.K = K; a.pos = pos;
-  a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
-  a.ids_masked = p.ids_masked; a.repeats = ctl ? p.repeats : nullptr; a.senti = ctl ? p.senti : nullptr;
-  launch_assemble(a, st);
+  if (c->has_text) {
+    // vocabularies with '##' pieces: every candidate caption through the device text pipeline; the row capacities
+    // are data dependent (a piece merges into its neighbour), so the two maxima are read back -- 16 bytes
+    if (L > TXT_MAX_TOK) { set_error("gibbs_step: caption longer than the text pipeline's token buffer"); return -1; }
+    TextAssembleArgs t{};
+    t.vocab = c->text;
+    t.inp = s->inp; t.ids = ids; t.token_mask = s->token_mask; t.senti_table = s->senti_table;
+    t.B = B; t.L = L; t.K = K; t.pos = pos;
+    t.special[0] = g.pad_id; t.special[1] = g.unk_id; t.special[2] = g.cls_id; t.special[3] = g.sep_id; t.special[4] = g.mask_id;
+    t.bos = g.clip_bos; t.eos = g.clip_eos; t.maxlen = g.clip_maxpos;
+    t.seq = p.seq; t.len = p.seq_len; t.p0 = p.p0; t.dims = p.dims;
+    t.ids_masked = p.ids_masked; t.repeats = ctl ? p.repeats : nullptr; t.senti = ctl ? p.senti : nullptr;
+    if (!cuda_ok(cudaMemsetAsync(p.dims, 0, 4 * sizeof(int32_t), st), "memset(text dims)")) return -4;
+    launch_text_tokenize(t, st);
+    int32_t* h = c->dims_host;
+    if (!cuda_ok(cudaMemcpyAsync(h, p.dims, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "read text dims") ||
+        !cuda_ok(cudaStreamSynchronize(st), "sync(text dims)"))
+      return -4;
+    if (h[2]) {
+      set_error("gibbs_step: a caption overflows the device text pipeline's buffers (TXT_ERR bits " + std::to_string(h[2]) + ")");
+      return -4;
+    }
+    P = h[0] < 1 ? 1 : h[0];
+    S = h[1] < 1 ? 1 : h[1];
+    if (P + S > 96) {  // one attention tile holds prefix + suffix keys: shorten the shared prefix, lengthen the suffixes
+      const int cut = P + S - 96;
+      P -= cut; S += cut;
+      if (P < 1 || S > cap) { set_error("gibbs_step: captions too long for the attention tile"); return -4; }
+    }
+    t.P = P; t.S = S; t.ids_prefix = p.ids_prefix; t.ids_suffix = p.ids_suffix; t.eos_idx = p.eos_idx;
+    launch_text_layout(t, st);
+  } else {
+    AssembleArgs a{};
+    fill_assemble(c, a);
+    a.inp = s->inp; a.ids = ids; a.token_mask = s->token_mask; a.senti_table = s->senti_table;
+    a.B = B; a.L = L; a.K = K; a.pos = pos;
+    a.ids_prefix = p.ids_prefix; a.ids_suffix = p.ids_suffix; a.p0 = p.p0; a.eos_idx = p.eos_idx; a.P = P; a.S = S;
+    a.ids_masked = p.ids_masked; a.repeats = ctl ? p.repeats : nullptr; a.senti = ctl ? p.senti : nullptr;
+    launch_assemble(a, st);
+  }
   if (!clip_encode(c, c->clip, p.main, c->chunk_rows, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.main.text, st))
     return -4;
   SelectArgs q{};

@@ -206,14 +206,38 @@ struct AssembleArgs {
   int64_t* ids_masked;  // [B,K]
   float* repeats;       // [B,K] or null
   float* senti;         // [B,K] or null
-  // optional per-image override of the table walk (captions that hold a merged '##' word outside `pos`): for images
-  // with ov_mask[b] != 0 the prefix tokens are ov_tok[ov_off[2b] .. ov_off[2b+1]) and the tail tokens
-  // ov_tok[ov_off[2b+1] .. ov_off[2b+2]) -- what the host's tokenizers made of the decoded strings
-  const int32_t* ov_mask = nullptr;  // [B]
-  const int32_t* ov_off = nullptr;   // [2B+1]
-  const int32_t* ov_tok = nullptr;
 };
 void launch_assemble(const AssembleArgs& a, cudaStream_t st);
+
+}  // namespace conzic
+#include "text_pipeline.cuh"
+namespace conzic {
+// Device text pipeline (text_ops.cu): the candidates of one Gibbs step through WordPiece decode + CLIP BPE
+struct TextAssembleArgs {
+  TextVocab vocab;
+  const int64_t* inp;       // [B,L], [MASK] at pos
+  const int64_t* ids;       // [B,K] top-k ids
+  const float* token_mask;  // [V]
+  const float* senti_table; // [V] or null
+  int B, L, K, pos;
+  int special[5];
+  int bos, eos, maxlen;     // maxlen = 77
+  // kernel 1 outputs
+  int32_t* seq;             // [B*K, maxlen] BOS ... EOS of every candidate caption
+  int32_t* len;             // [B*K] tokens including BOS and EOS
+  int32_t* p0;              // [B] rows of the image's shared prefix (>= 1: BOS)
+  int32_t* dims;            // [0] max p0, [1] max suffix rows, [2] TXT_ERR_* bits (all atomically merged; zeroed by the caller)
+  int64_t* ids_masked;      // [B,K]
+  float* repeats;           // [B,K] or null
+  float* senti;             // [B,K] or null
+  // kernel 2: the tower's row layout for capacities P, S
+  int P, S;
+  int32_t* ids_prefix;      // [B,P]
+  int32_t* ids_suffix;      // [B,K,S]
+  int32_t* eos_idx;         // [B*K] suffix-relative index of the EOS
+};
+void launch_text_tokenize(const TextAssembleArgs& a, cudaStream_t st);
+void launch_text_layout(const TextAssembleArgs& a, cudaStream_t st);
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st);

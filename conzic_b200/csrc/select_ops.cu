@@ -163,10 +163,6 @@ __global__ void assemble_kernel(AssembleArgs a) {
   const int body_max = a.maxlen - 2;
   if (threadIdx.x == 0) {
     int np = 0, nt = 0;
-    if (a.ov_mask && a.ov_mask[b]) {  // host-tokenised prefix / tail (a merged '##' word sits in this caption)
-      for (int t = a.ov_off[2 * b]; t < a.ov_off[2 * b + 1]; ++t) if (np < MAX_BODY) pre[np++] = a.ov_tok[t];
-      for (int t = a.ov_off[2 * b + 1]; t < a.ov_off[2 * b + 2]; ++t) if (nt < MAX_BODY) tail[nt++] = a.ov_tok[t];
-    } else
     for (int j = 0; j < a.L; ++j) {
       if (j == a.pos) continue;
       const int64_t id = row[j];

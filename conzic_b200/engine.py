@@ -139,6 +139,7 @@ class Engine:
         self._vws = None
         self.vision_cfg = None
         self.has_table = False
+        self.has_text_vocab = False
         if "vision_model.embeddings.patch_embedding.weight" in clip_sd:
             self.set_vision(clip_sd)
 
@@ -204,6 +205,19 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         self.max_tok_per_word = max(w, 1)
         self.has_table = True
+
+    def set_text_vocab(self, tv: Dict[str, object]):
+        """Uploads the device text pipeline's tables (tokens.build_text_vocab): vocabularies with '##' word pieces
+        then run the whole step on the device (conzic_set_text_vocab)."""
+        assert self.has_table, "call Engine.set_bert2clip first"
+        keep = {k: v.to(self.device).contiguous() for k, v in tv.items() if isinstance(v, torch.Tensor)}
+        t = _lib.TextVocab()
+        for name in ("tok_off", "tok_bytes", "tok_cls", "tok_flags", "byte_sym", "merge_keys", "merge_vals"):
+            setattr(t, name, keep[name].data_ptr())
+        t.n_bytes, t.merge_bits = int(keep["tok_bytes"].numel()), int(tv["merge_bits"])
+        _lib.check(self.lib.conzic_set_text_vocab(self.ctx, C.byref(t), self._stream()), "conzic_set_text_vocab")
+        self.has_text_vocab = True
+        self._ws = None  # the workspace plan grows by the per-candidate sequence buffer
 
     # ------------------------------------------------------------------ image tower (once per call)
     def set_vision(self, clip_sd: SD):
@@ -310,32 +324,6 @@ class Engine:
                                               self._stream())
         _lib.check(rc, "conzic_clip_text_encode")
         return out
-
-    def encode_candidates(self, inp: torch.Tensor, pos: int, ids: torch.Tensor, token_mask: torch.Tensor, P: int, S: int,
-                          senti_table: Optional[torch.Tensor] = None, want_repeats: bool = False, overrides=None):
-        """gen_utils.py:71-76 + clip/clip.py:71-83 without the string round trip: candidate ids -> CLIP ids via the
-        table (shared prefix of P rows per image, S rows per candidate) -> text tower.  Returns (text_embeds
-        f32[B*K, D], ids_masked int64[B,K], repeats f32[B,K] or None, senti_raw f32[B,K] or None) on the device.
-        `overrides` = (ov_mask int32[B], ov_off int32[2B+1], ov_tok int32[n]) host tensors: host-tokenised prefix /
-        tail CLIP ids for the images whose caption holds a merged '##' word (see conzic.h)."""
-        assert self.has_table, "call Engine.set_bert2clip first"
-        B, L = inp.shape
-        K = ids.shape[1]
-        text = torch.empty((B * K, self.D), dtype=torch.float32, device=self.device)
-        ids_masked = torch.empty((B, K), dtype=torch.int64, device=self.device)
-        repeats = torch.empty((B, K), dtype=torch.float32, device=self.device) if want_repeats else None
-        senti = torch.empty((B, K), dtype=torch.float32, device=self.device) if senti_table is not None else None
-        ws = self.workspace(B, L, K)
-        ov = [None, None, None]
-        if overrides is not None:
-            ov = [t.to(self.device, torch.int32, non_blocking=True).contiguous() for t in overrides]
-            assert ov[0].numel() == B and ov[1].numel() == 2 * B + 1
-        rc = self.lib.conzic_encode_candidates(self.ctx, _ptr(inp), B, L, int(pos), _ptr(ids.contiguous()),
-                                               _ptr(token_mask), K, int(P), int(S), _ptr(senti_table), _ptr(text),
-                                               _ptr(ids_masked), _ptr(repeats), _ptr(senti), _ptr(ov[0]), _ptr(ov[1]),
-                                               _ptr(ov[2]), _ptr(ws), ws.numel(), self._stream())
-        _lib.check(rc, "conzic_encode_candidates")
-        return text, ids_masked, repeats, senti
 
     def image_text_similarity(self, image_embeds: torch.Tensor, text_embeds: torch.Tensor):
         """compute_image_text_similarity_via_embeddings (clip/clip.py:86-98)."""

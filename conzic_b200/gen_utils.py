@@ -36,15 +36,11 @@ class _Chain:
         self.eng = runtime.engine_for(model, clip, tokenizer)
         eng = self.eng
         self.clip = clip
-        # CONZIC_STRING_PATH=1 forces the reference's string round trip for every candidate.  Vocabularies with '##'
-        # word pieces (real BERT vocabularies) take the hybrid step: table path on the device, plus a host string
-        # pass for just the captions that contain a piece
-        self.string_path = os.environ.get("CONZIC_STRING_PATH") == "1"
-        self.hybrid = bool(getattr(eng, "needs_host_ids", None)) and not self.string_path
-        if self.hybrid and eng.precision == "certified":
-            # the hybrid step patches host-encoded rows into the embedding matrix and has no CLIP ids for the certified
-            # re-score: vocabularies with '##' pieces take the string path under the certified precision
-            self.hybrid, self.string_path = False, True
+        # Candidate captions become CLIP ids on the device: through the per-token table (vocabularies whose tokens are
+        # whole words) or through the device text pipeline (Hugging Face BertTokenizer / CLIPTokenizer: '##' pieces,
+        # punctuation clean-up, byte-level BPE).  The reference's string round trip remains for what neither covers --
+        # duck-typed tokenizers whose vocabulary has '##' pieces -- and on request (CONZIC_STRING_PATH=1).
+        self.string_path = os.environ.get("CONZIC_STRING_PATH") == "1" or bool(getattr(eng, "needs_strings", False))
         self.tokenizer, self.max_len, self.B = tokenizer, max_len, batch_size
         self.seed_len = len(prompt.split()) + 1
         batch = get_init_text(tokenizer, prompt, max_len, batch_size)
@@ -62,15 +58,13 @@ class _Chain:
         self.clip_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device)
         self.senti_slots = torch.zeros((n, batch_size), dtype=torch.float32, device=eng.device) if ctl else None
         self.inp_slots = None
-        self.mask_h = None
-        self._ov_memo = {}
 
     def step_via_strings(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
                          pos_scorer=None):
         """The same step with the reference's string round trip (gen_utils.py:66-81): candidate ids -> host ->
         tokenizer.batch_decode -> CLIP tokenizer -> device.  Every arithmetic piece is still a libconzic kernel;
-        only the text handling runs on the host.  Used by POS-template control (the tagger needs every string) and
-        when CONZIC_STRING_PATH=1 asks for it; vocabularies with '##' word pieces use step_hybrid."""
+        only the text handling runs on the host.  Used by POS-template control (the tagger needs every string), by
+        duck-typed tokenizers with '##' pieces, and when CONZIC_STRING_PATH=1 asks for it."""
         eng, tok = self.eng, self.tokenizer
         pos = self.seed_len + ii
         T = 1.0 if temperature is None else temperature
@@ -111,93 +105,11 @@ class _Chain:
             self.pos_tags = [tags[int(win[i]) + i * top_k] for i in range(self.B)]
         self.holds_word[pos] = True
 
-    def _clip_ids_of(self, ids_row):
-        """CLIP ids (no BOS / EOS) of the decoded text of a run of BERT ids, as the reference would produce them
-        (batch_decode with skip_special_tokens, then the CLIP tokenizer); memoised per id tuple."""
-        key = tuple(int(v) for v in ids_row)
-        hit = self._ov_memo.get(key)
-        if hit is None:
-            text = self.tokenizer.decode(ids_row, skip_special_tokens=True)
-            ctok = self.clip.tokenizer
-            if not text:
-                hit = ()
-            elif hasattr(ctok, "tokens_of_text"):
-                hit = tuple(ctok.tokens_of_text(text))
-            else:
-                hit = tuple(ctok(text, add_special_tokens=False)["input_ids"])
-            self._ov_memo[key] = hit
-        return hit
-
-    def step_hybrid(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None):
-        """The step for vocabularies with '##' word pieces.  A piece merges into the previous word and changes
-        that word's CLIP BPE, so the per-token table is exact only for captions without pieces.  All candidates go
-        through the table path on the device (shared prefix, conzic_encode_candidates); the host reads the top-k
-        ids and sorts the captions (tokens.hybrid_flags): a candidate that is itself a piece, or any candidate of an
-        image where a piece directly follows `pos`, is rebuilt as a string exactly like the reference does
-        (gen_utils.py:75), encoded densely with the same kernels and patched in before the fused score / argmax; an
-        image that merely holds a merged word elsewhere keeps the table path for its candidates and only has its
-        prefix / tail strings tokenised by the host (memoised).  One device->host read per step; the string work
-        overlaps the main encode on the GPU."""
-        from . import tokens
-        eng, tok = self.eng, self.tokenizer
-        pos = self.seed_len + ii
-        T = 1.0 if temperature is None else temperature
-        self.mask.view(-1)[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0  # utils.py:53-59
-        self.inp[:, pos] = eng.mask_id
-        row = logits_in[:, : eng.V] if logits_in is not None else eng.bert_mlm_row(self.inp, pos)
-        probs, idxs = eng.topk_mask(row, self.mask, T, top_k)
-        idxs_h, inp_h = idxs.cpu(), self.inp.cpu()
-        if self.mask_h is None:  # host mirror of the token mask; only the '.' column changes between steps
-            self.mask_h = self.mask.view(-1).cpu()
-        self.mask_h[eng.cfg.dot_id] = 1.0 if ii == self.max_len - 1 else 0.0
-        ids_masked_h = (idxs_h * self.mask_h[idxs_h]).long()  # gen_utils.py:72
-        special = [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id]
-        flag, override = tokens.hybrid_flags(inp_h, pos, ids_masked_h, eng.piece_mask_h, special)
-        overrides, ov_lens = None, {}
-        if bool(override.any()):
-            # images whose caption already holds a merged word (away from `pos`): the host tokenises their prefix and
-            # tail strings (memoised per id run), the candidates stay on the table path
-            ov_mask = override.to(torch.int32)
-            ov_off, ov_tok = [0], []
-            for b in range(self.B):
-                if bool(override[b]):
-                    pre_t = self._clip_ids_of(inp_h[b, :pos])
-                    tail_t = self._clip_ids_of(inp_h[b, pos + 1:])
-                    ov_lens[b] = (len(pre_t), len(tail_t))
-                else:
-                    pre_t, tail_t = (), ()
-                ov_tok.extend(pre_t)
-                ov_off.append(len(ov_tok))
-                ov_tok.extend(tail_t)
-                ov_off.append(len(ov_tok))
-            overrides = (ov_mask, torch.tensor(ov_off, dtype=torch.int32), torch.tensor(ov_tok or [0], dtype=torch.int32))
-        P, S = tokens.hybrid_capacities(inp_h, pos, ids_masked_h, eng.tok_len_h, ov_lens, eng.cfg.clip_maxpos)
-        if P + S > 96:
-            # the longest prefix and the longest suffix of the batch do not fit one attention tile together (each
-            # caption is still <= 77 tokens): every candidate takes the dense string pass for this step
-            flag = torch.ones_like(flag)
-            P, S = min(P, 48), min(S, 48)
-        text, ids_masked, repeats, senti_raw = eng.encode_candidates(
-            self.inp, pos, idxs, self.mask, P, S, senti_table=senti_table if gamma is not None else None,
-            want_repeats=gamma is not None, overrides=overrides)
-        if bool(flag.any()):  # host strings for the flagged captions only, while the GPU runs the main encode
-            bi, ki = flag.nonzero(as_tuple=True)
-            rows = inp_h[bi].clone()
-            rows[:, pos] = ids_masked_h[bi, ki]
-            emb = self.clip.compute_text_representation(tok.batch_decode(rows, skip_special_tokens=True))
-            text.index_copy_(0, (bi * top_k + ki).to(eng.device), emb)
-        eng.score_select(text, self.image_embeds, probs, ids_masked, self.inp, pos, alpha, beta, gamma=gamma,
-                         senti_raw=senti_raw, repeats=repeats, out_clip_ref=self.clip_slots[slot],
-                         out_senti=self.senti_slots[slot] if self.senti_slots is not None else None)
-        self.holds_word[pos] = True
-
     def step(self, slot, ii, top_k, temperature, alpha, beta, gamma=None, senti_table=None, logits_in=None,
              pos_scorer=None):
         if self.string_path or pos_scorer is not None:
             return self.step_via_strings(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in,
                                          pos_scorer)
-        if self.hybrid:
-            return self.step_hybrid(slot, ii, top_k, temperature, alpha, beta, gamma, senti_table, logits_in)
         pos = self.seed_len + ii
         before = sum(self.holds_word[:pos])
         after = sum(self.holds_word[pos + 1:])

@@ -100,20 +100,28 @@ def engine_for(model, clip, tokenizer=None, precision: Optional[str] = None, dev
 
 
 def bind_tokenizers(eng: Engine, bert_tokenizer, clip_tokenizer):
-    """Builds (once per tokenizer pair) and uploads the BERT-id -> CLIP-id table."""
+    """Builds (once per tokenizer pair) and uploads the BERT-id -> CLIP-id table and, for the Hugging Face fast
+    tokenizer pair, the device text pipeline's tables (vocabularies with '##' word pieces stay on the device)."""
     key = (id(bert_tokenizer), id(clip_tokenizer))
+    special = [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id, eng.cfg.mask_id]
     if key not in _tables:
-        _tables[key] = tokens.build_bert2clip(bert_tokenizer, clip_tokenizer, eng.V,
-                                              [eng.cfg.pad_id, eng.cfg.unk_id, eng.cfg.cls_id, eng.cfg.sep_id,
-                                               eng.cfg.mask_id])
-    off, tok, needs_host = _tables[key]
+        off, tok, pieces = tokens.build_bert2clip(bert_tokenizer, clip_tokenizer, eng.V, special)
+        ok, why = tokens.text_vocab_supported(bert_tokenizer, clip_tokenizer)
+        tv = tokens.build_text_vocab(bert_tokenizer, clip_tokenizer, eng.V, special, off, tok) if ok else None
+        _tables[key] = (off, tok, pieces, tv, why)
+        for obj in (bert_tokenizer, clip_tokenizer):  # id() values are reused after collection
+            try:
+                weakref.finalize(obj, _tables.pop, key, None)
+            except TypeError:
+                pass
+    off, tok, pieces, tv, why = _tables[key]
     eng.set_bert2clip(off, tok)
-    eng.needs_host_ids = needs_host
-    # host copies for the hybrid path of vocabularies with '##' pieces (tokens.hybrid_flags)
-    eng.piece_mask_h = torch.zeros(eng.V, dtype=torch.bool)
-    if needs_host:
-        eng.piece_mask_h[torch.tensor(needs_host, dtype=torch.long)] = True
-    eng.tok_len_h = (off[1:] - off[:-1])[: eng.V].to(torch.int32)
+    if tv is not None:
+        eng.set_text_vocab(tv)
+    # a vocabulary with '##' pieces that the device pipeline does not restate (duck-typed tokenizers) takes the
+    # reference's string round trip every step
+    eng.needs_strings = bool(pieces) and tv is None
+    eng.text_vocab_note = why
 
 
 def any_engine() -> Engine:

@@ -43,8 +43,10 @@ enum {
                                 the decision is taken on exact scores -- same winners and same reported cosines as
                                 CONZIC_PREC_BF16X3 (gen_utils.py:77-80), at close to bf16 speed                     */
 };
-#define CONZIC_CERT_DCOS_DEFAULT 4e-3f   /* bound on |cos(bf16 tower) - cos(bf16x3 tower)| of one candidate; measured
-                                            maximum on the config-2 workload x safety factor */
+#define CONZIC_CERT_DCOS_DEFAULT 1.6e-3f /* bound on |cos(bf16 tower) - cos(bf16x3 tower)| of one candidate: 1.3 x the
+                                            maximum over 1.0 M candidates of the config-2 / config-3 workloads
+                                            (1.22e-3; 99.999 % quantile 1.06e-3; tools/cert_bound.py,
+                                            profiles/r02a_cert_bound.md) */
 #define CONZIC_CERT_STATS 8
 
 /* conzic_config.flags */
@@ -72,7 +74,7 @@ typedef struct conzic_config {
   int32_t gemm_impl;           /* CONZIC_GEMM_* */
   int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (303104 = 16 waves of 148 x 128-row tiles) */
   float cert_dcos;             /* CERTIFIED: bound on the cosine error of the bf16 tower; 0 = CONZIC_CERT_DCOS_DEFAULT */
-  int32_t cert_fcap;           /* CERTIFIED: an image with more unbeaten candidates than this is re-encoded in full; 0 = 16 */
+  int32_t cert_fcap;           /* CERTIFIED: an image with more unbeaten candidates than this is re-encoded in full; 0 = 64 */
   int32_t flags;               /* CONZIC_FLAG_* */
 } conzic_config;
 
@@ -105,6 +107,25 @@ int conzic_abi_version(void);
 int conzic_set_bert2clip(conzic_ctx* ctx, const int32_t* off_dev, const int32_t* tok_dev, int n_tok,
                          int max_tok_per_word, void* stream);
 
+/* Device text pipeline for vocabularies with '##' word pieces -- every real BERT vocabulary (replaces
+ * tokenizer.batch_decode + CLIPTokenizer, gen_utils.py:75 + clip/clip.py:71-72, for the Hugging Face fast
+ * BertTokenizer / CLIPTokenizer pair; csrc/text_pipeline.cuh states the algorithm).  All pointers are DEVICE arrays,
+ * copied into the context.  conzic_set_bert2clip must have been called: whole-word tokens keep their table rows.
+ * With a text vocabulary set, conzic_gibbs_step builds every candidate's CLIP ids from the candidate caption's
+ * bytes (a piece merges into its neighbour word and changes that word's BPE) and reads the two row capacities of
+ * the step back (16 bytes, one stream synchronisation per step). */
+typedef struct conzic_text_vocab {
+  const int32_t* tok_off;      /* [V+1] byte offsets of each BERT token's text ('##' stripped, NFC, lowercase) */
+  const uint8_t* tok_bytes;    /* UTF-8 */
+  const uint8_t* tok_cls;      /* per byte: 0 other / 1 letter / 2 number / 3 space, | 4 on a character's first byte */
+  const uint8_t* tok_flags;    /* [V]: 1 '##' piece, 2 no space before it (WordPiece clean-up), 4 dropped, 8 simple */
+  const int32_t* byte_sym;     /* [512] CLIP id of byte b inside a word / [256+b] as the last byte of a word */
+  const uint64_t* merge_keys;  /* open-addressing table of 1 << merge_bits slots: (id_a << 32 | id_b) + 1, 0 = empty */
+  const uint32_t* merge_vals;  /* rank << 16 | merged id */
+  int32_t n_bytes, merge_bits;
+} conzic_text_vocab;
+int conzic_set_text_vocab(conzic_ctx* ctx, const conzic_text_vocab* v, void* stream);
+
 /* Scratch bytes needed by any call below with at most B images, L BERT tokens, K candidates. */
 size_t conzic_workspace_bytes(const conzic_ctx* ctx, int B, int L, int K);
 
@@ -132,25 +153,6 @@ int conzic_build_clip_ids(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L,
  * text_embeds f32[N,proj]. */
 int conzic_clip_text_encode(conzic_ctx* ctx, const int32_t* clip_ids_dev, int N, int T, float* text_embeds_dev,
                             void* ws_dev, size_t ws_bytes, void* stream);
-
-/* The middle of a Gibbs step on its own (gen_utils.py:71-76 + clip/clip.py:71-83): candidates -> CLIP ids through the
- * BERT-id -> CLIP-id table (caption prefix before `pos` encoded once per image, the rest per candidate) -> CLIP text
- * tower -> text_embeds f32[B*K, proj].  For callers that know the ids on the host (vocabularies with '##' word
- * pieces: rows whose caption contains a piece are re-encoded from strings by the caller and patched into
- * text_embeds before conzic_score_select).  P = prefix rows per image including BOS (>= 1 + the longest prefix in
- * CLIP tokens), S = rows per candidate (>= the longest candidate word + tail in CLIP tokens, + 1 for EOS); both are
- * capacities, shorter sequences are padded with EOS, longer ones are cut like truncation at 77 would.
- * Also out: ids_masked int64[B,K] = ids * token_mask[ids]; repeats f32[B,K] (control_gen_utils.py:53) or NULL;
- * senti_raw f32[B,K] = sum of senti_table over the caption's words, or NULL (needs senti_table).
- * Optional override (all three or none; int32 device arrays): for images with ov_mask[b] != 0 the CLIP ids of the
- * words before `pos` are ov_tok[ov_off[2b] .. ov_off[2b+1]) and of the words after it ov_tok[ov_off[2b+1] ..
- * ov_off[2b+2]) instead of the table's -- the caller tokenised those two strings itself because they hold a merged
- * '##' word; the candidate word still comes from the table. */
-int conzic_encode_candidates(conzic_ctx* ctx, const int64_t* inp_dev, int B, int L, int pos, const int64_t* ids_dev,
-                             const float* token_mask_dev, int K, int P, int S, const float* senti_table_dev,
-                             float* text_embeds_dev, int64_t* ids_masked_dev, float* repeats_dev, float* senti_raw_dev,
-                             const int32_t* ov_mask_dev, const int32_t* ov_off_dev, const int32_t* ov_tok_dev,
-                             void* ws_dev, size_t ws_bytes, void* stream);
 
 /* compute_image_text_similarity_via_embeddings (clip/clip.py:86-98): text f32[B*K,D], image f32[B,D]
  * -> clip_score f32[B,K] (softmax over K of scale*cos) and clip_ref f32[B,K] (cos). */

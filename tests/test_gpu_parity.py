@@ -422,18 +422,16 @@ def test_host_string_path_matches_reference(name, prec, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["pieces_seq_b2_n5_k16", "pieces_shuffle_b3_n6_k16_multi"])
-@pytest.mark.parametrize("path", ["hybrid", "strings"])
-def test_piece_vocabulary_matches_reference(name, path, monkeypatch):
-    """A BERT vocabulary with '##' word pieces (the shape of real bert-base-uncased): pieces among the candidates and,
-    once one wins, inside the caption.  Default = hybrid step (table path on the device + host strings for just the
-    captions that contain a piece, conzic_encode_candidates); CONZIC_STRING_PATH=1 = every candidate through
-    strings.  Both must reproduce the unmodified reference's captions and scores."""
+@pytest.mark.parametrize("prec", ["certified", "bf16x3"])
+def test_duck_typed_piece_vocabulary_matches_reference(name, prec, monkeypatch):
+    """A duck-typed tokenizer pair whose BERT vocabulary has '##' word pieces (not the Hugging Face classes the
+    device text pipeline restates): the engine detects that and takes the reference's string round trip every step
+    (gen_utils.py:75); pieces among the candidates and, once one wins, inside the caption.  Must reproduce the
+    unmodified reference's captions and scores."""
     import logging
     from conzic_b200 import gen_utils, runtime
     from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
-    if path == "strings":
-        monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+    monkeypatch.setenv("CONZIC_PRECISION", prec)
     runtime.clear()
     g = gc.load_golden(name)
     case = g["case"]
@@ -445,12 +443,13 @@ def test_piece_vocabulary_matches_reference(name, path, monkeypatch):
     B, n, K = case["B"], case["n"], case["K"]
     pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
     set_seed(42)
+    bert_tok = synth.PieceBertTokenizer()  # engines are dropped when their tokenizer is collected: keep it alive
     texts, scores = gen_utils.generate_caption(
-        [f"img{i}.jpg" for i in range(B)], bert, clip, synth.PieceBertTokenizer(), pix, synth.make_token_mask("cuda"),
+        [f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix, synth.make_token_mask("cuda"),
         logging.getLogger("test"), prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1,
         max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
     eng = runtime.any_engine()
-    assert len(eng.needs_host_ids) > 5000 and int(eng.tok_len_h[eng.piece_mask_h].max()) == 0
+    assert eng.needs_strings and not eng.has_text_vocab
     runtime.clear()
     if "shuffle" in name:  # in this fixture a piece wins a slot, so later steps see a merged word inside the caption
         assert any("p" in w[1:] for t in g["texts"] for c in t for w in c.split()), "fixture holds no merged word"
@@ -519,73 +518,135 @@ def test_cabi_rejects_bad_arguments():
     assert rc < 0 and "workspace too small" in _lib.last_error()
     with pytest.raises(RuntimeError, match=r"T must be in \[1, 77\]"):
         eng.clip_text_encode(torch.full((2, 78), synth.CLIP_EOS, dtype=torch.int32))
-    with pytest.raises(RuntimeError, match="bad B / K / pos / P / S"):
-        eng.encode_candidates(inp, 4, torch.full((B, 4), 2000, device="cuda"), tm, 77, 4)
     # still healthy afterwards
     _, _, tr = eng.gibbs_step(inp, tm, img, 4, False, 8, 0.1, 0.02, 2.0, 3, 0, trace=True)
     torch.cuda.synchronize()
     assert bool((inp[:, 4] >= 1996).all())
 
 
-def test_real_hf_tokenizer_classes_match_reference(monkeypatch, tmp_path):
-    """generate_caption with the REAL transformers BertTokenizer / CLIPTokenizer classes (generated vocabulary files:
-    WordPiece decode with '##' joining and clean-up, byte-level BPE with merges, several CLIP tokens per word) against
-    the fixture the unmodified reference produced with the same tokenizers: the generic table builder
-    (tokens.build_bert2clip) and the hybrid step must reproduce its captions and scores."""
+@pytest.mark.parametrize("vocab", ["letters", "rich"])
+def test_device_text_kernel_matches_hf_tokenizers(vocab, tmp_path):
+    """text_tokenize_kernel (csrc/text_ops.cu around text_pipeline.cuh) against the real transformers classes at
+    scale: 48 images x 128 candidates, words / '##' pieces / punctuation / specials / masked candidates; every
+    candidate caption's CLIP ids must equal CLIPTokenizer(BertTokenizer.batch_decode(ids, skip_special_tokens=True))
+    (gen_utils.py:75 + clip/clip.py:71-72), BOS / EOS framing, EOS padding and lengths included."""
+    from conzic_b200 import runtime, tokens
+    from conzic_b200.engine import Engine
+    if vocab == "letters":
+        bert_tok, clip_tok = synth.make_hf_tokenizers(str(tmp_path))
+        V, lo_dense, n_dense = synth.BERT_VOCAB, 1996, synth.BERT_VOCAB - 1996
+    else:
+        bert_tok, clip_tok = synth.make_hf_tokenizers_rich(str(tmp_path))
+        V, lo_dense, n_dense = 3000, 1996, 116
+    sd = runtime._dummy_bert_sd()
+    sd["bert.embeddings.word_embeddings.weight"] = torch.zeros(V, 64)
+    sd["cls.predictions.bias"] = torch.zeros(V)
+    eng = Engine(sd, gc.weights("clip"), device="cuda:0", precision="bf16")
+    special = list(synth.SPECIAL_IDS)
+    off, tok, pieces = tokens.build_bert2clip(bert_tok, clip_tok, V, special)
+    eng.set_bert2clip(off, tok)
+    eng.set_text_vocab(tokens.build_text_vocab(bert_tok, clip_tok, V, special, off, tok))
+    g = torch.Generator().manual_seed(7)
+    B, L, K, pos = 48, 14, 128, 6
+    inp = torch.randint(1996, V, (B, L), generator=g)
+    dense = torch.rand((B, L), generator=g) < 0.6
+    inp[dense] = torch.randint(lo_dense, lo_dense + n_dense, (int(dense.sum()),), generator=g)
+    inp[torch.rand((B, L), generator=g) < 0.06] = synth.DOT_ID
+    inp[torch.rand((B, L), generator=g) < 0.04] = synth.PAD_ID
+    inp[:, 0], inp[:, -1] = synth.CLS_ID, synth.SEP_ID
+    inp[:, pos] = synth.MASK_ID
+    inp[0, 1:pos] = synth.PAD_ID  # the candidate becomes the first kept token: a piece candidate stays verbatim
+    ids = torch.randint(lo_dense, lo_dense + n_dense, (B, K), generator=g)
+    ids[:, ::7] = torch.randint(1996, V, (B, len(range(0, K, 7))), generator=g)
+    ids[:, 3] = synth.DOT_ID
+    mask = torch.ones(1, V)
+    mask[0, ids[1, 5]] = 0  # a masked candidate: the word vanishes from the caption (gen_utils.py:72)
+    idm = (ids * mask[0][ids]).long()
+    cand = inp.unsqueeze(1).repeat(1, K, 1)
+    cand[:, :, pos] = idm
+    texts = bert_tok.batch_decode(cand.view(-1, L), skip_special_tokens=True)
+    ref = clip_tok(texts, padding="max_length", max_length=77, truncation=True, return_tensors="pt")["input_ids"]
+    got, glen, gidm = eng.build_clip_ids(inp.cuda(), pos, ids.cuda(), mask.cuda(), 77)
+    torch.cuda.synchronize()
+    assert torch.equal(gidm.cpu(), idm)
+    # rows are compared up to the first EOS id (where the tower pools; with the letter vocabulary '#' is an unknown
+    # symbol whose id is the EOS id, like in the released CLIP vocabulary), the rest must be EOS padding
+    ref_len = (ref == synth.CLIP_EOS).int().argmax(1) + 1
+    assert torch.equal(glen.cpu().long(), ref_len)
+    live = torch.arange(77)[None, :] < ref_len[:, None]
+    want = torch.where(live, ref, torch.full_like(ref, synth.CLIP_EOS))
+    bad = (got.cpu().long() != want).any(dim=1).nonzero().flatten().tolist()
+    assert not bad, (len(bad), texts[bad[0]], got[bad[0]].tolist()[:24], want[bad[0]].tolist()[:24])
+    assert any("##" in t for t in texts) or vocab == "rich"
+    eng.close()
+
+
+def _hf_generate(prec, string_path, tmp_path, monkeypatch, B, n, K, iters, order, mode="caption", prompt=None):
     import logging
-    from conzic_b200 import gen_utils, runtime
+    from conzic_b200 import control_gen_utils, gen_utils, runtime
     from conzic_b200.clip.clip import CLIP
     from conzic_b200.models import BertMLM
     from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
+    monkeypatch.setenv("CONZIC_PRECISION", prec)
+    if string_path:
+        monkeypatch.setenv("CONZIC_STRING_PATH", "1")
+    else:
+        monkeypatch.delenv("CONZIC_STRING_PATH", raising=False)
     runtime.clear()
-    g = gc.load_golden("hf_shuffle_b3_n5_k24")
-    case = g["case"]
     bert_tok, clip_tok = synth.make_hf_tokenizers(str(tmp_path))
     bert = BertMLM(gc.weights("bert"))
     clip = CLIP(state_dict=gc.weights("clip"), tokenizer=clip_tok, processor=synth.SynthProcessor()).to("cuda:0")
-    B, n, K = case["B"], case["n"], case["K"]
     pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+    lines = []
+    logger = logging.getLogger(f"hf-{prec}-{string_path}-{mode}-{order}")
+    logger.setLevel(logging.INFO)
+    logger.propagate = False
+    h = logging.Handler()
+    h.emit = lambda rec: lines.append(rec.getMessage())
+    logger.addHandler(h)
+    kw = dict(prompt=prompt or synth.hf_prompt(), batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=iters,
+              alpha=0.02, beta=2.0)
+    names = [f"img{i}.jpg" for i in range(B)]
     set_seed(42)
-    texts, scores = gen_utils.generate_caption(
-        [f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix, synth.make_token_mask("cuda"),
-        logging.getLogger("test"), prompt=synth.hf_prompt(), batch_size=B, max_len=n, top_k=K, temperature=0.1,
-        max_iter=case["iters"], alpha=0.02, beta=2.0, generate_order=case["order"])
+    if mode == "sentiment":
+        out = control_gen_utils.control_generate_caption(
+            names, bert, clip, bert_tok, pix, synth.make_token_mask("cuda"), logger, gamma=5.0, ctl_type="sentiment",
+            style_type="positive", generate_order=order, sentiment_table=synth.make_sentiment_table(), **kw)
+    else:
+        out = gen_utils.generate_caption(names, bert, clip, bert_tok, pix, synth.make_token_mask("cuda"), logger,
+                                         generate_order=order, **kw)
     eng = runtime.any_engine()
-    assert len(eng.needs_host_ids) > 5000 and eng.max_tok_per_word > 3
+    info = dict(has_text=eng.has_text_vocab, W=eng.max_tok_per_word, launches=eng.launch_count())
     runtime.clear()
+    return out, [ln for ln in lines if ln.startswith("iter ")], info, clip_tok
+
+
+@pytest.mark.parametrize("prec", ["certified", "bf16x3"])
+def test_real_hf_tokenizer_classes_match_reference(prec, monkeypatch, tmp_path):
+    """generate_caption with the REAL transformers BertTokenizer / CLIPTokenizer classes (generated vocabulary files:
+    WordPiece decode with '##' joining and clean-up, byte-level BPE with merges, several CLIP tokens per word) against
+    the fixture the unmodified reference produced with the same tokenizers.  The whole step runs on the device: the
+    candidates' CLIP ids come from the device text pipeline (conzic_set_text_vocab), no string leaves the GPU."""
+    g = gc.load_golden("hf_shuffle_b3_n5_k24")
+    case = g["case"]
+    (texts, scores), _, info, _ = _hf_generate(prec, False, tmp_path, monkeypatch, case["B"], case["n"], case["K"],
+                                               case["iters"], case["order"])
+    assert info["has_text"] and info["W"] > 3
     assert texts == g["texts"]
     for a, b in zip(scores, g["scores"]):
         np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
 
 
-def test_long_token_heavy_captions_hybrid_equals_string_path(monkeypatch, tmp_path):
+def test_long_token_heavy_captions_device_text_equals_string_path(monkeypatch, tmp_path):
     """Real tokenizer classes, 3-5 CLIP tokens per word, 22-word sentences: captions reach the 77-token truncation
-    and the longest prefix + longest suffix exceed one attention tile (the hybrid step then sends the whole step
-    through the dense string pass).  Hybrid and all-strings must still agree exactly."""
-    import logging
-    from conzic_b200 import gen_utils, runtime
-    from conzic_b200.clip.clip import CLIP
-    from conzic_b200.models import BertMLM
-    from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
-    bert_tok, clip_tok = synth.make_hf_tokenizers(str(tmp_path))
+    and the longest prefix + longest suffix exceed one attention tile (the step then shortens the shared prefix).
+    The device text pipeline and the reference's string round trip must agree exactly."""
     B, n, K = 2, 22, 8
-    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
     out = {}
-    for path in ("hybrid", "strings"):
-        if path == "strings":
-            monkeypatch.setenv("CONZIC_STRING_PATH", "1")
-        runtime.clear()
-        bert = BertMLM(gc.weights("bert"))
-        clip = CLIP(state_dict=gc.weights("clip"), tokenizer=clip_tok, processor=synth.SynthProcessor()).to("cuda:0")
-        set_seed(42)
-        out[path] = gen_utils.generate_caption(
-            [f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix, synth.make_token_mask("cuda"),
-            logging.getLogger("test"), prompt=synth.hf_prompt(), batch_size=B, max_len=n, top_k=K, temperature=0.1,
-            max_iter=2, alpha=0.02, beta=2.0, generate_order="sequential")
-    runtime.clear()
-    (ta, sa), (tb, sb) = out["hybrid"], out["strings"]
+    for path in ("device", "strings"):
+        (t, s), _, info, clip_tok = _hf_generate("bf16x3", path == "strings", tmp_path, monkeypatch, B, n, K, 2, "sequential")
+        out[path] = (t, s)
+    (ta, sa), (tb, sb) = out["device"], out["strings"]
     assert ta == tb
     for a, b in zip(sa, sb):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
@@ -593,54 +654,22 @@ def test_long_token_heavy_captions_hybrid_equals_string_path(monkeypatch, tmp_pa
     assert n_tok > 75, "captions are not token heavy enough to exercise truncation / the tile guard"
 
 
-@pytest.mark.parametrize("mode", ["sentiment", "span", "random"])
-def test_piece_vocabulary_hybrid_equals_string_path(mode, monkeypatch):
-    """Piece vocabulary, modes the reference fixtures do not cover (its stub sentiment scorer cannot look up merged
-    words): the hybrid step and the all-strings step are two routes to the same numbers -- captions, CLIP scores and
-    (sentiment) the per-sweep log lines must agree exactly in bf16x3 mode."""
-    import logging
-    from conzic_b200 import control_gen_utils, gen_utils, runtime
-    from conzic_b200.clip.clip import CLIP
-    from conzic_b200.models import BertMLM
-    from conzic_b200.utils import set_seed
-    monkeypatch.setenv("CONZIC_PRECISION", "bf16x3")
-    B, n, K = 3, 5, 16
-    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
-    names = [f"img{i}.jpg" for i in range(B)]
-    results = {}
-    for path in ("hybrid", "strings"):
-        if path == "strings":
-            monkeypatch.setenv("CONZIC_STRING_PATH", "1")
-        runtime.clear()
-        bert = BertMLM(gc.weights("bert"))
-        clip = CLIP(state_dict=gc.weights("clip"), tokenizer=synth.PieceCLIPTokenizer(True),
-                    processor=synth.SynthProcessor()).to("cuda:0")
-        lines = []
-        logger = logging.getLogger(f"pieces-{mode}-{path}")
-        logger.setLevel(logging.INFO)
-        logger.propagate = False
-        h = logging.Handler()
-        h.emit = lambda rec: lines.append(rec.getMessage())
-        logger.addHandler(h)
-        kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=2, alpha=0.02,
-                  beta=2.0)
-        set_seed(42)
-        if mode == "sentiment":
-            out = control_gen_utils.control_generate_caption(
-                names, bert, clip, synth.PieceBertTokenizer(), pix, synth.make_token_mask("cuda"), logger, gamma=5.0,
-                ctl_type="sentiment", style_type="positive", generate_order="shuffle",
-                sentiment_table=synth.make_sentiment_table(), **kw)
-        else:
-            out = gen_utils.generate_caption(names, bert, clip, synth.PieceBertTokenizer(), pix,
-                                             synth.make_token_mask("cuda"), logger, generate_order=mode, **kw)
-        results[path] = (out, [ln for ln in lines if ln.startswith("iter ")])
-    runtime.clear()
-    (ta, sa), la = results["hybrid"]
-    (tb, sb), lb = results["strings"]
+@pytest.mark.parametrize("mode,order", [("sentiment", "shuffle"), ("caption", "span"), ("caption", "random"),
+                                        ("caption", "sequential")])
+def test_piece_vocabulary_device_text_equals_string_path(mode, order, monkeypatch, tmp_path):
+    """Piece vocabulary (real tokenizer classes), modes the reference fixtures do not cover: the device text pipeline
+    and the all-strings step are two routes to the same numbers -- captions, CLIP scores and the per-sweep log lines
+    must agree exactly, in the default (certified) precision; the device route must not be the slow one."""
+    B, n, K = 3, 6, 16
+    res = {}
+    for path in ("device", "strings"):
+        out, lines, info, _ = _hf_generate("certified", path == "strings", tmp_path, monkeypatch, B, n, K, 2, order, mode)
+        res[path] = (out, lines)
+    (ta, sa), la = res["device"]
+    (tb, sb), lb = res["strings"]
     assert ta == tb and la == lb and len(la) > 0
     for a, b in zip(sa, sb):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
-    assert any("p" in w[1:] for c in ta[-2] for w in c.split()) or mode != "sentiment"
 
 
 def test_long_sentence_free_running_matches_oracle():
@@ -812,7 +841,8 @@ def _run_generate(prec, B, n, K, sweeps, order, monkeypatch):
                 processor=synth.SynthProcessor()).to("cuda")  # index-less device, like the reference's scripts
     pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
     set_seed(42)
-    out = gen_utils.generate_caption([f"img{i}.jpg" for i in range(B)], bert, clip, synth.SynthBertTokenizer(), pix,
+    bert_tok = synth.SynthBertTokenizer()  # engines are dropped when their tokenizer is collected: keep it alive
+    out = gen_utils.generate_caption([f"img{i}.jpg" for i in range(B)], bert, clip, bert_tok, pix,
                                      synth.make_token_mask("cuda"), logging.getLogger("test"), prompt=synth.SYNTH_PROMPT,
                                      batch_size=B, max_len=n, top_k=K, temperature=0.1, max_iter=sweeps, alpha=0.02,
                                      beta=2.0, generate_order=order)
@@ -832,8 +862,10 @@ def test_config2_free_running_certified_equals_bf16x3(order, monkeypatch):
     assert tc == t3
     assert sc == s3
     assert st["calls"] == 50 and st["images"] == 3200 and st["rescored_candidates"] >= 3200
-    # the point of the bound: almost every candidate is ruled out by the bf16 scores alone
+    # the point of the bound: almost every candidate is ruled out by the bf16 scores alone, and (nearly) no image
+    # needs every candidate re-encoded
     assert st["rescored_candidates"] < 0.05 * 3200 * 200, st
+    assert st["images_full"] < 0.02 * 3200, st
 
 
 def test_config2_certified_lockstep_with_cpu_oracle():

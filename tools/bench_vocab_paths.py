@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""captions/s of generate_caption (BASELINE config 2 sizes, host pixels in, strings out) for the three candidate-text
-paths: the plain synthetic vocabulary (everything on the device), a vocabulary with '##' word pieces through the
-hybrid step (table path + host strings for the captions that contain a piece), and the same vocabulary with every
-candidate through host strings (CONZIC_STRING_PATH=1, what the reference does each step).
+"""Milliseconds per Gibbs step of generate_caption (BASELINE config 2 sizes, host pixels in, strings out) for the
+candidate-text paths: the per-token table (vocabularies of whole words), the device text pipeline (real transformers
+BertTokenizer / CLIPTokenizer classes with '##' pieces: WordPiece decode + CLIP BPE on the device) and the
+reference's string round trip (CONZIC_STRING_PATH=1, or a duck-typed tokenizer pair with pieces).
 
     python tools/bench_vocab_paths.py [--sweeps 2] [--batch 64]
 """
@@ -37,21 +37,27 @@ def main():
     names = [f"img{i}.jpg" for i in range(B)]
     import tempfile
     hf_bert, hf_clip = synth.make_hf_tokenizers(tempfile.mkdtemp())
-    for label, pieces, env in (("device (no pieces in the vocabulary)", False, {}),
-                               ("hybrid (pieces: table path + host strings for flagged captions)", True, {}),
-                               ("strings (pieces: every candidate through host strings)", True, {"CONZIC_STRING_PATH": "1"}),
-                               ("hybrid, real transformers tokenizer classes (pieces, ~5 CLIP tokens per word)", "hf", {}),
-                               ("strings, real transformers tokenizer classes", "hf", {"CONZIC_STRING_PATH": "1"})):
+    hf1_bert, hf1_clip = synth.make_hf_tokenizers(tempfile.mkdtemp(), single_token_words=True)
+    S1 = {"CONZIC_STRING_PATH": "1"}
+    for label, kind, env in (("device table path (synthetic tokenizers, no pieces, 1 CLIP token per word)", "synth", {}),
+                             ("device text pipeline (real transformers classes, '##' pieces, 1 CLIP token per whole word)", "hf1", {}),
+                             ("string round trip, same tokenizers", "hf1", S1),
+                             ("device text pipeline (real transformers classes, '##' pieces, ~4 CLIP tokens per word)", "hf", {}),
+                             ("string round trip, same tokenizers", "hf", S1),
+                             ("string round trip (duck-typed tokenizers with pieces: what the engine falls back to)", "pieces", {})):
         os.environ.update(env)
         runtime.clear()
         bert = BertMLM(bert_sd)
-        if pieces == "hf":
+        pieces = kind
+        if kind == "hf":
             ctok, btok = hf_clip, hf_bert
+        elif kind == "hf1":
+            ctok, btok = hf1_clip, hf1_bert
         else:
-            ctok = synth.PieceCLIPTokenizer() if pieces else synth.SynthCLIPTokenizer()
-            btok = synth.PieceBertTokenizer() if pieces else synth.SynthBertTokenizer()
+            ctok = synth.PieceCLIPTokenizer() if kind == "pieces" else synth.SynthCLIPTokenizer()
+            btok = synth.PieceBertTokenizer() if kind == "pieces" else synth.SynthBertTokenizer()
         clip = CLIP(state_dict=clip_sd, tokenizer=ctok, processor=synth.SynthProcessor()).to("cuda:0")
-        prompt = synth.hf_prompt() if pieces == "hf" else synth.SYNTH_PROMPT
+        prompt = synth.hf_prompt() if kind in ("hf", "hf1") else synth.SYNTH_PROMPT
 
         def call():
             return gen_utils.generate_caption(names, bert, clip, btok, pix, synth.make_token_mask("cuda"), log,
@@ -64,10 +70,11 @@ def main():
         texts, _ = call()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        merged = sum(1 for c in texts[-2] for w in c.split() if "p" in w[1:]) if pieces != "hf" else None
-        print(json.dumps({"path": label, "batch": B, "sweeps": a.sweeps, "seconds": round(dt, 3),
+        eng = runtime.any_engine()
+        print(json.dumps({"path": label, "precision": eng.precision, "batch": B, "sweeps": a.sweeps, "seconds": round(dt, 3),
                           "ms_per_gibbs_step": round(1e3 * dt / (a.sweeps * n), 2),
-                          "merged_words_in_final_captions": merged}), flush=True)
+                          "device_text_pipeline": bool(eng.has_text_vocab), "string_path": bool(env) or bool(eng.needs_strings),
+                          "max_clip_tokens_per_word": eng.max_tok_per_word}), flush=True)
         for k in env:
             os.environ.pop(k)
     runtime.clear()

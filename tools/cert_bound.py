@@ -69,7 +69,7 @@ def main():
         random.seed(42)
         random.shuffle(order)
     eps_grid = [1e-3, 1.5e-3, 2e-3, 3e-3, 4e-3, 6e-3, 8e-3]
-    all_d, flips, steps = [], 0, 0
+    all_d, all_sd, all_cen, flips, steps = [], [], [], 0, 0
     surv = {e: [] for e in eps_grid}
     per_step = []
     for it in range(args.sweeps):
@@ -86,8 +86,12 @@ def main():
             _, _, t16 = e16.gibbs_step(i16, tm16, img, pos, ii == n - 1, K, 0.1, 0.02, 2.0, before, after, **kw)
             torch.cuda.synchronize()
             assert torch.equal(t3["idxs"], t16["idxs"])
-            d = (t16["clip_ref"] - t3["clip_ref"]).abs()
+            sd = t16["clip_ref"] - t3["clip_ref"]  # signed: the softmax only sees differences between candidates
+            d = sd.abs()
             all_d.append(d.flatten().cpu())
+            all_sd.append(sd.flatten().cpu())
+            cen = sd - sd.mean(dim=1, keepdim=True)
+            all_cen.append(cen.flatten().cpu())
             nf = int((i3[:, pos] != i16[:, pos]).sum())
             flips += nf
             steps += 1
@@ -100,7 +104,11 @@ def main():
     qs = [0.5, 0.9, 0.99, 0.999, 0.9999, 0.99999]
     ds = d.sort().values
     quant = {str(q): float(ds[min(int(q * ds.numel()), ds.numel() - 1)]) for q in qs}
-    rep = dict(workload=dict(images=B, sweeps=args.sweeps, K=K, sentence_len=n, order=args.order, steps=steps,
+    sd, cen = torch.cat(all_sd), torch.cat(all_cen)
+    signed = dict(mean=float(sd.mean()), std=float(sd.std()), min=float(sd.min()), max=float(sd.max()),
+                  max_abs_minus_global_mean=float((sd - sd.mean()).abs().max()),
+                  max_abs_minus_image_mean=float(cen.abs().max()), std_minus_image_mean=float(cen.std()))
+    rep = dict(signed_error=signed, workload=dict(images=B, sweeps=args.sweeps, K=K, sentence_len=n, order=args.order, steps=steps,
                              candidates=int(d.numel())),
                max_dcos=float(d.max()), mean_dcos=float(d.mean()), quantiles=quant,
                image_embed_min_cos_bf16_vs_x3=float(icos.min()),

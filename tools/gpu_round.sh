@@ -13,7 +13,7 @@ if has smoke; then
   timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.log
 fi
 if has test; then
-  timeout 2400 python -m pytest tests -m gpu -x -q --durations=15 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+  timeout 2400 python -m pytest tests -m gpu -q --maxfail=40 --durations=15 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
   tail -30 $OUT/pytest_gpu.log
 fi
 if has bound; then
@@ -36,9 +36,16 @@ if has configs; then
   done
   timeout 1800 python bench.py --config 5 --steps 2 --warmup 3 --no-cpu > $OUT/bench_config5.json 2> $OUT/bench_config5.err; echo "config 5 rc=$?"; cat $OUT/bench_config5.json | cut -c1-600
 fi
+if has vocab; then
+  timeout 900 python tools/bench_vocab_paths.py > $OUT/vocab_paths.jsonl 2> $OUT/vocab_paths.err; echo "vocab rc=$?"; cat $OUT/vocab_paths.jsonl
+fi
 if has breakdown; then
   for ii in 0 3 6 9; do timeout 300 python tools/profile_step.py --ii $ii --steps 3 --breakdown >> $OUT/breakdown.jsonl 2>> $OUT/breakdown.err; done
   cat $OUT/breakdown.jsonl
+fi
+if has ncustep; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches_step.csv \
+      python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_step.log 2>&1; echo "ncu list rc=$?"
 fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_step.csv \
