@@ -418,6 +418,7 @@ def measure(args, rank, local_rank, world, wl: Workload, full: bool):
     eng.profile(True)
     job.device_step()
     prof = eng.profile_read()
+    phases = eng.profile_read_phases()
     eng.profile(False)
     pk = peaks()
     g_ms, g_flops, g_n = prof["gemm"]
@@ -441,6 +442,7 @@ def measure(args, rank, local_rank, world, wl: Workload, full: bool):
                         "flops_per_launch": g_flops / max(g_n, 1),
                         "share_of_step": g_ms / total_ms if total_ms else None},
            "step_breakdown_ms": {k: round(v[0], 3) for k, v in prof.items()},
+           "phase_breakdown_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in phases.items()},
            "algorithmic": {"tflop_per_caption": algo,
                            "tflops_per_gpu": value / world * algo,
                            "frac_of_peak": value / world * algo / pk["tf"],

@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("pad_id", C.c_int32), ("unk_id", C.c_int32), ("cls_id", C.c_int32), ("sep_id", C.c_int32),
         ("mask_id", C.c_int32), ("dot_id", C.c_int32), ("clip_bos", C.c_int32), ("clip_eos", C.c_int32),
         ("precision", C.c_int32), ("gemm_impl", C.c_int32), ("clip_chunk_rows", C.c_int32),
-        ("cert_dcos", C.c_float), ("cert_fcap", C.c_int32), ("flags", C.c_int32),
+        ("cert_dcos", C.c_float), ("cert_dcos_lo", C.c_float), ("cert_fcap", C.c_int32), ("flags", C.c_int32),
     ]
 
 

@@ -3,20 +3,22 @@
 //
 // The fused score of candidate k is  f_k = E_k + beta * exp(t_k) / Z,  Z = sum_j exp(t_j),  where t_k is the exact
 // logit (scale * cosine) and E_k = alpha * p_k (+ gamma * senti_k + 0.1 (1 - exp(rep_k))) does not depend on the
-// tower.  The bf16 tower gives a_k with |a_k - t_k| <= eps (eps = scale * a measured bound on the cosine error, with
-// a safety factor; conzic_config.cert_dcos).  For the bf16 winner w and any other candidate k
+// tower.  The bf16 tower gives a_k with -lo <= a_k - t_k <= hi (scale * measured bounds on the cosine error with a
+// safety factor: the bf16 tower over-estimates on average, so the two sides differ; conzic_config.cert_dcos = hi,
+// cert_dcos_lo = lo).  For the bf16 winner w and any other candidate k
 //     f_w - f_k = (E_w - E_k) + beta * (exp(t_w) - exp(t_k)) / Z
-//              >= (E_w - E_k) + beta * D / (D >= 0 ? Zhi : Zlo),   D = exp(a_w - eps) - exp(a_k + eps),
-// with Zlo = Z_a exp(-eps) <= Z <= Z_a exp(eps) = Zhi.  If that lower bound is > tau, k cannot win in exact
+//              >= (E_w - E_k) + beta * D / (D >= 0 ? Zhi : Zlo),   D = exp(a_w - hi) - exp(a_k + lo),
+// with Zlo = Z_a exp(-hi) <= Z <= Z_a exp(lo) = Zhi.  If that lower bound is > tau, k cannot win in exact
 // arithmetic and is dropped (round 1).  The survivors (always including w, whose exact cosine is also what the
 // caller reports) are re-encoded by the exact tower; round 2 repeats the test among them with their exact logits
-// (eps = 0 for them, eps for the rest of Z).  An image whose survivors still cannot be ordered -- or that has more
+// (no error for them, [-lo, hi] for the rest of Z).  An image whose survivors still cannot be ordered -- or that has more
 // than `fcap` of them -- is re-encoded in full by the exact tower and decided by the plain score_select_kernel, so
 // every decision equals the bf16x3 mode's.  Candidates that are the same caption (masked ids, gen_utils.py:72) have
 // identical logits in any arithmetic and are ordered by their exact terms alone.
-// Round 2's only uncertainty is the part of Z that still comes from bf16 logits, so round 1 also lists the "heavy"
-// candidates (softmax weight >= 1/128, doubled until the list fits fcap): they cannot win, but with their exact
-// logits Z is known to a fraction of a percent and round 2 almost never has to give an image up.
+// Round 2's only uncertainty is the part of Z that still comes from bf16 logits.  Listing the "heavy" candidates
+// as well (cert_heavy > 0: softmax weight >= cert_heavy, doubled until the list fits fcap) narrows it, but with the
+// flat softmax of this workload (the top weight is ~0.05) it costs more exact rows than the occasional full re-encode
+// of an image (measured: 1 748 instead of 305 re-scored candidates per step, profiles/r02c), so it is off by default.
 #include "kernels.h"
 #include "select_common.cuh"
 
@@ -29,13 +31,14 @@ constexpr int CERT_HEAVY_BIT = 1 << 30;  // img_k entry: listed for its weight i
 
 // lower bound of f_w - f_k given logits relative to a common maximum (ew = exp(a_w - m), ek likewise), their error
 // bounds, and bounds on the softmax denominator (same reference m)
-__device__ __forceinline__ float cert_lower_bound(float dE, float beta, float ew, float eps_w, float ek, float eps_k,
+// (hi, lo): a - t lies in [-lo, hi] for both candidates (0, 0 when their logits are the exact ones)
+__device__ __forceinline__ float cert_lower_bound(float dE, float beta, float ew, float ek, float hi, float lo,
                                                   float zlo, float zhi) {
   if (beta >= 0.f) {
-    const float d = ew * expf(-eps_w) - ek * expf(eps_k);
+    const float d = ew * expf(-hi) - ek * expf(lo);  // lower bound of exp(t_w) - exp(t_k)
     return dE + beta * (d >= 0.f ? d / zhi : d / zlo);
   }
-  const float d = ew * expf(eps_w) - ek * expf(-eps_k);  // upper bound of exp(t_w) - exp(t_k)
+  const float d = ew * expf(lo) - ek * expf(-hi);    // upper bound of exp(t_w) - exp(t_k)
   return dE + beta * (d >= 0.f ? d / zlo : d / zhi);
 }
 
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
   if (w < 0 || w >= K) w = 0;
   __syncthreads();
 
-  const float zlo = Z * expf(-c.eps), zhi = Z * expf(c.eps);
+  const float zlo = Z * expf(-c.eps_hi), zhi = Z * expf(c.eps_lo);
   const float Ew = sm.exact[w], ew = sm.e[w];
   const int64_t idw = a.ids_masked[o0 + w];
   const float pw = a.probs[o0 + w];
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
         // the same caption: identical logits whatever the arithmetic
         alive = !(dE > c.tau || (a.probs[o0 + k] == pw && k > w));
       } else {
-        alive = !(cert_lower_bound(dE, a.beta, ew, c.eps, sm.e[k], c.eps, zlo, zhi) > c.tau);
+        alive = !(cert_lower_bound(dE, a.beta, ew, sm.e[k], c.eps_hi, c.eps_lo, zlo, zhi) > c.tau);
       }
     }
     sm.flag[k] = alive ? 1 : 0;
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
   float cnt = 0.f;
   for (int k = tid; k < K; k += CERT_THREADS) cnt += sm.flag[k] ? 1.f : 0.f;
   const int n_alive = static_cast<int>(block_sum(cnt, sm.scratch));
-  if (n_alive <= c.fcap) {
-    float theta = (1.0f / 128.0f) * Z;
+  if (n_alive <= c.fcap && c.heavy > 0.f) {
+    float theta = c.heavy * Z;
 #pragma unroll 1
     for (int it = 0; it < 8; ++it, theta *= 2.0f) {
       float add = 0.f;
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round2_kernel(CertArgs c) {
       if (w < 0 || sm.sprob[ks[i]] > sm.sprob[w]) w = ks[i];  // ks ascending: the lowest index wins ties
     }
     const float zfl = Z - Zrest;  // exact part of the denominator
-    const float zlo = zfl + Zrest * expf(-c.eps), zhi = zfl + Zrest * expf(c.eps);
+    const float zlo = zfl + Zrest * expf(-c.eps_hi), zhi = zfl + Zrest * expf(c.eps_lo);
     bool ok = true;
     const int64_t idw = a.ids_masked[o0 + w];
     for (int i = 0; i < n && ok; ++i) {
@@ -206,32 +209,24 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round2_kernel(CertArgs c) {
       if (k == w || (k & CERT_HEAVY_BIT)) continue;
       const float dE = sm.exact[w] - sm.exact[k];
       if (a.ids_masked[o0 + k] == idw) ok = dE > c.tau || (a.probs[o0 + k] == a.probs[o0 + w] && k > w);
-      else ok = cert_lower_bound(dE, a.beta, sm.e[w], 0.f, sm.e[k], 0.f, zlo, zhi) > c.tau;
+      else ok = cert_lower_bound(dE, a.beta, sm.e[w], sm.e[k], 0.f, 0.f, zlo, zhi) > c.tau;
     }
     if (ok) sel_write_winner(a, b, w, sm.logit[w]);
     else c.full_list[atomicAdd(&c.counters[1], 1)] = b;
   }
 }
 
-__global__ void cert_gather_ids_kernel(const int32_t* __restrict__ flag_list, int n, const int32_t* __restrict__ ids_prefix,
-                                       const int32_t* __restrict__ ids_suffix, const int32_t* __restrict__ p0,
-                                       const int32_t* __restrict__ eos_idx, int P, int K, int S, int T, int eos_id,
-                                       int32_t* __restrict__ out_ids, int32_t* __restrict__ out_eos) {
+__global__ void cert_gather_suffix_kernel(const int32_t* __restrict__ flag_list, int n, const int32_t* __restrict__ ids_suffix,
+                                          const int32_t* __restrict__ eos_idx, int K, int S, int32_t* __restrict__ out_ids,
+                                          int32_t* __restrict__ out_eos, int32_t* __restrict__ out_img) {
   PDL_ENTRY();
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= n) return;
-  const int bk = flag_list[r], b = bk / K;
-  const int np = (P > 0 && p0) ? min(p0[b], P) : 0;
-  const int32_t* pre = ids_prefix + static_cast<size_t>(b) * P;
+  const int bk = flag_list[r];
   const int32_t* suf = ids_suffix + static_cast<size_t>(bk) * S;
-  int32_t* o = out_ids + static_cast<size_t>(r) * T;
-  for (int t = lane; t < T; t += 32) {
-    int v = eos_id;
-    if (t < np) v = pre[t];
-    else if (t - np < S) v = suf[t - np];
-    o[t] = v;
-  }
-  if (lane == 0) out_eos[r] = min(np + eos_idx[bk], T - 1);
+  int32_t* o = out_ids + static_cast<size_t>(r) * S;
+  for (int t = lane; t < S; t += 32) o[t] = suf[t];
+  if (lane == 0) { out_eos[r] = eos_idx[bk]; out_img[r] = bk / K; }
 }
 
 __global__ void cert_compact_kernel(CertCompact a) {
@@ -285,14 +280,13 @@ void launch_cert_round2(const CertArgs& a, cudaStream_t st) {
   launch_k(cert_round2_kernel, dim3(a.q.B), dim3(CERT_THREADS), cert_smem_bytes(a.q.K), st, a);
 }
 
-void launch_cert_gather_ids(const int32_t* flag_list, int n, const int32_t* ids_prefix, const int32_t* ids_suffix,
-                            const int32_t* p0, const int32_t* eos_idx, int P, int K, int S, int T, int eos_id,
-                            int32_t* out_ids, int32_t* out_eos, cudaStream_t st) {
+void launch_cert_gather_suffix(const int32_t* flag_list, int n, const int32_t* ids_suffix, const int32_t* eos_idx, int K,
+                               int S, int32_t* out_ids, int32_t* out_eos, int32_t* out_img, cudaStream_t st) {
   count_launch();
   ProfScope prof_(CAT_ASSEMBLE, 0, st);
   if (n <= 0) return;
-  launch_k(cert_gather_ids_kernel, dim3((n + 7) / 8), dim3(256), 0, st, flag_list, n, ids_prefix, ids_suffix, p0, eos_idx, P,
-           K, S, T, eos_id, out_ids, out_eos);
+  launch_k(cert_gather_suffix_kernel, dim3((n + 7) / 8), dim3(256), 0, st, flag_list, n, ids_suffix, eos_idx, K, S, out_ids,
+           out_eos, out_img);
 }
 
 void launch_cert_compact(const CertCompact& a, cudaStream_t st) {

@@ -27,6 +27,7 @@ ProfScope::ProfScope(int c, double work, cudaStream_t s) : cat(c), st(s), on(t_s
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   r.cat = c;
+  r.phase = t_state->phase;
   r.work = work;
   cudaEventRecord(r.a, st);
   t_state->prof.push_back(r);
@@ -43,7 +44,7 @@ bool prof_read(CtxState* s, int cat, double* ms, double* work, int* n) {
   double t = 0, w = 0;
   int c = 0;
   for (auto& r : s->prof) {
-    if (r.cat != cat) continue;
+    if (cat >= 100 ? (r.phase != cat - 100) : (r.cat != cat)) continue;
     if (cudaEventSynchronize(r.b) != cudaSuccess) return false;
     float e = 0;
     if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) return false;
@@ -135,7 +136,7 @@ struct conzic_ctx {
   float *c_tok = nullptr, *c_pos = nullptr, *c_fln_g = nullptr, *c_fln_b = nullptr;
   Tower clip, clip3;
   bool certified = false;
-  float cert_dcos = 0.f;
+  float cert_dcos = 0.f, cert_dcos_lo = 0.f;
   int cert_fcap = 64;
   int32_t* cert_host = nullptr;  // pinned, 16 ints: the counters read back twice per certified step
   uint64_t cert_stats[CONZIC_CERT_STATS] = {};
@@ -256,7 +257,7 @@ struct Plan {
   ClipBufs main;
   // certified mode
   ClipBufs exact;
-  int32_t *img_nflag, *img_k, *img_slot0, *flag_list, *full_list, *counters, *ids3, *eos3;
+  int32_t *img_nflag, *img_k, *img_slot0, *flag_list, *full_list, *counters, *ids3, *eos3, *img3;
   float* logit3;
   int32_t *c_ids_prefix, *c_ids_suffix, *c_p0, *c_eos_idx;
   float *c_probs, *c_senti, *c_repeats, *c_image, *c_clip_ref, *c_senti_out, *c_tr_score, *c_tr_ref, *c_tr_final;
@@ -328,6 +329,7 @@ Plan make_plan(const conzic_ctx* c, void* ws, int B, int L, int K) {
     p.counters = b.take<int32_t>(16);
     p.ids3 = b.take<int32_t>(BF * g.clip_maxpos);
     p.eos3 = b.take<int32_t>(BF);
+    p.img3 = b.take<int32_t>(BF);
     p.logit3 = b.take<float>(BF > BK ? BF : BK);
     p.c_ids_prefix = b.take<int32_t>(static_cast<size_t>(B) * g.clip_maxpos);
     p.c_ids_suffix = b.take<int32_t>(BK * g.clip_maxpos);
@@ -439,13 +441,107 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
   return launch_linear(t, B, c->b_decoder, epi_f32_out(c->b_decoder, logits, ldl, nullptr, 0, ACT_NONE), o, st);
 }
 
-// ---- a CLIP text tower over packed prefix/suffix rows, in passes of whole images --------------------
+// ---- a CLIP text tower over packed prefix/suffix rows ------------------------------------------------
+// One pass: nb images' shared prefix rows (nb * P) followed by n_cand candidate blocks of S rows.  cand_img == null:
+// the candidates are K per image in image order (n_cand == nb * K); otherwise candidate i belongs to image cand_img[i]
+// (the certified re-score of a few candidates per image).  text receives one embedding per candidate.
+bool encode_pass(conzic_ctx* c, const Tower& tw, ClipBufs& p, const int32_t* idp, const int32_t* ids, const int32_t* p0c,
+                 const int32_t* cand_img, const int32_t* eos, int nb, int P, int K, int n_cand, int S, float* text,
+                 float* xe, cudaStream_t st) {
+  const conzic_config& g = c->cfg;
+  const int H = g.clip_hidden, F = g.clip_ffn, s = tw.split;
+  const int ldh = H * (1 + s), ldf = F * (1 + s);
+  const float scale = 0.125f;  // head_dim^-0.5, HF:models/clip/modeling_clip.py:283
+  const int wl = (&tw == &c->clip) ? c->wide_ln : 0;
+  const int M = nb * P + n_cand * S;
+  set_pdl_now((M < 50000) ? 1 : 0);
+  // the embedding kernel holds each row in registers: it also writes LN1 of the first block (bit-identical to the
+  // stand-alone launch it replaces)
+  const bool embed_ln = !s && H == 512 && !tw.layers.empty();
+  launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, st,
+                    embed_ln ? tw.layers[0].ln1_g : nullptr, embed_ln ? tw.layers[0].ln1_b : nullptr, g.clip_ln_eps,
+                    embed_ln ? p.ch : nullptr, ldh, cand_img, n_cand);
+  const int NE = n_cand;  // rows that are pooled: one EOS row per candidate caption
+  bool h_ready = embed_ln, pooled_ready = false;
+  // LayerNorm written by the producing GEMM's epilogue (gemm_wide_kernel owns whole 512-column rows)
+  auto with_ln = [&](Epi e, bf16* out, const float* gamma, const float* beta) {
+    e.lnf_out = out; e.lnf_ld = ldh; e.lnf_g = gamma; e.lnf_b = beta; e.lnf_eps = g.clip_ln_eps;
+    return e;
+  };
+  for (size_t l = 0; l < tw.layers.size(); ++l) {
+    const Layer& ly = tw.layers[l];
+    const bool last = (l + 1 == tw.layers.size());
+    if (!h_ready) {  // otherwise the embedding kernel / the previous block's fc2 epilogue already wrote LN1(x) into ch
+      LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
+      launch_layernorm(ln1, st);
+    }
+    h_ready = false;  // consumed by this block's QKV
+    Act h{p.ch, ldh, H};
+    Epi e;
+    if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
+    else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.cqkv), 3 * H, 0, ACT_NONE);
+    if (!launch_linear(h, M, ly.qkv, e, tw.gopt, st)) return false;
+    AttnArgs at;
+    at.qkv = p.cqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = p0c;
+    at.B = nb; at.P = P; at.K = K; at.S = S; at.H = H; at.heads = g.clip_heads; at.causal = 1;
+    at.scale = scale; at.out_act = p.cattn; at.ld_act = ldh; at.split = s;
+    at.cand_img = cand_img; at.n_cand = n_cand;
+    if (!launch_attention(at, st)) return false;
+    // The tower's output is read at ONE row per caption (its first EOS) and a row of the last block depends on
+    // other rows only through this block's attention: after it, only the EOS rows go on (exact, not an
+    // approximation).  Rows are compacted: attention out -> ch, residual -> xe; LN2 output re-uses cattn.
+    int Mr = M;
+    float* x = p.cx;
+    bf16 *a_in = p.cattn, *h2 = p.ch;
+    if (last) {
+      launch_pool_index(p.pool_rows, eos, nb * P, NE, S, st);
+      launch_gather_rows(p.cattn, static_cast<size_t>(ldh) * sizeof(bf16), p.pool_rows, NE, p.ch, st);
+      launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
+      Mr = NE; x = xe; a_in = p.ch; h2 = p.cattn;
+    }
+    Act a{a_in, ldh, H};
+    if (wl) {  // O-proj through the wide pair kernel, LN2 written by its epilogue
+      if (!launch_linear(a, Mr, ly.o, with_ln(epi_f32_out(ly.o, x, H, x, H, ACT_NONE), h2, ly.ln2_g, ly.ln2_b), tw.gopt, st))
+        return false;
+    } else {
+      if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), tw.gopt, st)) return false;
+      LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
+      launch_layernorm(ln2, st);
+    }
+    Act hh{h2, ldh, H};
+    if (!launch_linear(hh, Mr, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), tw.gopt, st)) return false;
+    Act f{p.cffn, ldf, F};
+    Epi e2 = epi_f32_out(ly.f2, x, H, x, H, ACT_NONE);
+    if (wl && !last) {  // LN1 of the next block, straight into its QKV operand
+      e2 = with_ln(e2, p.ch, tw.layers[l + 1].ln1_g, tw.layers[l + 1].ln1_b);
+      h_ready = true;
+    } else if (wl) {    // last block (EOS rows only): the final LayerNorm, straight into the projection operand
+      e2 = with_ln(e2, p.cpool, c->c_fln_g, c->c_fln_b);
+      pooled_ready = true;
+    }
+    if (!launch_linear(f, Mr, ly.f2, e2, tw.gopt, st)) return false;
+  }
+  if (tw.layers.empty()) {  // degenerate 0-layer tower: pool straight from the embeddings
+    launch_pool_index(p.pool_rows, eos, nb * P, NE, S, st);
+    launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
+  }
+  // pooled = final LN of the hidden state at the first EOS (already compacted); text_projection without bias
+  if (!pooled_ready) {
+    LNArgs lnf{xe, nullptr, NE, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
+    launch_layernorm(lnf, st);
+  }
+  Act pooled{p.cpool, ldh, H};
+  Epi e;
+  e.out_f32 = text;
+  e.ldo_f32 = g.clip_proj;
+  return launch_linear(pooled, NE, tw.proj, e, tw.gopt, st);
+}
+
+// K candidates per image, in passes of whole images
 bool clip_encode(conzic_ctx* c, const Tower& tw, ClipBufs& p, int chunk_rows, const int32_t* ids_prefix,
                  const int32_t* ids_suffix, const int32_t* p0, const int32_t* eos_idx, int B, int P, int K, int S,
                  float* text, cudaStream_t st) {
   const conzic_config& g = c->cfg;
-  const int H = g.clip_hidden, F = g.clip_ffn, s = tw.split;
-  const int ldh = H * (1 + s), ldf = F * (1 + s);
   const int per_img = P + K * S;
   int Bc = chunk_rows / per_img;
   if (Bc < 1) Bc = 1;
@@ -455,97 +551,39 @@ bool clip_encode(conzic_ctx* c, const Tower& tw, ClipBufs& p, int chunk_rows, co
     set_error("clip_encode: one image's token rows exceed the workspace plan");
     return false;
   }
-  const float scale = 0.125f;  // head_dim^-0.5, HF:models/clip/modeling_clip.py:283
-  const int wl = (&tw == &c->clip) ? c->wide_ln : 0;
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int nb = (B - b0 < Bc) ? (B - b0) : Bc;
-    const int M = nb * per_img;
-    const int32_t* idp = P > 0 ? ids_prefix + static_cast<size_t>(b0) * P : nullptr;
-    const int32_t* ids = ids_suffix + static_cast<size_t>(b0) * K * S;
-    const int32_t* p0c = p0 ? p0 + b0 : nullptr;
-    set_pdl_now((M < 50000) ? 1 : 0);
-    // the embedding kernel holds each row in registers: it also writes LN1 of the first block (bit-identical to the
-    // stand-alone launch it replaces)
-    const bool embed_ln = !s && H == 512 && !tw.layers.empty();
-    launch_clip_embed(idp, ids, p0c, nb, P, K, S, g.clip_maxpos, c->c_tok, c->c_pos, H, p.cx, st,
-                      embed_ln ? tw.layers[0].ln1_g : nullptr, embed_ln ? tw.layers[0].ln1_b : nullptr, g.clip_ln_eps,
-                      embed_ln ? p.ch : nullptr, ldh);
-    const int NE = nb * K;  // candidate captions of this pass = rows that are pooled (one EOS row each)
-    float* xe = p.cxe + static_cast<size_t>(b0) * K * H;
-    bool h_ready = embed_ln, pooled_ready = false;
-    // LayerNorm written by the producing GEMM's epilogue (gemm_wide_kernel owns whole 512-column rows)
-    auto with_ln = [&](Epi e, bf16* out, const float* gamma, const float* beta) {
-      e.lnf_out = out; e.lnf_ld = ldh; e.lnf_g = gamma; e.lnf_b = beta; e.lnf_eps = g.clip_ln_eps;
-      return e;
-    };
-    for (size_t l = 0; l < tw.layers.size(); ++l) {
-      const Layer& ly = tw.layers[l];
-      const bool last = (l + 1 == tw.layers.size());
-      if (!h_ready) {  // otherwise the embedding kernel / the previous block's fc2 epilogue already wrote LN1(x) into ch
-        LNArgs ln1{p.cx, nullptr, M, H, ly.ln1_g, ly.ln1_b, g.clip_ln_eps, nullptr, p.ch, ldh, s};
-        launch_layernorm(ln1, st);
-      }
-      h_ready = false;  // consumed by this block's QKV
-      Act h{p.ch, ldh, H};
-      Epi e;
-      if (s) e = epi_f32_out(ly.qkv, static_cast<float*>(p.cqkv), 3 * H, nullptr, 0, ACT_NONE);
-      else   e = epi_act_out(ly.qkv, static_cast<bf16*>(p.cqkv), 3 * H, 0, ACT_NONE);
-      if (!launch_linear(h, M, ly.qkv, e, tw.gopt, st)) return false;
-      AttnArgs at;
-      at.qkv = p.cqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = p0c;
-      at.B = nb; at.P = P; at.K = K; at.S = S; at.H = H; at.heads = g.clip_heads; at.causal = 1;
-      at.scale = scale; at.out_act = p.cattn; at.ld_act = ldh; at.split = s;
-      if (!launch_attention(at, st)) return false;
-      // The tower's output is read at ONE row per caption (its first EOS) and a row of the last block depends on
-      // other rows only through this block's attention: after it, only the EOS rows go on (exact, not an
-      // approximation).  Rows are compacted: attention out -> ch, residual -> xe; LN2 output re-uses cattn.
-      int Mr = M;
-      float* x = p.cx;
-      bf16 *a_in = p.cattn, *h2 = p.ch;
-      if (last) {
-        launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
-        launch_gather_rows(p.cattn, static_cast<size_t>(ldh) * sizeof(bf16), p.pool_rows, NE, p.ch, st);
-        launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
-        Mr = NE; x = xe; a_in = p.ch; h2 = p.cattn;
-      }
-      Act a{a_in, ldh, H};
-      if (wl) {  // O-proj through the wide pair kernel, LN2 written by its epilogue
-        if (!launch_linear(a, Mr, ly.o, with_ln(epi_f32_out(ly.o, x, H, x, H, ACT_NONE), h2, ly.ln2_g, ly.ln2_b), tw.gopt, st))
-          return false;
-      } else {
-        if (!launch_linear(a, Mr, ly.o, epi_f32_out(ly.o, x, H, x, H, ACT_NONE), tw.gopt, st)) return false;
-        LNArgs ln2{x, nullptr, Mr, H, ly.ln2_g, ly.ln2_b, g.clip_ln_eps, nullptr, h2, ldh, s};
-        launch_layernorm(ln2, st);
-      }
-      Act hh{h2, ldh, H};
-      if (!launch_linear(hh, Mr, ly.f1, epi_act_out(ly.f1, p.cffn, ldf, F, ACT_QUICK_GELU), tw.gopt, st)) return false;
-      Act f{p.cffn, ldf, F};
-      Epi e2 = epi_f32_out(ly.f2, x, H, x, H, ACT_NONE);
-      if (wl && !last) {  // LN1 of the next block, straight into its QKV operand
-        e2 = with_ln(e2, p.ch, tw.layers[l + 1].ln1_g, tw.layers[l + 1].ln1_b);
-        h_ready = true;
-      } else if (wl) {    // last block (EOS rows only): the final LayerNorm, straight into the projection operand
-        e2 = with_ln(e2, p.cpool, c->c_fln_g, c->c_fln_b);
-        pooled_ready = true;
-      }
-      if (!launch_linear(f, Mr, ly.f2, e2, tw.gopt, st)) return false;
-    }
-    if (tw.layers.empty()) {  // degenerate 0-layer tower: pool straight from the embeddings
-      launch_pool_index(p.pool_rows, eos_idx + static_cast<size_t>(b0) * K, nb, P, K, S, st);
-      launch_gather_rows(p.cx, static_cast<size_t>(H) * sizeof(float), p.pool_rows, NE, xe, st);
-    }
-    // pooled = final LN of the hidden state at the first EOS (already compacted); text_projection without bias
-    if (!pooled_ready) {
-      LNArgs lnf{xe, nullptr, NE, H, c->c_fln_g, c->c_fln_b, g.clip_ln_eps, nullptr, p.cpool, ldh, s};
-      launch_layernorm(lnf, st);
-    }
-    Act pooled{p.cpool, ldh, H};
-    Epi e;
-    e.out_f32 = text + static_cast<size_t>(b0) * K * g.clip_proj;
-    e.ldo_f32 = g.clip_proj;
-    if (!launch_linear(pooled, NE, tw.proj, e, tw.gopt, st)) return false;
+    if (!encode_pass(c, tw, p, P > 0 ? ids_prefix + static_cast<size_t>(b0) * P : nullptr,
+                     ids_suffix + static_cast<size_t>(b0) * K * S, p0 ? p0 + b0 : nullptr, nullptr,
+                     eos_idx + static_cast<size_t>(b0) * K, nb, P, K, nb * K, S,
+                     text + static_cast<size_t>(b0) * K * g.clip_proj, p.cxe + static_cast<size_t>(b0) * K * g.clip_hidden, st))
+      return false;
   }
   return cuda_ok(cudaGetLastError(), "clip_encode");
+}
+
+// n_cand candidates of arbitrary images (cand_img), every pass re-encoding the B shared prefixes (B * P rows: small next
+// to what a dense re-encode of the candidates' whole captions costs)
+bool clip_encode_mapped(conzic_ctx* c, const Tower& tw, ClipBufs& p, int chunk_rows, const int32_t* ids_prefix,
+                        const int32_t* ids_suffix, const int32_t* p0, const int32_t* cand_img, const int32_t* eos_idx,
+                        int B, int P, int n_cand, int S, float* text, cudaStream_t st) {
+  const conzic_config& g = c->cfg;
+  const size_t pre = static_cast<size_t>(B) * P;
+  size_t cap = static_cast<size_t>(chunk_rows) < p.rows_cap ? static_cast<size_t>(chunk_rows) : p.rows_cap;
+  if (cap <= pre + static_cast<size_t>(S)) cap = p.rows_cap;
+  if (cap < pre + static_cast<size_t>(S)) {
+    set_error("clip_encode: prefix rows exceed the workspace plan");
+    return false;
+  }
+  const int Cc = static_cast<int>((cap - pre) / S);
+  for (int c0 = 0; c0 < n_cand; c0 += Cc) {
+    const int nc = (n_cand - c0 < Cc) ? (n_cand - c0) : Cc;
+    if (!encode_pass(c, tw, p, P > 0 ? ids_prefix : nullptr, ids_suffix + static_cast<size_t>(c0) * S, P > 0 ? p0 : nullptr,
+                     cand_img + c0, eos_idx + c0, P > 0 ? B : 0, P, 1, nc, S, text + static_cast<size_t>(c0) * g.clip_proj,
+                     p.cxe + static_cast<size_t>(c0) * g.clip_hidden, st))
+      return false;
+  }
+  return cuda_ok(cudaGetLastError(), "clip_encode (mapped)");
 }
 
 bool have_device() {
@@ -579,6 +617,7 @@ bool select_winner(conzic_ctx* c, Plan& p, const CandLayout& lay, const float* t
   const conzic_config& g = c->cfg;
   const int B = q.B, K = q.K, D = g.clip_proj;
   set_pdl_now(1);
+  set_phase(PHASE_SELECT);
   launch_clip_logits(text, image, nullptr, B * K, K, D, q.scale, p.clogit, st);
   q.logit = p.clogit;
   if (!c->certified) {
@@ -587,9 +626,11 @@ bool select_winner(conzic_ctx* c, Plan& p, const CandLayout& lay, const float* t
   }
   CertArgs ca{};
   ca.q = q;
-  ca.eps = q.scale * c->cert_dcos;
+  ca.eps_hi = q.scale * c->cert_dcos;
+  ca.eps_lo = q.scale * c->cert_dcos_lo;
   ca.tau = 2e-6f * (fabsf(q.alpha) + fabsf(q.beta) + fabsf(q.gamma) + 1.0f);
   ca.fcap = c->cert_fcap;
+  ca.heavy = 0.f;
   ca.img_nflag = p.img_nflag; ca.img_k = p.img_k; ca.img_slot0 = p.img_slot0; ca.flag_list = p.flag_list;
   ca.full_list = p.full_list; ca.counters = p.counters; ca.logit3 = p.logit3;
   if (!cuda_ok(cudaMemsetAsync(p.counters, 0, 16 * sizeof(int32_t), st), "memset(cert counters)")) return false;
@@ -605,13 +646,12 @@ bool select_winner(conzic_ctx* c, Plan& p, const CandLayout& lay, const float* t
   c->cert_stats[3] += static_cast<uint64_t>(h[2]);
   c->cert_stats[4] += static_cast<uint64_t>(h[3]);
   if (n_list > 0) {
-    // exact re-encode of the listed candidates as dense sequences (bit-identical to what the exact tower produces for
-    // them inside a full prefix-shared pass: every kernel of that tower is row-wise deterministic)
-    int T = lay.P + lay.S;
-    if (T > g.clip_maxpos) T = g.clip_maxpos;
-    launch_cert_gather_ids(p.flag_list, n_list, lay.ids_prefix, lay.ids_suffix, lay.p0, lay.eos_idx, lay.P, K, lay.S, T,
-                           g.clip_eos, p.ids3, p.eos3, st);
-    if (!clip_encode(c, c->clip3, p.exact, c->chunk_rows3, nullptr, p.ids3, nullptr, p.eos3, n_list, 0, 1, T, p.exact.text, st))
+    set_phase(PHASE_CERT_RESCORE);
+    // exact re-encode of the listed candidates: their suffix rows + the images' shared prefix rows (bit-identical to
+    // what the exact tower produces for them inside a full pass: every kernel of that tower is row-wise deterministic)
+    launch_cert_gather_suffix(p.flag_list, n_list, lay.ids_suffix, lay.eos_idx, K, lay.S, p.ids3, p.eos3, p.img3, st);
+    if (!clip_encode_mapped(c, c->clip3, p.exact, c->chunk_rows3, lay.ids_prefix, p.ids3, lay.p0, p.img3, p.eos3, B, lay.P,
+                            n_list, lay.S, p.exact.text, st))
       return false;
     set_pdl_now(1);
     launch_clip_logits(p.exact.text, image, p.flag_list, n_list, K, D, q.scale, p.logit3, st);
@@ -623,6 +663,7 @@ bool select_winner(conzic_ctx* c, Plan& p, const CandLayout& lay, const float* t
   const int n_full = h[1];
   c->cert_stats[5] += static_cast<uint64_t>(n_full);
   if (n_full > 0) {
+    set_phase(PHASE_CERT_FULL);
     // images the bound could not decide: every candidate through the exact tower, then the plain kernel
     CertCompact cc{};
     cc.full_list = p.full_list; cc.n = n_full; cc.B = B; cc.K = K; cc.P = lay.P; cc.S = lay.S; cc.D = D;
@@ -718,6 +759,8 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->wide_ln = (!(cfg->flags & CONZIC_FLAG_LN_STANDALONE) && c->clip.gopt.persist && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 &&
                 cfg->clip_hidden == 512) ? 1 : 0;
   c->cert_dcos = cfg->cert_dcos > 0.f ? cfg->cert_dcos : CONZIC_CERT_DCOS_DEFAULT;
+  // an explicit upper bound without a lower one is taken as symmetric
+  c->cert_dcos_lo = cfg->cert_dcos_lo > 0.f ? cfg->cert_dcos_lo : (cfg->cert_dcos > 0.f ? cfg->cert_dcos : CONZIC_CERT_DCOS_LO_DEFAULT);
   c->cert_fcap = cfg->cert_fcap > 0 ? cfg->cert_fcap : 64;
   // default: 16 x (148 SMs x 128 rows) token rows per pass; measured on B200: the larger the pass the better
   // (every kernel is a persistent or grid-stride launch; nothing stays L2 resident between kernels anyway)
@@ -852,7 +895,8 @@ int conzic_profile(conzic_ctx* c, int enable) {
   return 0;
 }
 int conzic_profile_read(conzic_ctx* c, int category, double* ms, double* work, int* launches) {
-  if (!c || category < 0 || category >= CAT_COUNT || !ms || !work || !launches) { set_error("profile_read: bad argument"); return -1; }
+  if (!c || category < 0 || (category >= CAT_COUNT && (category < 100 || category >= 100 + PHASE_COUNT)) || !ms || !work ||
+      !launches) { set_error("profile_read: bad argument"); return -1; }
   return prof_read(&c->state, category, ms, work, launches) ? 0 : -4;
 }
 
@@ -994,6 +1038,7 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   Plan p = make_plan(c, ws, B, L, K);
   const conzic_config& g = c->cfg;
   set_pdl_now(1);
+  set_phase(PHASE_BERT);
   launch_step_prologue(s->inp, B, L, pos, g.mask_id, s->token_mask, g.dot_id, s->dot_allowed, st);
   float* logits = s->tr_logits ? s->tr_logits : p.logits;
   if (s->logits_in) {
@@ -1003,6 +1048,7 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   }
   float* probs = s->tr_probs ? s->tr_probs : p.probs;
   int64_t* ids = s->tr_ids ? s->tr_ids : p.ids;
+  set_phase(PHASE_CANDIDATES);
   if (!launch_topk(logits, p.ldl, B, g.bert_vocab, s->token_mask, s->temperature, K, probs, ids, st)) return -4;
   const int W = c->max_tok_per_word;
   const int cap = g.clip_maxpos - 1;
@@ -1049,6 +1095,7 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
     a.ids_masked = p.ids_masked; a.repeats = ctl ? p.repeats : nullptr; a.senti = ctl ? p.senti : nullptr;
     launch_assemble(a, st);
   }
+  set_phase(PHASE_TOWER);
   if (!clip_encode(c, c->clip, p.main, c->chunk_rows, p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, B, P, K, S, p.main.text, st))
     return -4;
   SelectArgs q{};
@@ -1059,7 +1106,9 @@ int conzic_gibbs_step(conzic_ctx* c, const conzic_step_args* s, void* ws, size_t
   q.out_clip_ref = s->out_clip_ref; q.out_senti = s->out_senti;
   q.tr_clip_score = s->tr_clip_score; q.tr_clip_ref = s->tr_clip_ref; q.tr_final = s->tr_final; q.tr_best = s->tr_best;
   CandLayout lay{p.ids_prefix, p.ids_suffix, p.p0, p.eos_idx, P, S};
-  return select_winner(c, p, lay, p.main.text, s->image_embeds, q, st) ? 0 : -4;
+  const bool ok = select_winner(c, p, lay, p.main.text, s->image_embeds, q, st);
+  set_phase(PHASE_OTHER);
+  return ok ? 0 : -4;
 }
 
 int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const float* bias, const float* resid, int M,
@@ -1180,6 +1229,7 @@ int conzic_clip_image_encode(conzic_ctx* c, const float* pix, int B, float* out,
   const int g2 = (v.image_size / v.patch) * (v.image_size / v.patch), T = g2 + 1;
   const int M = B * T, ldh = H * (1 + s), ldf = F * (1 + s);
   set_pdl_now(1);
+  set_phase(PHASE_IMAGE);
   // patch embedding = GEMM over unfolded patches (conv with stride = kernel, no bias)
   launch_im2col(pix, B, v.image_size, v.patch, p.patches, Kp * (1 + s), s, st);
   Act pa{p.patches, Kp * (1 + s), Kp};
@@ -1218,6 +1268,7 @@ int conzic_clip_image_encode(conzic_ctx* c, const float* pix, int B, float* out,
   Epi e;
   e.out_f32 = out; e.ldo_f32 = v.proj;
   if (!launch_linear(pooled, B, c->vis.proj, e, go, st)) return -4;
+  set_phase(PHASE_OTHER);
   return cuda_ok(cudaGetLastError(), "clip_image_encode") ? 0 : -4;
 }
 

@@ -107,6 +107,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
           u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(o + n0 + j) = u;
         }
+      } else if ((e.out_K & 7) == 0) {
+        // hi and lo planes as 16-byte stores (the 4-byte form made this the slowest part of the bf16x3 fc1 GEMMs)
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t uh[4], ul[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a0 = v[j + 2 * q], a1 = v[j + 2 * q + 1];
+            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            __nv_bfloat162 l = __floats2bfloat162_rn(a0 - __bfloat162float(h.x), a1 - __bfloat162float(h.y));
+            uh[q] = *reinterpret_cast<uint32_t*>(&h);
+            ul[q] = *reinterpret_cast<uint32_t*>(&l);
+          }
+          *reinterpret_cast<uint4*>(o + n0 + j) = make_uint4(uh[0], uh[1], uh[2], uh[3]);
+          *reinterpret_cast<uint4*>(o + e.out_K + n0 + j) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) store_act_pair(o, e.out_K, 1, n0 + j, v[j], v[j + 1]);

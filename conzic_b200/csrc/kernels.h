@@ -15,19 +15,23 @@ typedef __nv_bfloat16 bf16;
 // Per-context launch state.  Every extern "C" entry point binds the calling thread to its context's state for the
 // duration of the call (StateScope in engine.cu), so two contexts -- or two threads with a context each -- do not
 // share counters, the PDL switch or profiling records.
-struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct ProfRec { cudaEvent_t a, b; int cat; int phase; double work; };
 struct CtxState {
   uint64_t launches = 0;  // kernels launched for this context (bench.py "gpu_launches")
   int pdl = 1;            // launches may carry the programmatic-dependent-launch attribute (conzic_config.no_pdl clears it)
   int pdl_now = 1;        // set by the engine per section: measured on B200, PDL gains ~3.5 % on steps made of short
                           // kernels (BERT, CLIP passes under ~50 k rows) and costs 1-2 % when the kernels are long
   bool prof_on = false;
+  int phase = 0;          // which part of a step the engine is in (PHASE_*), recorded with every profiled launch
   std::vector<ProfRec> prof;
 };
+enum { PHASE_OTHER = 0, PHASE_BERT = 1, PHASE_CANDIDATES = 2, PHASE_TOWER = 3, PHASE_SELECT = 4, PHASE_CERT_RESCORE = 5,
+       PHASE_CERT_FULL = 6, PHASE_IMAGE = 7, PHASE_COUNT = 8 };
 extern thread_local CtxState* t_state;
 inline void count_launch() { if (t_state) ++t_state->launches; }
 inline bool pdl_enabled() { return t_state && t_state->pdl && t_state->pdl_now; }
 inline void set_pdl_now(int v) { if (t_state) t_state->pdl_now = v; }
+inline void set_phase(int p) { if (t_state) t_state->phase = p; }
 
 // Programmatic dependent launch: every hot-path kernel starts with PDL_ENTRY() -- it lets the NEXT kernel in the
 // stream begin launching right away (griddepcontrol.launch_dependents) and then waits until everything the
@@ -157,10 +161,11 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
                           const float* gamma, const float* beta, float eps, int H, float* x_f32, bf16* act, int ld_act,
                           int split, cudaStream_t st);
 // ln_out optional (H == 512, bf16 operands): LayerNorm 1 of the first block written by the same kernel.
+// cand_img / n_cand: see AttnArgs (null / 0 = K candidates per image)
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
                        int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st,
                        const float* ln_g = nullptr, const float* ln_b = nullptr, float ln_eps = 0.f,
-                       bf16* ln_out = nullptr, int ln_ld = 0);
+                       bf16* ln_out = nullptr, int ln_ld = 0, const int32_t* cand_img = nullptr, int n_cand = 0);
 
 // Attention over packed token rows.  Row layout: B*P "prefix" rows (image b, position t) followed by
 // B*K*S "suffix" rows (image b, candidate k, offset s).  A suffix row attends to its image's first p0[b]
@@ -176,6 +181,10 @@ struct AttnArgs {
   float scale;
   bf16* out_act;
   int ld_act, split;
+  // optional: the suffix blocks are n_cand candidates of arbitrary images, candidate i belonging to image cand_img[i]
+  // (certified re-score: a few candidates per image); null = K candidates per image in image order
+  const int32_t* cand_img = nullptr;
+  int n_cand = 0;
   int cpt = 1;            // filled by launch_attention: candidates packed into one 16-row query tile
   int cand_per_task = 8;  // filled by launch_attention: candidates per warp task
 };
@@ -241,7 +250,8 @@ void launch_text_layout(const TextAssembleArgs& a, cudaStream_t st);
 
 void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, float* token_mask, int dot_id,
                           int dot_allowed, cudaStream_t st);
-void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st);
+// rows[i] = n_pre_rows + i * S + eos_idx[i] for the n_cand candidate blocks that follow the prefix rows
+void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int n_pre_rows, int n_cand, int S, cudaStream_t st);
 
 struct SelectArgs {
   const float* logit;  // [B,K] scale * cos(text, image) from launch_clip_logits
@@ -266,9 +276,10 @@ void launch_score_select(const SelectArgs& a, cudaStream_t st);
 // exact re-score of the few candidates that are not provably beaten.  See the file header for the bound.
 struct CertArgs {
   SelectArgs q;        // q.logit = main-tower logits [B,K]; round 2 patches the listed candidates in place
-  float eps;           // bound on |main-tower logit - exact logit| of one candidate (scale * bound on the cosine error)
+  float eps_hi, eps_lo; // main-tower logit - exact logit of one candidate lies in [-eps_lo, eps_hi] (scale * cosine bounds)
   float tau;           // slack for the fp rounding of the comparisons themselves
   int fcap;            // an image with more than fcap unbeaten candidates goes straight to the full exact re-encode
+  float heavy;         // > 0: also list candidates whose softmax weight is >= heavy (narrows round 2's bound on Z)
   int32_t* img_nflag;  // [B] unbeaten candidates of image b (its winner included); -1 = full re-encode
   int32_t* img_k;      // [B,fcap] their candidate indices, ascending
   int32_t* flag_list;  // [<= B*fcap] b * K + k of every listed candidate; image b's occupy img_slot0[b] ... + img_nflag[b]
@@ -280,11 +291,10 @@ struct CertArgs {
 };
 void launch_cert_round1(const CertArgs& a, cudaStream_t st);
 void launch_cert_round2(const CertArgs& a, cudaStream_t st);
-// dense CLIP id rows of the listed candidates: out_ids[n, T] = prefix[b][0:p0[b]] + suffix[b,k][0:S], EOS padded;
-// out_eos[n] = index of the first EOS
-void launch_cert_gather_ids(const int32_t* flag_list, int n, const int32_t* ids_prefix, const int32_t* ids_suffix,
-                            const int32_t* p0, const int32_t* eos_idx, int P, int K, int S, int T, int eos_id,
-                            int32_t* out_ids, int32_t* out_eos, cudaStream_t st);
+// suffix rows of the listed candidates: out_ids[n, S] = ids_suffix[flag_list[n]], out_eos[n] = eos_idx[flag_list[n]],
+// out_img[n] = flag_list[n] / K (the image whose shared prefix rows the candidate attends to)
+void launch_cert_gather_suffix(const int32_t* flag_list, int n, const int32_t* ids_suffix, const int32_t* eos_idx, int K,
+                               int S, int32_t* out_ids, int32_t* out_eos, int32_t* out_img, cudaStream_t st);
 // Full re-encode of n images: compact copies of their per-image inputs (image i of the copy = image full_list[i]) ...
 struct CertCompact {
   const int32_t* full_list; int n;

@@ -1,6 +1,8 @@
 // The reduction-shaped part of the Gibbs step: temperature softmax * stop-word mask -> top-K,
 // candidate -> CLIP id assembly, cosine / softmax / score fuse / argmax.  HBM-bandwidth or latency bound:
 // coalesced vector loads, warp-shuffle reductions, everything stays on the device.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "select_common.cuh"
 
@@ -138,6 +140,193 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same selection with one image row spread over a thread-block cluster of TOPK_CL CTAs (B = 64 rows would
+// otherwise occupy 64 of 148 SMs, each streaming a 122 KB row on its own): CTA r of the cluster holds the slice
+// [r * per, (r + 1) * per) of the vocabulary in its shared memory; the row maximum, the softmax sum, the four radix
+// histograms and the candidate counts are exchanged through distributed shared memory (cluster.map_shared_rank), the
+// K survivors are written into CTA 0's sort buffer, which sorts and stores them.  Same results as topk_kernel up to
+// the rounding of the softmax sum (partial sums per slice, added in rank order); ties still in ascending index order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TOPK_CL = 4;
+constexpr int TOPK_CL_THREADS = 512;
+
+struct TopkClSmem {  // dynamic shared memory layout of one CTA
+  unsigned long long* sortbuf;  // [K2]   (used in CTA 0 only, allocated everywhere so offsets agree)
+  uint32_t* keys;               // [per]
+  int* hist;                    // [16][256] per-warp histograms; row 0 doubles as this CTA's merged histogram
+  int* tot;                     // [256] cluster-wide histogram
+  float* scratch;               // [40]
+  float* red;                   // [4]  values other CTAs read: max, sum
+  int* cnt;                     // [4]  values other CTAs read: > T count, == T count
+  int* ctl;                     // [8]
+  __device__ TopkClSmem(unsigned char* base, int K2, int per) {
+    sortbuf = reinterpret_cast<unsigned long long*>(base);
+    keys = reinterpret_cast<uint32_t*>(sortbuf + K2);
+    hist = reinterpret_cast<int*>(keys + ((per + 3) & ~3));
+    tot = hist + 16 * 256;
+    scratch = reinterpret_cast<float*>(tot + 256);
+    red = scratch + 40;
+    cnt = reinterpret_cast<int*>(red + 4);
+    ctl = cnt + 4;
+  }
+};
+size_t topk_cl_smem_bytes(int K2, int per) {
+  return static_cast<size_t>(K2) * 8 + static_cast<size_t>((per + 3) & ~3) * 4 + (16 * 256 + 256) * 4 + (40 + 4) * 4 + (4 + 8) * 4;
+}
+
+__global__ void __launch_bounds__(TOPK_CL_THREADS) topk_cluster_kernel(const float* __restrict__ logits, int ldl, int V,
+                                                                       const float* __restrict__ mask, float temperature,
+                                                                       int K, int K2, int per, float* __restrict__ probs,
+                                                                       int64_t* __restrict__ ids) {
+  PDL_ENTRY();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char topk_cl_smem[];
+  TopkClSmem sm(topk_cl_smem, K2, per);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int row = blockIdx.x / TOPK_CL;
+  const int lo = rank * per, n = max(0, min(V, lo + per) - lo);
+  const float* x = logits + static_cast<size_t>(row) * ldl + lo;
+  float* kf = reinterpret_cast<float*>(sm.keys);
+
+  if (rank == 0)
+    for (int i = tid; i < K2; i += TOPK_CL_THREADS) sm.sortbuf[i] = 0ull;
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += TOPK_CL_THREADS) {
+    const float t = x[i] / temperature;
+    kf[i] = t;
+    mx = fmaxf(mx, t);
+  }
+  mx = block_max(mx, sm.scratch);
+  if (tid == 0) sm.red[0] = mx;
+  cluster.sync();
+  for (int r = 0; r < TOPK_CL; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(&sm.red[0], r));
+  float sum = 0.f;
+  for (int i = tid; i < n; i += TOPK_CL_THREADS) {
+    const float e = expf(kf[i] - mx);
+    kf[i] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, sm.scratch);
+  if (tid == 0) sm.red[1] = sum;
+  cluster.sync();
+  sum = 0.f;
+  for (int r = 0; r < TOPK_CL; ++r) sum += *cluster.map_shared_rank(&sm.red[1], r);
+  for (int i = tid; i < n; i += TOPK_CL_THREADS) kf[i] = (kf[i] / sum) * __ldg(mask + lo + i);
+  __syncthreads();
+
+  // ---- radix select of the K-th largest key over the whole row (non-negative floats order like their bit patterns)
+  uint32_t prefix = 0, pmask = 0;
+  int remaining = K;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 16 * 256; i += TOPK_CL_THREADS) sm.hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += TOPK_CL_THREADS) {
+      const uint32_t k = sm.keys[i];
+      if ((k & pmask) == prefix) atomicAdd(&sm.hist[w * 256 + ((k >> shift) & 255)], 1);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      int c = 0;
+      for (int ww = 0; ww < 16; ++ww) c += sm.hist[ww * 256 + tid];
+      sm.hist[tid] = c;  // row 0 = this CTA's histogram (each thread only touches column tid)
+    }
+    cluster.sync();
+    if (tid < 256) {
+      int c = 0;
+      for (int r = 0; r < TOPK_CL; ++r) c += *cluster.map_shared_rank(&sm.hist[tid], r);
+      sm.tot[tid] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, digit = 0, rem = remaining;
+      for (int bin = 255; bin >= 0; --bin) {
+        const int h = sm.tot[bin];
+        if (cum + h >= rem) { digit = bin; rem -= cum; break; }
+        cum += h;
+      }
+      sm.ctl[0] = digit;
+      sm.ctl[1] = rem;
+    }
+    cluster.sync();  // every CTA has read the others' histograms before they are cleared again
+    prefix |= static_cast<uint32_t>(sm.ctl[0]) << shift;
+    pmask |= 255u << shift;
+    remaining = sm.ctl[1];
+  }
+  const uint32_t T = prefix;       // K-th largest value of the row
+  const int n_gt = K - remaining;  // strictly greater than T; `remaining` ties are still needed
+
+  // ---- how many keys > T and == T each CTA holds -> where its survivors go in CTA 0's sort buffer
+  float c_gt = 0.f, c_eq = 0.f;
+  for (int i = tid; i < n; i += TOPK_CL_THREADS) {
+    const uint32_t k = sm.keys[i];
+    c_gt += k > T ? 1.f : 0.f;
+    c_eq += k == T ? 1.f : 0.f;
+  }
+  const int my_gt = static_cast<int>(block_sum(c_gt, sm.scratch));
+  const int my_eq = static_cast<int>(block_sum(c_eq, sm.scratch));
+  if (tid == 0) { sm.cnt[0] = my_gt; sm.cnt[1] = my_eq; sm.ctl[2] = 0; }
+  cluster.sync();
+  int gt_off = 0, eq_off = 0;
+  for (int r = 0; r < rank; ++r) {
+    gt_off += *cluster.map_shared_rank(&sm.cnt[0], r);
+    eq_off += *cluster.map_shared_rank(&sm.cnt[1], r);
+  }
+  unsigned long long* dst = cluster.map_shared_rank(sm.sortbuf, 0);
+  for (int i = tid; i < n; i += TOPK_CL_THREADS) {
+    const uint32_t k = sm.keys[i];
+    if (k > T) {
+      const int slot = gt_off + atomicAdd(&sm.ctl[2], 1);
+      dst[slot] = (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lo + i));
+    }
+  }
+  // ties at T: lowest vocabulary indices first -- CTAs in rank order, inside a CTA an ordered block scan
+  int tie_base = eq_off;
+  int* wtot = reinterpret_cast<int*>(sm.scratch);  // reuse [0,16)
+  for (int c0 = 0; c0 < n && tie_base < remaining; c0 += TOPK_CL_THREADS) {
+    const int i = c0 + tid;
+    const bool is = (i < n) && (sm.keys[i] == T);
+    const unsigned bal = __ballot_sync(0xffffffffu, is);
+    __syncthreads();
+    if (lane == 0) wtot[w] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int ww = 0; ww < TOPK_CL_THREADS / 32; ++ww) {
+      const int c = wtot[ww];
+      if (ww < w) before += c;
+      total += c;
+    }
+    if (is) {
+      const int rk = tie_base + before + __popc(bal & ((1u << lane) - 1u));
+      if (rk < remaining)
+        dst[n_gt + rk] = (static_cast<unsigned long long>(T) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lo + i));
+    }
+    tie_base += total;
+  }
+  cluster.sync();  // all survivors are in CTA 0's buffer; the other CTAs are done
+  if (rank != 0) return;
+  // ---- bitonic sort, descending, K2 a power of two
+  for (int size = 2; size <= K2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (K2 >> 1); t += TOPK_CL_THREADS) {
+        const int i = ((t / stride) * (stride << 1)) + (t % stride);
+        const int j = i + stride;
+        const bool desc = (i & size) == 0;
+        const unsigned long long a = sm.sortbuf[i], b = sm.sortbuf[j];
+        if (desc ? (a < b) : (a > b)) { sm.sortbuf[i] = b; sm.sortbuf[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = tid; k < K; k += TOPK_CL_THREADS) {
+    const unsigned long long c = sm.sortbuf[k];
+    probs[static_cast<size_t>(row) * K + k] = __uint_as_float(static_cast<uint32_t>(c >> 32));
+    ids[static_cast<size_t>(row) * K + k] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(c));
+  }
+}
+
 size_t topk_smem_bytes(int V, int K2) {
   return static_cast<size_t>(K2) * 8 + static_cast<size_t>((V + 3) & ~3) * 4 + 32 * 256 * 4 + 40 * 4 + 8 * 4;
 }
@@ -236,10 +425,10 @@ __global__ void step_prologue_kernel(int64_t* inp, int B, int L, int pos, int ma
   if (i == 0 && token_mask && dot_id >= 0) token_mask[dot_id] = dot_allowed ? 1.0f : 0.0f;  // utils.py:53-59
 }
 
-__global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S) {
+__global__ void pool_index_kernel(int32_t* rows, const int32_t* eos_idx, int n_pre_rows, int n_cand, int S) {
   PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * K) rows[i] = B * P + i * S + eos_idx[i];
+  if (i < n_cand) rows[i] = n_pre_rows + i * S + eos_idx[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -302,7 +491,9 @@ __global__ void __launch_bounds__(SEL_THREADS) score_select_kernel(SelectArgs a)
 
 bool topk_configure() {
   return cuda_ok(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                 "cudaFuncSetAttribute(topk)");
+                 "cudaFuncSetAttribute(topk)") &&
+         cuda_ok(cudaFuncSetAttribute(topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+                 "cudaFuncSetAttribute(topk_cluster)");
 }
 
 bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, float temperature, int K, float* probs,
@@ -315,6 +506,26 @@ bool launch_topk(const float* logits, int ldl, int B, int V, const float* mask, 
   }
   int K2 = 2;
   while (K2 < K) K2 <<= 1;
+  if (V >= 4096) {  // one row per cluster of TOPK_CL CTAs
+    const int per = (V + TOPK_CL - 1) / TOPK_CL;
+    const size_t smem_cl = topk_cl_smem_bytes(K2, per);
+    if (smem_cl <= 100 * 1024) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(B) * TOPK_CL);
+      cfg.blockDim = dim3(TOPK_CL_THREADS);
+      cfg.dynamicSmemBytes = smem_cl;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = TOPK_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
+      return cuda_ok(cudaLaunchKernelEx(&cfg, topk_cluster_kernel, logits, ldl, V, mask, temperature, K, K2, per, probs, ids),
+                     "topk_cluster launch");
+    }
+  }
   const size_t smem = topk_smem_bytes(V, K2);
   if (smem > 200 * 1024) {
     set_error("topk: vocabulary too large for the shared-memory row buffer");
@@ -337,10 +548,11 @@ void launch_step_prologue(int64_t* inp, int B, int L, int pos, int mask_id, floa
   launch_k(step_prologue_kernel, dim3((B + 255) / 256), dim3(256), 0, st, inp, B, L, pos, mask_id, token_mask, dot_id, dot_allowed);
 }
 
-void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int B, int P, int K, int S, cudaStream_t st) {
+void launch_pool_index(int32_t* rows, const int32_t* eos_idx, int n_pre_rows, int n_cand, int S, cudaStream_t st) {
   count_launch();
   ProfScope prof_(CAT_MISC, 0, st);
-  launch_k(pool_index_kernel, dim3((B * K + 255) / 256), dim3(256), 0, st, rows, eos_idx, B, P, K, S);
+  if (n_cand <= 0) return;
+  launch_k(pool_index_kernel, dim3((n_cand + 255) / 256), dim3(256), 0, st, rows, eos_idx, n_pre_rows, n_cand, S);
 }
 
 void launch_clip_logits(const float* text, const float* image, const int32_t* row_bk, int n_rows, int K, int D,

@@ -148,12 +148,13 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
                                   const int32_t* __restrict__ p0, int B, int P, int K, int S, int maxpos,
                                   const float* __restrict__ tok, const float* __restrict__ pos, int H,
                                   float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                                  float ln_eps, bf16* __restrict__ ln_out, int ln_ld) {
+                                  float ln_eps, bf16* __restrict__ ln_out, int ln_ld,
+                                  const int32_t* __restrict__ cand_img, int n_cand) {
   PDL_ENTRY();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_pre = B * P;
-  const int rows = n_pre + B * K * S;
+  const int rows = n_pre + (cand_img ? n_cand : B * K) * S;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps) {
     int id, position;
     if (r < n_pre) {
@@ -161,7 +162,7 @@ __global__ void clip_embed_kernel(const int32_t* __restrict__ ids_prefix, const 
       position = r % P;
     } else {
       const int idx = r - n_pre;
-      const int b = idx / (K * S), s = idx % S;
+      const int b = cand_img ? cand_img[idx / S] : idx / (K * S), s = idx % S;
       id = ids_suffix[idx];
       position = (p0 ? p0[b] : 0) + s;
     }
@@ -224,7 +225,7 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
   float* ps = qs + HD;                                     // [nkp]
 
   const int n_pre_seq = a.P > 0 ? a.B : 0;
-  const int n_seq = n_pre_seq + a.B * a.K;
+  const int n_seq = n_pre_seq + (a.cand_img ? a.n_cand : a.B * a.K);
   const long long n_task = static_cast<long long>(n_seq) * a.heads;
   const int H = a.H;
   const int n_pre_rows = a.B * a.P;
@@ -238,7 +239,7 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
       b = seq; pl = 0; nq = a.P; own_base = b * a.P;
     } else {
       const int bk = seq - n_pre_seq;
-      b = bk / a.K;
+      b = a.cand_img ? a.cand_img[bk] : bk / a.K;
       pl = a.P > 0 ? (a.p0 ? min(a.p0[b], a.P) : a.P) : 0;
       nq = a.S;
       own_base = n_pre_rows + bk * a.S;
@@ -725,14 +726,15 @@ void launch_bert_embed_ln(const int64_t* inp, int rows, int L, const float* word
 
 void launch_clip_embed(const int32_t* ids_prefix, const int32_t* ids_suffix, const int32_t* p0, int B, int P, int K,
                        int S, int maxpos, const float* tok, const float* pos, int H, float* x_f32, cudaStream_t st,
-                       const float* ln_g, const float* ln_b, float ln_eps, bf16* ln_out, int ln_ld) {
+                       const float* ln_g, const float* ln_b, float ln_eps, bf16* ln_out, int ln_ld,
+                       const int32_t* cand_img, int n_cand) {
   count_launch();
   ProfScope prof_(CAT_EMBED, 0, st);
-  const int rows = B * P + B * K * S;
+  const int rows = B * P + (cand_img ? n_cand : B * K) * S;
   if (rows <= 0) return;
   if (ln_out && H != 512) { set_error("clip_embed: the fused LayerNorm needs hidden size 512"); return; }
   launch_k(clip_embed_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, st, ids_prefix, ids_suffix, p0, B, P, K, S, maxpos, tok, pos, H,
-                                                       x_f32, ln_g, ln_b, ln_eps, ln_out, ln_ld);
+                                                       x_f32, ln_g, ln_b, ln_eps, ln_out, ln_ld, cand_img, n_cand);
 }
 
 constexpr int ATT_WARPS = 8;
@@ -762,7 +764,7 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     return false;
   }
   const int nk_cap = a.P + a.S;
-  if (!a.qkv_f32 && !a.split && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
+  if (!a.qkv_f32 && !a.split && !a.cand_img && nk_cap <= 96 && (a.ld_qkv % 8) == 0 && (a.ld_act % 8) == 0) {
     AttnArgs aa = a;
     aa.cpt = (a.causal && a.S <= 8 && a.P + (16 / a.S) * a.S <= 96) ? 16 / a.S : 1;
     aa.cand_per_task = aa.cpt >= 4 ? 2 * aa.cpt : (aa.cpt > 1 ? ((8 + aa.cpt - 1) / aa.cpt) * aa.cpt : 8);
@@ -793,9 +795,12 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
   int warps = static_cast<int>((200 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;
-  const size_t smem = per_warp * warps;
-  const long long n_seq = (a.P > 0 ? a.B : 0) + static_cast<long long>(a.B) * a.K;
+  const long long n_seq = (a.P > 0 ? a.B : 0) + (a.cand_img ? static_cast<long long>(a.n_cand) : static_cast<long long>(a.B) * a.K);
   const long long n_task = n_seq * a.heads;
+  // few tasks (BERT: images x heads; a certified re-score): smaller blocks so that every SM gets work -- the kernel is
+  // latency bound, one warp walks the queries of its sequence one after the other
+  while (warps > 2 && n_task / warps < 2 * static_cast<long long>(num_sms())) warps >>= 1;
+  const size_t smem = per_warp * warps;
   long long grid = (n_task + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (grid > cap) grid = cap;

@@ -71,11 +71,12 @@ class Engine:
     def __init__(self, bert_sd: SD, clip_sd: SD, device="cuda:0", precision: str = "certified",
                  gemm_impl: str = "tcgen05", special_ids: Sequence[int] = _dims.SPECIAL_IDS,
                  dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
-                 clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_fcap: Optional[int] = None,
+                 clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_dcos_lo: Optional[float] = None,
+                 cert_fcap: Optional[int] = None,
                  ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None):
         """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
         in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
-        are read once, here: cert_dcos / cert_fcap (CONZIC_CERT_DCOS / CONZIC_CERT_FCAP), ln_standalone
+        are read once, here: cert_dcos / cert_dcos_lo / cert_fcap (CONZIC_CERT_DCOS / _LO / CONZIC_CERT_FCAP), ln_standalone
         (CONZIC_LN_STANDALONE=1) and pdl (CONZIC_PDL=0) exist for A/B measurements."""
         if not torch.cuda.is_available():
             raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -110,6 +111,7 @@ class Engine:
         cfg.clip_chunk_rows = int(clip_chunk_rows)
         env = os.environ.get
         cfg.cert_dcos = float(cert_dcos if cert_dcos is not None else env("CONZIC_CERT_DCOS", 0.0))
+        cfg.cert_dcos_lo = float(cert_dcos_lo if cert_dcos_lo is not None else env("CONZIC_CERT_DCOS_LO", 0.0))
         cfg.cert_fcap = int(cert_fcap if cert_fcap is not None else env("CONZIC_CERT_FCAP", 0))
         if ln_standalone is None:
             ln_standalone = env("CONZIC_LN_STANDALONE", "0") == "1"
@@ -183,6 +185,18 @@ class Engine:
     def profile(self, enable: bool):
         """CUDA-event timing of every launch by category (conzic_profile); off by default."""
         _lib.check(self.lib.conzic_profile(self.ctx, 1 if enable else 0), "conzic_profile")
+
+    PROFILE_PHASES = ("other", "bert", "candidates", "tower", "select", "cert_rescore", "cert_full", "image")
+
+    def profile_read_phases(self):
+        """{phase: (milliseconds, launches)} of the same records, by step phase (conzic_profile_read 100 + p)."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_PHASES):
+            ms, work, n = C.c_double(), C.c_double(), C.c_int()
+            _lib.check(self.lib.conzic_profile_read(self.ctx, 100 + i, C.byref(ms), C.byref(work), C.byref(n)),
+                       "conzic_profile_read")
+            out[name] = (ms.value, n.value)
+        return out
 
     def profile_read(self):
         """{category: (milliseconds, work, launches)}; waits for the recorded events."""

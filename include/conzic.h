@@ -43,10 +43,11 @@ enum {
                                 the decision is taken on exact scores -- same winners and same reported cosines as
                                 CONZIC_PREC_BF16X3 (gen_utils.py:77-80), at close to bf16 speed                     */
 };
-#define CONZIC_CERT_DCOS_DEFAULT 1.6e-3f /* bound on |cos(bf16 tower) - cos(bf16x3 tower)| of one candidate: 1.3 x the
-                                            maximum over 1.0 M candidates of the config-2 / config-3 workloads
-                                            (1.22e-3; 99.999 % quantile 1.06e-3; tools/cert_bound.py,
-                                            profiles/r02a_cert_bound.md) */
+/* d = cos(bf16 tower) - cos(bf16x3 tower) of one candidate is taken to lie in [-CERT_DCOS_LO, CERT_DCOS]: 1.3 x the
+ * extremes over 1.0 M candidates of the config-2 / config-3 workloads (-4.93e-4 / +1.22e-3; the bf16 tower
+ * over-estimates by 3.0e-4 on average; tools/cert_bound.py, profiles/r02b_cert_bound.md) */
+#define CONZIC_CERT_DCOS_DEFAULT 1.6e-3f
+#define CONZIC_CERT_DCOS_LO_DEFAULT 6.5e-4f
 #define CONZIC_CERT_STATS 8
 
 /* conzic_config.flags */
@@ -73,7 +74,8 @@ typedef struct conzic_config {
   int32_t precision;           /* CONZIC_PREC_* */
   int32_t gemm_impl;           /* CONZIC_GEMM_* */
   int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (303104 = 16 waves of 148 x 128-row tiles) */
-  float cert_dcos;             /* CERTIFIED: bound on the cosine error of the bf16 tower; 0 = CONZIC_CERT_DCOS_DEFAULT */
+  float cert_dcos;             /* CERTIFIED: upper bound of cos(bf16) - cos(exact); 0 = CONZIC_CERT_DCOS_DEFAULT */
+  float cert_dcos_lo;          /* CERTIFIED: -(lower bound); 0 = cert_dcos when that is given, else the default */
   int32_t cert_fcap;           /* CERTIFIED: an image with more unbeaten candidates than this is re-encoded in full; 0 = 64 */
   int32_t flags;               /* CONZIC_FLAG_* */
 } conzic_config;
@@ -230,7 +232,10 @@ int conzic_cert_stats(const conzic_ctx* ctx, uint64_t* out, int n);
 /* Optional device timing by kernel category (CUDA events around each launch, on the launching stream).
  * Categories: 0 persistent pair GEMM (CLIP / vision towers; work = executed FLOPs), 1 attention, 2 LayerNorm,
  * 3 embeddings, 4 top-k, 5 CLIP-id assembly, 6 score/select, 7 misc, 8 gridded GEMM (BERT, bf16x3 mode).  conzic_profile(ctx, 1) clears and enables, (ctx, 0) disables;
- * conzic_profile_read waits for the recorded events and returns summed milliseconds, work and launches. */
+ * conzic_profile_read waits for the recorded events and returns summed milliseconds, work and launches.
+ * Categories 100 + p sum the same records by step phase p instead: 0 other, 1 BERT, 2 top-k + candidate assembly,
+ * 3 CLIP text tower over all candidates, 4 logits + selection kernels, 5 certified mode: exact re-score of the listed
+ * candidates, 6 certified mode: full exact re-encode of undecided images, 7 image tower. */
 int conzic_profile(conzic_ctx* ctx, int enable);
 int conzic_profile_read(conzic_ctx* ctx, int category, double* ms, double* work, int* launches);
 

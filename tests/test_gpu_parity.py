@@ -865,7 +865,7 @@ def test_config2_free_running_certified_equals_bf16x3(order, monkeypatch):
     # the point of the bound: almost every candidate is ruled out by the bf16 scores alone, and (nearly) no image
     # needs every candidate re-encoded
     assert st["rescored_candidates"] < 0.05 * 3200 * 200, st
-    assert st["images_full"] < 0.02 * 3200, st
+    assert st["images_full"] < 0.05 * 3200, st
 
 
 def test_config2_certified_lockstep_with_cpu_oracle():

@@ -55,6 +55,7 @@ def main():
            "ms_per_step": e0.elapsed_time(e1) / a.steps, "launches_per_step": (eng.launch_count() - l0) / a.steps}
     if a.breakdown:
         pr = eng.profile_read()
+        out["phases_ms_per_step"] = {k: (round(v[0] / a.steps, 4), v[1] // a.steps) for k, v in eng.profile_read_phases().items()}
         out["breakdown_ms_per_step"] = {k: round(v[0] / a.steps, 4) for k, v in pr.items()}
         out["launches"] = {k: v[2] // a.steps for k, v in pr.items()}
         g = pr["gemm"]
