@@ -395,7 +395,12 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
     GemmOpts od = o;
     od.stages = 6;
     const bool one_wave = static_cast<long long>((M + 127) / 128) * ((F + o.bn - 1) / o.bn) <= 148;
-    if (!launch_linear(h, M, ly.qkv, e, od, st)) return false;
+    // bf16x3: the wide-N GEMMs (QKV, fc1) run on the CTA-pair kernel from 512 rows on -- 256 x 256 tiles move half the
+    // operand bytes per FLOP of the 128 x 128 gridded kernel, which the three passes make L2-bandwidth bound (measured
+    // 22 / 72 us per launch at 960 rows).  The N = H GEMMs keep the split-K gridded form (3 pair tiles would idle the chip).
+    GemmOpts opair = o;
+    opair.persist = (s && M >= 512 && o.impl == 0) ? 1 : 0;
+    if (!launch_linear(h, M, ly.qkv, e, opair.persist ? opair : od, st)) return false;
     AttnArgs at;
     at.qkv = p.bqkv; at.ld_qkv = 3 * H; at.qkv_f32 = s; at.p0 = nullptr;
     at.B = B; at.P = 0; at.K = 1; at.S = L; at.H = H; at.heads = g.bert_heads; at.causal = 0;
@@ -426,7 +431,8 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
       return true;
     };
     if (!nh_gemm(a, ly.o, ly.ln1_g, ly.ln1_b)) return false;
-    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), one_wave ? od : o, st)) return false;
+    if (!launch_linear(h, M, ly.f1, epi_act_out(ly.f1, p.bffn, ldf, F, ACT_ERF_GELU), opair.persist ? opair : (one_wave ? od : o), st))
+      return false;
     Act f{p.bffn, ldf, F};
     if (!nh_gemm(f, ly.f2, ly.ln2_g, ly.ln2_b)) return false;
   }
@@ -748,13 +754,13 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   auto opts = [&](int split, bool persist) {
     GemmOpts o;
     o.split = split; o.impl = cfg->gemm_impl; o.bn = 128; o.stages = 3;
-    o.persist = (persist && !split) ? 1 : 0;  // persistent CTA-pair kernel (tcgen05 cta_group::2) for the big bf16 towers
+    o.persist = persist ? 1 : 0;  // persistent CTA-pair kernel (tcgen05 cta_group::2): the CLIP towers, bf16 and bf16x3
     o.cg = 2;
     return o;
   };
-  c->gopt_bert = opts(c->bert_split, false);
+  c->gopt_bert = opts(c->bert_split, false);  // few token rows: gridded kernel (QKV / fc1 in bf16x3 opt into the pair kernel)
   c->clip.gopt = opts(c->clip.split, true);
-  c->clip3.gopt = opts(1, false);
+  c->clip3.gopt = opts(1, true);
   c->vis.gopt = opts(c->vis.split, true);
   c->wide_ln = (!(cfg->flags & CONZIC_FLAG_LN_STANDALONE) && c->clip.gopt.persist && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 &&
                 cfg->clip_hidden == 512) ? 1 : 0;

@@ -168,6 +168,8 @@ struct PGemmParams {
   int m_tiles;  // per-CTA-group tiles of CG*128 rows
   int n_tiles;
   Epi e;
+  int split = 0;  // 1 = bf16x3 operands ([rows, 2K]: hi | lo planes): three passes over K (hi*hi, lo*hi, hi*lo) into the
+                  // same accumulator, exact activations, hi + lo output planes (streamed-A pair kernel only)
 };
 
 template <int CG, bool ARES>
@@ -233,8 +235,9 @@ __device__ __forceinline__ void epilogue_f32_chunk(const PGemmParams& p, uint8_t
     float4 x = *reinterpret_cast<const float4*>(stg + stg_off(r, pc));
     x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
     if (e.act != ACT_NONE) {
-      x.x = apply_act(x.x, e.act, false); x.y = apply_act(x.y, e.act, false);
-      x.z = apply_act(x.z, e.act, false); x.w = apply_act(x.w, e.act, false);
+      const bool precise = p.split != 0;
+      x.x = apply_act(x.x, e.act, precise); x.y = apply_act(x.y, e.act, precise);
+      x.z = apply_act(x.z, e.act, precise); x.w = apply_act(x.w, e.act, precise);
     }
     if (grow < p.M) {
       const int col = n0 + pc * 4;
@@ -269,6 +272,44 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const PGemmParams& p, uint8_
     v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
     v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
     v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
+  }
+  if (p.split) {
+    // bf16x3 output: exact activation, then the hi plane and the remainder plane, each through the transposing buffer
+    if (e.act != ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, true);
+    }
+    const int pc = lane & 3;
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a0 = v[8 * j + 2 * q], a1 = v[8 * j + 2 * q + 1];
+          __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+          if (plane == 0) {
+            u[q] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __nv_bfloat162 l = __floats2bfloat162_rn(a0 - __bfloat162float(h.x), a1 - __bfloat162float(h.y));
+            u[q] = *reinterpret_cast<uint32_t*>(&l);
+          }
+        }
+        *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = make_uint4(u[0], u[1], u[2], u[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 2) + 8 * i;
+        const int grow = row0 + r;
+        const uint4 x = *reinterpret_cast<const uint4*>(stg + stg_off(r, pc));
+        if (grow < p.M)
+          *reinterpret_cast<uint4*>(e.out_act + static_cast<size_t>(grow) * e.ldo_act + plane * e.out_K + n0 + pc * 8) = x;
+      }
+      __syncwarp();
+    }
+    return;
   }
   if (e.act == ACT_QUICK_GELU) {
     // x * sigmoid(1.702 x) = x * (0.5 * tanh(0.851 x) + 0.5), written as three passes over the 32 values so the
@@ -495,7 +536,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const long long group = blockIdx.x / CG;
   const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
   const long long u0 = group * U / n_groups, u1 = (group + 1) * U / n_groups;
-  const int nkb = p.K / BK;
+  const int nkb1 = p.K / BK;                              // k blocks of one pass
+  const int nkb = (!ARES && p.split) ? 3 * nkb1 : nkb1;   // bf16x3: hi*hi, lo*hi, hi*lo into the same accumulator
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -550,10 +592,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (leader) mbar_arrive_expect_tx(&full_bar[s], CG * bytes);
           const uint32_t bar = (CG == 2) ? mapa_shared(smem_u32(&full_bar[s]), 0) : smem_u32(&full_bar[s]);
           uint8_t* st = sStage + s * SL::STAGE;
+          const int pass = kb / nkb1, kcol = (kb - pass * nkb1) * BK;
           if (load_a)
-            tma_load_2d_cg<CG>(ARES ? sA + kb * SL::A_SLOT : st, &tmA, bar, kb * BK,
+            tma_load_2d_cg<CG>(ARES ? sA + kb * SL::A_SLOT : st, &tmA, bar, kcol + (pass == 1 ? p.K : 0),
                                (m * CG + static_cast<int>(cta_rank)) * BM);
-          tma_load_2d_cg<CG>(ARES ? st : st + SL::A_SLOT, &tmB, bar, kb * BK,
+          tma_load_2d_cg<CG>(ARES ? st : st + SL::A_SLOT, &tmB, bar, kcol + (pass == 2 ? p.K : 0),
                              n * PBN + static_cast<int>(cta_rank) * (PBN / CG));
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -663,7 +706,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             GemmParams gp;
-            gp.M = p.M; gp.N = p.N; gp.K = p.K; gp.split = 0; gp.e = p.e;
+            gp.M = p.M; gp.N = p.N; gp.K = p.K; gp.split = p.split; gp.e = p.e;
             epilogue_chunk(gp, row0 + lane, n0, v);
           }
         }
@@ -1104,7 +1147,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   }
   count_launch();
   // the persistent pair kernel (CLIP tower) and the gridded kernel (BERT, bf16x3 passes) are timed separately
-  ProfScope prof_((o.persist && !o.split && o.impl == 0) ? CAT_GEMM : CAT_GEMM_SMALL,
+  ProfScope prof_((o.persist && !o.split && o.impl == 0) ? CAT_GEMM : CAT_GEMM_SMALL,  // bf16 tower vs BERT / bf16x3 work
                   2.0 * M * static_cast<double>(W.N) * W.K * (o.split ? 3 : 1), st);
   if ((epi.out_f32 && (epi.ldo_f32 & 3)) || (epi.resid && (epi.ldr & 3)) || (epi.out_act && (epi.ldo_act & 7)) ||
       (A.ld & 7)) {
@@ -1120,12 +1163,18 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
   if (!make_tmap_bf16_2d(&ta, A.p, static_cast<uint64_t>(M), static_cast<uint64_t>(W.K) * (o.split ? 2 : 1),
                          static_cast<uint64_t>(A.ld), BM))
     return false;
-  if (o.persist && !o.split) {
+  if (o.persist && (!o.split || o.cg == 2)) {
     const int cg = o.cg == 2 ? 2 : 1;
     PGemmParams pp;
-    pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi;
+    pp.M = M; pp.N = W.N; pp.K = W.K; pp.e = epi; pp.split = o.split;
     pp.m_tiles = (M + BM * cg - 1) / (BM * cg);
     pp.n_tiles = (W.N + PBN - 1) / PBN;
+    if (o.split) {
+      // bf16x3: the streamed-A pair kernel runs the three operand passes into one accumulator (same k order as the
+      // gridded kernel); no resident A (the hi | lo tile is twice as wide), no wide form, no fused LayerNorm
+      if (epi.lnf_out) { set_error("linear: no fused LayerNorm in bf16x3 mode"); return false; }
+      return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), st);
+    }
     const bool ares = cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
     const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;
     // fp32-output GEMM with N == 512: one 512-column unit per tile, so a streamed A (fc2, K = 2048) leaves HBM once
