@@ -23,7 +23,7 @@ EXPORTS = [
     "conzic_workspace_bytes", "conzic_bert_mlm_row", "conzic_topk_mask", "conzic_build_clip_ids",
     "conzic_clip_text_encode", "conzic_image_text_similarity", "conzic_gibbs_step", "conzic_launch_count",
     "conzic_debug_linear", "conzic_profile", "conzic_profile_read", "conzic_cert_stats",
-    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_set_text_vocab",
+    "conzic_set_vision", "conzic_vision_workspace_bytes", "conzic_clip_image_encode", "conzic_score_select", "conzic_set_text_vocab", "conzic_image_preprocess",
 ]
 
 
@@ -44,6 +44,11 @@ class TextVocab(C.Structure):
     _fields_ = [("tok_off", C.c_void_p), ("tok_bytes", C.c_void_p), ("tok_cls", C.c_void_p), ("tok_flags", C.c_void_p),
                 ("byte_sym", C.c_void_p), ("merge_keys", C.c_void_p), ("merge_vals", C.c_void_p),
                 ("n_bytes", C.c_int32), ("merge_bits", C.c_int32)]
+
+
+class ResizeAxis(C.Structure):
+    _fields_ = [("weights", C.c_void_p), ("first", C.c_void_p), ("count", C.c_void_p), ("taps", C.c_int32),
+                ("precision", C.c_int32), ("n_out", C.c_int32), ("identity", C.c_int32)]
 
 
 class VisionConfig(C.Structure):
@@ -109,6 +114,9 @@ def _declare(lib):
     lib.conzic_vision_workspace_bytes.argtypes = [vp, i32]
     lib.conzic_clip_image_encode.restype = C.c_int
     lib.conzic_clip_image_encode.argtypes = [vp, vp, i32, vp, vp, sz, vp]
+    lib.conzic_image_preprocess.restype = C.c_int
+    lib.conzic_image_preprocess.argtypes = [vp, vp, i32, i32, i32, C.POINTER(ResizeAxis), C.POINTER(ResizeAxis), i32, i32,
+                                            C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, sz, vp]
     lib.conzic_profile.restype = C.c_int
     lib.conzic_profile.argtypes = [vp, i32]
     lib.conzic_profile_read.restype = C.c_int

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libconzic.so")
 STAMP = os.path.join(PKG, ".libconzic.stamp")
 OBJDIR = os.path.join(PKG, "_obj")
-SOURCES = ["engine.cu", "gemm.cu", "transformer_ops.cu", "select_ops.cu", "cert_ops.cu", "text_ops.cu"]
+SOURCES = ["engine.cu", "gemm.cu", "transformer_ops.cu", "select_ops.cu", "cert_ops.cu", "text_ops.cu", "image_ops.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", "select_common.cuh", "text_pipeline.cuh", os.path.join(ROOT, "include", "conzic.h")]
 
 NVCC_FLAGS = [

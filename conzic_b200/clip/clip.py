@@ -43,6 +43,17 @@ class CLIP:
     # ---- image side: once per call, before the hot loop (clip/clip.py:48-62)
     @torch.no_grad()
     def compute_image_representation_from_image_instance(self, image):
+        """PIL image(s) / uint8 arrays -> image embeddings.  With the Hugging Face CLIPImageProcessor in its standard
+        configuration the pre-processing (antialiased bicubic resize, centre crop, normalise) runs on the device too
+        (conzic_image_preprocess); any other processor is called as the reference calls it (clip/clip.py:55-58)."""
+        from .. import imageproc
+        cfg = imageproc.processor_config(self.processor)
+        if cfg is not None:
+            items = list(image) if isinstance(image, (list, tuple)) else [image]
+            arrays = [imageproc.to_uint8_hwc(im) for im in items]
+            if all(a is not None for a in arrays):
+                eng = self._engine()
+                return eng.image_encode(eng.preprocess_images(arrays, cfg))
         pixel_values = self.processor(images=image, return_tensors="pt")["pixel_values"]
         return self.compute_image_representation_from_pixels(pixel_values)
 

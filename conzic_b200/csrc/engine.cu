@@ -762,7 +762,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   c->clip.gopt = opts(c->clip.split, true);
   c->clip3.gopt = opts(1, true);
   c->vis.gopt = opts(c->vis.split, true);
-  c->wide_ln = (!(cfg->flags & CONZIC_FLAG_LN_STANDALONE) && c->clip.gopt.persist && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 &&
+  c->wide_ln = (!(cfg->flags & CONZIC_FLAG_LN_STANDALONE) && !c->clip.split && cfg->gemm_impl == CONZIC_GEMM_TCGEN05 &&
                 cfg->clip_hidden == 512) ? 1 : 0;
   c->cert_dcos = cfg->cert_dcos > 0.f ? cfg->cert_dcos : CONZIC_CERT_DCOS_DEFAULT;
   // an explicit upper bound without a lower one is taken as symmetric
@@ -1124,6 +1124,8 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16_out = (act & 16) != 0;  // exercise the bf16 activation output path (bf16 operands only)
   const bool exact = (act & 32) != 0;     // CERTIFIED contexts: use the exact (bf16x3) operand format
+  const bool gridded = (act & 64) != 0;   // force the gridded 128 x 128 kernel (bit-identity checks against the pair kernel)
+  const int act_flags = act;              // | 128: force the pair kernel
   act &= 15;
   const Tower& tw = (exact && c->certified) ? c->clip3 : c->clip;
   const int s = tw.split;
@@ -1152,7 +1154,10 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
     e.out_f32 = out; e.ldo_f32 = N;
   }
   Act a{a_act, ld, K};
-  if (!launch_linear(a, M, W, e, tw.gopt, st)) return -4;
+  GemmOpts go = tw.gopt;
+  if (gridded) { go.persist = 0; go.stages = 6; }
+  if (act_flags & 128) go.force_pair = 1;
+  if (!launch_linear(a, M, W, e, go, st)) return -4;
   if (bf16_out) {
     bf16_to_f32_kernel<<<1184, 256, 0, st>>>(o16, out, static_cast<size_t>(M) * N);
     count_launch();
@@ -1276,6 +1281,32 @@ int conzic_clip_image_encode(conzic_ctx* c, const float* pix, int B, float* out,
   if (!launch_linear(pooled, B, c->vis.proj, e, go, st)) return -4;
   set_phase(PHASE_OTHER);
   return cuda_ok(cudaGetLastError(), "clip_image_encode") ? 0 : -4;
+}
+
+int conzic_image_preprocess(conzic_ctx* c, const uint8_t* images, int n, int H, int W, const conzic_resize_axis* hz,
+                            const conzic_resize_axis* vt, int row_lo, int row_hi, const float* mean3, const float* std3,
+                            float* pixel_values, void* ws, size_t ws_bytes, void* stream) {
+  if (!c || !images || !hz || !vt || !mean3 || !std3 || !pixel_values || !ws) { set_error("image_preprocess: null argument"); return -1; }
+  if (n < 1 || H < 1 || W < 1 || row_lo < 0 || row_hi > H || row_lo >= row_hi || hz->n_out < 1 || vt->n_out < 1 ||
+      (!hz->identity && (hz->precision < 1 || hz->precision > 22)) || (!vt->identity && (vt->precision < 1 || vt->precision > 22))) {
+    set_error("image_preprocess: bad geometry");
+    return -1;
+  }
+  const size_t need = static_cast<size_t>(n) * (row_hi - row_lo) * hz->n_out * 3;
+  if (ws_bytes < need) { set_error("image_preprocess: workspace too small, need " + std::to_string(need)); return -1; }
+  StateScope scope(&c->state);
+  set_phase(PHASE_IMAGE);
+  set_pdl_now(1);
+  ImagePreArgs a{};
+  a.src = images; a.n = n; a.H = H; a.W = W;
+  a.hz = ResizeAxis{hz->weights, hz->first, hz->count, hz->taps, hz->precision, hz->n_out, hz->identity};
+  a.vt = ResizeAxis{vt->weights, vt->first, vt->count, vt->taps, vt->precision, vt->n_out, vt->identity};
+  a.row_lo = row_lo; a.row_hi = row_hi;
+  for (int i = 0; i < 3; ++i) { a.mean[i] = mean3[i]; a.std[i] = std3[i]; }
+  a.tmp = static_cast<uint8_t*>(ws); a.out = pixel_values;
+  launch_image_preprocess(a, static_cast<cudaStream_t>(stream));
+  set_phase(PHASE_OTHER);
+  return cuda_ok(cudaGetLastError(), "image_preprocess") ? 0 : -4;
 }
 
 }  // extern "C"

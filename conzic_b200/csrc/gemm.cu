@@ -1171,9 +1171,16 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     pp.n_tiles = (W.N + PBN - 1) / PBN;
     if (o.split) {
       // bf16x3: the streamed-A pair kernel runs the three operand passes into one accumulator (same k order as the
-      // gridded kernel); no resident A (the hi | lo tile is twice as wide), no wide form, no fused LayerNorm
+      // gridded kernel, bit-identical results: tests/test_gpu_parity.py); no resident A (the hi | lo tile is twice as
+      // wide), no wide form, no fused LayerNorm.  With fewer 256 x 256 units than half the CTA pairs (narrow N on a few
+      // thousand rows: the certified re-score's O-proj / fc2) the 128 x 128 gridded kernel spreads the work better.
       if (epi.lnf_out) { set_error("linear: no fused LayerNorm in bf16x3 mode"); return false; }
-      return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), st);
+      const long long units = static_cast<long long>(pp.m_tiles) * pp.n_tiles;
+      if (units * 2 >= sm_count() / 2 || (W.N % BM) != 0 || o.force_pair)
+        return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), st);
+      p.split = 1;
+      launch_one<128, 6>(ta, W.tmap128, p, st);
+      return cuda_ok(cudaGetLastError(), "gemm_tcgen05 launch");
     }
     const bool ares = cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages
     const CUtensorMap& tb = cg == 2 ? W.tmap128 : W.tmap256;

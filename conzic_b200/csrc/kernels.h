@@ -120,6 +120,7 @@ struct GemmOpts {
   int persist = 0;  // 1 = persistent A-resident kernel with double-buffered TMEM accumulators (bf16 mode only)
   int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
   int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
+  int force_pair = 0;  // bf16x3 + persist: the pair kernel whatever the tile count (tests)
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
@@ -190,6 +191,24 @@ struct AttnArgs {
 };
 bool attention_configure();  // opt-in to large dynamic shared memory for every instantiation (current device)
 bool launch_attention(const AttnArgs& a, cudaStream_t st);
+
+// ---- image pre-processing (image_ops.cu) ---------------------------------------------------------------
+struct ResizeAxis {
+  const int16_t* w;      // [n_out, taps] fixed-point filter taps
+  const int32_t* first;  // [n_out] first input index
+  const int32_t* count;  // [n_out] taps used
+  int taps, precision, n_out, identity;
+};
+struct ImagePreArgs {
+  const uint8_t* src;  // [n, H, W, 3]
+  int n, H, W;
+  ResizeAxis hz, vt;
+  int row_lo, row_hi;  // input rows the vertical pass reads
+  float mean[3], std[3];
+  uint8_t* tmp;        // [n, row_hi - row_lo, hz.n_out, 3]
+  float* out;          // [n, 3, vt.n_out, hz.n_out]
+};
+void launch_image_preprocess(const ImagePreArgs& a, cudaStream_t st);
 
 // ---- selection pieces (select_ops.cu) -----------------------------------------------------------------
 bool topk_configure();

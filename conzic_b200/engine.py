@@ -266,6 +266,50 @@ class Engine:
         self.vision_cfg = vc
         self._vws = None
 
+    def preprocess_images(self, images, cfg: dict) -> torch.Tensor:
+        """CLIPImageProcessor on the device (conzic_image_preprocess): a list of uint8 HWC arrays (any sizes) ->
+        pixel_values f32[n, 3, S, S] on the device.  `cfg` = imageproc.processor_config(processor)."""
+        from . import imageproc
+        n, S = len(images), cfg["crop"]
+        out = torch.empty((n, 3, S, S), dtype=torch.float32, device=self.device)
+        groups = {}
+        for i, im in enumerate(images):
+            groups.setdefault(im.shape[:2], []).append(i)
+        if not hasattr(self, "_img_plans"):
+            self._img_plans = {}
+        for (H, W), idx in groups.items():
+            key = (H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
+            if key not in self._img_plans:
+                pl = imageproc.make_plan(H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
+                dev = {}
+                for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
+                    dev[name] = (torch.from_numpy(ax.weights).to(self.device), torch.from_numpy(ax.first).to(self.device),
+                                 torch.from_numpy(ax.count).to(self.device))
+                self._img_plans[key] = (pl, dev)
+            pl, dev = self._img_plans[key]
+            import numpy as np
+            host = torch.from_numpy(np.stack([images[i] for i in idx])).pin_memory()
+            src = host.to(self.device, non_blocking=True)
+            m = len(idx)
+            dst = out if m == n else torch.empty((m, 3, S, S), dtype=torch.float32, device=self.device)
+            ws = torch.empty(m * (pl.row_hi - pl.row_lo) * S * 3, dtype=torch.uint8, device=self.device)
+            axes = []
+            for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
+                a = _lib.ResizeAxis()
+                w, f, c = dev[name]
+                a.weights, a.first, a.count = w.data_ptr(), f.data_ptr(), c.data_ptr()
+                a.taps, a.precision, a.n_out, a.identity = int(ax.weights.shape[1]), int(ax.precision), S, int(ax.identity)
+                axes.append(a)
+            mean = (C.c_float * 3)(*pl.mean255)
+            std = (C.c_float * 3)(*pl.std255)
+            rc = self.lib.conzic_image_preprocess(self.ctx, _ptr(src), m, H, W, C.byref(axes[0]), C.byref(axes[1]),
+                                                  pl.row_lo, pl.row_hi, mean, std, _ptr(dst), _ptr(ws), ws.numel(),
+                                                  self._stream())
+            _lib.check(rc, "conzic_image_preprocess")
+            if dst is not out:
+                out[torch.tensor(idx, device=self.device)] = dst
+        return out
+
     def image_encode(self, pixel_values: torch.Tensor) -> torch.Tensor:
         """CLIP.compute_image_representation_from_image_instance after the processor: f32[B,3,S,S] -> f32[B,proj]."""
         if getattr(self, "vision_cfg", None) is None:

@@ -244,7 +244,7 @@ int conzic_profile_read(conzic_ctx* ctx, int category, double* ms, double* work,
  *   context's operand format; exercises exactly the kernel the towers use.  act: 0 none, 1 quick_gelu,
  *   2 erf-gelu; act | 16 routes the result through the kernel's bf16 activation output (bf16 operands, no
  *   residual) before it is widened into out; act | 32 (CERTIFIED contexts) uses the exact tower's operand format and
- *   kernel instead of the bf16 one.  out fp32[M,N]. */
+ *   kernel instead of the bf16 one; act | 64 forces the gridded 128 x 128 kernel, act | 128 the CTA-pair kernel (bf16x3 operands).  out fp32[M,N]. */
 int conzic_debug_linear(conzic_ctx* ctx, const float* A_dev, const float* W_dev, const float* bias_dev,
                         const float* resid_dev, int M, int N, int K, int act, float* out_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
@@ -266,6 +266,24 @@ size_t conzic_vision_workspace_bytes(const conzic_ctx* ctx, int B);
  * f32[B,proj] dev (not L2-normalised, like compute_image_representation_from_image_instance). */
 int conzic_clip_image_encode(conzic_ctx* ctx, const float* pixel_values_dev, int B, float* image_embeds_dev,
                              void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---- CLIPImageProcessor on the device (clip/clip.py:55-58 -> HF CLIPImageProcessor, torchvision backend): n uint8
+ * HWC images of ONE size -> pixel_values f32[n, 3, S, S].  Antialiased bicubic resize of the shortest edge on uint8
+ * in ATen's fixed-point arithmetic (horizontal pass, vertical pass, a rounded uint8 after each), centre crop, fused
+ * (x - mean) / std with mean / std in 0..255 units.  The caller supplies, per axis and for the output positions inside
+ * the crop only, the integer filter taps ATen computes (conzic_b200/imageproc.py restates that computation; identity
+ * != 0: the axis is not resized, `first` just crops).  All pointers are DEVICE pointers.
+ * ws: n * (row_hi - row_lo) * horiz.n_out * 3 bytes. */
+typedef struct conzic_resize_axis {
+  const int16_t* weights;  /* [n_out, taps] */
+  const int32_t* first;    /* [n_out] first input index read by each output position */
+  const int32_t* count;    /* [n_out] taps used */
+  int32_t taps, precision, n_out, identity;
+} conzic_resize_axis;
+int conzic_image_preprocess(conzic_ctx* ctx, const uint8_t* images_dev, int n, int H, int W,
+                            const conzic_resize_axis* horiz, const conzic_resize_axis* vert, int row_lo, int row_hi,
+                            const float* mean3_host, const float* std3_host, float* pixel_values_dev, void* ws_dev,
+                            size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

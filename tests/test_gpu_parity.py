@@ -125,6 +125,28 @@ def test_certified_context_exact_tower_linear(shape):
     assert float((fast - ref16).abs().max()) < 3e-4 * float(ref16.abs().max())
 
 
+@pytest.mark.parametrize("shape", [(2000, 512, 512, 0), (2100, 512, 2048, 0), (960, 2304, 768, 0), (5000, 2048, 512, 1),
+                                   (300, 1536, 512, 0)])
+def test_bf16x3_pair_and_gridded_kernels_are_bit_identical(shape):
+    """The bf16x3 GEMM runs on the CTA-pair kernel or on the gridded 128 x 128 kernel depending on how many tiles the
+    shape has (the certified re-score is a few thousand rows, the bf16x3 mode's full pass 100 k+): both accumulate the
+    same k blocks in the same order, so their results must agree bit for bit -- which is what lets the certified mode
+    reproduce the bf16x3 mode's scores exactly."""
+    M, N, K, act = shape
+    eng = gc.engine("bf16x3", "tcgen05")
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    pair = eng.debug_linear(A, W, bias, resid, act | 128)
+    grid = eng.debug_linear(A, W, bias, resid, act | 64)
+    auto = eng.debug_linear(A, W, bias, resid, act)
+    assert torch.equal(pair, grid) and torch.equal(auto, pair)
+    ref = _ref_linear(A, W, bias, resid, act, False)
+    assert float((pair - ref).abs().max()) < 3e-4 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-3), ("certified", 1e-3), ("bf16", 0.04)])
 def test_bert_row_logits_vs_oracle(prec, tol):
     from oracle import conzic_oracle as orc
