@@ -13,9 +13,10 @@ scaling) with one NCCL all-gather of the final ids/scores per call.
                certified argmax with exact (bf16x3) re-score of every candidate the bf16 scores cannot rule out --
                the same token ids and scores as the all-bf16x3 run; the `parity` key reports the check made in
                this very run (one extra call in bf16x3 on the same inputs) and how many candidates were re-scored;
-  value        captions/s with the pixel tensors already resident in HBM (device loop, no host reads of results);
-  e2e          captions/s through the public drop-in API conzic_b200.gen_utils.generate_caption with the pixels
-               in pinned HOST memory: H2D copy, per-sweep D2H reads of ids/scores and string decoding included;
+  value        captions/s with the uint8 images already resident in HBM (device loop, no host reads of results);
+  e2e          captions/s through the public drop-in API conzic_b200.gen_utils.generate_caption with uint8 images
+               (320 x 480, as a camera / PIL would hand them over) in HOST memory: H2D copy, CLIPImageProcessor's resize /
+               crop / normalise (on the device), per-sweep D2H reads of ids/scores and string decoding included;
   roofline     the dominant kernel (tcgen05 GEMM of the CLIP tower): executed FLOPs / CUDA-event time of its
                launches during one extra profiled step, against the measured sustained bf16 peak;
   cpu_baseline the reference's CPU path on a bounded sample, all host cores: the UNMODIFIED reference modules from
@@ -84,6 +85,8 @@ class Workload:
                             + (", sentiment control gamma 5 positive" if self.ctl else "")
                             + f" ({what[self.config]}), bert-base + CLIP ViT-B/32 shapes, synthetic weights",
                 "images_per_gpu": BATCH, "samples": self.samples, "n_gpus": n_gpus,
+                "images": "synthetic uint8 320x480 HWC; CLIPImageProcessor (antialiased bicubic resize to 224, centre crop, "
+                          "normalise) runs inside the timed regions, on the device",
                 "sharding": "images by global index, one all-gather per call",
                 "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -180,10 +183,11 @@ def _cpu_runner(wl: Workload):
         tok = synth.SynthBertTokenizer()
         utils, gen_utils, control_gen_utils, CLIP = ref_loader.load(REF_DIR, table, lambda w: tok.vocab[w],
                                                                     synth.synth_pos_tagger)
-        bert, clip = ref_loader.build_models(bert_sd, clip_sd, CLIP, synth.SynthCLIPTokenizer(), synth.SynthProcessor())
+        from transformers import CLIPImageProcessor
+        bert, clip = ref_loader.build_models(bert_sd, clip_sd, CLIP, synth.SynthCLIPTokenizer(), CLIPImageProcessor())
 
         def run(B, sweeps):
-            pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+            pix = [synth.make_uint8_image(i) for i in range(B)]  # the reference's processor resizes / crops / normalises
             names = [f"img{i}.jpg" for i in range(B)]
             kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=B, max_len=wl.n_len, top_k=wl.top_k, temperature=TEMP,
                       max_iter=sweeps, alpha=ALPHA, beta=BETA, generate_order=wl.order)
@@ -205,8 +209,9 @@ def _cpu_runner(wl: Workload):
                        full_logits=True)
 
         def run(B, sweeps):
-            pix = torch.stack([synth.make_pixel_values(i) for i in range(B)])
+            from transformers import CLIPImageProcessor
             t0 = time.perf_counter()
+            pix = CLIPImageProcessor()(images=[synth.make_uint8_image(i) for i in range(B)], return_tensors="pt")["pixel_values"]
             with torch.no_grad():
                 o.generate(pix, synth.make_token_mask(), synth.SYNTH_PROMPT, order=wl.order, max_len=wl.n_len,
                            top_k=wl.top_k, temperature=TEMP, alpha=ALPHA, beta=BETA, max_iters=sweeps,
@@ -269,14 +274,21 @@ class Job:
         self.dev = torch.device("cuda", local_rank)
         torch.cuda.set_device(self.dev)
         self.bert = BertMLM(synth.make_bert_state_dict(0))
+        from transformers import CLIPImageProcessor
+        from conzic_b200 import imageproc
         self.clip = CLIP(state_dict=synth.make_clip_state_dict(0), tokenizer=synth.SynthCLIPTokenizer(),
-                         processor=synth.SynthProcessor()).to(self.dev)
+                         processor=CLIPImageProcessor()).to(self.dev)
+        self.img_cfg = imageproc.processor_config(self.clip.processor)
+        assert self.img_cfg is not None, "the device image pre-processing does not cover this processor configuration"
         self.tok = synth.SynthBertTokenizer()
         os.environ["CONZIC_PRECISION"] = precision
         self.eng = runtime.engine_for(self.bert, self.clip, self.tok, precision=precision, device=self.dev)
         idx = range(rank * BATCH, (rank + 1) * BATCH)  # images keyed by global index
-        self.pix_host = torch.stack([synth.make_pixel_values(i) for i in idx]).pin_memory()
-        self.pix_dev = self.pix_host.to(self.dev)
+        # raw camera-style inputs: uint8 HWC images, resized / cropped / normalised by the engine (CLIPImageProcessor on the
+        # device) inside both timed regions
+        self.raw = [synth.make_uint8_image(i) for i in idx]
+        self.raw_host = torch.from_numpy(__import__("numpy").stack(self.raw)).pin_memory()
+        self.raw_dev = self.raw_host.to(self.dev)
         self.names = [f"img{i}.jpg" for i in idx]
         self.logger = logging.getLogger("bench")
         self.logger.addHandler(logging.NullHandler())
@@ -306,7 +318,7 @@ class Job:
         wl = self.wl
         last = None
         for order in self.orders:
-            img = eng.image_encode(self.pix_dev)
+            img = eng.image_encode(eng.preprocess_uint8(self.raw_dev, self.img_cfg))
             inp = self.init_ids.clone()
             tm = synth.make_token_mask(self.dev)
             holds = [True] * 4 + [False] * wl.n_len + [False]
@@ -334,11 +346,11 @@ class Job:
             kw = dict(prompt=synth.SYNTH_PROMPT, batch_size=BATCH, max_len=wl.n_len, top_k=wl.top_k, temperature=TEMP,
                       max_iter=wl.sweeps, alpha=ALPHA, beta=BETA, generate_order=wl.order)
             if wl.ctl:
-                out = control_gen_utils.control_generate_caption(self.names, self.bert, self.clip, self.tok, self.pix_host,
+                out = control_gen_utils.control_generate_caption(self.names, self.bert, self.clip, self.tok, self.raw,
                                                                  tm, self.logger, gamma=GAMMA, ctl_type="sentiment",
                                                                  style_type="positive", sentiment_table=self.table, **kw)
             else:
-                out = gen_utils.generate_caption(self.names, self.bert, self.clip, self.tok, self.pix_host, tm,
+                out = gen_utils.generate_caption(self.names, self.bert, self.clip, self.tok, self.raw, tm,
                                                  self.logger, **kw)
             if self.world > 1:  # rank 0 collects every rank's final captions (a few KB of strings)
                 cdist.gather_objects(out[0][-2], self.world)
@@ -410,7 +422,7 @@ def measure(args, rank, local_rank, world, wl: Workload, full: bool):
         torch.distributed.barrier()
     e2e_s = cdist.max_over_ranks(time.perf_counter() - t0, world, job.dev)
     e2e = world * per_call * args.steps / e2e_s
-    h2d = job.pix_host.numel() * 4 * wl.samples
+    h2d = job.raw_host.numel() * wl.samples  # uint8 images
     d2h = wl.samples * wl.sweeps * (BATCH * job.L * 8 + BATCH * 4 * (2 if wl.ctl else 1))
     if args.precision == "certified":
         d2h += wl.samples * wl.sweeps * wl.n_len * 2 * 64  # the two counter blocks the certified argmax reads per step

@@ -266,48 +266,57 @@ class Engine:
         self.vision_cfg = vc
         self._vws = None
 
-    def preprocess_images(self, images, cfg: dict) -> torch.Tensor:
-        """CLIPImageProcessor on the device (conzic_image_preprocess): a list of uint8 HWC arrays (any sizes) ->
-        pixel_values f32[n, 3, S, S] on the device.  `cfg` = imageproc.processor_config(processor)."""
+    def preprocess_uint8(self, src: torch.Tensor, cfg: dict, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """CLIPImageProcessor on the device for n same-sized images already in HBM: uint8 [n, H, W, 3] ->
+        pixel_values f32[n, 3, S, S] (conzic_image_preprocess).  `cfg` = imageproc.processor_config(processor)."""
         from . import imageproc
+        assert src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3 and src.is_contiguous()
+        m, H, W = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+        S = cfg["crop"]
+        if not hasattr(self, "_img_plans"):
+            self._img_plans = {}
+        key = (H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
+        if key not in self._img_plans:
+            pl = imageproc.make_plan(H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
+            dev = {}
+            for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
+                dev[name] = (torch.from_numpy(ax.weights).to(self.device), torch.from_numpy(ax.first).to(self.device),
+                             torch.from_numpy(ax.count).to(self.device))
+            self._img_plans[key] = (pl, dev)
+        pl, dev = self._img_plans[key]
+        if out is None:
+            out = torch.empty((m, 3, S, S), dtype=torch.float32, device=self.device)
+        ws = torch.empty(m * (pl.row_hi - pl.row_lo) * S * 3, dtype=torch.uint8, device=self.device)
+        axes = []
+        for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
+            a = _lib.ResizeAxis()
+            w, f, c = dev[name]
+            a.weights, a.first, a.count = w.data_ptr(), f.data_ptr(), c.data_ptr()
+            a.taps, a.precision, a.n_out, a.identity = int(ax.weights.shape[1]), int(ax.precision), S, int(ax.identity)
+            axes.append(a)
+        mean = (C.c_float * 3)(*pl.mean255)
+        std = (C.c_float * 3)(*pl.std255)
+        rc = self.lib.conzic_image_preprocess(self.ctx, _ptr(src), m, H, W, C.byref(axes[0]), C.byref(axes[1]),
+                                              pl.row_lo, pl.row_hi, mean, std, _ptr(out), _ptr(ws), ws.numel(),
+                                              self._stream())
+        _lib.check(rc, "conzic_image_preprocess")
+        return out
+
+    def preprocess_images(self, images, cfg: dict) -> torch.Tensor:
+        """The same for a list of uint8 HWC host arrays of any sizes (grouped by size, copied from pinned memory)."""
+        import numpy as np
         n, S = len(images), cfg["crop"]
         out = torch.empty((n, 3, S, S), dtype=torch.float32, device=self.device)
         groups = {}
         for i, im in enumerate(images):
             groups.setdefault(im.shape[:2], []).append(i)
-        if not hasattr(self, "_img_plans"):
-            self._img_plans = {}
         for (H, W), idx in groups.items():
-            key = (H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
-            if key not in self._img_plans:
-                pl = imageproc.make_plan(H, W, cfg["shortest_edge"], S, cfg["mean"], cfg["std"], cfg["rescale_factor"])
-                dev = {}
-                for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
-                    dev[name] = (torch.from_numpy(ax.weights).to(self.device), torch.from_numpy(ax.first).to(self.device),
-                                 torch.from_numpy(ax.count).to(self.device))
-                self._img_plans[key] = (pl, dev)
-            pl, dev = self._img_plans[key]
-            import numpy as np
             host = torch.from_numpy(np.stack([images[i] for i in idx])).pin_memory()
             src = host.to(self.device, non_blocking=True)
-            m = len(idx)
-            dst = out if m == n else torch.empty((m, 3, S, S), dtype=torch.float32, device=self.device)
-            ws = torch.empty(m * (pl.row_hi - pl.row_lo) * S * 3, dtype=torch.uint8, device=self.device)
-            axes = []
-            for name, ax in (("hz", pl.horiz), ("vt", pl.vert)):
-                a = _lib.ResizeAxis()
-                w, f, c = dev[name]
-                a.weights, a.first, a.count = w.data_ptr(), f.data_ptr(), c.data_ptr()
-                a.taps, a.precision, a.n_out, a.identity = int(ax.weights.shape[1]), int(ax.precision), S, int(ax.identity)
-                axes.append(a)
-            mean = (C.c_float * 3)(*pl.mean255)
-            std = (C.c_float * 3)(*pl.std255)
-            rc = self.lib.conzic_image_preprocess(self.ctx, _ptr(src), m, H, W, C.byref(axes[0]), C.byref(axes[1]),
-                                                  pl.row_lo, pl.row_hi, mean, std, _ptr(dst), _ptr(ws), ws.numel(),
-                                                  self._stream())
-            _lib.check(rc, "conzic_image_preprocess")
-            if dst is not out:
-                out[torch.tensor(idx, device=self.device)] = dst
+            if len(idx) == n:
+                self.preprocess_uint8(src, cfg, out)
+            else:
+                out[torch.tensor(idx, device=self.device)] = self.preprocess_uint8(src, cfg)
         return out
 
     def image_encode(self, pixel_values: torch.Tensor) -> torch.Tensor:

@@ -50,7 +50,7 @@ fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_step.csv \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_step.log 2>&1; echo "ncu list rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_persist -s 40 -c 3 -f -o $OUT/prof_gemm \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_persist -s 30 -c 4 -f -o $OUT/prof_gemm \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_wide -s 26 -c 2 -f -o $OUT/prof_gemm_wide \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm_wide.log 2>&1; echo "ncu gemm_wide rc=$?"
@@ -58,7 +58,7 @@ if has ncu; then
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 fi
 if has ncusmall; then
-  for k in topk_kernel score_select_kernel clip_logits_kernel assemble_kernel layernorm_kernel cert_round1_kernel cert_round2_kernel clip_embed_kernel; do
+  for k in topk_cluster_kernel score_select_kernel clip_logits_kernel assemble_kernel layernorm_kernel cert_round1_kernel cert_round2_kernel clip_embed_kernel bert_embed_ln_kernel attention_kernel; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $OUT/prof_$k \
         python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_$k.log 2>&1; echo "ncu $k rc=$?"
   done

@@ -73,9 +73,47 @@ def full(src, dst, traffic_shape=None):
         print(json.dumps(t))
 
 
+def small(srcs, dst, peak_gbs=None):
+    """One table row per capture: duration, DRAM bytes, achieved GB/s against the measured HBM peak -- for the
+    HBM / latency bound kernels of the step (top-k, cosine logits, selection, assembly, LayerNorm, embeddings)."""
+    if peak_gbs is None:
+        p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak_gbs = json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6549.0
+    lines = ["| kernel | grid x block | regs | time us | DRAM read MB | DRAM write MB | achieved GB/s | % of HBM peak (%.0f GB/s) | "
+             "L2 throughput %% | SM throughput %% | warps active %% | capture |" % peak_gbs, "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for src in srcs:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            def val(name, scale=True):
+                if name not in hdr:
+                    return float("nan")
+                i = hdr.index(name)
+                v = float(r[i].replace(",", "") or "nan")
+                if scale:
+                    v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[i], 1.0)
+                return v
+            t_us = val("gpu__time_duration.sum")
+            rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+            gbs = (rd + wr) / (t_us * 1e-6) / 1e9 if t_us > 0 else 0.0
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("conzic::<unnamed>::", "")
+            lines.append(f"| {name} | {r[hdr.index('Grid Size')]} x {r[hdr.index('Block Size')]} | "
+                         f"{val('launch__registers_per_thread', False):.0f} | {t_us:.1f} | {rd / 1e6:.2f} | {wr / 1e6:.2f} | {gbs:.0f} | "
+                         f"{100 * gbs / peak_gbs:.1f} | {val('lts__throughput.avg.pct_of_peak_sustained_elapsed', False):.1f} | "
+                         f"{val('sm__throughput.avg.pct_of_peak_sustained_elapsed', False):.1f} | "
+                         f"{val('sm__warps_active.avg.pct_of_peak_sustained_active', False):.1f} | {os.path.basename(src)} |")
+    open(dst, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "small":
+        small(sys.argv[3:], sys.argv[2])
     else:
         shape = None
         if "--traffic" in sys.argv:
