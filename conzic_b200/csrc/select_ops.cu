@@ -154,7 +154,8 @@ constexpr int TOPK_CL_THREADS = 512;
 struct TopkClSmem {  // dynamic shared memory layout of one CTA
   unsigned long long* sortbuf;  // [K2]   (used in CTA 0 only, allocated everywhere so offsets agree)
   uint32_t* keys;               // [per]
-  int* hist;                    // [16][256] per-warp histograms; row 0 doubles as this CTA's merged histogram
+  int* hist;                    // [16][256] per-warp histograms
+  int* mine;                    // [2][256] this CTA's merged histogram, double buffered over the radix passes
   int* tot;                     // [256] cluster-wide histogram
   float* scratch;               // [40]
   float* red;                   // [4]  values other CTAs read: max, sum
@@ -164,7 +165,8 @@ struct TopkClSmem {  // dynamic shared memory layout of one CTA
     sortbuf = reinterpret_cast<unsigned long long*>(base);
     keys = reinterpret_cast<uint32_t*>(sortbuf + K2);
     hist = reinterpret_cast<int*>(keys + ((per + 3) & ~3));
-    tot = hist + 16 * 256;
+    mine = hist + 16 * 256;
+    tot = mine + 2 * 256;
     scratch = reinterpret_cast<float*>(tot + 256);
     red = scratch + 40;
     cnt = reinterpret_cast<int*>(red + 4);
@@ -172,7 +174,7 @@ struct TopkClSmem {  // dynamic shared memory layout of one CTA
   }
 };
 size_t topk_cl_smem_bytes(int K2, int per) {
-  return static_cast<size_t>(K2) * 8 + static_cast<size_t>((per + 3) & ~3) * 4 + (16 * 256 + 256) * 4 + (40 + 4) * 4 + (4 + 8) * 4;
+  return static_cast<size_t>(K2) * 8 + static_cast<size_t>((per + 3) & ~3) * 4 + (16 * 256 + 3 * 256) * 4 + (40 + 4) * 4 + (4 + 8) * 4;
 }
 
 __global__ void __launch_bounds__(TOPK_CL_THREADS) topk_cluster_kernel(const float* __restrict__ logits, int ldl, int V,
@@ -217,10 +219,13 @@ __global__ void __launch_bounds__(TOPK_CL_THREADS) topk_cluster_kernel(const flo
   for (int i = tid; i < n; i += TOPK_CL_THREADS) kf[i] = (kf[i] / sum) * __ldg(mask + lo + i);
   __syncthreads();
 
-  // ---- radix select of the K-th largest key over the whole row (non-negative floats order like their bit patterns)
+  // ---- radix select of the K-th largest key over the whole row (non-negative floats order like their bit patterns).
+  // One cluster barrier per pass: the merged histograms are double buffered, so a CTA can only overwrite buffer p & 1
+  // after the barrier of pass p + 1, which every CTA reaches after it has read the pass-p histograms.
   uint32_t prefix = 0, pmask = 0;
   int remaining = K;
-  for (int shift = 24; shift >= 0; shift -= 8) {
+  for (int shift = 24, pass = 0; shift >= 0; shift -= 8, ++pass) {
+    int* mine = sm.mine + (pass & 1) * 256;
     for (int i = tid; i < 16 * 256; i += TOPK_CL_THREADS) sm.hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += TOPK_CL_THREADS) {
@@ -231,26 +236,39 @@ __global__ void __launch_bounds__(TOPK_CL_THREADS) topk_cluster_kernel(const flo
     if (tid < 256) {
       int c = 0;
       for (int ww = 0; ww < 16; ++ww) c += sm.hist[ww * 256 + tid];
-      sm.hist[tid] = c;  // row 0 = this CTA's histogram (each thread only touches column tid)
+      mine[tid] = c;
     }
     cluster.sync();
     if (tid < 256) {
       int c = 0;
-      for (int r = 0; r < TOPK_CL; ++r) c += *cluster.map_shared_rank(&sm.hist[tid], r);
+      for (int r = 0; r < TOPK_CL; ++r) c += *cluster.map_shared_rank(&mine[tid], r);
       sm.tot[tid] = c;
     }
     __syncthreads();
-    if (tid == 0) {
-      int cum = 0, digit = 0, rem = remaining;
-      for (int bin = 255; bin >= 0; --bin) {
-        const int h = sm.tot[bin];
-        if (cum + h >= rem) { digit = bin; rem -= cum; break; }
-        cum += h;
+    if (w == 0) {
+      // the highest bin whose count, added to everything above it, reaches `remaining`: lane l scans bins
+      // 255 - 8 l ... 248 - 8 l, a warp scan orders the lanes (every CTA computes the same digit)
+      int loc[8], ssum = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { loc[u] = sm.tot[255 - (8 * lane + u)]; ssum += loc[u]; }
+      int incl = ssum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      sm.ctl[0] = digit;
-      sm.ctl[1] = rem;
+      const unsigned hit = __ballot_sync(0xffffffffu, incl >= remaining);
+      const int first = __ffs(hit) - 1;  // some lane always hits: the row holds at least `remaining` matching keys
+      if (lane == first) {
+        int cum = incl - ssum;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (cum + loc[u] >= remaining) { sm.ctl[0] = 255 - (8 * lane + u); sm.ctl[1] = remaining - cum; break; }
+          cum += loc[u];
+        }
+      }
     }
-    cluster.sync();  // every CTA has read the others' histograms before they are cleared again
+    __syncthreads();
     prefix |= static_cast<uint32_t>(sm.ctl[0]) << shift;
     pmask |= 255u << shift;
     remaining = sm.ctl[1];
@@ -269,23 +287,28 @@ __global__ void __launch_bounds__(TOPK_CL_THREADS) topk_cluster_kernel(const flo
   const int my_eq = static_cast<int>(block_sum(c_eq, sm.scratch));
   if (tid == 0) { sm.cnt[0] = my_gt; sm.cnt[1] = my_eq; sm.ctl[2] = 0; }
   cluster.sync();
-  int gt_off = 0, eq_off = 0;
-  for (int r = 0; r < rank; ++r) {
-    gt_off += *cluster.map_shared_rank(&sm.cnt[0], r);
-    eq_off += *cluster.map_shared_rank(&sm.cnt[1], r);
+  int gt_off = 0, eq_off = 0, eq_total = 0;
+  for (int r = 0; r < TOPK_CL; ++r) {
+    const int g = *cluster.map_shared_rank(&sm.cnt[0], r), e = *cluster.map_shared_rank(&sm.cnt[1], r);
+    if (r < rank) { gt_off += g; eq_off += e; }
+    eq_total += e;
   }
   unsigned long long* dst = cluster.map_shared_rank(sm.sortbuf, 0);
+  // the usual case: every key equal to T is needed (the K-th value is unique): all keys >= T go in, in any order
+  const bool all_ties = (eq_total == remaining);
+  const int base = all_ties ? gt_off + eq_off : gt_off;
   for (int i = tid; i < n; i += TOPK_CL_THREADS) {
     const uint32_t k = sm.keys[i];
-    if (k > T) {
-      const int slot = gt_off + atomicAdd(&sm.ctl[2], 1);
+    if (k > T || (all_ties && k == T)) {
+      const int slot = base + atomicAdd(&sm.ctl[2], 1);
       dst[slot] = (static_cast<unsigned long long>(k) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(lo + i));
     }
   }
-  // ties at T: lowest vocabulary indices first -- CTAs in rank order, inside a CTA an ordered block scan
+  // more ties than needed (e.g. underflowed zeros): lowest vocabulary indices first -- CTAs in rank order, inside a CTA
+  // an ordered block scan
   int tie_base = eq_off;
   int* wtot = reinterpret_cast<int*>(sm.scratch);  // reuse [0,16)
-  for (int c0 = 0; c0 < n && tie_base < remaining; c0 += TOPK_CL_THREADS) {
+  for (int c0 = 0; !all_ties && c0 < n && tie_base < remaining; c0 += TOPK_CL_THREADS) {
     const int i = c0 + tid;
     const bool is = (i < n) && (sm.keys[i] == T);
     const unsigned bal = __ballot_sync(0xffffffffu, is);

@@ -211,18 +211,18 @@ __device__ __forceinline__ float2 load_pair(const void* base, size_t elem) {
 }
 
 template <bool F32>
-__global__ void attention_kernel(AttnArgs a, int nk_cap) {
+__global__ void attention_kernel(AttnArgs a, int nk_cap, int nq_cap) {
   PDL_ENTRY();
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkp = nk_cap | 1;  // odd stride for the transposed K
-  const int per_warp = (HD * nkp + HD * nk_cap + HD + nkp + 3) & ~3;  // keep every warp's slice 16B aligned
+  const int per_warp = (HD * nkp + HD * nk_cap + HD * nq_cap + nkp + 3) & ~3;  // keep every warp's slice 16B aligned
   float* Kt = sm + static_cast<size_t>(wib) * per_warp;  // [64][nkp]
   float* Vs = Kt + HD * nkp;                               // [nk][64]
-  float* qs = Vs + HD * nk_cap;                            // [64]
-  float* ps = qs + HD;                                     // [nkp]
+  float* Qs = Vs + HD * nk_cap;                            // [nq][64]
+  float* ps = Qs + HD * nq_cap;                            // [nkp]
 
   const int n_pre_seq = a.P > 0 ? a.B : 0;
   const int n_seq = n_pre_seq + (a.cand_img ? a.n_cand : a.B * a.K);
@@ -246,22 +246,35 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap) {
     }
     const int nk = pl + nq;
     const int pre_base = b * a.P;
-    // ---- stage K^T and V
-    for (int j = 0; j < nk; ++j) {
-      const int row = j < pl ? pre_base + j : own_base + (j - pl);
-      const size_t e = static_cast<size_t>(row) * a.ld_qkv + head * HD + 2 * lane;
-      float2 k2 = load_pair<F32>(a.qkv, e + H);
-      float2 v2 = load_pair<F32>(a.qkv, e + 2 * H);
-      Kt[(2 * lane) * nkp + j] = k2.x;
-      Kt[(2 * lane + 1) * nkp + j] = k2.y;
-      *reinterpret_cast<float2*>(Vs + j * HD + 2 * lane) = v2;
+    // ---- stage K^T, V and the queries: 8 rows per round, every global load of a round issued before its first
+    // shared-memory store, so the warp pays one memory latency per 8 rows (this kernel is latency bound: a few
+    // hundred short sequences; the row-by-row form waited on every row and again on every query)
+    for (int j0 = 0; j0 < nk; j0 += 8) {
+      float2 kk[8], vv[8], qq[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = min(j0 + u, nk - 1);  // clamp instead of predicate: keeps the arrays in registers
+        const int row = j < pl ? pre_base + j : own_base + (j - pl);
+        const size_t e = static_cast<size_t>(row) * a.ld_qkv + head * HD + 2 * lane;
+        kk[u] = load_pair<F32>(a.qkv, e + H);
+        vv[u] = load_pair<F32>(a.qkv, e + 2 * H);
+        qq[u] = load_pair<F32>(a.qkv, e);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j < nk) {
+          Kt[(2 * lane) * nkp + j] = kk[u].x;
+          Kt[(2 * lane + 1) * nkp + j] = kk[u].y;
+          *reinterpret_cast<float2*>(Vs + j * HD + 2 * lane) = vv[u];
+          if (j >= pl) *reinterpret_cast<float2*>(Qs + (j - pl) * HD + 2 * lane) = qq[u];  // own rows are the queries
+        }
+      }
     }
     __syncwarp();
     for (int t = 0; t < nq; ++t) {
       const int qrow = own_base + t;
-      float2 q2 = load_pair<F32>(a.qkv, static_cast<size_t>(qrow) * a.ld_qkv + head * HD + 2 * lane);
-      *reinterpret_cast<float2*>(qs + 2 * lane) = q2;
-      __syncwarp();
+      const float* qs = Qs + t * HD;
       const int nvis = a.causal ? pl + t + 1 : nk;
       float sc[MAX_SLOTS];
       float mx = -INFINITY;
@@ -791,7 +804,8 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
     return false;
   }
   const int nkp = nk_cap | 1;
-  const size_t per_warp = static_cast<size_t>((HD * nkp + HD * nk_cap + HD + nkp + 3) & ~3) * sizeof(float);
+  const int nq_cap = a.P > a.S ? a.P : a.S;
+  const size_t per_warp = static_cast<size_t>((HD * nkp + HD * nk_cap + HD * nq_cap + nkp + 3) & ~3) * sizeof(float);
   int warps = static_cast<int>((200 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;
@@ -806,9 +820,9 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   if (a.qkv_f32)
-    launch_k(attention_kernel<true>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap);
+    launch_k(attention_kernel<true>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap, nq_cap);
   else
-    launch_k(attention_kernel<false>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap);
+    launch_k(attention_kernel<false>, dim3(static_cast<int>(grid)), dim3(warps * 32), smem, st, a, nk_cap, nq_cap);
   return cuda_ok(cudaGetLastError(), "attention launch");
 }
 

@@ -22,6 +22,23 @@ sys.path.insert(0, ROOT)
 from synthetic import synth  # noqa: E402
 
 
+def survivor_mask(tr16, hi, lo, alpha=0.02, beta=2.0):
+    """Round 1 of cert_ops.cu in torch with the asymmetric bounds (logit units): True = cannot be ruled out."""
+    a = tr16["clip_ref"].double() * 100.0
+    p = tr16["probs"].double()
+    m = a.max(dim=1, keepdim=True).values
+    e = torch.exp(a - m)
+    Z = e.sum(dim=1, keepdim=True)
+    f = alpha * p + beta * e / Z
+    w = f.argmax(dim=1, keepdim=True)
+    ew, Ew = e.gather(1, w), (alpha * p).gather(1, w)
+    d = ew * math.exp(-hi) - e * math.exp(lo)
+    x = torch.where(d >= 0, d / (Z * math.exp(lo)), d / (Z * math.exp(-hi)))
+    alive = ~((Ew - alpha * p) + beta * x > 1e-5)
+    alive.scatter_(1, w, True)
+    return alive
+
+
 def survivors(tr3, tr16, eps_logit, alpha=0.02, beta=2.0):
     """Round 1 of the certified argmax in torch, on the bf16 cosines: candidates whose lower bound does not clear 0."""
     a = tr16["clip_ref"].double() * 100.0
@@ -56,7 +73,13 @@ def main():
     e3.set_bert2clip(off, tok)
     e16.set_bert2clip(off, tok)
     B, n, K = args.images, args.len, args.K
-    pix = torch.stack([synth.make_pixel_values(i) for i in range(B)]).cuda()
+    # the bench's inputs: uint8 images through the device CLIPImageProcessor
+    import numpy as np
+    from transformers import CLIPImageProcessor
+    from conzic_b200 import imageproc
+    cfg = imageproc.processor_config(CLIPImageProcessor())
+    raw = torch.from_numpy(np.stack([synth.make_uint8_image(i) for i in range(B)])).cuda()
+    pix = e3.preprocess_uint8(raw, cfg)
     img = e3.image_encode(pix)
     img16 = e16.image_encode(pix)
     icos = torch.nn.functional.cosine_similarity(img, img16, dim=-1)
@@ -70,6 +93,7 @@ def main():
         random.shuffle(order)
     eps_grid = [1e-3, 1.5e-3, 2e-3, 3e-3, 4e-3, 6e-3, 8e-3]
     all_d, all_sd, all_cen, flips, steps = [], [], [], 0, 0
+    r_all, r_rest = [], []  # sum_j exp(exact logit) / sum_j exp(bf16 logit) over all candidates / over the ones ruled out
     surv = {e: [] for e in eps_grid}
     per_step = []
     for it in range(args.sweeps):
@@ -92,6 +116,13 @@ def main():
             all_sd.append(sd.flatten().cpu())
             cen = sd - sd.mean(dim=1, keepdim=True)
             all_cen.append(cen.flatten().cpu())
+            a16, a3 = t16["clip_ref"].double() * 100.0, t3["clip_ref"].double() * 100.0
+            mref = a16.max(dim=1, keepdim=True).values
+            e16, e3 = torch.exp(a16 - mref), torch.exp(a3 - mref)
+            r_all.append((e3.sum(1) / e16.sum(1)).cpu())
+            rest = ~survivor_mask(t16, 0.16, 0.065)
+            has = rest.any(dim=1)
+            r_rest.append(((e3 * rest).sum(1)[has] / (e16 * rest).sum(1)[has]).cpu())
             nf = int((i3[:, pos] != i16[:, pos]).sum())
             flips += nf
             steps += 1
@@ -108,7 +139,10 @@ def main():
     signed = dict(mean=float(sd.mean()), std=float(sd.std()), min=float(sd.min()), max=float(sd.max()),
                   max_abs_minus_global_mean=float((sd - sd.mean()).abs().max()),
                   max_abs_minus_image_mean=float(cen.abs().max()), std_minus_image_mean=float(cen.std()))
-    rep = dict(signed_error=signed, workload=dict(images=B, sweeps=args.sweeps, K=K, sentence_len=n, order=args.order, steps=steps,
+    ra, rr = torch.cat(r_all), torch.cat(r_rest)
+    zratio = dict(all=dict(min=float(ra.min()), max=float(ra.max()), mean=float(ra.mean())),
+                  ruled_out=dict(min=float(rr.min()), max=float(rr.max()), mean=float(rr.mean()), n=int(rr.numel())))
+    rep = dict(signed_error=signed, softmax_denominator_ratio_exact_over_bf16=zratio, workload=dict(images=B, sweeps=args.sweeps, K=K, sentence_len=n, order=args.order, steps=steps,
                              candidates=int(d.numel())),
                max_dcos=float(d.max()), mean_dcos=float(d.mean()), quantiles=quant,
                image_embed_min_cos_bf16_vs_x3=float(icos.min()),

@@ -79,8 +79,8 @@ def small(srcs, dst, peak_gbs=None):
     if peak_gbs is None:
         p = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak_gbs = json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6549.0
-    lines = ["| kernel | grid x block | regs | time us | DRAM read MB | DRAM write MB | achieved GB/s | % of HBM peak (%.0f GB/s) | "
-             "L2 throughput %% | SM throughput %% | warps active %% | capture |" % peak_gbs, "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    lines = [f"| kernel | grid x block | regs | time us | DRAM read MB | DRAM write MB | achieved GB/s | % of HBM peak ({peak_gbs:.0f} GB/s) | "
+             "L2 throughput % | SM throughput % | warps active % | capture |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for src in srcs:
         out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
