@@ -466,7 +466,7 @@ def measure(args, rank, local_rank, world, wl: Workload, full: bool):
         traffic, traffic_detail = ncu_traffic()
         rec["roofline"]["traffic"] = traffic
         rec["roofline"]["traffic_detail"] = traffic_detail
-        if args.precision == "certified":
+        if args.precision == "certified" and not args.no_parity:
             rec["parity"] = parity_check(job)
     from conzic_b200 import runtime
     runtime.clear()
@@ -510,6 +510,7 @@ def main():
     ap.add_argument("--precision", default="certified", choices=["certified", "bf16", "bf16x3"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run id-identity check against bf16x3 (A/B runs)")
     args = ap.parse_args()
     rank, local_rank, world = cdist.env_world()
     if args.impl == "reference":

@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libconzic.so")
 
 PREC_BF16, PREC_BF16X3, PREC_CERTIFIED = 0, 1, 2
-FLAG_NO_PDL, FLAG_LN_STANDALONE = 1, 2
+FLAG_NO_PDL, FLAG_LN_STANDALONE, FLAG_WIDE_EW8 = 1, 2, 4
 CERT_STATS = 8
 GEMM_TCGEN05, GEMM_SIMT_DEBUG = 0, 1
 BERT_GLOBALS, CLIP_GLOBALS, PER_LAYER = 10, 5, 16
@@ -36,7 +36,8 @@ class Config(C.Structure):
         ("pad_id", C.c_int32), ("unk_id", C.c_int32), ("cls_id", C.c_int32), ("sep_id", C.c_int32),
         ("mask_id", C.c_int32), ("dot_id", C.c_int32), ("clip_bos", C.c_int32), ("clip_eos", C.c_int32),
         ("precision", C.c_int32), ("gemm_impl", C.c_int32), ("clip_chunk_rows", C.c_int32),
-        ("cert_dcos", C.c_float), ("cert_dcos_lo", C.c_float), ("cert_fcap", C.c_int32), ("flags", C.c_int32),
+        ("cert_dcos", C.c_float), ("cert_dcos_lo", C.c_float), ("cert_zratio_lo", C.c_float), ("cert_zratio_hi", C.c_float),
+        ("cert_fcap", C.c_int32), ("flags", C.c_int32),
     ]
 
 

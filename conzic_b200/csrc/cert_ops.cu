@@ -8,7 +8,9 @@
 // cert_dcos_lo = lo).  For the bf16 winner w and any other candidate k
 //     f_w - f_k = (E_w - E_k) + beta * (exp(t_w) - exp(t_k)) / Z
 //              >= (E_w - E_k) + beta * D / (D >= 0 ? Zhi : Zlo),   D = exp(a_w - hi) - exp(a_k + lo),
-// with Zlo = Z_a exp(-hi) <= Z <= Z_a exp(lo) = Zhi.  If that lower bound is > tau, k cannot win in exact
+// with Zlo = r_lo Z_a <= Z <= r_hi Z_a = Zhi (r_lo = exp(-hi), r_hi = exp(lo) follow from the per-candidate bounds; the
+// sum over ~200 candidates is far better behaved than its worst term, and cert_zratio_lo / _hi carry measured bounds on
+// the ratio exact / bf16 of the part of the denominator that comes from bf16 logits).  If that lower bound is > tau, k cannot win in exact
 // arithmetic and is dropped (round 1).  The survivors (always including w, whose exact cosine is also what the
 // caller reports) are re-encoded by the exact tower; round 2 repeats the test among them with their exact logits
 // (no error for them, [-lo, hi] for the rest of Z).  An image whose survivors still cannot be ordered -- or that has more
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round1_kernel(CertArgs c) {
   if (w < 0 || w >= K) w = 0;
   __syncthreads();
 
-  const float zlo = Z * expf(-c.eps_hi), zhi = Z * expf(c.eps_lo);
+  const float zlo = Z * c.zr_lo, zhi = Z * c.zr_hi;
   const float Ew = sm.exact[w], ew = sm.e[w];
   const int64_t idw = a.ids_masked[o0 + w];
   const float pw = a.probs[o0 + w];
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(CERT_THREADS) cert_round2_kernel(CertArgs c) {
       if (w < 0 || sm.sprob[ks[i]] > sm.sprob[w]) w = ks[i];  // ks ascending: the lowest index wins ties
     }
     const float zfl = Z - Zrest;  // exact part of the denominator
-    const float zlo = zfl + Zrest * expf(-c.eps_hi), zhi = zfl + Zrest * expf(c.eps_lo);
+    const float zlo = zfl + Zrest * c.zr_lo, zhi = zfl + Zrest * c.zr_hi;
     bool ok = true;
     const int64_t idw = a.ids_masked[o0 + w];
     for (int i = 0; i < n && ok; ++i) {

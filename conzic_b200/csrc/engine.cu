@@ -136,7 +136,7 @@ struct conzic_ctx {
   float *c_tok = nullptr, *c_pos = nullptr, *c_fln_g = nullptr, *c_fln_b = nullptr;
   Tower clip, clip3;
   bool certified = false;
-  float cert_dcos = 0.f, cert_dcos_lo = 0.f;
+  float cert_dcos = 0.f, cert_dcos_lo = 0.f, cert_zratio_lo = 0.f, cert_zratio_hi = 0.f;
   int cert_fcap = 64;
   int32_t* cert_host = nullptr;  // pinned, 16 ints: the counters read back twice per certified step
   uint64_t cert_stats[CONZIC_CERT_STATS] = {};
@@ -634,6 +634,9 @@ bool select_winner(conzic_ctx* c, Plan& p, const CandLayout& lay, const float* t
   ca.q = q;
   ca.eps_hi = q.scale * c->cert_dcos;
   ca.eps_lo = q.scale * c->cert_dcos_lo;
+  // the denominator ratio: the measured bounds, never wider than what the per-candidate bounds imply
+  ca.zr_lo = fmaxf(expf(-ca.eps_hi), c->cert_zratio_lo);
+  ca.zr_hi = c->cert_zratio_hi > 0.f ? fminf(expf(ca.eps_lo), c->cert_zratio_hi) : expf(ca.eps_lo);
   ca.tau = 2e-6f * (fabsf(q.alpha) + fabsf(q.beta) + fabsf(q.gamma) + 1.0f);
   ca.fcap = c->cert_fcap;
   ca.heavy = 0.f;
@@ -756,6 +759,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
     o.split = split; o.impl = cfg->gemm_impl; o.bn = 128; o.stages = 3;
     o.persist = persist ? 1 : 0;  // persistent CTA-pair kernel (tcgen05 cta_group::2): the CLIP towers, bf16 and bf16x3
     o.cg = 2;
+    o.wide_ew8 = (cfg->flags & CONZIC_FLAG_WIDE_EW8) ? 1 : 0;
     return o;
   };
   c->gopt_bert = opts(c->bert_split, false);  // few token rows: gridded kernel (QKV / fc1 in bf16x3 opt into the pair kernel)
@@ -768,6 +772,11 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
   // an explicit upper bound without a lower one is taken as symmetric
   c->cert_dcos_lo = cfg->cert_dcos_lo > 0.f ? cfg->cert_dcos_lo : (cfg->cert_dcos > 0.f ? cfg->cert_dcos : CONZIC_CERT_DCOS_LO_DEFAULT);
   c->cert_fcap = cfg->cert_fcap > 0 ? cfg->cert_fcap : 64;
+  // measured denominator-ratio bounds go with the measured default error bounds; explicit error bounds without explicit
+  // ratio bounds fall back to what the error bounds imply (negative = "none")
+  const bool own_bounds = cfg->cert_dcos > 0.f || cfg->cert_dcos_lo > 0.f;
+  c->cert_zratio_lo = cfg->cert_zratio_lo > 0.f ? cfg->cert_zratio_lo : (own_bounds || cfg->cert_zratio_lo < 0.f ? 0.f : CONZIC_CERT_ZRATIO_LO_DEFAULT);
+  c->cert_zratio_hi = cfg->cert_zratio_hi > 0.f ? cfg->cert_zratio_hi : (own_bounds || cfg->cert_zratio_hi < 0.f ? 0.f : CONZIC_CERT_ZRATIO_HI_DEFAULT);
   // default: 16 x (148 SMs x 128 rows) token rows per pass; measured on B200: the larger the pass the better
   // (every kernel is a persistent or grid-stride launch; nothing stays L2 resident between kernels anyway)
   c->chunk_rows = cfg->clip_chunk_rows > 0 ? cfg->clip_chunk_rows : 303104;

@@ -731,15 +731,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
 // back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
 // ---------------------------------------------------------------------------------------------------
-template <int EW>  // EW epilogue warps: 8 (each drains 128 columns of BOTH halves; can fuse a LayerNorm) or 16
+template <int EW>  // EW epilogue warps: 8 (each drains 128 columns of BOTH halves) or 16 (128 columns of one half)
 struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
   static constexpr int STAGES = 4;
   static constexpr int STG_OFF = STAGES * STAGE;
-  static constexpr int LNS_OFF = STG_OFF + EW * 2048;  // fused LN (EW == 8): float2 [2 parities][2 column halves][128 rows]
-  static constexpr int BAR_OFF = LNS_OFF + (EW == 8 ? 2 * 2 * BM * 8 : 0);
+  static constexpr int BAR_OFF = STG_OFF + EW * 2048;  // one 2 KB staging buffer per epilogue warp
   static constexpr int N_BARS = 2 * STAGES + 4;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int THREADS = 64 + 32 * EW;
@@ -852,7 +851,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = EW == 8 ? slice : (slice & 1);  // columns [sub*128, sub*128+128) of a 256-column half
     const int h_lo = EW == 8 ? 0 : (slice >> 1), h_hi = EW == 8 ? 2 : (slice >> 1) + 1;
     uint32_t uph = 0;
-    const bool lnf = EW == 8 && p.e.lnf_out != nullptr;
+    const bool lnf = p.e.lnf_out != nullptr;
     const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     uint8_t* stg = smem + SL::STG_OFF + (warp - 2) * 2048;
     // this warp's bias values (columns do not depend on the tile): fetched once, before the first accumulator is
@@ -897,31 +896,38 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ls1[i] += st1[i]; ls2[i] += st2[i]; }
       }
-      if constexpr (EW == 8) if (lnf) {
-        // Fused LayerNorm of the rows just written.  This warp covered 256 of a row's 512 columns, the warp with
-        // the other `sub` the rest: exchange (sum, sum of squares) through shared memory, read the kept values
-        // back from TMEM, write bf16(LN(x) * g + b), and only then hand the accumulators back to the MMA warp.
+      if (lnf) {
+        // Fused LayerNorm of the rows just written.  The EW / 4 warps of this TMEM lane quarter each covered
+        // 512 / (EW / 4) of a row's columns: exchange (sum, sum of squares) through the warps' own staging buffers
+        // (idle between units), re-read the values this lane stored, write bf16(LN(x) * g + b).
         const Epi& e = p.e;
-        float2* xs = reinterpret_cast<float2*>(smem + SL::LNS_OFF) + uph * (2 * BM);
-        float mean[4], rstd[4];
+        constexpr int NSL = EW / 4;
+        float2* mine = reinterpret_cast<float2*>(stg);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float a = ls1[i], b = ls2[i];
           a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
           b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
-          mean[i] = a; rstd[i] = b;
-          if ((lane & 3) == 0) xs[sub * BM + q * 32 + (lane >> 2) + 8 * i] = make_float2(a, b);
+          if ((lane & 3) == 0) mine[(lane >> 2) + 8 * i] = make_float2(a, b);
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of TMEM lane quarter q
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * NSL) : "memory");  // the warps of lane quarter q
+        float mean[4], rstd[4];
+        const int wq = (warp - 2) & 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 o = xs[(1 - sub) * BM + q * 32 + (lane >> 2) + 8 * i];
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < NSL; ++sl) {  // same order in every warp: identical statistics for all columns of a row
+            const float2 o = reinterpret_cast<const float2*>(smem + SL::STG_OFF + (4 * sl + wq) * 2048)[(lane >> 2) + 8 * i];
+            a += o.x; b += o.y;
+          }
           const float inv = 1.0f / static_cast<float>(2 * PBN);
-          const float mu = (mean[i] + o.x) * inv;
-          const float var = fmaxf((rstd[i] + o.y) * inv - mu * mu, 0.f);
+          const float mu = a * inv;
+          const float var = fmaxf(b * inv - mu * mu, 0.f);
           rstd[i] = rsqrtf(var + e.lnf_eps);
           mean[i] = -mu * rstd[i];  // y = x * rstd + (-mean * rstd)
         }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * NSL) : "memory");  // all read: staging may be reused
         const int pc = lane & 3;
         auto write_ln = [&](int col, const float4& g4, const float4& b4, int i, float x0, float x1, float x2, float x3) {
           const int grow = row0 + (lane >> 2) + 8 * i;
@@ -934,15 +940,16 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + col) = u;
         };
         {
-          // re-read what this lane stored (same addresses, program order; L2 hits mostly), 4 chunks = 16 loads
+          // re-read what this lane stored (same addresses, program order; L2 hits mostly), GC chunks = 4 GC loads
           // in flight per lane so the pass is bandwidth- and not latency-bound; it overlaps the next unit's MMAs
+          constexpr int NCH = EW == 8 ? 16 : 8, GC = EW == 8 ? 4 : 2;
 #pragma unroll 1
-          for (int g0 = 0; g0 < 16; g0 += 4) {
-            float4 x[4][4];
+          for (int g0 = 0; g0 < NCH; g0 += GC) {
+            float4 x[GC][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < GC; ++j) {
               const int hc = g0 + j;
-              const int col = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
+              const int col = (EW == 8 ? (hc >> 3) : h_lo) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int grow = row0 + (lane >> 2) + 8 * i;
@@ -952,9 +959,9 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < GC; ++j) {
               const int hc = g0 + j;
-              const int col = (hc >> 3) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
+              const int col = (EW == 8 ? (hc >> 3) : h_lo) * PBN + sub * (PBN / 2) + (hc & 7) * 16 + pc * 4;
               const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.lnf_g + col));
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.lnf_b + col));
 #pragma unroll
@@ -1099,13 +1106,12 @@ static bool configure_wide() {
          cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<16>::DYN_BYTES),
                  "cudaFuncSetAttribute(gemm_wide<16>)");
 }
-// 16 epilogue warps (twice the residual loads in flight) unless the epilogue also writes a LayerNorm, which needs the
-// 8-warp form where one warp pair covers whole rows
-static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, cudaStream_t st) {
+// 16 epilogue warps: twice the residual loads in flight of the 8-warp form (kept for A/B measurements)
+static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, bool ew8, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
   if (groups < 1) groups = 1;
-  const bool w16 = !p.e.lnf_out;
+  const bool w16 = !ew8;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
   cfg.blockDim = dim3(w16 ? WideSmem<16>::THREADS : WideSmem<8>::THREADS);
@@ -1189,7 +1195,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     const bool wide_ok = cg == 2 && W.N == 2 * PBN && epi.out_f32 != nullptr;
     if (wide_ok && ((!ares && W.K >= 1024) || epi.lnf_out)) {
       pp.n_tiles = 1;
-      return launch_wide(ta, tb, pp, st);
+      return launch_wide(ta, tb, pp, o.wide_ew8 != 0, st);
     }
     if (epi.lnf_out) {
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");

@@ -121,6 +121,7 @@ struct GemmOpts {
   int cg = 1;       // persistent kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs
   int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
   int force_pair = 0;  // bf16x3 + persist: the pair kernel whatever the tile count (tests)
+  int wide_ew8 = 0;    // N = 512 wide kernel: 8 instead of 16 epilogue warps (A/B measurements)
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
@@ -296,6 +297,7 @@ void launch_score_select(const SelectArgs& a, cudaStream_t st);
 struct CertArgs {
   SelectArgs q;        // q.logit = main-tower logits [B,K]; round 2 patches the listed candidates in place
   float eps_hi, eps_lo; // main-tower logit - exact logit of one candidate lies in [-eps_lo, eps_hi] (scale * cosine bounds)
+  float zr_lo, zr_hi;   // sum exp(exact logit) / sum exp(main-tower logit) over the candidates not re-scored lies in [zr_lo, zr_hi]
   float tau;           // slack for the fp rounding of the comparisons themselves
   int fcap;            // an image with more than fcap unbeaten candidates goes straight to the full exact re-encode
   float heavy;         // > 0: also list candidates whose softmax weight is >= heavy (narrows round 2's bound on Z)

@@ -72,7 +72,7 @@ class Engine:
                  gemm_impl: str = "tcgen05", special_ids: Sequence[int] = _dims.SPECIAL_IDS,
                  dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
                  clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_dcos_lo: Optional[float] = None,
-                 cert_fcap: Optional[int] = None,
+                 cert_zratio: Optional[Sequence[float]] = None, cert_fcap: Optional[int] = None,
                  ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None):
         """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
         in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
@@ -112,12 +112,16 @@ class Engine:
         env = os.environ.get
         cfg.cert_dcos = float(cert_dcos if cert_dcos is not None else env("CONZIC_CERT_DCOS", 0.0))
         cfg.cert_dcos_lo = float(cert_dcos_lo if cert_dcos_lo is not None else env("CONZIC_CERT_DCOS_LO", 0.0))
+        if cert_zratio is None and env("CONZIC_CERT_ZRATIO"):
+            cert_zratio = [float(v) for v in env("CONZIC_CERT_ZRATIO").split(",")]
+        cfg.cert_zratio_lo, cfg.cert_zratio_hi = (float(cert_zratio[0]), float(cert_zratio[1])) if cert_zratio else (0.0, 0.0)
         cfg.cert_fcap = int(cert_fcap if cert_fcap is not None else env("CONZIC_CERT_FCAP", 0))
         if ln_standalone is None:
             ln_standalone = env("CONZIC_LN_STANDALONE", "0") == "1"
         if pdl is None:
             pdl = env("CONZIC_PDL", "1") != "0"
-        cfg.flags = (_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL)
+        cfg.flags = ((_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL) |
+                     (_lib.FLAG_WIDE_EW8 if env("CONZIC_WIDE_EW8", "0") == "1" else 0))
         self.cfg = cfg
         self.V, self.D = cfg.bert_vocab, cfg.clip_proj
         self.ldl = (self.V + 3) & ~3

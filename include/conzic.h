@@ -48,11 +48,20 @@ enum {
  * over-estimates by 3.0e-4 on average; tools/cert_bound.py, profiles/r02b_cert_bound.md) */
 #define CONZIC_CERT_DCOS_DEFAULT 1.6e-3f
 #define CONZIC_CERT_DCOS_LO_DEFAULT 6.5e-4f
+/* R = sum_j exp(exact logit_j) / sum_j exp(bf16 logit_j) over the candidates of an image that are NOT re-scored (the part
+ * of the softmax denominator that stays approximate) is taken to lie in [ZRATIO_LO, ZRATIO_HI]; the per-candidate bounds
+ * alone only give [exp(-100 hi), exp(100 lo)] = [0.852, 1.067]; measured over 5 120 image-steps R stays within
+ * [0.9406, 1.0003] (a sum over ~190 candidates averages the per-candidate errors: profiles/r02j_cert_bound.md); the
+ * defaults leave the same kind of margin as the per-candidate bounds (3.3e-4 / 3.0e-4 in mean-cosine terms).
+ * Used only with the default error bounds; conzic_config.cert_zratio_* < 0 switches them off. */
+#define CONZIC_CERT_ZRATIO_LO_DEFAULT 0.91f
+#define CONZIC_CERT_ZRATIO_HI_DEFAULT 1.03f
 #define CONZIC_CERT_STATS 8
 
 /* conzic_config.flags */
 enum {
   CONZIC_FLAG_NO_PDL = 1,         /* launch without programmatic dependent launch (A/B measurements)                */
+  CONZIC_FLAG_WIDE_EW8 = 4,       /* N = 512 GEMM kernel with 8 instead of 16 epilogue warps (A/B measurements)     */
   CONZIC_FLAG_LN_STANDALONE = 2   /* CLIP bf16 tower: LayerNorm as its own kernel instead of in the O-proj / fc2
                                      epilogues (A/B measurements; HF:models/clip/modeling_clip.py:369-384)          */
 };
@@ -76,6 +85,8 @@ typedef struct conzic_config {
   int32_t clip_chunk_rows;     /* CLIP token rows processed per pass; 0 = default (303104 = 16 waves of 148 x 128-row tiles) */
   float cert_dcos;             /* CERTIFIED: upper bound of cos(bf16) - cos(exact); 0 = CONZIC_CERT_DCOS_DEFAULT */
   float cert_dcos_lo;          /* CERTIFIED: -(lower bound); 0 = cert_dcos when that is given, else the default */
+  float cert_zratio_lo;        /* CERTIFIED: bounds on the denominator ratio R (see CONZIC_CERT_ZRATIO_*); 0 = default when the */
+  float cert_zratio_hi;        /*   error bounds are the defaults too, < 0 = only what the error bounds imply */
   int32_t cert_fcap;           /* CERTIFIED: an image with more unbeaten candidates than this is re-encoded in full; 0 = 64 */
   int32_t flags;               /* CONZIC_FLAG_* */
 } conzic_config;

@@ -322,7 +322,8 @@ def test_gibbs_step_teacher_forced_bf16x3(name):
     assert m["winner_cos_err"] < 2e-5
 
 
-@pytest.mark.parametrize("kw", [{}, {"cert_dcos": 1.0}, {"cert_dcos": 0.05, "cert_fcap": 2}, {"cert_dcos": 0.02, "cert_fcap": 64}])
+@pytest.mark.parametrize("kw", [{}, {"cert_zratio": (-1.0, -1.0)}, {"cert_dcos": 1.0}, {"cert_dcos": 0.05, "cert_fcap": 2},
+                                {"cert_dcos": 0.02, "cert_fcap": 64}])
 @pytest.mark.parametrize("name", FIXTURES)
 def test_gibbs_step_teacher_forced_certified(name, kw):
     """The default precision, teacher-forced on every recorded step of the unmodified reference: exact logits and

@@ -71,7 +71,11 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         eng = runtime.any_engine()
-        print(json.dumps({"path": label, "precision": eng.precision, "batch": B, "sweeps": a.sweeps, "seconds": round(dt, 3),
+        eng.profile(True)
+        call()
+        ph = {k: round(v[0] / (a.sweeps * n), 3) for k, v in eng.profile_read_phases().items() if v[1]}
+        eng.profile(False)
+        print(json.dumps({"path": label, "phases_ms_per_step": ph, "precision": eng.precision, "batch": B, "sweeps": a.sweeps, "seconds": round(dt, 3),
                           "ms_per_gibbs_step": round(1e3 * dt / (a.sweeps * n), 2),
                           "device_text_pipeline": bool(eng.has_text_vocab), "string_path": bool(env) or bool(eng.needs_strings),
                           "max_clip_tokens_per_word": eng.max_tok_per_word}), flush=True)

@@ -118,11 +118,11 @@ def main():
             all_cen.append(cen.flatten().cpu())
             a16, a3 = t16["clip_ref"].double() * 100.0, t3["clip_ref"].double() * 100.0
             mref = a16.max(dim=1, keepdim=True).values
-            e16, e3 = torch.exp(a16 - mref), torch.exp(a3 - mref)
-            r_all.append((e3.sum(1) / e16.sum(1)).cpu())
+            x16, x3 = torch.exp(a16 - mref), torch.exp(a3 - mref)
+            r_all.append((x3.sum(1) / x16.sum(1)).cpu())
             rest = ~survivor_mask(t16, 0.16, 0.065)
             has = rest.any(dim=1)
-            r_rest.append(((e3 * rest).sum(1)[has] / (e16 * rest).sum(1)[has]).cpu())
+            r_rest.append(((x3 * rest).sum(1)[has] / (x16 * rest).sum(1)[has]).cpu())
             nf = int((i3[:, pos] != i16[:, pos]).sum())
             flips += nf
             steps += 1

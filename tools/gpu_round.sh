@@ -36,6 +36,14 @@ if has configs; then
   done
   timeout 1800 python bench.py --config 5 --steps 2 --warmup 3 --no-cpu > $OUT/bench_config5.json 2> $OUT/bench_config5.err; echo "config 5 rc=$?"; cat $OUT/bench_config5.json | cut -c1-600
 fi
+if has ab; then  # A/B of the switches named in $AB_ENVS (space separated VAR=VALUE), interleaved with the default
+  for rep in 1 2; do
+    for ev in "X=0" $AB_ENVS; do
+      env $ev timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-parity > $OUT/ab_${ev//=/_}_$rep.json 2>> $OUT/ab.err
+      python -c "import json,sys;d=json.load(open('$OUT/ab_${ev//=/_}_$rep.json'));print('$ev',d['value'],d['e2e']['value'],d.get('phase_breakdown_ms'))"
+    done
+  done
+fi
 if has vocab; then
   timeout 900 python tools/bench_vocab_paths.py > $OUT/vocab_paths.jsonl 2> $OUT/vocab_paths.err; echo "vocab rc=$?"; cat $OUT/vocab_paths.jsonl
 fi

@@ -48,7 +48,7 @@ def launches(src, dst):
     print(open(dst).read())
 
 
-def full(src, dst, traffic_shape=None):
+def full(src, dst, traffic_shape=None, pick=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -65,10 +65,13 @@ def full(src, dst, traffic_shape=None):
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
             return [float(r[i].replace(",", "")) * mult for r in data]
         rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+        if pick:  # only the captured launches that have this shape
+            rd, wr = [rd[i] for i in pick], [wr[i] for i in pick]
         t = {"kernel": data[0][hdr.index("Kernel Name")].split("(")[0], "shape": {"M": M, "N": N, "K": K},
              "dram_bytes_per_launch": (sum(rd) + sum(wr)) / len(rd),
              "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
-             "source": os.path.basename(src)}
+             "launches_averaged": pick if pick else list(range(len(rd))),
+             "source": "profiles/" + os.path.basename(dst) + " (ncu --set full capture " + os.path.basename(src) + ")"}
         json.dump(t, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
         print(json.dumps(t))
 
@@ -119,4 +122,7 @@ if __name__ == "__main__":
         if "--traffic" in sys.argv:
             i = sys.argv.index("--traffic")
             shape = tuple(int(x) for x in sys.argv[i + 1:i + 4])
-        full(sys.argv[2], sys.argv[3], shape)
+        pick = None
+        if "--pick" in sys.argv:
+            pick = [int(x) for x in sys.argv[sys.argv.index("--pick") + 1].split(",")]
+        full(sys.argv[2], sys.argv[3], shape, pick)
