@@ -869,32 +869,33 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       prefetch_resid(p, lane, row0, h_lo * PBN + sub * (PBN / 2), rr);
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
-      float ls1[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};  // row sums over both halves (fused LN)
+      float ls1[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};  // row sums over this warp's columns (fused LN)
+      // 16-column chunks; the residual of chunk t + 1 is requested before chunk t is drained, so that its latency
+      // (the epilogue's largest stall in the ncu source view) is covered by one whole chunk of work
+      constexpr int NT = EW == 8 ? 16 : 8;
 #pragma unroll 1
-      for (int h = h_lo; h < h_hi; ++h) {
-        const int nbase = h * PBN + sub * (PBN / 2);
-        const float4 bias4 = h == 0 ? bias_h[0] : bias_h[1];
+      for (int t = 0; t < NT; ++t) {
+        const int h = h_lo + (t >> 3), c = t & 7;
+        const int n0 = h * PBN + sub * (PBN / 2) + c * 16;
+        float4 rn[4];
+        if (t + 1 < NT) prefetch_resid(p, lane, row0, (h_lo + ((t + 1) >> 3)) * PBN + sub * (PBN / 2) + ((t + 1) & 7) * 16, rn);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * PBN + sub * (PBN / 2);
-        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          const int n0 = nbase + c * 16;
-          if (c > 0 || h > h_lo) prefetch_resid(p, lane, row0, n0, rr);
-          uint32_t r[16];
-          tmem_ld16(taddr + c * 16, r);
-          tmem_ld_wait();
-          if (c == 7) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + h * 8);
-          }
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, bias4, c, st1, st2);
+        uint32_t r[16];
+        tmem_ld16(taddr + c * 16, r);
+        tmem_ld_wait();
+        if (c == 7) {  // this warp's part of accumulator half h is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + h * 8);
         }
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ls1[i] += st1[i]; ls2[i] += st2[i]; }
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_f32_chunk(p, stg, lane, row0, n0, v, rr, h == 0 ? bias_h[0] : bias_h[1], c, ls1, ls2);
+        if (t + 1 < NT) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rr[i] = rn[i];
+        }
       }
       if (lnf) {
         // Fused LayerNorm of the rows just written.  The EW / 4 warps of this TMEM lane quarter each covered

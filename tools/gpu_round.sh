@@ -16,6 +16,10 @@ if has test; then
   timeout 2400 python -m pytest tests -m gpu -q --maxfail=40 --durations=15 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
   tail -30 $OUT/pytest_gpu.log
 fi
+if has testq; then  # the kernels a GEMM / tower change touches
+  timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -k "linear or clip_text or teacher_forced_certified or free_running_certified" > $OUT/pytest_gpu_quick.log 2>&1; echo "pytest quick rc=$?"
+  tail -4 $OUT/pytest_gpu_quick.log
+fi
 if has bound; then
   timeout 600 python tools/cert_bound.py > $OUT/cert_bound.json 2> $OUT/cert_bound.err; echo "bound rc=$?"
   python -c "import json;d=json.load(open('$OUT/cert_bound.json'));d.pop('per_step');print(json.dumps(d,indent=1))"
