@@ -731,25 +731,35 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
 // back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
 // ---------------------------------------------------------------------------------------------------
-template <int EW>  // EW epilogue warps: 8 (each drains 128 columns of BOTH halves) or 16 (128 columns of one half)
+// Two epilogue forms.  TMAE == false: EW = 8 / 16 warps move the tile with per-lane loads and stores through a small
+// transposing staging buffer (64 contiguous bytes per row and instruction).  TMAE == true: EW = 4 warps (one per TMEM
+// lane quarter, each owning whole rows); the residual tile arrives and the result leaves as 32 x 32 fp32 boxes moved by
+// the TMA engine (cp.async.bulk.tensor, 128-byte swizzle), so the load/store units only see shared memory.
+template <int EW, bool TMAE>
 struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
-  static constexpr int STAGES = 4;
-  static constexpr int STG_OFF = STAGES * STAGE;
-  static constexpr int BAR_OFF = STG_OFF + EW * 2048;  // one 2 KB staging buffer per epilogue warp
-  static constexpr int N_BARS = 2 * STAGES + 4;
+  static constexpr int STAGES = TMAE ? 3 : 4;
+  static constexpr int STG_OFF = STAGES * STAGE;       // !TMAE: one 2 KB staging buffer per epilogue warp
+  static constexpr int NR = 3;                          // TMAE: residual boxes in flight per warp
+  static constexpr int BOX = 32 * 32 * 4;               // TMAE: one 32-row x 32-column fp32 box
+  static constexpr int EPI_WARP = (NR + 2) * BOX;       // TMAE: NR residual boxes + 2 output boxes per warp
+  static constexpr int BIAS_OFF = STG_OFF + (TMAE ? EW * EPI_WARP : EW * 2048);
+  static constexpr int BAR_OFF = BIAS_OFF + (TMAE ? 2 * PBN * 4 : 0);
+  static constexpr int N_BARS = 2 * STAGES + 4 + (TMAE ? EW * NR : 0);
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int THREADS = 64 + 32 * EW;
   static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
+  static_assert(!TMAE || EW == 4, "the TMA epilogue uses one warp per TMEM lane quarter");
 };
 
-template <int EW>
+template <int EW, bool TMAE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PGemmParams p) {
+gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const PGemmParams p) {
   PDL_ENTRY();
-  using SL = WideSmem<EW>;
+  using SL = WideSmem<EW, TMAE>;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
@@ -759,7 +769,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [0]: both halves of the unit are complete
   uint64_t* tempty_bar = tfull_bar + 2;       // [h]: half h has been read by every epilogue warp of the pair
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;          // TMAE: [warp][NR] a residual box has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + (TMAE ? EW * SL::NR : 0));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -769,13 +780,22 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int group = blockIdx.x / CG;
   const int nkb = p.K / BK;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (TMAE) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO); }
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
-    // arrivals per half: EW == 8 -> all 8 warps of each CTA read both halves; EW == 16 -> 8 of the 16 read each half
-    mbar_init(&tempty_bar[0], CG * 8); mbar_init(&tempty_bar[1], CG * 8);
+    // arrivals per half: EW == 8 -> all 8 warps of each CTA read both halves; EW == 16 -> 8 of the 16 read each half;
+    // TMA epilogue -> its 4 warps read both halves
+    mbar_init(&tempty_bar[0], CG * (TMAE ? 4 : 8)); mbar_init(&tempty_bar[1], CG * (TMAE ? 4 : 8));
+    if (TMAE) for (int i = 0; i < EW * SL::NR; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
+  }
+  if (TMAE && warp >= 2) {  // the bias of all 512 columns, read as shared-memory broadcasts by the epilogue
+    float* bias_s = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
+    for (int i = threadIdx.x - 64; i < 2 * PBN; i += 32 * EW) bias_s[i] = p.e.bias ? __ldg(p.e.bias + i) : 0.f;
   }
   if (warp == 2) {
     tmem_alloc_cg<CG>(tmem_slot, 512);
@@ -841,6 +861,140 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit_cg<CG>(&tfull_bar[0]);
       }
     }
+    __syncwarp();
+  } else if constexpr (TMAE) {
+    // ---- TMA epilogue: this warp owns rows [q*32, q*32+32) of the CTA's 128 and all 512 columns (16 boxes of 32).
+    // Per box: accumulator from TMEM (lane = row), + bias (shared-memory broadcast) + residual box (landed by TMA,
+    // requested NR boxes ahead), row statistics in registers, result into a swizzled output box, TMA store.
+    constexpr int NR = SL::NR;
+    constexpr int NBOX = 2 * PBN / 32;  // 16
+    const int q = warp & 3;
+    const int we = warp - 2;
+    uint8_t* Rb = smem + SL::STG_OFF + we * SL::EPI_WARP;
+    uint8_t* Ob = Rb + NR * SL::BOX;
+    uint64_t* rbar = res_bar + we * NR;
+    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF);
+    const Epi& e = p.e;
+    const bool has_res = e.resid != nullptr;
+    const bool lnf = e.lnf_out != nullptr;
+    const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    uint32_t uph = 0;
+    int cs = 0; uint32_t cph = 0;  // consumer side of the residual ring
+    int is = 0;                     // producer side (lane 0): next slot, next box (unit im, box it) to request
+    int im = group, it = 0;
+    auto request = [&]() {  // lane 0 only
+      if (im < p.m_tiles) {
+        const int r0 = (im * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+        mbar_arrive_expect_tx(&rbar[is], SL::BOX);
+        tma_load_2d(Rb + is * SL::BOX, &tmR, &rbar[is], it * 32, r0);
+        if (++is == NR) is = 0;
+        if (++it == NBOX) { it = 0; im += n_groups; }
+      }
+    };
+    if (has_res && lane == 0) {
+#pragma unroll 1
+      for (int i = 0; i < NR; ++i) request();
+    }
+    float4 g4[4], b4[4];
+    if (lnf) {
+#pragma unroll
+      for (int sg = 0; sg < 4; ++sg) {
+        g4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
+        b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
+      }
+    }
+    const uint32_t swz = static_cast<uint32_t>(lane & 7);
+    for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
+      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      mbar_wait(&tfull_bar[0], uph);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;  // this lane's row: sum and sum of squares over the 512 columns (fused LN)
+#pragma unroll 1
+      for (int t = 0; t < NBOX; ++t) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
+        if (has_res) mbar_wait(&rbar[cs], cph);
+        // the output box written two boxes ago must have been read by its TMA store before it is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tmem_ld_wait();
+        if ((t & 7) == 7) {  // this warp's part of accumulator half t / 8 is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + (t >> 3) * 8);
+        }
+        __syncwarp();
+        const uint8_t* R = Rb + cs * SL::BOX + lane * 128;
+        uint8_t* O = Ob + (t & 1) * SL::BOX + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
+          float4 x = make_float4(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
+                                 __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
+          const uint32_t so = (static_cast<uint32_t>(j) ^ swz) << 4;
+          if (has_res) {
+            const float4 rr = *reinterpret_cast<const float4*>(R + so);
+            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+          }
+          s1 += (x.x + x.y) + (x.z + x.w);
+          s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          *reinterpret_cast<float4*>(O + so) = x;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (t & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (has_res) request();  // every lane has read residual slot cs: refill it, NR boxes ahead
+        }
+        if (++cs == NR) { cs = 0; cph ^= 1; }
+      }
+      if (lnf) {
+        // Fused LayerNorm: the row statistics are complete in this lane; the rows are re-read (L2) with whole-row
+        // coalescing -- one instruction = 512 contiguous bytes of one row -- once their TMA stores have completed.
+        const float inv = 1.0f / static_cast<float>(2 * PBN);
+        const float mu = s1 * inv;
+        const float var = fmaxf(s2 * inv - mu * mu, 0.f);
+        const float rstd = rsqrtf(var + e.lnf_eps);
+        const float nmr = -mu * rstd;  // y = x * rstd + (-mean * rstd)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          float4 x[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int grow = row0 + r0 + u;
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < p.M)
+                x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int grow = row0 + r0 + u;
+            const float rs = __shfl_sync(0xffffffffu, rstd, r0 + u), nm = __shfl_sync(0xffffffffu, nmr, r0 + u);
+            if (grow < p.M) {
+#pragma unroll
+              for (int sg = 0; sg < 4; ++sg) {
+                const float4 v = x[u][sg];
+                const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
+                const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+                uint2 u2;
+                u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
     __syncwarp();
   } else {
     // warp % 4 = TMEM lane quarter.  EW == 8: (warp - 2) / 4 = which 128-column slice of EACH 256-column half;
@@ -1060,6 +1214,23 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return true;
 }
 
+// fp32 [rows, cols] tensor as 32-row x 32-column boxes (128-byte rows, 128-byte swizzle): the wide kernel's TMA epilogue
+static bool make_tmap_f32_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+  if (!tma_init()) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 boxes) failed, CUresult=" + std::to_string(static_cast<int>(r)));
+    return false;
+  }
+  return true;
+}
+
 template <int CG, bool ARES>
 bool configure_persist() {
   return cuda_ok(cudaFuncSetAttribute(gemm_persist_kernel<CG, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1101,22 +1272,35 @@ int sm_count() {
   return g_sm_count;
 }
 
-static bool configure_wide() {
-  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<8>::DYN_BYTES),
-                 "cudaFuncSetAttribute(gemm_wide<8>)") &&
-         cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<16>::DYN_BYTES),
-                 "cudaFuncSetAttribute(gemm_wide<16>)");
+template <int EW, bool TMAE>
+static bool configure_wide_one() {
+  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<EW, TMAE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      WideSmem<EW, TMAE>::DYN_BYTES), "cudaFuncSetAttribute(gemm_wide)");
 }
-// 16 epilogue warps: twice the residual loads in flight of the 8-warp form (kept for A/B measurements)
-static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, bool ew8, cudaStream_t st) {
+static bool configure_wide() {
+  return configure_wide_one<8, false>() && configure_wide_one<16, false>() && configure_wide_one<4, true>();
+}
+// variant 0: TMA epilogue (4 warps; residual and result move as TMA boxes); 1 / 2: 16 / 8 epilogue warps with per-lane
+// loads and stores (A/B measurements; also taken when the epilogue has something the TMA form does not do)
+static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int variant, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
   if (groups < 1) groups = 1;
-  const bool w16 = !ew8;
+  const Epi& e = p.e;
+  const bool tma_ok = e.out_f32 && !e.out_act && e.act == ACT_NONE && e.ldo_f32 == 2 * PBN && (!e.resid || e.ldr == 2 * PBN) &&
+                      (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0;
+  if (!tma_ok && variant == 0) variant = 1;
+  CUtensorMap tr = ta, to = ta;
+  if (variant == 0) {
+    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
+    tr = to;
+    if (e.resid && e.resid != e.out_f32 && !make_tmap_f32_box32(&tr, e.resid, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN))
+      return false;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
-  cfg.blockDim = dim3(w16 ? WideSmem<16>::THREADS : WideSmem<8>::THREADS);
-  cfg.dynamicSmemBytes = w16 ? WideSmem<16>::DYN_BYTES : WideSmem<8>::DYN_BYTES;
+  cfg.blockDim = dim3(variant == 0 ? WideSmem<4, true>::THREADS : variant == 1 ? WideSmem<16, false>::THREADS : WideSmem<8, false>::THREADS);
+  cfg.dynamicSmemBytes = variant == 0 ? WideSmem<4, true>::DYN_BYTES : variant == 1 ? WideSmem<16, false>::DYN_BYTES : WideSmem<8, false>::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1125,8 +1309,9 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  if (w16) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<16>, ta, tb, p), "gemm_wide<16> launch");
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<8>, ta, tb, p), "gemm_wide<8> launch");
+  if (variant == 0) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<4, true>, ta, tb, tr, to, p), "gemm_wide<tma> launch");
+  if (variant == 1) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<16, false>, ta, tb, tr, to, p), "gemm_wide<16> launch");
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<8, false>, ta, tb, tr, to, p), "gemm_wide<8> launch");
 }
 
 bool gemm_configure() {
@@ -1196,7 +1381,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     const bool wide_ok = cg == 2 && W.N == 2 * PBN && epi.out_f32 != nullptr;
     if (wide_ok && ((!ares && W.K >= 1024) || epi.lnf_out)) {
       pp.n_tiles = 1;
-      return launch_wide(ta, tb, pp, o.wide_ew8 != 0, st);
+      return launch_wide(ta, tb, pp, o.wide_variant, st);
     }
     if (epi.lnf_out) {
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");

@@ -73,11 +73,12 @@ class Engine:
                  dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
                  clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_dcos_lo: Optional[float] = None,
                  cert_zratio: Optional[Sequence[float]] = None, cert_fcap: Optional[int] = None,
-                 ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None):
+                 ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None, wide_variant: Optional[int] = None):
         """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
         in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
         are read once, here: cert_dcos / cert_dcos_lo / cert_fcap (CONZIC_CERT_DCOS / _LO / CONZIC_CERT_FCAP), ln_standalone
-        (CONZIC_LN_STANDALONE=1) and pdl (CONZIC_PDL=0) exist for A/B measurements."""
+        (CONZIC_LN_STANDALONE=1), pdl (CONZIC_PDL=0) and wide_variant (CONZIC_WIDE_VARIANT: 0 = TMA epilogue of the
+        N = 512 GEMM, 1 / 2 = per-lane epilogue with 16 / 8 warps) exist for A/B measurements."""
         if not torch.cuda.is_available():
             raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -121,7 +122,8 @@ class Engine:
         if pdl is None:
             pdl = env("CONZIC_PDL", "1") != "0"
         cfg.flags = ((_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL) |
-                     (_lib.FLAG_WIDE_EW8 if env("CONZIC_WIDE_EW8", "0") == "1" else 0))
+                     {1: _lib.FLAG_WIDE_LSU16, 2: _lib.FLAG_WIDE_LSU8}.get(
+                         int(wide_variant if wide_variant is not None else env("CONZIC_WIDE_VARIANT", "0")), 0))
         self.cfg = cfg
         self.V, self.D = cfg.bert_vocab, cfg.clip_proj
         self.ldl = (self.V + 3) & ~3
