@@ -213,9 +213,13 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
 def test_wide_gemm_epilogue_forms_agree():
     """The three epilogue forms of the N = 512 GEMM (TMA boxes; per-lane accesses with 16 / 8 warps) compute the same
     x = acc + bias + residual (same accumulators, same fp32 adds) and LayerNorm statistics that differ only in summation
-    order: text embeddings of the bf16 tower agree to bf16 rounding of a few LayerNorm outputs, far inside the 0.04 that
-    separates the bf16 tower from the oracle.  Ragged row counts exercise the clipped last tile."""
+    order, so a rare bf16 rounding of a LayerNorm output is all that can differ.  Checked on a 2-block tower (block 0: all
+    rows through both fused-LayerNorm GEMMs; block 1: the compacted EOS rows) -- over 12 blocks such roundings grow to
+    the bf16 tower's own noise (~1e-3 on every element), which the oracle comparison above covers.  Ragged row counts
+    exercise the clipped last tile."""
     from conzic_b200.engine import Engine
+    sd = {k: v for k, v in gc.weights("clip").items()
+          if ".layers." not in k or k.split(".layers.")[1].split(".")[0] in ("0", "1")}
     outs = []
     torch.manual_seed(5)
     cases = []
@@ -227,13 +231,14 @@ def test_wide_gemm_epilogue_forms_agree():
             ids[i, lens[i] - 1:] = synth.CLIP_EOS
         cases.append(ids.int().cuda())
     for v in (0, 1, 2):
-        eng = Engine(gc.weights("bert"), gc.weights("clip"), device="cuda:0", precision="bf16", wide_variant=v)
+        eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision="bf16", wide_variant=v)
         outs.append([eng.clip_text_encode(ids).cpu() for ids in cases])
         eng.close()
     for v in (1, 2):
         for a, b in zip(outs[0], outs[v]):
             assert torch.isfinite(a).all()
-            assert float((a - b).abs().max()) < 5e-3
+            assert float((a - b).abs().max()) < 3e-3
+            assert float((a - b).abs().mean()) < 1e-4
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("certified", 1e-4), ("bf16", 2e-2)])

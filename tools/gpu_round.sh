@@ -69,6 +69,10 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_mma -s 18 -c 1 -f -o $OUT/prof_attn \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 fi
+if has ncuwide; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_wide -s 26 -c 2 -f -o $OUT/prof_gemm_wide \
+      python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm_wide.log 2>&1; echo "ncu gemm_wide rc=$?"
+fi
 if has ncusmall; then
   for k in topk_cluster_kernel score_select_kernel clip_logits_kernel assemble_kernel layernorm_kernel cert_round1_kernel cert_round2_kernel clip_embed_kernel bert_embed_ln_kernel attention_kernel; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $OUT/prof_$k \
