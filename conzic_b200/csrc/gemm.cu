@@ -914,6 +914,17 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
         if (has_res) mbar_wait(&rbar[cs], cph);
+        // every shared-memory load of the box is issued before the first dependent instruction: one warp per
+        // scheduler has nothing else to hide their latency behind
+        const uint8_t* R = Rb + cs * SL::BOX + lane * 128;
+        uint8_t* O = Ob + (t & 1) * SL::BOX + lane * 128;
+        float4 bb[8], rr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
+          rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res) rr[j] = *reinterpret_cast<const float4*>(R + ((static_cast<uint32_t>(j) ^ swz) << 4));
+        }
         // the output box written two boxes ago must have been read by its TMA store before it is overwritten
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         tmem_ld_wait();
@@ -923,22 +934,20 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + (t >> 3) * 8);
         }
         __syncwarp();
-        const uint8_t* R = Rb + cs * SL::BOX + lane * 128;
-        uint8_t* O = Ob + (t & 1) * SL::BOX + lane * 128;
+        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
-          float4 x = make_float4(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
-                                 __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
-          const uint32_t so = (static_cast<uint32_t>(j) ^ swz) << 4;
-          if (has_res) {
-            const float4 rr = *reinterpret_cast<const float4*>(R + so);
-            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-          }
-          s1 += (x.x + x.y) + (x.z + x.w);
-          s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-          *reinterpret_cast<float4*>(O + so) = x;
+          float4 x;
+          x.x = (__uint_as_float(r[4 * j]) + bb[j].x) + rr[j].x;
+          x.y = (__uint_as_float(r[4 * j + 1]) + bb[j].y) + rr[j].y;
+          x.z = (__uint_as_float(r[4 * j + 2]) + bb[j].z) + rr[j].z;
+          x.w = (__uint_as_float(r[4 * j + 3]) + bb[j].w) + rr[j].w;
+          p1[j & 3] += (x.x + x.y) + (x.z + x.w);
+          p2[j & 3] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          *reinterpret_cast<float4*>(O + ((static_cast<uint32_t>(j) ^ swz) << 4)) = x;
         }
+        s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+        s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
         __syncwarp();
         if (lane == 0) {
@@ -961,11 +970,12 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
         asm volatile("fence.proxy.async;" ::: "memory");
+        constexpr int LNR = 8;  // rows per round: 32 loads of 16 bytes in flight per lane
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += 4) {
-          float4 x[4][4];
+        for (int r0 = 0; r0 < 32; r0 += LNR) {
+          float4 x[LNR][4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < LNR; ++u) {
             const int grow = row0 + r0 + u;
 #pragma unroll
             for (int sg = 0; sg < 4; ++sg) {
@@ -975,7 +985,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < LNR; ++u) {
             const int grow = row0 + r0 + u;
             const float rs = __shfl_sync(0xffffffffu, rstd, r0 + u), nm = __shfl_sync(0xffffffffu, nmr, r0 + u);
             if (grow < p.M) {

@@ -237,8 +237,10 @@ def test_wide_gemm_epilogue_forms_agree():
     for v in (1, 2):
         for a, b in zip(outs[0], outs[v]):
             assert torch.isfinite(a).all()
-            assert float((a - b).abs().max()) < 3e-3
-            assert float((a - b).abs().mean()) < 1e-4
+            d = (a - b).abs()
+            assert float(d.max()) < 2e-2                      # one flipped bf16 rounding moves an embedding by ~5e-3
+            assert float((d.amax(dim=1) > 0).float().mean()) < 0.1 or a.shape[0] < 20   # ... and most rows not at all
+            assert float(d.mean()) < 1e-4
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("certified", 1e-4), ("bf16", 2e-2)])
