@@ -731,35 +731,40 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
 // back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
 // ---------------------------------------------------------------------------------------------------
-// Two epilogue forms.  TMAE == false: EW = 8 / 16 warps move the tile with per-lane loads and stores through a small
-// transposing staging buffer (64 contiguous bytes per row and instruction).  TMAE == true: EW = 4 warps (one per TMEM
-// lane quarter, each owning whole rows); the residual tile arrives and the result leaves as 32 x 32 fp32 boxes moved by
-// the TMA engine (cp.async.bulk.tensor, 128-byte swizzle), so the load/store units only see shared memory.
-template <int EW, bool TMAE>
+// Three epilogue forms (EPI).  0: EW = 8 / 16 warps move the tile with per-lane loads and stores through a small
+// transposing staging buffer (64 contiguous bytes per row and instruction).  1: EW = 4 warps (one per TMEM lane quarter,
+// each owning whole rows); the residual tile arrives and the result leaves as 32 x 32 fp32 boxes moved by the TMA engine
+// (cp.async.bulk.tensor, 128-byte swizzle), so the load/store units only see shared memory.  2: EW = 8 warps (two per
+// lane quarter, one per accumulator half); acc + bias leaves as TMA boxes that the L2 ADDS to the residual stream in
+// place (cp.reduce.async.bulk.tensor .add.f32: x += ..., no residual load at all); the LayerNorm statistics come from
+// the row-coalesced re-read that the LayerNorm pass makes anyway.
+template <int EW, int EPI>
 struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
-  static constexpr int STAGES = TMAE ? 3 : 4;
-  static constexpr int STG_OFF = STAGES * STAGE;       // !TMAE: one 2 KB staging buffer per epilogue warp
-  static constexpr int NR = 3;                          // TMAE: residual boxes in flight per warp
-  static constexpr int BOX = 32 * 32 * 4;               // TMAE: one 32-row x 32-column fp32 box
-  static constexpr int EPI_WARP = (NR + 2) * BOX;       // TMAE: NR residual boxes + 2 output boxes per warp
-  static constexpr int BIAS_OFF = STG_OFF + (TMAE ? EW * EPI_WARP : EW * 2048);
-  static constexpr int BAR_OFF = BIAS_OFF + (TMAE ? 2 * PBN * 4 : 0);
-  static constexpr int N_BARS = 2 * STAGES + 4 + (TMAE ? EW * NR : 0);
+  static constexpr int STAGES = EPI ? 3 : 4;
+  static constexpr int STG_OFF = STAGES * STAGE;       // EPI 0: one 2 KB staging buffer per epilogue warp
+  static constexpr int NR = EPI == 1 ? 3 : 0;           // EPI 1: residual boxes in flight per warp
+  static constexpr int BOX = 32 * 32 * 4;               // EPI 1, 2: one 32-row x 32-column fp32 box
+  static constexpr int EPI_WARP = (NR + 2) * BOX;       // EPI 1, 2: NR residual boxes + 2 output boxes per warp
+  static constexpr int BIAS_OFF = STG_OFF + (EPI ? EW * EPI_WARP : EW * 2048);
+  static constexpr int BAR_OFF = BIAS_OFF + (EPI ? 2 * PBN * 4 : 0);
+  static constexpr int N_BARS = 2 * STAGES + 4 + EW * NR;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int THREADS = 64 + 32 * EW;
   static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
-  static_assert(!TMAE || EW == 4, "the TMA epilogue uses one warp per TMEM lane quarter");
+  static_assert(EPI != 1 || EW == 4, "the TMA load/store epilogue uses one warp per TMEM lane quarter");
+  static_assert(EPI != 2 || EW == 8, "the TMA reduce epilogue uses two warps per TMEM lane quarter");
 };
 
-template <int EW, bool TMAE>
+template <int EW, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const PGemmParams p) {
   PDL_ENTRY();
-  using SL = WideSmem<EW, TMAE>;
+  using SL = WideSmem<EW, EPI>;
+  constexpr bool TMAE = EPI == 1;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
@@ -770,7 +775,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;   // [0]: both halves of the unit are complete
   uint64_t* tempty_bar = tfull_bar + 2;       // [h]: half h has been read by every epilogue warp of the pair
   uint64_t* res_bar = tempty_bar + 2;          // TMAE: [warp][NR] a residual box has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + (TMAE ? EW * SL::NR : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EW * SL::NR);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -782,18 +787,18 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-    if (TMAE) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO); }
+    if (EPI) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     // arrivals per half: EW == 8 -> all 8 warps of each CTA read both halves; EW == 16 -> 8 of the 16 read each half;
     // TMA epilogue -> its 4 warps read both halves
-    mbar_init(&tempty_bar[0], CG * (TMAE ? 4 : 8)); mbar_init(&tempty_bar[1], CG * (TMAE ? 4 : 8));
+    mbar_init(&tempty_bar[0], CG * (EPI ? 4 : 8)); mbar_init(&tempty_bar[1], CG * (EPI ? 4 : 8));
     if (TMAE) for (int i = 0; i < EW * SL::NR; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
-  if (TMAE && warp >= 2) {  // the bias of all 512 columns, read as shared-memory broadcasts by the epilogue
+  if (EPI && warp >= 2) {  // the bias of all 512 columns, read as shared-memory broadcasts by the epilogue
     float* bias_s = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
     for (int i = threadIdx.x - 64; i < 2 * PBN; i += 32 * EW) bias_s[i] = p.e.bias ? __ldg(p.e.bias + i) : 0.f;
   }
@@ -861,6 +866,140 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit_cg<CG>(&tfull_bar[0]);
       }
     }
+    __syncwarp();
+  } else if constexpr (EPI == 2) {
+    // ---- TMA reduce epilogue: warp (q, half) drains the 8 boxes of accumulator half `half` for rows [q*32, q*32+32):
+    // acc + bias -> swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by the L2, in place)
+    // or a plain TMA store when there is no residual.
+    const int q = warp & 3;
+    const int we = warp - 2;
+    const int half = we >> 2;
+    uint8_t* Ob = smem + SL::STG_OFF + we * SL::EPI_WARP;
+    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF);
+    const Epi& e = p.e;
+    const bool has_res = e.resid != nullptr;
+    const bool lnf = e.lnf_out != nullptr;
+    const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty_bar[half]), 0);
+    uint32_t uph = 0;
+    float4 g4[4], b4[4];
+    if (lnf) {
+#pragma unroll
+      for (int sg = 0; sg < 4; ++sg) {
+        g4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
+        b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
+      }
+    }
+    const uint32_t swz = static_cast<uint32_t>(lane & 7);
+    for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
+      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
+      mbar_wait(&tfull_bar[0], uph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tt = 0; tt < 8; ++tt) {
+        const int t = half * 8 + tt;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
+        float4 bb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
+        // the output box written two boxes ago must have been read by its TMA operation before it is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tmem_ld_wait();
+        if (tt == 7) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr);
+        }
+        __syncwarp();
+        uint8_t* O = Ob + (tt & 1) * SL::BOX + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x;
+          x.x = __uint_as_float(r[4 * j]) + bb[j].x;
+          x.y = __uint_as_float(r[4 * j + 1]) + bb[j].y;
+          x.z = __uint_as_float(r[4 * j + 2]) + bb[j].z;
+          x.w = __uint_as_float(r[4 * j + 3]) + bb[j].w;
+          *reinterpret_cast<float4*>(O + ((static_cast<uint32_t>(j) ^ swz) << 4)) = x;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
+        __syncwarp();
+        if (lane == 0) {
+          if (has_res)
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (lnf) {
+        // Fused LayerNorm: once both warps of the lane quarter have seen their boxes complete, each takes 16 of the
+        // 32 rows: whole-row coalesced re-read (L2), statistics by warp reduction, bf16(LN(x) * g + b).
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const float inv = 1.0f / static_cast<float>(2 * PBN);
+        constexpr int LNR = 4;
+#pragma unroll 1
+        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += LNR) {
+          float4 x[LNR][4];
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            const int grow = row0 + r0 + u;
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < p.M)
+                x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
+            }
+          }
+          float s1[LNR], s2[LNR];
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            s1[u] = 0.f; s2[u] = 0.f;
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              const float4 v = x[u][sg];
+              s1[u] += (v.x + v.y) + (v.z + v.w);
+              s2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < LNR; ++u) {
+              s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+              s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            const int grow = row0 + r0 + u;
+            const float mu = s1[u] * inv;
+            const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
+            const float rs = rsqrtf(var + e.lnf_eps);
+            const float nm = -mu * rs;
+            if (grow < p.M) {
+#pragma unroll
+              for (int sg = 0; sg < 4; ++sg) {
+                const float4 v = x[u][sg];
+                const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
+                const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+                uint2 u2;
+                u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
     __syncwarp();
   } else if constexpr (TMAE) {
     // ---- TMA epilogue: this warp owns rows [q*32, q*32+32) of the CTA's 128 and all 512 columns (16 boxes of 32).
@@ -1282,16 +1421,24 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int EW, bool TMAE>
+template <int EW, int EPI>
 static bool configure_wide_one() {
-  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<EW, TMAE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      WideSmem<EW, TMAE>::DYN_BYTES), "cudaFuncSetAttribute(gemm_wide)");
+  return cuda_ok(cudaFuncSetAttribute(gemm_wide_kernel<EW, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      WideSmem<EW, EPI>::DYN_BYTES), "cudaFuncSetAttribute(gemm_wide)");
 }
 static bool configure_wide() {
-  return configure_wide_one<8, false>() && configure_wide_one<16, false>() && configure_wide_one<4, true>();
+  return configure_wide_one<8, 0>() && configure_wide_one<16, 0>() && configure_wide_one<4, 1>() && configure_wide_one<8, 2>();
 }
-// variant 0: TMA epilogue (4 warps; residual and result move as TMA boxes); 1 / 2: 16 / 8 epilogue warps with per-lane
-// loads and stores (A/B measurements; also taken when the epilogue has something the TMA form does not do)
+// variant 0: TMA load/store epilogue (4 warps; residual and result move as TMA boxes); 3: TMA reduce epilogue (8 warps;
+// the L2 adds acc + bias to the residual stream in place -- needs resid == out); 1 / 2: 16 / 8 epilogue warps with
+// per-lane loads and stores (A/B measurements; also taken when the epilogue has something the TMA forms do not do)
+template <int EW, int EPI>
+static bool launch_wide_one(cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
+                            const CUtensorMap& to, const PGemmParams& p) {
+  cfg.blockDim = dim3(WideSmem<EW, EPI>::THREADS);
+  cfg.dynamicSmemBytes = WideSmem<EW, EPI>::DYN_BYTES;
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<EW, EPI>, ta, tb, tr, to, p), "gemm_wide launch");
+}
 static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int variant, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
@@ -1299,9 +1446,10 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   const Epi& e = p.e;
   const bool tma_ok = e.out_f32 && !e.out_act && e.act == ACT_NONE && e.ldo_f32 == 2 * PBN && (!e.resid || e.ldr == 2 * PBN) &&
                       (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0;
-  if (!tma_ok && variant == 0) variant = 1;
+  if (variant == 3 && e.resid && e.resid != e.out_f32) variant = 0;
+  if (!tma_ok && (variant == 0 || variant == 3)) variant = 1;
   CUtensorMap tr = ta, to = ta;
-  if (variant == 0) {
+  if (variant == 0 || variant == 3) {
     if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
     tr = to;
     if (e.resid && e.resid != e.out_f32 && !make_tmap_f32_box32(&tr, e.resid, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN))
@@ -1309,8 +1457,6 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
-  cfg.blockDim = dim3(variant == 0 ? WideSmem<4, true>::THREADS : variant == 1 ? WideSmem<16, false>::THREADS : WideSmem<8, false>::THREADS);
-  cfg.dynamicSmemBytes = variant == 0 ? WideSmem<4, true>::DYN_BYTES : variant == 1 ? WideSmem<16, false>::DYN_BYTES : WideSmem<8, false>::DYN_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1319,9 +1465,12 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  if (variant == 0) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<4, true>, ta, tb, tr, to, p), "gemm_wide<tma> launch");
-  if (variant == 1) return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<16, false>, ta, tb, tr, to, p), "gemm_wide<16> launch");
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<8, false>, ta, tb, tr, to, p), "gemm_wide<8> launch");
+  switch (variant) {
+    case 0: return launch_wide_one<4, 1>(cfg, ta, tb, tr, to, p);
+    case 3: return launch_wide_one<8, 2>(cfg, ta, tb, tr, to, p);
+    case 1: return launch_wide_one<16, 0>(cfg, ta, tb, tr, to, p);
+    default: return launch_wide_one<8, 0>(cfg, ta, tb, tr, to, p);
+  }
 }
 
 bool gemm_configure() {

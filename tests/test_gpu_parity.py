@@ -180,7 +180,8 @@ def test_clip_text_encode_vs_oracle(prec, tol):
 
 @pytest.mark.parametrize("prec,tol,kw", [("bf16x3", 3e-4, {}), ("bf16", 0.04, {}),
                                          ("bf16", 0.04, {"ln_standalone": True}), ("bf16", 0.04, {"pdl": False}),
-                                         ("bf16", 0.04, {"wide_variant": 1}), ("bf16", 0.04, {"wide_variant": 2})])
+                                         ("bf16", 0.04, {"wide_variant": 1}), ("bf16", 0.04, {"wide_variant": 2}),
+                                         ("bf16", 0.04, {"wide_variant": 3})])
 def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
     """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
     the oracle: the default path (LayerNorm written by the O-proj / fc2 epilogues of the wide pair kernel and by the
@@ -211,7 +212,7 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
 
 
 def test_wide_gemm_epilogue_forms_agree():
-    """The three epilogue forms of the N = 512 GEMM (TMA boxes; per-lane accesses with 16 / 8 warps) compute the same
+    """The epilogue forms of the N = 512 GEMM (TMA load/store boxes; TMA reduce-add boxes; per-lane accesses with 16 / 8 warps) compute the same
     x = acc + bias + residual (same accumulators, same fp32 adds) and LayerNorm statistics that differ only in summation
     order, so a rare bf16 rounding of a LayerNorm output is all that can differ.  Checked on a 2-block tower (block 0: all
     rows through both fused-LayerNorm GEMMs; block 1: the compacted EOS rows) -- over 12 blocks such roundings grow to
@@ -230,11 +231,11 @@ def test_wide_gemm_epilogue_forms_agree():
         for i in range(N):
             ids[i, lens[i] - 1:] = synth.CLIP_EOS
         cases.append(ids.int().cuda())
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision="bf16", wide_variant=v)
         outs.append([eng.clip_text_encode(ids).cpu() for ids in cases])
         eng.close()
-    for v in (1, 2):
+    for v in (1, 2, 3):
         for a, b in zip(outs[0], outs[v]):
             assert torch.isfinite(a).all()
             d = (a - b).abs()

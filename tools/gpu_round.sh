@@ -70,7 +70,7 @@ if has ncu; then
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 fi
 if has ncuwide; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_wide -s 26 -c 2 -f -o $OUT/prof_gemm_wide \
+  env $NCU_ENV timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_wide -s 26 -c 2 -f -o $OUT/prof_gemm_wide \
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm_wide.log 2>&1; echo "ncu gemm_wide rc=$?"
 fi
 if has ncusmall; then
