@@ -439,7 +439,9 @@ bool bert_row_logits(conzic_ctx* c, const int64_t* inp, int B, int L, int pos, f
   // MLM head on row `pos` only: a strided view of the hidden states (row stride L*ldh) needs no gather.
   Act hrow{p.bh + static_cast<size_t>(pos) * ldh, L * ldh, H};
   const GemmOpts o = c->gopt_bert;
-  if (!launch_linear(hrow, B, c->b_transform, epi_f32_out(c->b_transform, p.bt, H, nullptr, 0, ACT_ERF_GELU), o, st))
+  GemmOpts ot = o;
+  ot.stages = 6;  // 6 CTAs, 36 k blocks each: latency bound, the deep TMA ring is all that helps
+  if (!launch_linear(hrow, B, c->b_transform, epi_f32_out(c->b_transform, p.bt, H, nullptr, 0, ACT_ERF_GELU), ot, st))
     return false;
   LNArgs lnh{p.bt, nullptr, B, H, c->b_hln_g, c->b_hln_b, g.bert_ln_eps, nullptr, p.bt_act, ldh, s};
   launch_layernorm(lnh, st);

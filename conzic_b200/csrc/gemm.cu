@@ -743,10 +743,11 @@ struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
-  static constexpr int STAGES = EPI ? 3 : 4;
+  static constexpr int STAGES = EPI == 1 ? 3 : 4;
   static constexpr int STG_OFF = STAGES * STAGE;       // EPI 0: one 2 KB staging buffer per epilogue warp
   static constexpr int NR = EPI == 1 ? 3 : 0;           // EPI 1: residual boxes in flight per warp
-  static constexpr int BOX = 32 * 32 * 4;               // EPI 1, 2: one 32-row x 32-column fp32 box
+  static constexpr int BW = EPI == 2 ? 16 : 32;         // EPI 1 / 2: columns of one TMA box (32 rows, fp32)
+  static constexpr int BOX = 32 * BW * 4;
   static constexpr int EPI_WARP = (NR + 2) * BOX;       // EPI 1, 2: NR residual boxes + 2 output boxes per warp
   static constexpr int BIAS_OFF = STG_OFF + (EPI ? EW * EPI_WARP : EW * 2048);
   static constexpr int BAR_OFF = BIAS_OFF + (EPI ? 2 * PBN * 4 : 0);
@@ -816,6 +817,13 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0; uint32_t ph = 0;
       for (int m = group; m < p.m_tiles; m += n_groups) {
         const int arow = (m * CG + static_cast<int>(cta_rank)) * BM;
+        // Short K (O-proj: 8 k blocks): a unit's MMAs restart on STAGES loaded k blocks and then wait out the HBM
+        // latency of the rest; requesting the NEXT unit's A tile into L2 now turns that into L2 latency.
+        if (nkb <= 8 && m + n_groups < p.m_tiles) {
+          const int nrow = ((m + n_groups) * CG + static_cast<int>(cta_rank)) * BM;
+          if (nrow < p.M)
+            for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmA, kb * BK, nrow);
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (p.e.resid) {
@@ -868,18 +876,21 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if constexpr (EPI == 2) {
-    // ---- TMA reduce epilogue: warp (q, half) drains the 8 boxes of accumulator half `half` for rows [q*32, q*32+32):
-    // acc + bias -> swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by the L2, in place)
-    // or a plain TMA store when there is no residual.
+    // ---- TMA reduce epilogue: warp (q, half) drains accumulator half `half` for rows [q*32, q*32+32) as 16 boxes of
+    // 16 columns: acc + bias -> 64-byte-swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by
+    // the L2, in place), or a plain TMA store when there is no residual.  The fused LayerNorm of a unit runs one unit
+    // late, when its boxes have long completed, so nothing in the loop waits for the memory system.
+    constexpr int BW = SL::BW, NBOX = PBN / BW;  // 16 boxes per warp and unit
     const int q = warp & 3;
     const int we = warp - 2;
     const int half = we >> 2;
     uint8_t* Ob = smem + SL::STG_OFF + we * SL::EPI_WARP;
-    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF);
+    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF) + half * PBN;
     const Epi& e = p.e;
     const bool has_res = e.resid != nullptr;
     const bool lnf = e.lnf_out != nullptr;
     const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty_bar[half]), 0);
+    const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * PBN;
     uint32_t uph = 0;
     float4 g4[4], b4[4];
     if (lnf) {
@@ -889,118 +900,127 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
       }
     }
-    const uint32_t swz = static_cast<uint32_t>(lane & 7);
+    // LayerNorm of the 16 rows [rbase, rbase + 16) this warp owns of a unit whose boxes (both warps of the lane
+    // quarter) are complete: whole-row coalesced re-read (L2), statistics by warp reduction, bf16(LN(x) * g + b)
+    auto layer_norm = [&](int rbase) {
+      const float inv = 1.0f / static_cast<float>(2 * PBN);
+      constexpr int LNR = 4;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 16; r0 += LNR) {
+        float4 x[LNR][4];
+#pragma unroll
+        for (int u = 0; u < LNR; ++u) {
+          const int grow = rbase + r0 + u;
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) {
+            x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < p.M)
+              x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
+          }
+        }
+        float s1[LNR], s2[LNR];
+#pragma unroll
+        for (int u = 0; u < LNR; ++u) {
+          s1[u] = 0.f; s2[u] = 0.f;
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) {
+            const float4 v = x[u][sg];
+            s1[u] += (v.x + v.y) + (v.z + v.w);
+            s2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+            s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < LNR; ++u) {
+          const int grow = rbase + r0 + u;
+          const float mu = s1[u] * inv;
+          const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
+          const float rs = rsqrtf(var + e.lnf_eps);
+          const float nm = -mu * rs;
+          if (grow < p.M) {
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              const float4 v = x[u][sg];
+              const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
+              const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+              uint2 u2;
+              u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
+            }
+          }
+        }
+      }
+    };
+    int prev_row0 = -1;
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
 #pragma unroll 1
-      for (int tt = 0; tt < 8; ++tt) {
-        const int t = half * 8 + tt;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
-        float4 bb[8];
+      for (int tt = 0; tt < NBOX; ++tt) {
+        uint32_t r[16];
+        tmem_ld16(tbase + tt * BW, r);
+        float4 bb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
+        for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + tt * BW + 4 * j);
         // the output box written two boxes ago must have been read by its TMA operation before it is overwritten
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         tmem_ld_wait();
-        if (tt == 7) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
+        if (tt == NBOX - 1) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr);
         }
         __syncwarp();
-        uint8_t* O = Ob + (tt & 1) * SL::BOX + lane * 128;
+        uint8_t* O = Ob + (tt & 1) * SL::BOX;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float4 x;
           x.x = __uint_as_float(r[4 * j]) + bb[j].x;
           x.y = __uint_as_float(r[4 * j + 1]) + bb[j].y;
           x.z = __uint_as_float(r[4 * j + 2]) + bb[j].z;
           x.w = __uint_as_float(r[4 * j + 3]) + bb[j].w;
-          *reinterpret_cast<float4*>(O + ((static_cast<uint32_t>(j) ^ swz) << 4)) = x;
+          *reinterpret_cast<float4*>(O + stg_off(lane, j)) = x;  // = the TMA engine's 64-byte swizzle
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
         __syncwarp();
         if (lane == 0) {
           if (has_res)
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(O)), "r"(half * PBN + tt * BW), "r"(row0)
                          : "memory");
           else
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(O)), "r"(half * PBN + tt * BW), "r"(row0)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       if (lnf) {
-        // Fused LayerNorm: once both warps of the lane quarter have seen their boxes complete, each takes 16 of the
-        // 32 rows: whole-row coalesced re-read (L2), statistics by warp reduction, bf16(LN(x) * g + b).
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncwarp();
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-        const float inv = 1.0f / static_cast<float>(2 * PBN);
-        constexpr int LNR = 4;
-#pragma unroll 1
-        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += LNR) {
-          float4 x[LNR][4];
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            const int grow = row0 + r0 + u;
-#pragma unroll
-            for (int sg = 0; sg < 4; ++sg) {
-              x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (grow < p.M)
-                x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
-            }
-          }
-          float s1[LNR], s2[LNR];
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            s1[u] = 0.f; s2[u] = 0.f;
-#pragma unroll
-            for (int sg = 0; sg < 4; ++sg) {
-              const float4 v = x[u][sg];
-              s1[u] += (v.x + v.y) + (v.z + v.w);
-              s2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < LNR; ++u) {
-              s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
-              s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            const int grow = row0 + r0 + u;
-            const float mu = s1[u] * inv;
-            const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
-            const float rs = rsqrtf(var + e.lnf_eps);
-            const float nm = -mu * rs;
-            if (grow < p.M) {
-#pragma unroll
-              for (int sg = 0; sg < 4; ++sg) {
-                const float4 v = x[u][sg];
-                const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
-                const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-                uint2 u2;
-                u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
-              }
-            }
-          }
+        if (prev_row0 >= 0) {
+          // all but this unit's NBOX box operations of this warp are complete; so are its partner's once it arrives
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(NBOX) : "memory");
+          __syncwarp();
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          layer_norm(prev_row0 + half * 16);
         }
+        prev_row0 = row0;
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // completion; shared memory stays valid
     __syncwarp();
+    if (lnf && prev_row0 >= 0) {
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      layer_norm(prev_row0 + half * 16);
+    }
   } else if constexpr (TMAE) {
     // ---- TMA epilogue: this warp owns rows [q*32, q*32+32) of the CTA's 128 and all 512 columns (16 boxes of 32).
     // Per box: accumulator from TMEM (lane = row), + bias (shared-memory broadcast) + residual box (landed by TMA,
@@ -1364,14 +1384,15 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
 }
 
 // fp32 [rows, cols] tensor as 32-row x 32-column boxes (128-byte rows, 128-byte swizzle): the wide kernel's TMA epilogue
-static bool make_tmap_f32_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+static bool make_tmap_f32_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                                uint32_t box_cols = 32) {
   if (!tma_init()) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * 4};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {box_cols, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (fp32 boxes) failed, CUresult=" + std::to_string(static_cast<int>(r)));
@@ -1450,7 +1471,7 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   if (!tma_ok && (variant == 0 || variant == 3)) variant = 1;
   CUtensorMap tr = ta, to = ta;
   if (variant == 0 || variant == 3) {
-    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
+    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN, variant == 3 ? 16 : 32)) return false;
     tr = to;
     if (e.resid && e.resid != e.out_f32 && !make_tmap_f32_box32(&tr, e.resid, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN))
       return false;
