@@ -170,6 +170,7 @@ struct PGemmParams {
   Epi e;
   int split = 0;  // 1 = bf16x3 operands ([rows, 2K]: hi | lo planes): three passes over K (hi*hi, lo*hi, hi*lo) into the
                   // same accumulator, exact activations, hi + lo output planes (streamed-A pair kernel only)
+  int tma_out = 0;  // persistent kernel, bf16-only output: 32 x 32 boxes leave through the TMA engine (tmO is valid)
 };
 
 template <int CG, bool ARES>
@@ -507,10 +508,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// bf16-only output through the TMA engine: the same 32-row x 64-byte staging tile as epilogue_bf16_chunk (its XOR
+// swizzle is the TMA engine's 64-byte swizzle), but instead of reading it back and storing 16 bytes per lane -- 64
+// contiguous bytes per row and instruction, which keeps the load/store unit busy for most of a tile's MMA time (ncu:
+// the epilogue warps of fc1 never wait for an accumulator) -- one cp.async.bulk.tensor store moves the box.
+__device__ __forceinline__ void epilogue_bf16_box(const PGemmParams& p, const CUtensorMap* tmO, uint8_t* stg, int lane,
+                                                  int row0, int n0, float (&v)[32], const float4& bias4, int chunk) {
+  const Epi& e = p.e;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {  // columns 4jj..4jj+3 of the chunk: bias held by lane chunk*8 + jj
+    const int src = chunk * 8 + jj;
+    v[4 * jj] += __shfl_sync(0xffffffffu, bias4.x, src);
+    v[4 * jj + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+    v[4 * jj + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+    v[4 * jj + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
+  }
+  if (e.act == ACT_QUICK_GELU) {  // see epilogue_bf16_chunk
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = 0.851f * v[j];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) asm("tanh.approx.f32 %0, %1;" : "=f"(t[j]) : "f"(t[j]));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= fmaf(0.5f, t[j], 0.5f);
+  } else if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, false);
+  }
+  // the previous box of this warp must have been read by its store before the staging tile is overwritten
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = u;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmO)), "r"(smem_u32(stg)), "r"(n0), "r"(row0) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 template <int CG, bool ARES>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const PGemmParams p) {
+                    const __grid_constant__ CUtensorMap tmO, const PGemmParams p) {
   PDL_ENTRY();
   using SL = PSmem<CG, ARES>;
   constexpr int EW = P_EPI_WARPS;
@@ -674,7 +725,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          if (p.tma_out) epilogue_bf16_box(p, &tmO, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          else epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
         }
       } else if (nbase + PBN / 2 <= p.N) {
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -714,6 +766,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
+    if (p.tma_out) {  // the staging tile must outlive the last store's read of it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -743,11 +799,10 @@ struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
-  static constexpr int STAGES = EPI == 1 ? 3 : 4;
+  static constexpr int STAGES = EPI ? 3 : 4;
   static constexpr int STG_OFF = STAGES * STAGE;       // EPI 0: one 2 KB staging buffer per epilogue warp
   static constexpr int NR = EPI == 1 ? 3 : 0;           // EPI 1: residual boxes in flight per warp
-  static constexpr int BW = EPI == 2 ? 16 : 32;         // EPI 1 / 2: columns of one TMA box (32 rows, fp32)
-  static constexpr int BOX = 32 * BW * 4;
+  static constexpr int BOX = 32 * 32 * 4;               // EPI 1, 2: one 32-row x 32-column fp32 box
   static constexpr int EPI_WARP = (NR + 2) * BOX;       // EPI 1, 2: NR residual boxes + 2 output boxes per warp
   static constexpr int BIAS_OFF = STG_OFF + (EPI ? EW * EPI_WARP : EW * 2048);
   static constexpr int BAR_OFF = BIAS_OFF + (EPI ? 2 * PBN * 4 : 0);
@@ -876,21 +931,18 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if constexpr (EPI == 2) {
-    // ---- TMA reduce epilogue: warp (q, half) drains accumulator half `half` for rows [q*32, q*32+32) as 16 boxes of
-    // 16 columns: acc + bias -> 64-byte-swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by
-    // the L2, in place), or a plain TMA store when there is no residual.  The fused LayerNorm of a unit runs one unit
-    // late, when its boxes have long completed, so nothing in the loop waits for the memory system.
-    constexpr int BW = SL::BW, NBOX = PBN / BW;  // 16 boxes per warp and unit
+    // ---- TMA reduce epilogue: warp (q, half) drains the 8 boxes of accumulator half `half` for rows [q*32, q*32+32):
+    // acc + bias -> swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by the L2, in place)
+    // or a plain TMA store when there is no residual.
     const int q = warp & 3;
     const int we = warp - 2;
     const int half = we >> 2;
     uint8_t* Ob = smem + SL::STG_OFF + we * SL::EPI_WARP;
-    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF) + half * PBN;
+    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF);
     const Epi& e = p.e;
     const bool has_res = e.resid != nullptr;
     const bool lnf = e.lnf_out != nullptr;
     const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty_bar[half]), 0);
-    const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * PBN;
     uint32_t uph = 0;
     float4 g4[4], b4[4];
     if (lnf) {
@@ -900,127 +952,117 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
       }
     }
-    // LayerNorm of the 16 rows [rbase, rbase + 16) this warp owns of a unit whose boxes (both warps of the lane
-    // quarter) are complete: whole-row coalesced re-read (L2), statistics by warp reduction, bf16(LN(x) * g + b)
-    auto layer_norm = [&](int rbase) {
-      const float inv = 1.0f / static_cast<float>(2 * PBN);
-      constexpr int LNR = 4;
-#pragma unroll 1
-      for (int r0 = 0; r0 < 16; r0 += LNR) {
-        float4 x[LNR][4];
-#pragma unroll
-        for (int u = 0; u < LNR; ++u) {
-          const int grow = rbase + r0 + u;
-#pragma unroll
-          for (int sg = 0; sg < 4; ++sg) {
-            x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow < p.M)
-              x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
-          }
-        }
-        float s1[LNR], s2[LNR];
-#pragma unroll
-        for (int u = 0; u < LNR; ++u) {
-          s1[u] = 0.f; s2[u] = 0.f;
-#pragma unroll
-          for (int sg = 0; sg < 4; ++sg) {
-            const float4 v = x[u][sg];
-            s1[u] += (v.x + v.y) + (v.z + v.w);
-            s2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
-            s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < LNR; ++u) {
-          const int grow = rbase + r0 + u;
-          const float mu = s1[u] * inv;
-          const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
-          const float rs = rsqrtf(var + e.lnf_eps);
-          const float nm = -mu * rs;
-          if (grow < p.M) {
-#pragma unroll
-            for (int sg = 0; sg < 4; ++sg) {
-              const float4 v = x[u][sg];
-              const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
-              const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-              uint2 u2;
-              u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
-            }
-          }
-        }
-      }
-    };
-    int prev_row0 = -1;
+    const uint32_t swz = static_cast<uint32_t>(lane & 7);
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
 #pragma unroll 1
-      for (int tt = 0; tt < NBOX; ++tt) {
-        uint32_t r[16];
-        tmem_ld16(tbase + tt * BW, r);
-        float4 bb[4];
+      for (int tt = 0; tt < 8; ++tt) {
+        const int t = half * 8 + tt;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
+        float4 bb[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + tt * BW + 4 * j);
+        for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
         // the output box written two boxes ago must have been read by its TMA operation before it is overwritten
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         tmem_ld_wait();
-        if (tt == NBOX - 1) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
+        if (tt == 7) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr);
         }
         __syncwarp();
-        uint8_t* O = Ob + (tt & 1) * SL::BOX;
+        uint8_t* O = Ob + (tt & 1) * SL::BOX + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float4 x;
           x.x = __uint_as_float(r[4 * j]) + bb[j].x;
           x.y = __uint_as_float(r[4 * j + 1]) + bb[j].y;
           x.z = __uint_as_float(r[4 * j + 2]) + bb[j].z;
           x.w = __uint_as_float(r[4 * j + 3]) + bb[j].w;
-          *reinterpret_cast<float4*>(O + stg_off(lane, j)) = x;  // = the TMA engine's 64-byte swizzle
+          *reinterpret_cast<float4*>(O + ((static_cast<uint32_t>(j) ^ swz) << 4)) = x;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
         __syncwarp();
         if (lane == 0) {
           if (has_res)
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(O)), "r"(half * PBN + tt * BW), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
                          : "memory");
           else
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(O)), "r"(half * PBN + tt * BW), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       if (lnf) {
-        if (prev_row0 >= 0) {
-          // all but this unit's NBOX box operations of this warp are complete; so are its partner's once it arrives
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(NBOX) : "memory");
-          __syncwarp();
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-          layer_norm(prev_row0 + half * 16);
+        // Fused LayerNorm: once both warps of the lane quarter have seen their boxes complete, each takes 16 of the
+        // 32 rows: whole-row coalesced re-read (L2), statistics by warp reduction, bf16(LN(x) * g + b).
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float inv = 1.0f / static_cast<float>(2 * PBN);
+        constexpr int LNR = 4;
+#pragma unroll 1
+        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += LNR) {
+          float4 x[LNR][4];
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            const int grow = row0 + r0 + u;
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < p.M)
+                x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
+            }
+          }
+          float s1[LNR], s2[LNR];
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            s1[u] = 0.f; s2[u] = 0.f;
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              const float4 v = x[u][sg];
+              s1[u] += (v.x + v.y) + (v.z + v.w);
+              s2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < LNR; ++u) {
+              s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+              s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < LNR; ++u) {
+            const int grow = row0 + r0 + u;
+            const float mu = s1[u] * inv;
+            const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
+            const float rs = rsqrtf(var + e.lnf_eps);
+            const float nm = -mu * rs;
+            if (grow < p.M) {
+#pragma unroll
+              for (int sg = 0; sg < 4; ++sg) {
+                const float4 v = x[u][sg];
+                const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
+                const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+                uint2 u2;
+                u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
+              }
+            }
+          }
         }
-        prev_row0 = row0;
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // completion; shared memory stays valid
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
     __syncwarp();
-    if (lnf && prev_row0 >= 0) {
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      layer_norm(prev_row0 + half * 16);
-    }
   } else if constexpr (TMAE) {
     // ---- TMA epilogue: this warp owns rows [q*32, q*32+32) of the CTA's 128 and all 512 columns (16 boxes of 32).
     // Per box: accumulator from TMEM (lane = row), + bias (shared-memory broadcast) + residual box (landed by TMA,
@@ -1408,8 +1450,35 @@ bool configure_persist() {
                  "cudaFuncSetAttribute(gemm_persist)");
 }
 
+// bf16 [rows, cols] output as 32-row x 32-column boxes (64-byte rows, 64-byte swizzle): the persistent kernel's TMA stores
+static bool make_tmap_bf16_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+  if (!tma_init()) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 boxes) failed, CUresult=" + std::to_string(static_cast<int>(r)));
+    return false;
+  }
+  return true;
+}
+
 template <int CG, bool ARES>
-bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int sms, cudaStream_t st) {
+bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p_in, int sms, bool tma_out, cudaStream_t st) {
+  PGemmParams p = p_in;
+  const Epi& e = p.e;
+  CUtensorMap to = ta;
+  // bf16-only output of whole 128-column slices: boxes through the TMA engine
+  if (tma_out && !p.split && e.out_act && !e.out_f32 && !e.resid && (p.N % (PBN / 2)) == 0 && (e.ldo_act % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(e.out_act) & 15) == 0) {
+    if (!make_tmap_bf16_box32(&to, e.out_act, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), static_cast<uint64_t>(e.ldo_act)))
+      return false;
+    p.tma_out = 1;
+  }
   const long long U = static_cast<long long>(p.m_tiles) * p.n_tiles;
   long long groups = sms / CG;
   if (groups > U) groups = U;
@@ -1428,7 +1497,7 @@ bool launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmPar
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, p), "gemm_persist launch");
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<CG, ARES>, ta, tb, to, p), "gemm_persist launch");
 }
 
 int g_sm_count = 0;
@@ -1471,7 +1540,7 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   if (!tma_ok && (variant == 0 || variant == 3)) variant = 1;
   CUtensorMap tr = ta, to = ta;
   if (variant == 0 || variant == 3) {
-    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN, variant == 3 ? 16 : 32)) return false;
+    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
     tr = to;
     if (e.resid && e.resid != e.out_f32 && !make_tmap_f32_box32(&tr, e.resid, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN))
       return false;
@@ -1549,7 +1618,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       if (epi.lnf_out) { set_error("linear: no fused LayerNorm in bf16x3 mode"); return false; }
       const long long units = static_cast<long long>(pp.m_tiles) * pp.n_tiles;
       if (units * 2 >= sm_count() / 2 || (W.N % BM) != 0 || o.force_pair)
-        return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), st);
+        return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), false, st);
       p.split = 1;
       launch_one<128, 6>(ta, W.tmap128, p, st);
       return cuda_ok(cudaGetLastError(), "gemm_tcgen05 launch");
@@ -1567,8 +1636,8 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");
       return false;
     }
-    if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, sm_count(), st) : launch_persist<2, false>(ta, tb, pp, sm_count(), st);
-    return launch_persist<1, false>(ta, tb, pp, sm_count(), st);
+    if (cg == 2) return ares ? launch_persist<2, true>(ta, tb, pp, sm_count(), o.lsu_out == 0, st) : launch_persist<2, false>(ta, tb, pp, sm_count(), o.lsu_out == 0, st);
+    return launch_persist<1, false>(ta, tb, pp, sm_count(), o.lsu_out == 0, st);
   }
   if (epi.lnf_out) {
     set_error("linear: a fused LayerNorm output needs the persistent wide pair kernel");

@@ -122,6 +122,7 @@ class Engine:
         if pdl is None:
             pdl = env("CONZIC_PDL", "1") != "0"
         cfg.flags = ((_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL) |
+                     (_lib.FLAG_LSU_OUT if env("CONZIC_LSU_OUT", "0") == "1" else 0) |
                      {1: _lib.FLAG_WIDE_LSU16, 2: _lib.FLAG_WIDE_LSU8, 3: _lib.FLAG_WIDE_LSU16 | _lib.FLAG_WIDE_LSU8}.get(
                          int(wide_variant if wide_variant is not None else env("CONZIC_WIDE_VARIANT", "0")), 0))
         self.cfg = cfg
