@@ -944,14 +944,6 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool lnf = e.lnf_out != nullptr;
     const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty_bar[half]), 0);
     uint32_t uph = 0;
-    float4 g4[4], b4[4];
-    if (lnf) {
-#pragma unroll
-      for (int sg = 0; sg < 4; ++sg) {
-        g4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
-        b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
-      }
-    }
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
@@ -1005,7 +997,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         const float inv = 1.0f / static_cast<float>(2 * PBN);
-        constexpr int LNR = 4;
+        constexpr int LNR = 8;  // rows per round: 32 loads of 16 bytes in flight per lane
 #pragma unroll 1
         for (int r0 = half * 16; r0 < half * 16 + 16; r0 += LNR) {
           float4 x[LNR][4];
@@ -1049,8 +1041,10 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int sg = 0; sg < 4; ++sg) {
                 const float4 v = x[u][sg];
-                const float y0 = fmaf(v.x, rs, nm) * g4[sg].x + b4[sg].x, y1 = fmaf(v.y, rs, nm) * g4[sg].y + b4[sg].y;
-                const float y2 = fmaf(v.z, rs, nm) * g4[sg].z + b4[sg].z, y3 = fmaf(v.w, rs, nm) * g4[sg].w + b4[sg].w;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
+                const float y0 = fmaf(v.x, rs, nm) * g.x + bt.x, y1 = fmaf(v.y, rs, nm) * g.y + bt.y;
+                const float y2 = fmaf(v.z, rs, nm) * g.z + bt.z, y3 = fmaf(v.w, rs, nm) * g.w + bt.w;
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
                 uint2 u2;
                 u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -1519,9 +1513,9 @@ static bool configure_wide_one() {
 static bool configure_wide() {
   return configure_wide_one<8, 0>() && configure_wide_one<16, 0>() && configure_wide_one<4, 1>() && configure_wide_one<8, 2>();
 }
-// variant 0: TMA load/store epilogue (4 warps; residual and result move as TMA boxes); 3: TMA reduce epilogue (8 warps;
-// the L2 adds acc + bias to the residual stream in place -- needs resid == out); 1 / 2: 16 / 8 epilogue warps with
-// per-lane loads and stores (A/B measurements; also taken when the epilogue has something the TMA forms do not do)
+// variant 0: TMA reduce epilogue (8 warps; the L2 adds acc + bias to the residual stream in place -- needs resid == out,
+// else form 3); 3: TMA load/store epilogue (4 warps; residual and result move as TMA boxes); 1 / 2: 16 / 8 epilogue warps
+// with per-lane loads and stores (A/B measurements; also taken when the epilogue has something the TMA forms do not do)
 template <int EW, int EPI>
 static bool launch_wide_one(cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
                             const CUtensorMap& to, const PGemmParams& p) {
@@ -1536,7 +1530,7 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   const Epi& e = p.e;
   const bool tma_ok = e.out_f32 && !e.out_act && e.act == ACT_NONE && e.ldo_f32 == 2 * PBN && (!e.resid || e.ldr == 2 * PBN) &&
                       (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0;
-  if (variant == 3 && e.resid && e.resid != e.out_f32) variant = 0;
+  if (variant == 0 && e.resid && e.resid != e.out_f32) variant = 3;
   if (!tma_ok && (variant == 0 || variant == 3)) variant = 1;
   CUtensorMap tr = ta, to = ta;
   if (variant == 0 || variant == 3) {
@@ -1556,8 +1550,8 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   switch (variant) {
-    case 0: return launch_wide_one<4, 1>(cfg, ta, tb, tr, to, p);
-    case 3: return launch_wide_one<8, 2>(cfg, ta, tb, tr, to, p);
+    case 0: return launch_wide_one<8, 2>(cfg, ta, tb, tr, to, p);
+    case 3: return launch_wide_one<4, 1>(cfg, ta, tb, tr, to, p);
     case 1: return launch_wide_one<16, 0>(cfg, ta, tb, tr, to, p);
     default: return launch_wide_one<8, 0>(cfg, ta, tb, tr, to, p);
   }

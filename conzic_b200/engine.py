@@ -77,8 +77,8 @@ class Engine:
         """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
         in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
         are read once, here: cert_dcos / cert_dcos_lo / cert_fcap (CONZIC_CERT_DCOS / _LO / CONZIC_CERT_FCAP), ln_standalone
-        (CONZIC_LN_STANDALONE=1), pdl (CONZIC_PDL=0) and wide_variant (CONZIC_WIDE_VARIANT: 0 = TMA epilogue of the
-        N = 512 GEMM, 1 / 2 = per-lane epilogue with 16 / 8 warps) exist for A/B measurements."""
+        (CONZIC_LN_STANDALONE=1), pdl (CONZIC_PDL=0) and wide_variant (CONZIC_WIDE_VARIANT: 0 = TMA reduce epilogue of the
+        N = 512 GEMM, 3 = TMA load/store epilogue, 1 / 2 = per-lane epilogue with 16 / 8 warps) exist for A/B measurements."""
         if not torch.cuda.is_available():
             raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
