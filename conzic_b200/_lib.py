@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libconzic.so")
 
 PREC_BF16, PREC_BF16X3, PREC_CERTIFIED = 0, 1, 2
-FLAG_NO_PDL, FLAG_LN_STANDALONE, FLAG_WIDE_LSU16, FLAG_WIDE_LSU8, FLAG_LSU_OUT = 1, 2, 4, 8, 16
+FLAG_NO_PDL, FLAG_LN_STANDALONE, FLAG_WIDE_LSU, FLAG_LSU_OUT = 1, 2, 4, 16
 CERT_STATS = 8
 GEMM_TCGEN05, GEMM_SIMT_DEBUG = 0, 1
 BERT_GLOBALS, CLIP_GLOBALS, PER_LAYER = 10, 5, 16

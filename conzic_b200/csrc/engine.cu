@@ -761,7 +761,7 @@ int conzic_ctx_create(const conzic_config* cfg, const void* const* bw, int n_ber
     o.split = split; o.impl = cfg->gemm_impl; o.bn = 128; o.stages = 3;
     o.persist = persist ? 1 : 0;  // persistent CTA-pair kernel (tcgen05 cta_group::2): the CLIP towers, bf16 and bf16x3
     o.cg = 2;
-    o.wide_variant = (cfg->flags >> 2) & 3;
+    o.wide_lsu = (cfg->flags & CONZIC_FLAG_WIDE_LSU) ? 1 : 0;
     o.lsu_out = (cfg->flags & CONZIC_FLAG_LSU_OUT) ? 1 : 0;  // CONZIC_FLAG_WIDE_LSU16 / _LSU8
     return o;
   };

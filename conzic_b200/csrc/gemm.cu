@@ -787,13 +787,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // reads.  Cost: the accumulators are no longer double buffered across units; the epilogue hands the two halves
 // back separately so the next unit's MMAs restart on half 0 while half 1 is still being drained.
 // ---------------------------------------------------------------------------------------------------
-// Three epilogue forms (EPI).  0: EW = 8 / 16 warps move the tile with per-lane loads and stores through a small
-// transposing staging buffer (64 contiguous bytes per row and instruction).  1: EW = 4 warps (one per TMEM lane quarter,
-// each owning whole rows); the residual tile arrives and the result leaves as 32 x 32 fp32 boxes moved by the TMA engine
-// (cp.async.bulk.tensor, 128-byte swizzle), so the load/store units only see shared memory.  2: EW = 8 warps (two per
-// lane quarter, one per accumulator half); acc + bias leaves as TMA boxes that the L2 ADDS to the residual stream in
-// place (cp.reduce.async.bulk.tensor .add.f32: x += ..., no residual load at all); the LayerNorm statistics come from
-// the row-coalesced re-read that the LayerNorm pass makes anyway.
+// Two epilogue forms.  EPI 0: EW = 16 warps move the tile with per-lane loads and stores through a small transposing
+// staging buffer (64 contiguous bytes per row and instruction); the fallback for epilogues the other form does not do,
+// and the A/B reference.  EPI 2: EW = 8 warps (two per TMEM lane quarter, one per accumulator half); acc + bias leaves
+// as 32 x 32 fp32 boxes that the L2 ADDS to the residual stream in place (cp.reduce.async.bulk.tensor .add.f32: x += ...,
+// no residual load at all, the load/store units only see shared memory); the LayerNorm statistics come from the
+// row-coalesced re-read that the LayerNorm pass makes anyway.  (Measured and dropped: the same boxes with the residual
+// loaded by TMA and added in registers, 4 warps -- 2 % slower per step; 16-column boxes with 4 K stages and the
+// LayerNorm one unit late -- the late re-read misses L2; 8 warps with per-lane accesses.)
 template <int EW, int EPI>
 struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
@@ -801,26 +802,24 @@ struct WideSmem {
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
   static constexpr int STAGES = EPI ? 3 : 4;
   static constexpr int STG_OFF = STAGES * STAGE;       // EPI 0: one 2 KB staging buffer per epilogue warp
-  static constexpr int NR = EPI == 1 ? 3 : 0;           // EPI 1: residual boxes in flight per warp
-  static constexpr int BOX = 32 * 32 * 4;               // EPI 1, 2: one 32-row x 32-column fp32 box
-  static constexpr int EPI_WARP = (NR + 2) * BOX;       // EPI 1, 2: NR residual boxes + 2 output boxes per warp
+  static constexpr int BOX = 32 * 32 * 4;               // EPI 2: one 32-row x 32-column fp32 box
+  static constexpr int EPI_WARP = 2 * BOX;              // EPI 2: 2 output boxes per warp
   static constexpr int BIAS_OFF = STG_OFF + (EPI ? EW * EPI_WARP : EW * 2048);
   static constexpr int BAR_OFF = BIAS_OFF + (EPI ? 2 * PBN * 4 : 0);
-  static constexpr int N_BARS = 2 * STAGES + 4 + EW * NR;
+  static constexpr int N_BARS = 2 * STAGES + 4;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int THREADS = 64 + 32 * EW;
   static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
-  static_assert(EPI != 1 || EW == 4, "the TMA load/store epilogue uses one warp per TMEM lane quarter");
+  static_assert(EPI == 0 || EPI == 2, "epilogue form");
   static_assert(EPI != 2 || EW == 8, "the TMA reduce epilogue uses two warps per TMEM lane quarter");
 };
 
 template <int EW, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const PGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const PGemmParams p) {
   PDL_ENTRY();
   using SL = WideSmem<EW, EPI>;
-  constexpr bool TMAE = EPI == 1;
   constexpr int CG = 2;
   constexpr int STAGES = SL::STAGES;
   extern __shared__ __align__(1024) uint8_t psmem[];
@@ -830,8 +829,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [0]: both halves of the unit are complete
   uint64_t* tempty_bar = tfull_bar + 2;       // [h]: half h has been read by every epilogue warp of the pair
-  uint64_t* res_bar = tempty_bar + 2;          // TMAE: [warp][NR] a residual box has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EW * SL::NR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -843,15 +841,13 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-    if (EPI) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO); }
+    if (EPI) tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
-    // arrivals per half: EW == 8 -> all 8 warps of each CTA read both halves; EW == 16 -> 8 of the 16 read each half;
-    // TMA epilogue -> its 4 warps read both halves
+    // arrivals per half: EW == 16 -> 8 of the 16 warps read each half; reduce epilogue -> 4 of its 8 warps
     mbar_init(&tempty_bar[0], CG * (EPI ? 4 : 8)); mbar_init(&tempty_bar[1], CG * (EPI ? 4 : 8));
-    if (TMAE) for (int i = 0; i < EW * SL::NR; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (EPI && warp >= 2) {  // the bias of all 512 columns, read as shared-memory broadcasts by the epilogue
@@ -944,6 +940,14 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool lnf = e.lnf_out != nullptr;
     const uint32_t tempty_addr = mapa_shared(smem_u32(&tempty_bar[half]), 0);
     uint32_t uph = 0;
+    float4 g4[4], b4[4];
+    if (lnf) {
+#pragma unroll
+      for (int sg = 0; sg < 4; ++sg) {
+        g4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
+        b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
+      }
+    }
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
@@ -997,7 +1001,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         const float inv = 1.0f / static_cast<float>(2 * PBN);
-        constexpr int LNR = 8;  // rows per round: 32 loads of 16 bytes in flight per lane
+        constexpr int LNR = 4;  // rows per round: 16 loads of 16 bytes in flight per lane (8 rows: slower, measured)
 #pragma unroll 1
         for (int r0 = half * 16; r0 < half * 16 + 16; r0 += LNR) {
           float4 x[LNR][4];
@@ -1037,152 +1041,6 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float var = fmaxf(s2[u] * inv - mu * mu, 0.f);
             const float rs = rsqrtf(var + e.lnf_eps);
             const float nm = -mu * rs;
-            if (grow < p.M) {
-#pragma unroll
-              for (int sg = 0; sg < 4; ++sg) {
-                const float4 v = x[u][sg];
-                const float4 g = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
-                const float4 bt = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
-                const float y0 = fmaf(v.x, rs, nm) * g.x + bt.x, y1 = fmaf(v.y, rs, nm) * g.y + bt.y;
-                const float y2 = fmaf(v.z, rs, nm) * g.z + bt.z, y3 = fmaf(v.w, rs, nm) * g.w + bt.w;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-                uint2 u2;
-                u2.x = *reinterpret_cast<uint32_t*>(&h0); u2.y = *reinterpret_cast<uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(e.lnf_out + static_cast<size_t>(grow) * e.lnf_ld + sg * 128 + lane * 4) = u2;
-              }
-            }
-          }
-        }
-      }
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
-    __syncwarp();
-  } else if constexpr (TMAE) {
-    // ---- TMA epilogue: this warp owns rows [q*32, q*32+32) of the CTA's 128 and all 512 columns (16 boxes of 32).
-    // Per box: accumulator from TMEM (lane = row), + bias (shared-memory broadcast) + residual box (landed by TMA,
-    // requested NR boxes ahead), row statistics in registers, result into a swizzled output box, TMA store.
-    constexpr int NR = SL::NR;
-    constexpr int NBOX = 2 * PBN / 32;  // 16
-    const int q = warp & 3;
-    const int we = warp - 2;
-    uint8_t* Rb = smem + SL::STG_OFF + we * SL::EPI_WARP;
-    uint8_t* Ob = Rb + NR * SL::BOX;
-    uint64_t* rbar = res_bar + we * NR;
-    const float* bias_s = reinterpret_cast<const float*>(smem + SL::BIAS_OFF);
-    const Epi& e = p.e;
-    const bool has_res = e.resid != nullptr;
-    const bool lnf = e.lnf_out != nullptr;
-    const uint32_t tempty_addr0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
-    uint32_t uph = 0;
-    int cs = 0; uint32_t cph = 0;  // consumer side of the residual ring
-    int is = 0;                     // producer side (lane 0): next slot, next box (unit im, box it) to request
-    int im = group, it = 0;
-    auto request = [&]() {  // lane 0 only
-      if (im < p.m_tiles) {
-        const int r0 = (im * CG + static_cast<int>(cta_rank)) * BM + q * 32;
-        mbar_arrive_expect_tx(&rbar[is], SL::BOX);
-        tma_load_2d(Rb + is * SL::BOX, &tmR, &rbar[is], it * 32, r0);
-        if (++is == NR) is = 0;
-        if (++it == NBOX) { it = 0; im += n_groups; }
-      }
-    };
-    if (has_res && lane == 0) {
-#pragma unroll 1
-      for (int i = 0; i < NR; ++i) request();
-    }
-    float4 g4[4], b4[4];
-    if (lnf) {
-#pragma unroll
-      for (int sg = 0; sg < 4; ++sg) {
-        g4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_g + sg * 128 + lane * 4));
-        b4[sg] = __ldg(reinterpret_cast<const float4*>(e.lnf_b + sg * 128 + lane * 4));
-      }
-    }
-    const uint32_t swz = static_cast<uint32_t>(lane & 7);
-    for (int m = group; m < p.m_tiles; m += n_groups, uph ^= 1) {
-      const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
-      mbar_wait(&tfull_bar[0], uph);
-      tc_fence_after();
-      float s1 = 0.f, s2 = 0.f;  // this lane's row: sum and sum of squares over the 512 columns (fused LN)
-#pragma unroll 1
-      for (int t = 0; t < NBOX; ++t) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
-        if (has_res) mbar_wait(&rbar[cs], cph);
-        // every shared-memory load of the box is issued before the first dependent instruction: one warp per
-        // scheduler has nothing else to hide their latency behind
-        const uint8_t* R = Rb + cs * SL::BOX + lane * 128;
-        uint8_t* O = Ob + (t & 1) * SL::BOX + lane * 128;
-        float4 bb[8], rr[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
-          rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res) rr[j] = *reinterpret_cast<const float4*>(R + ((static_cast<uint32_t>(j) ^ swz) << 4));
-        }
-        // the output box written two boxes ago must have been read by its TMA store before it is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        tmem_ld_wait();
-        if ((t & 7) == 7) {  // this warp's part of accumulator half t / 8 is in registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr0 + (t >> 3) * 8);
-        }
-        __syncwarp();
-        float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x;
-          x.x = (__uint_as_float(r[4 * j]) + bb[j].x) + rr[j].x;
-          x.y = (__uint_as_float(r[4 * j + 1]) + bb[j].y) + rr[j].y;
-          x.z = (__uint_as_float(r[4 * j + 2]) + bb[j].z) + rr[j].z;
-          x.w = (__uint_as_float(r[4 * j + 3]) + bb[j].w) + rr[j].w;
-          p1[j & 3] += (x.x + x.y) + (x.z + x.w);
-          p2[j & 3] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-          *reinterpret_cast<float4*>(O + ((static_cast<uint32_t>(j) ^ swz) << 4)) = x;
-        }
-        s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
-        s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the box is read by the async proxy next
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (t & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (has_res) request();  // every lane has read residual slot cs: refill it, NR boxes ahead
-        }
-        if (++cs == NR) { cs = 0; cph ^= 1; }
-      }
-      if (lnf) {
-        // Fused LayerNorm: the row statistics are complete in this lane; the rows are re-read (L2) with whole-row
-        // coalescing -- one instruction = 512 contiguous bytes of one row -- once their TMA stores have completed.
-        const float inv = 1.0f / static_cast<float>(2 * PBN);
-        const float mu = s1 * inv;
-        const float var = fmaxf(s2 * inv - mu * mu, 0.f);
-        const float rstd = rsqrtf(var + e.lnf_eps);
-        const float nmr = -mu * rstd;  // y = x * rstd + (-mean * rstd)
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        constexpr int LNR = 8;  // rows per round: 32 loads of 16 bytes in flight per lane
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += LNR) {
-          float4 x[LNR][4];
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            const int grow = row0 + r0 + u;
-#pragma unroll
-            for (int sg = 0; sg < 4; ++sg) {
-              x[u][sg] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (grow < p.M)
-                x[u][sg] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + static_cast<size_t>(grow) * e.ldo_f32 + sg * 128 + lane * 4));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < LNR; ++u) {
-            const int grow = row0 + r0 + u;
-            const float rs = __shfl_sync(0xffffffffu, rstd, r0 + u), nm = __shfl_sync(0xffffffffu, nmr, r0 + u);
             if (grow < p.M) {
 #pragma unroll
               for (int sg = 0; sg < 4; ++sg) {
@@ -1420,15 +1278,14 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
 }
 
 // fp32 [rows, cols] tensor as 32-row x 32-column boxes (128-byte rows, 128-byte swizzle): the wide kernel's TMA epilogue
-static bool make_tmap_f32_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                                uint32_t box_cols = 32) {
+static bool make_tmap_f32_box32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
   if (!tma_init()) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * 4};
-  cuuint32_t box[2] = {box_cols, 32};
+  cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (fp32 boxes) failed, CUresult=" + std::to_string(static_cast<int>(r)));
@@ -1511,34 +1368,27 @@ static bool configure_wide_one() {
                                       WideSmem<EW, EPI>::DYN_BYTES), "cudaFuncSetAttribute(gemm_wide)");
 }
 static bool configure_wide() {
-  return configure_wide_one<8, 0>() && configure_wide_one<16, 0>() && configure_wide_one<4, 1>() && configure_wide_one<8, 2>();
+  return configure_wide_one<16, 0>() && configure_wide_one<8, 2>();
 }
-// variant 0: TMA reduce epilogue (8 warps; the L2 adds acc + bias to the residual stream in place -- needs resid == out,
-// else form 3); 3: TMA load/store epilogue (4 warps; residual and result move as TMA boxes); 1 / 2: 16 / 8 epilogue warps
-// with per-lane loads and stores (A/B measurements; also taken when the epilogue has something the TMA forms do not do)
+// lsu == false: TMA reduce epilogue (8 warps; the L2 adds acc + bias to the residual stream in place -- needs resid == out
+// or no residual, fp32 output only); otherwise / lsu == true: 16 epilogue warps with per-lane loads and stores
 template <int EW, int EPI>
-static bool launch_wide_one(cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
-                            const CUtensorMap& to, const PGemmParams& p) {
+static bool launch_wide_one(cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                            const PGemmParams& p) {
   cfg.blockDim = dim3(WideSmem<EW, EPI>::THREADS);
   cfg.dynamicSmemBytes = WideSmem<EW, EPI>::DYN_BYTES;
-  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<EW, EPI>, ta, tb, tr, to, p), "gemm_wide launch");
+  return cuda_ok(cudaLaunchKernelEx(&cfg, gemm_wide_kernel<EW, EPI>, ta, tb, to, p), "gemm_wide launch");
 }
-static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, int variant, cudaStream_t st) {
+static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGemmParams& p, bool lsu, cudaStream_t st) {
   int groups = sm_count() / 2;
   if (groups > p.m_tiles) groups = p.m_tiles;
   if (groups < 1) groups = 1;
   const Epi& e = p.e;
-  const bool tma_ok = e.out_f32 && !e.out_act && e.act == ACT_NONE && e.ldo_f32 == 2 * PBN && (!e.resid || e.ldr == 2 * PBN) &&
-                      (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0;
-  if (variant == 0 && e.resid && e.resid != e.out_f32) variant = 3;
-  if (!tma_ok && (variant == 0 || variant == 3)) variant = 1;
-  CUtensorMap tr = ta, to = ta;
-  if (variant == 0 || variant == 3) {
-    if (!make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
-    tr = to;
-    if (e.resid && e.resid != e.out_f32 && !make_tmap_f32_box32(&tr, e.resid, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN))
-      return false;
-  }
+  const bool tma_ok = e.out_f32 && !e.out_act && e.act == ACT_NONE && e.ldo_f32 == 2 * PBN && (!e.resid || e.resid == e.out_f32) &&
+                      (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0;
+  if (!tma_ok) lsu = true;
+  CUtensorMap to = ta;
+  if (!lsu && !make_tmap_f32_box32(&to, e.out_f32, static_cast<uint64_t>(p.M), 2 * PBN, 2 * PBN)) return false;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
   cfg.stream = st;
@@ -1549,12 +1399,7 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  switch (variant) {
-    case 0: return launch_wide_one<8, 2>(cfg, ta, tb, tr, to, p);
-    case 3: return launch_wide_one<4, 1>(cfg, ta, tb, tr, to, p);
-    case 1: return launch_wide_one<16, 0>(cfg, ta, tb, tr, to, p);
-    default: return launch_wide_one<8, 0>(cfg, ta, tb, tr, to, p);
-  }
+  return lsu ? launch_wide_one<16, 0>(cfg, ta, tb, to, p) : launch_wide_one<8, 2>(cfg, ta, tb, to, p);
 }
 
 bool gemm_configure() {
@@ -1624,7 +1469,7 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
     const bool wide_ok = cg == 2 && W.N == 2 * PBN && epi.out_f32 != nullptr;
     if (wide_ok && ((!ares && W.K >= 1024) || epi.lnf_out)) {
       pp.n_tiles = 1;
-      return launch_wide(ta, tb, pp, o.wide_variant, st);
+      return launch_wide(ta, tb, pp, o.wide_lsu != 0, st);
     }
     if (epi.lnf_out) {
       set_error("linear: a fused LayerNorm output needs the wide pair kernel (N == 512, fp32 output, CTA pairs)");

@@ -122,7 +122,7 @@ struct GemmOpts {
   int ksplit = 1;   // gridded kernel: split-K factor (raw fp32 partials, summed by the following LayerNorm)
   int force_pair = 0;  // bf16x3 + persist: the pair kernel whatever the tile count (tests)
   int lsu_out = 0;       // persistent kernel: bf16 outputs by per-lane stores instead of TMA boxes (A/B)
-  int wide_variant = 0;  // N = 512 wide kernel: 0 TMA reduce epilogue, 3 TMA load/store epilogue, 1 / 2 = 16 / 8 warps, per-lane accesses
+  int wide_lsu = 0;      // N = 512 wide kernel: per-lane epilogue accesses (16 warps) instead of the TMA reduce epilogue (A/B)
 };
 
 bool tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)

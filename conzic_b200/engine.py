@@ -73,12 +73,14 @@ class Engine:
                  dot_id: int = _dims.DOT_ID, clip_bos: int = _dims.CLIP_BOS, clip_eos: int = _dims.CLIP_EOS,
                  clip_chunk_rows: int = 0, cert_dcos: Optional[float] = None, cert_dcos_lo: Optional[float] = None,
                  cert_zratio: Optional[Sequence[float]] = None, cert_fcap: Optional[int] = None,
-                 ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None, wide_variant: Optional[int] = None):
+                 ln_standalone: Optional[bool] = None, pdl: Optional[bool] = None, wide_lsu: Optional[bool] = None,
+                 lsu_out: Optional[bool] = None):
         """precision: "certified" (default; the reference's token ids at close to bf16 speed), "bf16x3" (everything
         in the fp32-grade split mode) or "bf16" (tolerance-only parity); see include/conzic.h.  The remaining switches
         are read once, here: cert_dcos / cert_dcos_lo / cert_fcap (CONZIC_CERT_DCOS / _LO / CONZIC_CERT_FCAP), ln_standalone
-        (CONZIC_LN_STANDALONE=1), pdl (CONZIC_PDL=0) and wide_variant (CONZIC_WIDE_VARIANT: 0 = TMA reduce epilogue of the
-        N = 512 GEMM, 3 = TMA load/store epilogue, 1 / 2 = per-lane epilogue with 16 / 8 warps) exist for A/B measurements."""
+        (CONZIC_LN_STANDALONE=1), pdl (CONZIC_PDL=0), wide_lsu (CONZIC_WIDE_LSU=1: per-lane instead of TMA reduce-add
+        epilogue of the N = 512 GEMM) and lsu_out (CONZIC_LSU_OUT=1: per-lane instead of TMA stores of the bf16 GEMM
+        outputs) exist for A/B measurements."""
         if not torch.cuda.is_available():
             raise RuntimeError("conzic_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -121,10 +123,12 @@ class Engine:
             ln_standalone = env("CONZIC_LN_STANDALONE", "0") == "1"
         if pdl is None:
             pdl = env("CONZIC_PDL", "1") != "0"
+        if wide_lsu is None:
+            wide_lsu = env("CONZIC_WIDE_LSU", "0") == "1"
+        if lsu_out is None:
+            lsu_out = env("CONZIC_LSU_OUT", "0") == "1"
         cfg.flags = ((_lib.FLAG_LN_STANDALONE if ln_standalone else 0) | (0 if pdl else _lib.FLAG_NO_PDL) |
-                     (_lib.FLAG_LSU_OUT if env("CONZIC_LSU_OUT", "0") == "1" else 0) |
-                     {1: _lib.FLAG_WIDE_LSU16, 2: _lib.FLAG_WIDE_LSU8, 3: _lib.FLAG_WIDE_LSU16 | _lib.FLAG_WIDE_LSU8}.get(
-                         int(wide_variant if wide_variant is not None else env("CONZIC_WIDE_VARIANT", "0")), 0))
+                     (_lib.FLAG_WIDE_LSU if wide_lsu else 0) | (_lib.FLAG_LSU_OUT if lsu_out else 0))
         self.cfg = cfg
         self.V, self.D = cfg.bert_vocab, cfg.clip_proj
         self.ldl = (self.V + 3) & ~3

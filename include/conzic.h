@@ -61,8 +61,8 @@ enum {
 /* conzic_config.flags */
 enum {
   CONZIC_FLAG_NO_PDL = 1,         /* launch without programmatic dependent launch (A/B measurements)                */
-  CONZIC_FLAG_WIDE_LSU16 = 4,     /* N = 512 GEMM kernel: per-lane epilogue accesses with 16 warps instead of the TMA  */
-  CONZIC_FLAG_WIDE_LSU8 = 8,      /*   epilogue / with 8 warps (A/B measurements)                                      */
+  CONZIC_FLAG_WIDE_LSU = 4,       /* N = 512 GEMM kernel: per-lane epilogue accesses (16 warps) instead of the TMA      */
+                                  /*   reduce-add epilogue (A/B measurements)                                          */
   CONZIC_FLAG_LSU_OUT = 16,       /* persistent GEMM kernel: bf16 outputs by per-lane stores instead of TMA boxes (A/B) */
   CONZIC_FLAG_LN_STANDALONE = 2   /* CLIP bf16 tower: LayerNorm as its own kernel instead of in the O-proj / fc2
                                      epilogues (A/B measurements; HF:models/clip/modeling_clip.py:369-384)          */

@@ -180,8 +180,7 @@ def test_clip_text_encode_vs_oracle(prec, tol):
 
 @pytest.mark.parametrize("prec,tol,kw", [("bf16x3", 3e-4, {}), ("bf16", 0.04, {}),
                                          ("bf16", 0.04, {"ln_standalone": True}), ("bf16", 0.04, {"pdl": False}),
-                                         ("bf16", 0.04, {"wide_variant": 1}), ("bf16", 0.04, {"wide_variant": 2}),
-                                         ("bf16", 0.04, {"wide_variant": 3})])
+                                         ("bf16", 0.04, {"wide_lsu": True}), ("bf16", 0.04, {"lsu_out": True})])
 def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
     """CLIP tower with perturbed LayerNorm gamma / beta (the synthetic checkpoint has gamma = 1, beta = 0) against
     the oracle: the default path (LayerNorm written by the O-proj / fc2 epilogues of the wide pair kernel and by the
@@ -211,17 +210,17 @@ def test_clip_text_encode_with_nontrivial_layernorm(prec, tol, kw):
     eng.close()
 
 
-def test_wide_gemm_epilogue_forms_agree():
-    """The epilogue forms of the N = 512 GEMM (TMA load/store boxes; TMA reduce-add boxes; per-lane accesses with 16 / 8 warps) compute the same
-    x = acc + bias + residual (same accumulators, same fp32 adds) and LayerNorm statistics that differ only in summation
-    order, so a rare bf16 rounding of a LayerNorm output is all that can differ.  Checked on a 2-block tower (block 0: all
-    rows through both fused-LayerNorm GEMMs; block 1: the compacted EOS rows) -- over 12 blocks such roundings grow to
-    the bf16 tower's own noise (~1e-3 on every element), which the oracle comparison above covers.  Ragged row counts
-    exercise the clipped last tile."""
+def test_gemm_epilogue_forms_agree():
+    """The TMA epilogues against the per-lane ones they replace.  N = 512 GEMM: the reduce-add form (the L2 adds
+    acc + bias to the residual stream) computes the same fp32 sums as the per-lane form -- one add per element, fp32
+    addition commutes -- and LayerNorm statistics that differ only in summation order, so a rare bf16 rounding of a
+    LayerNorm output is all that can differ.  bf16 outputs of the persistent kernel as TMA boxes: same bytes.  Checked
+    on a 2-block tower (block 0: all rows through both fused-LayerNorm GEMMs; block 1: the compacted EOS rows) -- over
+    12 blocks such roundings grow to the bf16 tower's own noise (~1e-3 on every element), which the oracle comparison
+    above covers.  Ragged row counts exercise the clipped last tile."""
     from conzic_b200.engine import Engine
     sd = {k: v for k, v in gc.weights("clip").items()
           if ".layers." not in k or k.split(".layers.")[1].split(".")[0] in ("0", "1")}
-    outs = []
     torch.manual_seed(5)
     cases = []
     for N, T in ((700, 9), (37, 12), (1, 5)):
@@ -231,17 +230,19 @@ def test_wide_gemm_epilogue_forms_agree():
         for i in range(N):
             ids[i, lens[i] - 1:] = synth.CLIP_EOS
         cases.append(ids.int().cuda())
-    for v in (0, 1, 2, 3):
-        eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision="bf16", wide_variant=v)
-        outs.append([eng.clip_text_encode(ids).cpu() for ids in cases])
+    outs = {}
+    for name, kw in (("tma", {}), ("wide_lsu", {"wide_lsu": True}), ("lsu_out", {"lsu_out": True})):
+        eng = Engine(gc.weights("bert"), sd, device="cuda:0", precision="bf16", **kw)
+        outs[name] = [eng.clip_text_encode(ids).cpu() for ids in cases]
         eng.close()
-    for v in (1, 2, 3):
-        for a, b in zip(outs[0], outs[v]):
-            assert torch.isfinite(a).all()
-            d = (a - b).abs()
-            assert float(d.max()) < 2e-2                      # one flipped bf16 rounding moves an embedding by ~5e-3
-            assert float((d.amax(dim=1) > 0).float().mean()) < 0.1 or a.shape[0] < 20   # ... and most rows not at all
-            assert float(d.mean()) < 1e-4
+    for a, b in zip(outs["tma"], outs["lsu_out"]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs["tma"], outs["wide_lsu"]):
+        assert torch.isfinite(a).all()
+        d = (a - b).abs()
+        assert float(d.max()) < 2e-2                      # one flipped bf16 rounding moves an embedding by ~5e-3
+        assert float((d.amax(dim=1) > 0).float().mean()) < 0.1 or a.shape[0] < 20   # ... and most rows not at all
+        assert float(d.mean()) < 1e-4
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("certified", 1e-4), ("bf16", 2e-2)])

@@ -17,7 +17,7 @@ if has test; then
   tail -30 $OUT/pytest_gpu.log
 fi
 if has testq; then  # the kernels a GEMM / tower change touches
-  timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -k "linear or clip_text or wide_gemm or teacher_forced_certified or free_running_certified" > $OUT/pytest_gpu_quick.log 2>&1; echo "pytest quick rc=$?"
+  timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -k "linear or clip_text or gemm_epilogue or teacher_forced_certified or free_running_certified" > $OUT/pytest_gpu_quick.log 2>&1; echo "pytest quick rc=$?"
   tail -4 $OUT/pytest_gpu_quick.log
 fi
 if has bound; then
