@@ -210,6 +210,92 @@ __device__ __forceinline__ float2 load_pair(const void* base, size_t elem) {
   }
 }
 
+constexpr int QS_LD = HD + 2;  // query rows 2 banks apart: the queries of one pass are read conflict free
+
+// The queries of one (sequence, head) task, W lanes per query: W = 32 is one query per pass (up to 96 keys, 3 per
+// lane); short sequences (<= 16 / <= 8 keys: BERT, the certified re-score) take 2 / 4 queries per pass, which halves /
+// quarters the number of dependent passes of this latency-bound kernel.  Every query sees the same arithmetic in each
+// form -- 4 interleaved partial dot products summed (a0 + a1) + (a2 + a3), probabilities x V accumulated key by key --
+// and the form depends on the sequence's own key count only, so a caption gets the same bits wherever it is encoded.
+template <int W>
+__device__ __forceinline__ void attention_queries(const AttnArgs& a, const float* Kt, int nkp, const float* Vs, const float* Qs,
+                                                  float* ps, int nq, int pl, int nk, int own_base, int head, int lane) {
+  constexpr int G = 32 / W, DPL = HD / W, NSLOT = W == 32 ? MAX_SLOTS : 1;
+  const int g = lane / W, jl = lane % W;
+  const int H = a.H;
+  for (int t0 = 0; t0 < nq; t0 += G) {
+    const bool live = t0 + g < nq;
+    const int t = live ? t0 + g : nq - 1;  // idle lane groups repeat the last query and store nothing
+    const float* qs = Qs + t * QS_LD;
+    const int nvis = a.causal ? pl + t + 1 : nk;
+    float sc[NSLOT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NSLOT; ++c) {
+      const int j = jl + W * c;
+      float s = -INFINITY;
+      if (j < nvis) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* kt = Kt + j;
+#pragma unroll 4
+        for (int d = 0; d < HD; d += 4) {
+          a0 = fmaf(qs[d], kt[d * nkp], a0);
+          a1 = fmaf(qs[d + 1], kt[(d + 1) * nkp], a1);
+          a2 = fmaf(qs[d + 2], kt[(d + 2) * nkp], a2);
+          a3 = fmaf(qs[d + 3], kt[(d + 3) * nkp], a3);
+        }
+        s = ((a0 + a1) + (a2 + a3)) * a.scale;
+      }
+      sc[c] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NSLOT; ++c) {
+      const int j = jl + W * c;
+      const float e = j < nvis ? expf(sc[c] - mx) : 0.f;
+      sc[c] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float* pq = ps + g * W;  // W == 32: g == 0 and the row holds up to nkp probabilities
+#pragma unroll
+    for (int c = 0; c < NSLOT; ++c) {
+      const int j = jl + W * c;
+      if (W == 32 ? (j < nvis) : true) pq[j] = j < nvis ? sc[c] * inv : 0.f;  // short forms: zeros past the visible keys
+    }
+    __syncwarp();
+    // probabilities x V: DPL output dims per lane; the short forms run to the longest query of the pass (the zeros
+    // written above add exactly nothing)
+    const int nloop = W == 32 ? nvis : (a.causal ? min(nk, pl + min(t0 + G, nq)) : nk);
+    float o[DPL];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) o[e] = 0.f;
+    for (int j = 0; j < nloop; ++j) {
+      const float pj = pq[j];
+      const float* v = Vs + j * HD + jl * DPL;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) o[e] = fmaf(pj, v[e], o[e]);
+    }
+    if (live) {
+      bf16* orow = a.out_act + static_cast<size_t>(own_base + t) * a.ld_act + head * HD + jl * DPL;
+#pragma unroll
+      for (int e = 0; e < DPL; e += 2) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(o[e], o[e + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(orow + e) = h;
+        if (a.split)
+          *reinterpret_cast<__nv_bfloat162*>(orow + H + e) =
+              __floats2bfloat162_rn(o[e] - __bfloat162float(h.x), o[e + 1] - __bfloat162float(h.y));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <bool F32>
 __global__ void attention_kernel(AttnArgs a, int nk_cap, int nq_cap) {
   PDL_ENTRY();
@@ -218,11 +304,12 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap, int nq_cap) {
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkp = nk_cap | 1;  // odd stride for the transposed K
-  const int per_warp = (HD * nkp + HD * nk_cap + HD * nq_cap + nkp + 3) & ~3;  // keep every warp's slice 16B aligned
+  const int psz = nkp > 32 ? nkp : 32;
+  const int per_warp = (HD * nkp + HD * nk_cap + QS_LD * nq_cap + psz + 3) & ~3;  // keep every warp's slice 16B aligned
   float* Kt = sm + static_cast<size_t>(wib) * per_warp;  // [64][nkp]
   float* Vs = Kt + HD * nkp;                               // [nk][64]
-  float* Qs = Vs + HD * nk_cap;                            // [nq][64]
-  float* ps = Qs + HD * nq_cap;                            // [nkp]
+  float* Qs = Vs + HD * nk_cap;                            // [nq][QS_LD]
+  float* ps = Qs + QS_LD * nq_cap;                         // [max(nkp, 32)]
 
   const int n_pre_seq = a.P > 0 ? a.B : 0;
   const int n_seq = n_pre_seq + (a.cand_img ? a.n_cand : a.B * a.K);
@@ -267,66 +354,18 @@ __global__ void attention_kernel(AttnArgs a, int nk_cap, int nq_cap) {
           Kt[(2 * lane) * nkp + j] = kk[u].x;
           Kt[(2 * lane + 1) * nkp + j] = kk[u].y;
           *reinterpret_cast<float2*>(Vs + j * HD + 2 * lane) = vv[u];
-          if (j >= pl) *reinterpret_cast<float2*>(Qs + (j - pl) * HD + 2 * lane) = qq[u];  // own rows are the queries
+          if (j >= pl) *reinterpret_cast<float2*>(Qs + (j - pl) * QS_LD + 2 * lane) = qq[u];  // own rows are the queries
         }
       }
     }
     __syncwarp();
-    for (int t = 0; t < nq; ++t) {
-      const int qrow = own_base + t;
-      const float* qs = Qs + t * HD;
-      const int nvis = a.causal ? pl + t + 1 : nk;
-      float sc[MAX_SLOTS];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < MAX_SLOTS; ++c) {
-        const int j = lane + 32 * c;
-        float s = -INFINITY;
-        if (j < nvis) {
-          float acc = 0.f;
-#pragma unroll 16
-          for (int d = 0; d < HD; ++d) acc = fmaf(qs[d], Kt[d * nkp + j], acc);
-          s = acc * a.scale;
-        }
-        sc[c] = s;
-        mx = fmaxf(mx, s);
-      }
-      mx = warp_max(mx);
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < MAX_SLOTS; ++c) {
-        const int j = lane + 32 * c;
-        const float e = j < nvis ? expf(sc[c] - mx) : 0.f;
-        sc[c] = e;
-        sum += e;
-      }
-      sum = warp_sum(sum);
-      const float inv = 1.0f / sum;
-#pragma unroll
-      for (int c = 0; c < MAX_SLOTS; ++c) {
-        const int j = lane + 32 * c;
-        if (j < nvis) ps[j] = sc[c] * inv;
-      }
-      __syncwarp();
-      float o0 = 0.f, o1 = 0.f;
-      for (int j = 0; j < nvis; ++j) {
-        const float pj = ps[j];
-        float2 v2 = *reinterpret_cast<const float2*>(Vs + j * HD + 2 * lane);
-        o0 = fmaf(pj, v2.x, o0);
-        o1 = fmaf(pj, v2.y, o1);
-      }
-      bf16* orow = a.out_act + static_cast<size_t>(qrow) * a.ld_act;
-      const int col = head * HD + 2 * lane;
-      __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
-      *reinterpret_cast<__nv_bfloat162*>(orow + col) = h;
-      if (a.split) {
-        *reinterpret_cast<__nv_bfloat162*>(orow + H + col) =
-            __floats2bfloat162_rn(o0 - __bfloat162float(h.x), o1 - __bfloat162float(h.y));
-      }
-      __syncwarp();
-    }
+    if (nk <= 8) attention_queries<8>(a, Kt, nkp, Vs, Qs, ps, nq, pl, nk, own_base, head, lane);
+    else if (nk <= 16) attention_queries<16>(a, Kt, nkp, Vs, Qs, ps, nq, pl, nk, own_base, head, lane);
+    else attention_queries<32>(a, Kt, nkp, Vs, Qs, ps, nq, pl, nk, own_base, head, lane);
+    __syncwarp();
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------------
 // bf16 attention for many very short sequences on the warp-level tensor-core path (mma.sync m16n8k16; the
@@ -805,7 +844,8 @@ bool launch_attention(const AttnArgs& a, cudaStream_t st) {
   }
   const int nkp = nk_cap | 1;
   const int nq_cap = a.P > a.S ? a.P : a.S;
-  const size_t per_warp = static_cast<size_t>((HD * nkp + HD * nk_cap + HD * nq_cap + nkp + 3) & ~3) * sizeof(float);
+  const int psz = nkp > 32 ? nkp : 32;
+  const size_t per_warp = static_cast<size_t>((HD * nkp + HD * nk_cap + QS_LD * nq_cap + psz + 3) & ~3) * sizeof(float);
   int warps = static_cast<int>((200 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;
