@@ -44,10 +44,11 @@ enum {
                                 CONZIC_PREC_BF16X3 (gen_utils.py:77-80), at close to bf16 speed                     */
 };
 /* d = cos(bf16 tower) - cos(bf16x3 tower) of one candidate is taken to lie in [-CERT_DCOS_LO, CERT_DCOS]: 1.3 x the
- * extremes over 1.0 M candidates of the config-2 / config-3 workloads (-4.93e-4 / +1.22e-3; the bf16 tower
- * over-estimates by 3.0e-4 on average; tools/cert_bound.py, profiles/r02b_cert_bound.md) */
+ * extremes over 3.0 M candidates of the config-2 / config-3 workloads (-5.45e-4 / +1.26e-3; the bf16 tower
+ * over-estimates by 3.3e-4 on average; tools/cert_bound.py, profiles/r02b_cert_bound.md, profiles/r02j_cert_bound.md,
+ * DESIGN.md section 2) */
 #define CONZIC_CERT_DCOS_DEFAULT 1.6e-3f
-#define CONZIC_CERT_DCOS_LO_DEFAULT 6.5e-4f
+#define CONZIC_CERT_DCOS_LO_DEFAULT 7.1e-4f
 /* R = sum_j exp(exact logit_j) / sum_j exp(bf16 logit_j) over the candidates of an image that are NOT re-scored (the part
  * of the softmax denominator that stays approximate) is taken to lie in [ZRATIO_LO, ZRATIO_HI]; the per-candidate bounds
  * alone only give [exp(-100 hi), exp(100 lo)] = [0.852, 1.067]; measured over 5 120 image-steps R stays within

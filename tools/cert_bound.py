@@ -120,7 +120,7 @@ def main():
             mref = a16.max(dim=1, keepdim=True).values
             x16, x3 = torch.exp(a16 - mref), torch.exp(a3 - mref)
             r_all.append((x3.sum(1) / x16.sum(1)).cpu())
-            rest = ~survivor_mask(t16, 0.16, 0.065)
+            rest = ~survivor_mask(t16, 0.16, 0.071)
             has = rest.any(dim=1)
             r_rest.append(((x3 * rest).sum(1)[has] / (x16 * rest).sum(1)[has]).cpu())
             nf = int((i3[:, pos] != i16[:, pos]).sum())

@@ -48,6 +48,15 @@ if has ab; then  # A/B of the switches named in $AB_ENVS (space separated VAR=VA
     done
   done
 fi
+if has multi; then  # gpurun --gpus N: the BASELINE configurations that name a GPU count ($MULTI_CONFIGS, e.g. "3 5")
+  N=${NGPU:-8}
+  nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+  for c in $MULTI_CONFIGS; do
+    timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$c \
+        bench.py --gpus $N --config $c --steps ${MULTI_STEPS:-3} --warmup 3 --no-cpu > $OUT/bench_config${c}_n$N.json 2> $OUT/bench_config${c}_n$N.err
+    echo "config $c x $N GPUs rc=$?"; cut -c1-1200 $OUT/bench_config${c}_n$N.json; tail -3 $OUT/bench_config${c}_n$N.err
+  done
+fi
 if has vocab; then
   timeout 900 python tools/bench_vocab_paths.py > $OUT/vocab_paths.jsonl 2> $OUT/vocab_paths.err; echo "vocab rc=$?"; cat $OUT/vocab_paths.jsonl
 fi
