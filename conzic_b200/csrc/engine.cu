@@ -205,6 +205,7 @@ struct conzic_ctx {
     if (cfg.gemm_impl == CONZIC_GEMM_TCGEN05) {
       if (!make_tmap_bf16_2d(&L->tmap128, L->w, N, ld, ld, 128)) return false;
       if (!make_tmap_bf16_2d(&L->tmap256, L->w, N, ld, ld, 256)) return false;
+      if (!make_tmap_bf16_2d(&L->tmap64, L->w, N, ld, ld, 64)) return false;
     }
     return true;
   }
@@ -1155,6 +1156,7 @@ int conzic_debug_linear(conzic_ctx* c, const float* A, const float* Wf, const fl
   if (c->cfg.gemm_impl == CONZIC_GEMM_TCGEN05) {
     if (!make_tmap_bf16_2d(&W.tmap128, w_act, N, ld, ld, 128)) return -4;
     if (!make_tmap_bf16_2d(&W.tmap256, w_act, N, ld, ld, 256)) return -4;
+    if (!make_tmap_bf16_2d(&W.tmap64, w_act, N, ld, ld, 64)) return -4;
   }
   Epi e;
   e.bias = bias; e.resid = resid; e.ldr = N; e.act = act;

@@ -1405,7 +1405,7 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
 bool gemm_configure() {
   if (!configure_wide()) return false;
   if (!(configure_persist<1, false>() && configure_persist<2, true>() && configure_persist<2, false>())) return false;
-  return configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
+  return configure_one<64, 8>() && configure_one<128, 2>() && configure_one<128, 3>() && configure_one<128, 4>() && configure_one<128, 6>() &&
          configure_one<256, 2>() && configure_one<256, 4>();
 }
 
@@ -1459,7 +1459,11 @@ bool launch_linear(const Act& A, int M, const LinearW& W, const Epi& epi, const 
       if (units * 2 >= sm_count() / 2 || (W.N % BM) != 0 || o.force_pair)
         return launch_persist<2, false>(ta, W.tmap128, pp, sm_count(), false, st);
       p.split = 1;
-      launch_one<128, 6>(ta, W.tmap128, p, st);
+      // N = 512 on ~2 k rows (the re-score's O-proj / fc2): 128 x 64 tiles double the CTAs that stream the 24 - 96 k blocks
+      // (each CTA is bound by what it can pull from L2); same k order per element, bit-identical
+      const long long ctas64 = static_cast<long long>((M + BM - 1) / BM) * ((W.N + 63) / 64);
+      if ((W.N % 64) == 0 && ctas64 <= sm_count()) launch_one<64, 8>(ta, W.tmap64, p, st);
+      else launch_one<128, 6>(ta, W.tmap128, p, st);
       return cuda_ok(cudaGetLastError(), "gemm_tcgen05 launch");
     }
     const bool ares = cg == 2 && W.K <= P_MAX_KB * BK;  // a single CTA has no room for a resident A tile + 32 KB B stages

@@ -87,6 +87,7 @@ struct LinearW {
   int N = 0, K = 0;
   CUtensorMap tmap128;  // box 128 rows x 64 cols, 128B swizzle
   CUtensorMap tmap256;  // box 256 rows x 64 cols
+  CUtensorMap tmap64;   // box 64 rows x 64 cols (narrow-N bf16x3 GEMMs on a few thousand rows)
 };
 
 enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_ERF_GELU = 2 };
