@@ -715,7 +715,27 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else mbar_arrive_relaxed(&tempty_bar[acc]);
         }
       };
-      if (bf16_only && nbase + PBN / 2 <= p.N) {
+      if (bf16_only && p.tma_out && nbase + PBN / 2 <= p.N) {
+        // two register sets: the accumulator columns of chunk c + 1 are on their way while chunk c is activated, packed
+        // and handed to the TMA engine; the accumulator goes back to the MMA warp before the last chunk is processed
+        uint32_t ra[32], rb[32];
+        float v[32];
+        tmem_ld32(taddr, ra);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32(taddr + (c + 1) * 32, rb);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          epilogue_bf16_box(p, &tmO, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          tmem_ld_wait();
+          if (c + 2 < 4) tmem_ld32(taddr + (c + 2) * 32, ra);
+          else release();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
+          epilogue_bf16_box(p, &tmO, stg, lane, row0, nbase + (c + 1) * 32, v, bias4, c + 1);
+        }
+      } else if (bf16_only && nbase + PBN / 2 <= p.N) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -725,8 +745,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.tma_out) epilogue_bf16_box(p, &tmO, stg, lane, row0, nbase + c * 32, v, bias4, c);
-          else epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
+          epilogue_bf16_chunk(p, stg, lane, row0, nbase + c * 32, v, bias4, c);
         }
       } else if (nbase + PBN / 2 <= p.N) {
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
