@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "conzic_b200", "libconzic.so")
-KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMAPF", "UTMACCTL", "LDTM", "STTM", "UTCATOM", "HMMA", "LDSM", "SYNCS",
+KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UTMACCTL", "UTMACMDFLUSH", "LDTM", "STTM", "UTCATOM", "HMMA", "LDSM", "SYNCS",
        "UCGABAR", "CGABAR", "MUFU", "ATOMS", "RED", "SHFL", "LDG", "STG", "LDS", "STS", "BAR", "MEMBAR", "ERRBAR", "STL", "LDL")
 
 
@@ -30,7 +30,7 @@ def main():
         if m and fn:
             hist[fn][m.group(1)] += 1
             full = m.group(1) + m.group(2)
-            if m.group(1) in ("UTCHMMA", "UTMALDG", "UTCBAR", "LDTM", "STTM", "HMMA"):
+            if m.group(1) in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UTCBAR", "LDTM", "STTM", "HMMA"):
                 hist[fn]["~" + full] += 1
     demangle = subprocess.run(["c++filt"], input="\n".join(hist), capture_output=True, text=True).stdout.splitlines()
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)}: instructions per kernel, selected opcodes, and the distinct forms of the")
