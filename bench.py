@@ -395,6 +395,7 @@ def parity_check(job: Job):
             "decisions": st["images"], "rescored_candidates_per_step": st["rescored_candidates"] / calls,
             "images_with_several_unbeaten_per_step": st["images_multi"] / calls,
             "images_fully_reencoded_per_step": st["images_full"] / calls,
+            "of_which_over_the_survivor_cap_per_step": st["images_full_overflow"] / calls,
             "candidates_per_step": BATCH * job.wl.top_k}
 
 

@@ -57,6 +57,10 @@ if has multi; then  # gpurun --gpus N: the BASELINE configurations that name a G
     echo "config $c x $N GPUs rc=$?"; cut -c1-1200 $OUT/bench_config${c}_n$N.json; tail -3 $OUT/bench_config${c}_n$N.err
   done
 fi
+if has config4; then
+  timeout 600 python bench.py --config 4 --steps 2 --warmup 3 --no-cpu > $OUT/bench_config4.json 2> $OUT/bench_config4.err; echo "config 4 rc=$?"
+  python -c "import json;d=json.loads(open('$OUT/bench_config4.json').read().strip().splitlines()[-1]);print(d['value'],d['parity'])"
+fi
 if has vocab; then
   timeout 900 python tools/bench_vocab_paths.py > $OUT/vocab_paths.jsonl 2> $OUT/vocab_paths.err; echo "vocab rc=$?"; cat $OUT/vocab_paths.jsonl
 fi
@@ -83,9 +87,12 @@ if has ncuwide; then
       python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_gemm_wide.log 2>&1; echo "ncu gemm_wide rc=$?"
 fi
 if has ncusmall; then
-  for k in topk_cluster_kernel score_select_kernel clip_logits_kernel assemble_kernel layernorm_kernel cert_round1_kernel cert_round2_kernel clip_embed_kernel bert_embed_ln_kernel attention_kernel; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $OUT/prof_$k \
-        python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_$k.log 2>&1; echo "ncu $k rc=$?"
-  done
+  # the once-per-pass kernels of the measured step (the warm-up step launches ~12 of them first), then a few launches of the
+  # fp32 attention / LayerNorm kernels from the middle of the step
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:"topk_cluster|clip_logits|cert_round|cert_gather|assemble_kernel|clip_embed|bert_embed|pool_index|image_resize" -s 12 -c 16 -f -o $OUT/prof_small \
+      python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_small.log 2>&1; echo "ncu small rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_kernel|layernorm_kernel" -s 70 -c 6 -f -o $OUT/prof_small2 \
+      python tools/profile_step.py --ii 3 --steps 1 --warm 1 > $OUT/ncu_small2.log 2>&1; echo "ncu small2 rc=$?"
 fi
 ls -la $OUT
