@@ -126,6 +126,9 @@ def build_token_mask(args, tokenizer, dev):
     SURVEY.md 8(d) (ids < 1996 are specials / [unused] / punctuation / digits in bert-base-uncased)."""
     if args.synthetic and not os.path.exists(args.stop_words_path):
         return _synth().make_token_mask(dev)
+    if not os.path.exists(args.stop_words_path):
+        raise FileNotFoundError(f"--stop_words_path {args.stop_words_path!r} not found: point it at the reference checkout's "
+                                "stop_words.txt (the list is the reference's data file and is not duplicated here)")
     with open(args.stop_words_path, "r", encoding="utf-8") as fh:
         words = [w.rstrip("\n") for w in fh.readlines()] + list(args.add_extra_stopwords)
     mask = torch.ones((1, tokenizer.vocab_size))
