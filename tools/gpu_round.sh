@@ -57,6 +57,10 @@ if has multi; then  # gpurun --gpus N: the BASELINE configurations that name a G
     echo "config $c x $N GPUs rc=$?"; cut -c1-1200 $OUT/bench_config${c}_n$N.json; tail -3 $OUT/bench_config${c}_n$N.err
   done
 fi
+if has sanitize; then  # memcheck over the smoke step and the GEMM epilogue forms (TMA boxes, clipped last tiles)
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/sanitizer_smoke.log 2>&1; echo "memcheck smoke rc=$?"; tail -4 $OUT/sanitizer_smoke.log
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -q -x -k "gemm_epilogue or nontrivial_layernorm" > $OUT/sanitizer_epilogue.log 2>&1; echo "memcheck epilogue tests rc=$?"; tail -4 $OUT/sanitizer_epilogue.log
+fi
 if has config4; then
   timeout 600 python bench.py --config 4 --steps 2 --warmup 3 --no-cpu > $OUT/bench_config4.json 2> $OUT/bench_config4.err; echo "config 4 rc=$?"
   python -c "import json;d=json.loads(open('$OUT/bench_config4.json').read().strip().splitlines()[-1]);print(d['value'],d['parity'])"
