@@ -972,22 +972,14 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = (m * CG + static_cast<int>(cta_rank)) * BM + q * 32;
       mbar_wait(&tfull_bar[0], uph);
       tc_fence_after();
-#pragma unroll 1
-      for (int tt = 0; tt < 8; ++tt) {
+      // one box: registers of accumulator columns -> + bias -> swizzled shared-memory box -> TMA reduce / store
+      auto emit_box = [&](const uint32_t (&r)[32], int tt) {
         const int t = half * 8 + tt;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
         float4 bb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
         // the output box written two boxes ago must have been read by its TMA operation before it is overwritten
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        tmem_ld_wait();
-        if (tt == 7) {  // this warp's part of its accumulator half is in registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr);
-        }
         __syncwarp();
         uint8_t* O = Ob + (tt & 1) * SL::BOX + lane * 128;
 #pragma unroll
@@ -1012,6 +1004,26 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      };
+      // two register sets: the accumulator columns of box tt + 1 are on their way while box tt is emitted; the half goes
+      // back to the MMA warp as soon as its last columns are in registers (before the last box is emitted)
+      const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * PBN;
+      uint32_t ra[32], rb[32];
+      tmem_ld32(tcol, ra);
+#pragma unroll
+      for (int tt = 0; tt < 8; tt += 2) {
+        tmem_ld_wait();
+        tmem_ld32(tcol + (tt + 1) * 32, rb);
+        emit_box(ra, tt);
+        tmem_ld_wait();
+        if (tt + 2 < 8) {
+          tmem_ld32(tcol + (tt + 2) * 32, ra);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_addr);
+        }
+        emit_box(rb, tt + 1);
       }
       if (lnf) {
         // Fused LayerNorm: once both warps of the lane quarter have seen their boxes complete, each takes 16 of the
