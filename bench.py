@@ -494,9 +494,9 @@ def run_ours(args, rank, local_rank, world):
         if rank == 0 and world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cpu_sample(wl, 1, cores)  # warm-up (cold first call is several times slower)
-            v, s, kind = cpu_sample(wl, 1, cores)
+            v, s, kind = cpu_sample(wl, 4, cores)  # ~10 s of CPU work
             line["cpu_baseline"] = {"value": v, "unit": "captions/s", "cores": cores, "kind": kind,
-                                    "sample": f"1 image x (first sweep + one full-length sweep), {s:.1f} s of CPU work, "
+                                    "sample": f"4 images x (first sweep + one full-length sweep), {s:.1f} s of CPU work, "
                                               f"{wl.sweeps}-sweep time extrapolated as t_first + {wl.sweeps - 1}*t_full"}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -811,7 +811,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // and the A/B reference.  EPI 2: EW = 8 warps (two per TMEM lane quarter, one per accumulator half); acc + bias leaves
 // as 32 x 32 fp32 boxes that the L2 ADDS to the residual stream in place (cp.reduce.async.bulk.tensor .add.f32: x += ...,
 // no residual load at all, the load/store units only see shared memory); the LayerNorm statistics come from the
-// row-coalesced re-read that the LayerNorm pass makes anyway.  (Measured and dropped: the same boxes with the residual
+// row-coalesced re-read that the LayerNorm pass makes anyway.  EPI 3: the same with 4 K stages and one output box per
+// warp instead of 3 and 2 (long K).  (Measured and dropped: the same boxes with the residual
 // loaded by TMA and added in registers, 4 warps -- 2 % slower per step; 16-column boxes with 4 K stages and the
 // LayerNorm one unit late -- the late re-read misses L2; 8 warps with per-lane accesses.)
 template <int EW, int EPI>
@@ -819,18 +820,19 @@ struct WideSmem {
   static constexpr int A_SLOT = BM * BK * 2;           // 16 KB
   static constexpr int B_SLOT = (PBN / 2) * BK * 2;    // 16 KB: this CTA's 128 rows of one 256-row B tile
   static constexpr int STAGE = A_SLOT + 2 * B_SLOT;    // 48 KB
-  static constexpr int STAGES = EPI ? 3 : 4;
+  static constexpr int STAGES = (EPI == 0 || EPI == 3) ? 4 : 3;
+  static constexpr int NOB = EPI == 3 ? 1 : 2;          // EPI 2 / 3: output boxes per warp
   static constexpr int STG_OFF = STAGES * STAGE;       // EPI 0: one 2 KB staging buffer per epilogue warp
   static constexpr int BOX = 32 * 32 * 4;               // EPI 2: one 32-row x 32-column fp32 box
-  static constexpr int EPI_WARP = 2 * BOX;              // EPI 2: 2 output boxes per warp
+  static constexpr int EPI_WARP = NOB * BOX;
   static constexpr int BIAS_OFF = STG_OFF + (EPI ? EW * EPI_WARP : EW * 2048);
   static constexpr int BAR_OFF = BIAS_OFF + (EPI ? 2 * PBN * 4 : 0);
   static constexpr int N_BARS = 2 * STAGES + 4;
   static constexpr int DYN_BYTES = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int THREADS = 64 + 32 * EW;
   static_assert(DYN_BYTES <= 232448, "over the 227 KB shared-memory limit");
-  static_assert(EPI == 0 || EPI == 2, "epilogue form");
-  static_assert(EPI != 2 || EW == 8, "the TMA reduce epilogue uses two warps per TMEM lane quarter");
+  static_assert(EPI == 0 || EPI == 2 || EPI == 3, "epilogue form");
+  static_assert(EPI == 0 || EW == 8, "the TMA reduce epilogue uses two warps per TMEM lane quarter");
 };
 
 template <int EW, int EPI>
@@ -945,7 +947,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if constexpr (EPI == 2) {
+  } else if constexpr (EPI >= 2) {
     // ---- TMA reduce epilogue: warp (q, half) drains the 8 boxes of accumulator half `half` for rows [q*32, q*32+32):
     // acc + bias -> swizzled box -> cp.reduce.async.bulk.tensor (.add.f32: the residual is added by the L2, in place)
     // or a plain TMA store when there is no residual.
@@ -979,9 +981,9 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias_s + t * 32 + 4 * j);
         // the output box written two boxes ago must have been read by its TMA operation before it is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SL::NOB - 1) : "memory");
         __syncwarp();
-        uint8_t* O = Ob + (tt & 1) * SL::BOX + lane * 128;
+        uint8_t* O = Ob + (tt % SL::NOB) * SL::BOX + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 x;
@@ -996,11 +998,11 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
           if (has_res)
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt % SL::NOB) * SL::BOX)), "r"(t * 32), "r"(row0)
                          : "memory");
           else
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt & 1) * SL::BOX)), "r"(t * 32), "r"(row0)
+                         ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Ob + (tt % SL::NOB) * SL::BOX)), "r"(t * 32), "r"(row0)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -1399,7 +1401,7 @@ static bool configure_wide_one() {
                                       WideSmem<EW, EPI>::DYN_BYTES), "cudaFuncSetAttribute(gemm_wide)");
 }
 static bool configure_wide() {
-  return configure_wide_one<16, 0>() && configure_wide_one<8, 2>();
+  return configure_wide_one<16, 0>() && configure_wide_one<8, 2>() && configure_wide_one<8, 3>();
 }
 // lsu == false: TMA reduce epilogue (8 warps; the L2 adds acc + bias to the residual stream in place -- needs resid == out
 // or no residual, fp32 output only); otherwise / lsu == true: 16 epilogue warps with per-lane loads and stores
@@ -1430,7 +1432,10 @@ static bool launch_wide(const CUtensorMap& ta, const CUtensorMap& tb, const PGem
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return lsu ? launch_wide_one<16, 0>(cfg, ta, tb, to, p) : launch_wide_one<8, 2>(cfg, ta, tb, to, p);
+  if (lsu) return launch_wide_one<16, 0>(cfg, ta, tb, to, p);
+  // long K (fc2): the MMA phase dominates a unit -- a 4th K stage is worth more than the second output box (tower -1.4 %,
+  // same-box A/B); short K (O-proj): the drain dominates, two boxes per warp (the 4-stage form measured neutral there)
+  return p.K >= 1024 ? launch_wide_one<8, 3>(cfg, ta, tb, to, p) : launch_wide_one<8, 2>(cfg, ta, tb, to, p);
 }
 
 bool gemm_configure() {
