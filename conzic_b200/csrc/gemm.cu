@@ -1093,9 +1093,9 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory stays valid until read
     __syncwarp();
   } else {
-    // warp % 4 = TMEM lane quarter.  EW == 8: (warp - 2) / 4 = which 128-column slice of EACH 256-column half;
-    // EW == 16: (warp - 2) / 4 = which 128-column slice of the 512 columns (one half per warp), which doubles the
-    // loads in flight of this latency-bound, non-overlapped epilogue
+    // ---- per-lane epilogue (EPI 0; instantiated with EW == 16 only, the EW == 8 arithmetic is kept for reference).
+    // warp % 4 = TMEM lane quarter.  EW == 16: (warp - 2) / 4 = which 128-column slice of the 512 columns (one half per
+    // warp); EW == 8: (warp - 2) / 4 = which 128-column slice of EACH 256-column half
     const int q = warp & 3;
     const int slice = (warp - 2) >> 2;
     const int sub = EW == 8 ? slice : (slice & 1);  // columns [sub*128, sub*128+128) of a 256-column half
