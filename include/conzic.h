@@ -59,14 +59,14 @@ enum {
 #define CONZIC_CERT_ZRATIO_HI_DEFAULT 1.03f
 #define CONZIC_CERT_STATS 8
 
-/* conzic_config.flags */
+/* conzic_config.flags: each selects the slower form of a kernel choice, for same-box A/B measurements */
 enum {
-  CONZIC_FLAG_NO_PDL = 1,         /* launch without programmatic dependent launch (A/B measurements)                */
-  CONZIC_FLAG_WIDE_LSU = 4,       /* N = 512 GEMM kernel: per-lane epilogue accesses (16 warps) instead of the TMA      */
-                                  /*   reduce-add epilogue (A/B measurements)                                          */
-  CONZIC_FLAG_LSU_OUT = 16,       /* persistent GEMM kernel: bf16 outputs by per-lane stores instead of TMA boxes (A/B) */
-  CONZIC_FLAG_LN_STANDALONE = 2   /* CLIP bf16 tower: LayerNorm as its own kernel instead of in the O-proj / fc2
-                                     epilogues (A/B measurements; HF:models/clip/modeling_clip.py:369-384)          */
+  CONZIC_FLAG_NO_PDL = 1,         /* launch without programmatic dependent launch                                       */
+  CONZIC_FLAG_LN_STANDALONE = 2,  /* CLIP bf16 tower: LayerNorm as its own kernel instead of in the O-proj / fc2
+                                     epilogues (HF:models/clip/modeling_clip.py:369-384)                                */
+  CONZIC_FLAG_WIDE_LSU = 4,       /* N = 512 GEMM kernel: per-lane epilogue accesses (16 warps) instead of the TMA
+                                     reduce-add epilogue                                                                */
+  CONZIC_FLAG_LSU_OUT = 16        /* persistent GEMM kernel: bf16 outputs by per-lane stores instead of TMA boxes       */
 };
 
 /* GEMM implementation: 0 is the product path; 1 is a slow SIMT kernel kept for cross-checking in tests */
